@@ -1,0 +1,76 @@
+"""ctypes binding of libdt_b200.so (include/dt_b200.h).  No torch types cross
+the boundary: tensors are passed as raw device pointers + sizes + stream."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libdt_b200.so')
+_lib = None
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_sz = C.c_size_t
+
+# name -> argtypes (every function returns int unless listed in _RESTYPE)
+SIGNATURES = {
+    'dt_abi_version': [],
+    'dt_bbox_overlaps': [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p],
+    'dt_nms_workspace_bytes': [_i, _i, C.POINTER(_sz)],
+    'dt_nms_batched': [_p, _i, _i, _i, _i, _p, _f, _i, _i, _i, _p, _p, _p, _sz, _p],
+    'dt_lsa_batched': [_p, _i, _i, _i, _p, _p, _p, _p, _p],
+    'dt_match_frames': [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p],
+    'dt_assign_track_ids': [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p],
+    'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
+}
+_RESTYPE = {'dt_last_error': C.c_char_p}
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises RuntimeError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'libdt_b200.so is not built (%s). Run `python -m detectandtrack_b200.build` '
+                '(or __graft_entry__.build()). There is no CPU fallback.' % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.dt_last_error.restype = C.c_char_p
+        l.dt_last_error.argtypes = []
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, C.c_int)
+        _lib = l
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().dt_last_error().decode('utf-8', 'replace')
+        raise RuntimeError('%s failed (code %d): %s' % (what or 'libdt_b200 call', rc, msg))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('detectandtrack_b200 needs a CUDA device (B200, sm_100a); '
+                           'there is no CPU fallback.')
+    return torch
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) torch tensor, or NULL for None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'tensor must be contiguous'
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,17 @@
+#include "common.cuh"
+#include <stdarg.h>
+#include "../../include/dt_b200.h"
+
+namespace dt {
+static thread_local char g_err[512] = "";
+char* last_error_buf() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace dt
+
+extern "C" const char* dt_last_error(void) { return dt::last_error_buf(); }
+extern "C" int dt_abi_version(void) { return DT_B200_ABI_VERSION; }
