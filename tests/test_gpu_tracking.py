@@ -92,6 +92,9 @@ def test_match_frames_and_tracks_vs_oracle(T):
 
 def test_prune_and_center_vs_oracle():
     from detectandtrack_b200.core import tracking_engine as te
+    from detectandtrack_b200.core.config import cfg, reset_cfg
+    reset_cfg()
+    cfg.KRCNN.NUM_KEYPOINTS = 17
     rng = np.random.default_rng(8)
     T = 3
     boxes, json_data = [], []
