@@ -22,7 +22,16 @@ SIGNATURES = {
     'dt_match_frames': [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p],
     'dt_assign_track_ids': [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p],
     'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
+    'dt_conv3d': [_p, _p, _p, _p, _p, _p, _p, _p],
 }
+
+
+
+class ConvDesc(C.Structure):
+    """dt_conv_desc (include/dt_b200.h)."""
+    _fields_ = [(n, C.c_int) for n in (
+        'N', 'Ti', 'Hi', 'Wi', 'Cin', 'Cout', 'kT', 'kH', 'kW', 'sT', 'sH', 'sW', 'pT', 'pH', 'pW',
+        'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode')]
 _RESTYPE = {'dt_last_error': C.c_char_p}
 
 

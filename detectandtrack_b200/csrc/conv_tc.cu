@@ -1,0 +1,436 @@
+// Conv3d / Conv2d / FC as ONE implicit-GEMM kernel on the 5th-gen tensor cores (tcgen05),
+// NDHWC activations, fused AffineChannel (+bias) + residual / top-down-upsample add + ReLU.
+//
+// Replaces, on the reference's hot path:
+//   Caffe2 Conv / ConvNd engine=CUDNN        (lib/modeling/detector.py:318-322,410-436 and every
+//                                             call site listed in SURVEY.md §2.3 K5)
+//   AffineChannelNdOp<float,CUDAContext>     (lib/ops/affine_channel_nd_op.cu:19-70)  -> epilogue
+//   Relu / Sum (residual)                    (lib/modeling/ResNet3D.py:37,47,147-152) -> epilogue
+//   UpsampleNearest + Sum (FPN top-down)     (lib/modeling/FPN3D.py:211-222)          -> epilogue
+//   FC (cuBLAS)                              (lib/modeling/head_builder.py:33-36)     -> kT=kH=kW=1
+//
+// GEMM view: D[m, n] = sum_{tap, c} A[m @ tap, c] * W[tap, n, c]
+//   m = output position (img, t, ho, wo) tiled as TH x TW spatial patches (TH*TW <= 128 rows)
+//   n = output channel, BLOCK_N in {32, 64, 128, 256};  k-block = one tap x 128 bytes of channels
+//   A tile: one 5-D TMA box (C=128B, TW, TH, 1, 1) at the tap-shifted coordinate; out-of-bounds
+//           elements (spatial / temporal zero padding, ragged edge tiles, channel tail) are
+//           zero-filled by the TMA unit, so padding costs no instructions and no branches.
+//   W tile: 3-D TMA box (C=128B, BLOCK_N, 1) of the pre-packed [tap][Cout][Cin] weights.
+//   Both land in the 128B-swizzled K-major layout tcgen05.mma reads directly.
+// Roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0   : TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
+//   warp 1   : TMEM allocator + MMA issuer (one lane)   tcgen05.mma -> TMEM, tcgen05.commit
+//   warps 2-5: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32,
+//              16-byte stores to NDHWC.  Two TMEM accumulator stages overlap it with the next
+//              tile's MMAs.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/dt_b200.h"
+#include <cuda_bf16.h>
+
+namespace dt {
+
+using namespace tc;
+
+struct ConvKernelParams {
+  // output geometry
+  int N, To, Ho, Wo, Cout;
+  // filter
+  int kT, kH, kW, sT, sH, sW, pT, pH, pW;
+  int kchunks;                 // ceil(Cin / BK)
+  // tiling
+  int TH, TW, tiles_h, tiles_w, tiles_n, total_tiles;
+  uint32_t a_bytes;            // TH*TW*128
+  // epilogue
+  const float* scale;          // [Cout] or null (1)
+  const float* bias;           // [Cout] or null (0)
+  const void* residual;        // same dtype as out, or null
+  int res_mode;                // 0 none, 1 same shape, 2 nearest-2x upsample of (Ho/2, Wo/2)
+  int res_ld;
+  int relu;
+  void* out;
+  int out_ld;                  // elements between consecutive positions
+  int out_f32;                 // 1: fp32 output, 0: bf16
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int A_BYTES = 128 * 128;            // 128 rows x 128 B
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvKernelParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BK = TF32 ? 32 : 64;                 // elements per 128-byte k-block
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (required by SWIZZLE_128B)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + STAGES;             // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  const int taps = p.kT * p.kH * p.kW;
+  const int kiters = taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int mt = tile / p.tiles_n;
+        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+        const int thi = mt % p.tiles_h; mt /= p.tiles_h;
+        const int t = mt % p.To;
+        const int n = mt / p.To;
+        const int w_base = twi * p.TW * p.sW - p.pW;
+        const int h_base = thi * p.TH * p.sH - p.pH;
+        const int t_base = t * p.sT - p.pT;
+        int tap = 0;
+        for (int kt = 0; kt < p.kT; ++kt)
+          for (int kh = 0; kh < p.kH; ++kh)
+            for (int kw = 0; kw < p.kW; ++kw, ++tap)
+              for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                mbar_expect_tx(&full[stage], p.a_bytes + Cfg::B_BYTES);
+                tma_load_5d(a_dst, &tmA, &full[stage], kc * BK, w_base + kw, h_base + kh, t_base + kt, n);
+                tma_load_3d(b_dst, &tmB, &full[stage], kc * BK, nt * BN, tap);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, TF32 ? 2 : 1);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int ki = 0; ki < kiters; ++ki) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)          // 4 x 32 B = one 128-byte swizzle row of K
+            umma<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);           // accumulator ready for the epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lg = warp & 3;                   // TMEM lane group this warp may access
+    const int row = lg * 32 + lane;            // accumulator row == TMEM lane
+    const int th = row / p.TW, tw = row - th * p.TW;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
+      const int t = mt % p.To;
+      const int n = mt / p.To;
+      const int ho = thi * p.TH + th, wo = twi * p.TW + tw;
+      const bool valid = (th < p.TH) && (ho < p.Ho) && (wo < p.Wo);
+      const size_t pos = ((size_t)(n * p.To + t) * p.Ho + ho) * p.Wo + wo;
+      size_t rpos = pos;
+      if (p.res_mode == 2)
+        rpos = ((size_t)(n * p.To + t) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
+
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        const int cbase = nt * BN + c0;
+        if (valid && cbase < p.Cout) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            const bool cok = c < p.Cout;
+            const float s = (p.scale && cok) ? __ldg(p.scale + c) : 1.f;
+            const float b = (p.bias && cok) ? __ldg(p.bias + c) : 0.f;
+            v[j] = fmaf(__uint_as_float(r[j]), s, b);
+          }
+          const int ncols = min(32, p.Cout - cbase);
+          if (p.res_mode != 0) {
+            if (p.out_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + rpos * p.res_ld + cbase;
+              if (ncols == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j));
+                  v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                }
+              } else {
+                for (int j = 0; j < ncols; ++j) v[j] += __ldg(rp + j);
+              }
+            } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
+              if (ncols == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                  const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v[j + 2 * e] += __uint_as_float(w4[e] << 16);
+                    v[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                  }
+                }
+              } else {
+                for (int j = 0; j < ncols; ++j) v[j] += __bfloat162float(rp[j]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + pos * p.out_ld + cbase;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < ncols; ++j) op[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.out_ld + cbase;
+            if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 q;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+                q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(op + j) = q;
+              }
+            } else {
+              for (int j = 0; j < ncols; ++j) op[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
+                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, const uint32_t* estr) {
+  PFN_encodeTiled enc = get_encode();
+  DT_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t d[5], s[4]; cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                   const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DT_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu ..., box %u %u %u)",
+               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+  return 0;
+}
+
+static void pick_tile(int Ho, int Wo, int* TH, int* TW) {
+  // maximise useful rows per 128-row MMA tile over a small candidate set
+  const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
+  double best = -1;
+  int bh = 8, bw = 16;
+  auto consider = [&](int th, int tw) {
+    if (th < 1 || tw < 1 || th * tw > 128 || tw > 256 || th > 256) return;
+    const double eff = (double)Ho * Wo / ((double)cdiv(Ho, th) * cdiv(Wo, tw) * 128.0);
+    if (eff > best + 1e-9) { best = eff; bh = th; bw = tw; }
+  };
+  for (auto& c : cand) consider(c[0], c[1]);
+  if (Wo <= 128) { consider(128 / Wo, Wo); for (int d = 2; d <= 4; ++d) { const int tw = cdiv(Wo, d); consider(128 / tw, tw); } }
+  if (Ho <= 128) { consider(Ho, 128 / Ho); for (int d = 2; d <= 4; ++d) { const int th = cdiv(Ho, d); consider(th, 128 / th); } }
+  *TH = bh; *TW = bw;
+}
+
+template <int BN, bool TF32>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    DT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr = true;
+  }
+  conv_tc_kernel<BN, TF32><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace dt
+
+using namespace dt;
+
+extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, const float* scale, const float* bias,
+                         const void* residual, void* y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DT_CHECK_ARG(d != nullptr, "dt_conv3d: null descriptor");
+  DT_CHECK_ARG(d->dtype == DT_DTYPE_BF16 || d->dtype == DT_DTYPE_TF32, "dt_conv3d: dtype %d not in {BF16, TF32}", d->dtype);
+  const bool tf32 = d->dtype == DT_DTYPE_TF32;
+  const int esz = tf32 ? 4 : 2;
+  const int BK = tf32 ? 32 : 64;
+  DT_CHECK_ARG(d->N >= 1 && d->Ti >= 1 && d->Hi >= 1 && d->Wi >= 1 && d->Cin >= 1 && d->Cout >= 1,
+               "dt_conv3d: bad input shape N=%d T=%d H=%d W=%d Cin=%d Cout=%d", d->N, d->Ti, d->Hi, d->Wi, d->Cin, d->Cout);
+  DT_CHECK_ARG(d->kT >= 1 && d->kH >= 1 && d->kW >= 1 && d->sT >= 1 && d->sH >= 1 && d->sW >= 1 && d->pT >= 0 &&
+                   d->pH >= 0 && d->pW >= 0, "dt_conv3d: bad filter geometry");
+  const int To = (d->Ti + 2 * d->pT - d->kT) / d->sT + 1;
+  const int Ho = (d->Hi + 2 * d->pH - d->kH) / d->sH + 1;
+  const int Wo = (d->Wi + 2 * d->pW - d->kW) / d->sW + 1;
+  DT_CHECK_ARG(To >= 1 && Ho >= 1 && Wo >= 1, "dt_conv3d: empty output (%d,%d,%d)", To, Ho, Wo);
+  const int in_ld = d->in_ld > 0 ? d->in_ld : d->Cin;
+  const int w_ld = d->w_ld > 0 ? d->w_ld : d->Cin;
+  const int out_ld = d->out_ld > 0 ? d->out_ld : d->Cout;
+  const int res_ld = d->res_ld > 0 ? d->res_ld : d->Cout;
+  DT_CHECK_ARG((in_ld * esz) % 16 == 0 && (w_ld * esz) % 16 == 0,
+               "dt_conv3d: channel strides must be multiples of 16 bytes (in_ld=%d, w_ld=%d, %d B/elem)", in_ld, w_ld, esz);
+  DT_CHECK_ARG(in_ld >= d->Cin && w_ld >= d->Cin && out_ld >= d->Cout, "dt_conv3d: leading dims smaller than channels");
+  DT_CHECK_ARG(x && w && y, "dt_conv3d: null tensor pointer");
+  DT_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0,
+               "dt_conv3d: tensors must be 16-byte aligned");
+  DT_CHECK_ARG(d->res_mode >= 0 && d->res_mode <= 2 && (d->res_mode == 0 || residual), "dt_conv3d: bad residual mode/pointer");
+  DT_CHECK_ARG(d->res_mode != 2 || (Ho % 2 == 0 && Wo % 2 == 0), "dt_conv3d: upsample-add needs even output size, got %dx%d", Ho, Wo);
+  const int out_f32 = d->out_f32;
+  const int oesz = out_f32 ? 4 : 2;
+  // vector stores need 16-byte aligned rows
+  DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && (d->res_mode == 0 || (res_ld * oesz) % 16 == 0),
+               "dt_conv3d: out_ld/res_ld rows must be 16-byte multiples");
+
+  int TH, TW;
+  pick_tile(Ho, Wo, &TH, &TW);
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.To = To; p.Ho = Ho; p.Wo = Wo; p.Cout = d->Cout;
+  p.kT = d->kT; p.kH = d->kH; p.kW = d->kW; p.pT = d->pT; p.pH = d->pH; p.pW = d->pW;
+  p.sT = d->sT; p.sH = d->sH; p.sW = d->sW;
+  p.kchunks = cdiv(d->Cin, BK);
+  p.TH = TH; p.TW = TW; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW);
+  p.a_bytes = (uint32_t)TH * TW * 128u;
+  p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = d->res_mode; p.res_ld = res_ld;
+  p.relu = d->relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32;
+
+  int BN = d->Cout >= 256 ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32));
+  if (d->Cout > 128 && d->Cout < 256) BN = 128;
+  p.tiles_n = cdiv(d->Cout, BN);
+  const long long total = (long long)d->N * To * p.tiles_h * p.tiles_w * p.tiles_n;
+  DT_CHECK_ARG(total < (1ll << 31), "dt_conv3d: too many tiles");
+  p.total_tiles = (int)total;
+
+  // ---- tensor maps -------------------------------------------------------------
+  // A: dims (C, W, H, T, N) of the NDHWC input.  Pointwise strided convs (1x1x1, stride s, no
+  // padding) fold the stride into the global strides so no element-stride traversal is needed;
+  // other strided convs use TMA element strides (box covers s*TW input columns, every s-th kept).
+  CUtensorMap tmA, tmB;
+  const bool pointwise = d->kT == 1 && d->kH == 1 && d->kW == 1 && d->pT == 0 && d->pH == 0 && d->pW == 0;
+  uint64_t dims[5], strides[4]; uint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  const uint64_t sC = (uint64_t)in_ld * esz, sW = sC * d->Wi, sH = sW * d->Hi, sT = sH * d->Ti;
+  if (pointwise) {
+    dims[0] = d->Cin; dims[1] = Wo; dims[2] = Ho; dims[3] = To; dims[4] = d->N;
+    strides[0] = sC * d->sW; strides[1] = sW * d->sH; strides[2] = sH * d->sT; strides[3] = sT;
+    box[0] = BK; box[1] = TW; box[2] = TH; box[3] = 1; box[4] = 1;
+    p.sT = p.sH = p.sW = 1;
+  } else {
+    dims[0] = d->Cin; dims[1] = d->Wi; dims[2] = d->Hi; dims[3] = d->Ti; dims[4] = d->N;
+    strides[0] = sC; strides[1] = sW; strides[2] = sH; strides[3] = sT;
+    box[0] = BK; box[1] = (uint32_t)TW * d->sW; box[2] = (uint32_t)TH * d->sH; box[3] = 1; box[4] = 1;
+    estr[1] = d->sW; estr[2] = d->sH;
+    DT_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "dt_conv3d: strided tile too large for a TMA box");
+  }
+  if (encode_map(&tmA, tf32, 5, x, dims, strides, box, estr)) return 1;
+  {
+    const int taps = d->kT * d->kH * d->kW;
+    uint64_t wd[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)taps};
+    uint64_t ws[2] = {(uint64_t)w_ld * esz, (uint64_t)w_ld * esz * d->Cout};
+    uint32_t wb[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+    uint32_t we[3] = {1, 1, 1};
+    if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
+  }
+  int dev = 0, sms = 148;
+  DT_CHECK_CUDA(cudaGetDevice(&dev));
+  DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+#define DT_LAUNCH(BNv)                                                                      \
+  return tf32 ? launch_conv<BNv, true>(tmA, tmB, p, grid, stream) : launch_conv<BNv, false>(tmA, tmB, p, grid, stream)
+  switch (BN) {
+    case 256: DT_LAUNCH(256);
+    case 128: DT_LAUNCH(128);
+    case 64: DT_LAUNCH(64);
+    default: DT_LAUNCH(32);
+  }
+#undef DT_LAUNCH
+}

@@ -1,0 +1,66 @@
+"""Device-tensor API over csrc/conv_tc.cu (tcgen05 implicit-GEMM Conv3d/Conv2d/FC).
+Tensors are NDHWC ([N, T, H, W, C], channels innermost); torch is only the memory
+container.  See include/dt_b200.h (dt_conv_desc / dt_conv3d) for the contract."""
+import ctypes as C
+
+from .. import _lib as L
+
+BF16, TF32 = 0, 1
+
+
+def _dt(dtype, torch):
+    return torch.float32 if dtype == TF32 else torch.bfloat16
+
+
+def pack_weight(w, dtype=BF16):
+    """Caffe2 / torch filter (Cout, Cin, kT, kH, kW) [or 4-D (Cout, Cin, kH, kW), or 2-D FC
+    (Cout, Cin)] -> tap-major [kT*kH*kW, Cout, Cin_pad] in the compute dtype; Cin is padded with
+    zeros to a 16-byte multiple (TMA global-stride rule)."""
+    torch = L.require_cuda()
+    if w.dim() == 2:
+        w = w[:, :, None, None, None]
+    elif w.dim() == 4:
+        w = w[:, :, None, :, :]
+    Cout, Cin, kT, kH, kW = w.shape
+    mult = 4 if dtype == TF32 else 8
+    Cp = (Cin + mult - 1) // mult * mult
+    out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=_dt(dtype, torch), device='cuda')
+    out[:, :, :Cin] = w.to('cuda').permute(2, 3, 4, 0, 1).reshape(kT * kH * kW, Cout, Cin).to(out.dtype)
+    return out
+
+
+def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias=None,
+           residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None):
+    """x [N,T,H,W,Cx] (first `cin` channels are the conv input); returns y [N,To,Ho,Wo,Cout]."""
+    torch = L.require_cuda()
+    assert x.is_cuda and x.dim() == 5 and x.is_contiguous()
+    assert x.dtype == _dt(dtype, torch), (x.dtype, dtype)
+    N, Ti, Hi, Wi, Cx = x.shape
+    taps, Cout, w_ld = w_packed.shape
+    kT, kH, kW = ksize
+    assert taps == kT * kH * kW
+    cin = cin if cin is not None else min(Cx, w_ld)
+    sT, sH, sW = stride
+    pT, pH, pW = pad
+    To = (Ti + 2 * pT - kT) // sT + 1
+    Ho = (Hi + 2 * pH - kH) // sH + 1
+    Wo = (Wi + 2 * pW - kW) // sW + 1
+    if out_f32 is None:
+        out_f32 = dtype == TF32
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    if out is None:
+        out = torch.empty((N, To, Ho, Wo, Cout), dtype=odt, device='cuda')
+    assert out.dtype == odt and out.is_contiguous()
+    d = L.ConvDesc(N=N, Ti=Ti, Hi=Hi, Wi=Wi, Cin=cin, Cout=Cout, kT=kT, kH=kH, kW=kW, sT=sT, sH=sH, sW=sW,
+                   pT=pT, pH=pH, pW=pW, in_ld=Cx, w_ld=w_ld, out_ld=out.shape[-1],
+                   res_ld=(residual.shape[-1] if residual is not None else 0), dtype=dtype,
+                   out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode))
+    if residual is not None:
+        assert residual.dtype == odt and residual.is_contiguous()
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.numel() == Cout
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cout
+    L.call('dt_conv3d', C.byref(d), L.ptr(x), L.ptr(w_packed), L.ptr(scale), L.ptr(bias), L.ptr(residual),
+           L.ptr(out), L.stream_ptr())
+    return out

@@ -102,6 +102,39 @@ int dt_prune_detections(const float* boxes, int nframes, int dmax, int ld, int T
                         const int* counts_in, const float* hw, float conf, float min_area,
                         float* out, int* counts_out, int* sel, void* stream);
 
+/* ---- conv_tc.cu ---------------------------------------------------------- */
+
+#define DT_DTYPE_BF16 0   /* bf16 activations/weights, fp32 accumulate (tcgen05 kind::f16)   */
+#define DT_DTYPE_TF32 1   /* fp32 storage, tf32 multiply, fp32 accumulate (tcgen05 kind::tf32) */
+
+/* Geometry + fused epilogue of one convolution (host struct, plain ints).
+ * Replaces a Caffe2 Conv/ConvNd (engine=CUDNN) followed by AffineChannel[Nd]
+ * (lib/ops/affine_channel_nd_op.cu:19-70), Sum and Relu
+ * (lib/modeling/detector.py:410-436, lib/modeling/ResNet3D.py:21-101), the FPN
+ * top-down UpsampleNearest+Sum (lib/modeling/FPN3D.py:186-222) and FC
+ * (lib/modeling/head_builder.py:33-36; a 1x1x1 conv over W = #rows).
+ *   x  [N, Ti, Hi, Wi, in_ld]   NDHWC (channels innermost), first Cin channels used
+ *   w  [kT*kH*kW, Cout, w_ld]   tap-major, channels innermost (cross-correlation, as Caffe2)
+ *   y  [N, To, Ho, Wo, out_ld]  first Cout channels written
+ *   y = relu?( conv(x, w) * scale[c] + bias[c]  (+ residual) )
+ * res_mode 0: none; 1: residual has y's shape (ld res_ld); 2: residual is
+ * [N, To, Ho/2, Wo/2, res_ld] and is read at (ho/2, wo/2) (nearest 2x upsample).
+ * Leading dims 0 => dense.  x/w rows must be 16-byte multiples, y/residual rows too. */
+typedef struct dt_conv_desc {
+  int N, Ti, Hi, Wi, Cin, Cout;
+  int kT, kH, kW;
+  int sT, sH, sW;
+  int pT, pH, pW;
+  int in_ld, w_ld, out_ld, res_ld;
+  int dtype;      /* DT_DTYPE_* : type of x and w */
+  int out_f32;    /* 1: y/residual fp32, 0: bf16 */
+  int relu;
+  int res_mode;
+} dt_conv_desc;
+
+int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
+              const float* bias, const void* residual, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,117 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (through the C ABI) against a plain
+PyTorch fp32 reference of the same op (torch.nn.functional.conv3d on the CPU, the stand-in
+for the un-vendored Caffe2 ConvNd + AffineChannelNd + Sum + Relu; "parity unpinned" by the
+reference).
+
+Tolerances (north star: 1e-3 relative fp32):
+  bf16 mode: the reference is evaluated on the SAME bf16-rounded x and w, so only fp32
+             accumulation order differs: |err| <= 2e-4 * max|y| (fp32 output).
+  tf32 mode: fp32 inputs, tf32 multiplies: |err| <= 1e-3 * max|y|.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x, w, stride, pad, scale, bias, residual, res_mode, relu):
+    import torch
+    import torch.nn.functional as F
+    # x [N,T,H,W,C] -> NCTHW
+    y = F.conv3d(x.permute(0, 4, 1, 2, 3).double(), w.double(), None, stride, pad)
+    if scale is not None:
+        y = y * scale.double().view(1, -1, 1, 1, 1)
+    if bias is not None:
+        y = y + bias.double().view(1, -1, 1, 1, 1)
+    y = y.permute(0, 2, 3, 4, 1)
+    if res_mode == 1:
+        y = y + residual.double()
+    elif res_mode == 2:
+        y = y + residual.double().repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+    if relu:
+        y = y.clamp_min(0)
+    return y.float()
+
+
+CASES = [
+    # N, T, H, W, Cin, Cout, k, stride, pad, affine, res_mode, relu
+    dict(N=1, T=1, H=16, W=16, Cin=64, Cout=64, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0)),
+    dict(N=1, T=1, H=16, W=32, Cin=64, Cout=128, k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1), affine=True, relu=True),
+    dict(N=2, T=3, H=20, W=28, Cin=128, Cout=256, k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1), affine=True, res_mode=1, relu=True),
+    dict(N=1, T=3, H=13, W=21, Cin=256, Cout=256, k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1)),
+    dict(N=1, T=3, H=25, W=42, Cin=256, Cout=512, k=(1, 1, 1), s=(1, 2, 2), p=(0, 0, 0), affine=True),
+    dict(N=1, T=2, H=24, W=40, Cin=192, Cout=64, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0), res_mode=2),
+    dict(N=1, T=1, H=50, W=84, Cin=256, Cout=12, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0), bias=True),
+    dict(N=1, T=1, H=1, W=300, Cin=1000, Cout=1024, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0), bias=True, relu=True),
+    dict(N=1, T=1, H=14, W=14, Cin=512, Cout=512, k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1), bias=True, relu=True),
+    dict(N=3, T=1, H=9, W=7, Cin=72, Cout=40, k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1)),
+]
+
+
+@pytest.mark.parametrize('mode', ['bf16', 'tf32'])
+@pytest.mark.parametrize('case', range(len(CASES)))
+def test_conv_parity(case, mode):
+    import torch
+    from detectandtrack_b200.ops import conv as cv
+    c = CASES[case]
+    g = torch.Generator().manual_seed(100 + case)
+    N, T, H, W, Cin, Cout = c['N'], c['T'], c['H'], c['W'], c['Cin'], c['Cout']
+    k, s, p = c['k'], c['s'], c['p']
+    x = torch.randn((N, T, H, W, Cin), generator=g)
+    w = torch.randn((Cout, Cin) + k, generator=g) * (2.0 / (Cin * k[0] * k[1] * k[2])) ** 0.5
+    scale = (torch.rand(Cout, generator=g) + 0.5) if c.get('affine') else None
+    bias = (torch.randn(Cout, generator=g) * 0.1) if (c.get('affine') or c.get('bias')) else None
+    To = (T + 2 * p[0] - k[0]) // s[0] + 1
+    Ho = (H + 2 * p[1] - k[1]) // s[1] + 1
+    Wo = (W + 2 * p[2] - k[2]) // s[2] + 1
+    rm = c.get('res_mode', 0)
+    res = None
+    if rm == 1:
+        res = torch.randn((N, To, Ho, Wo, Cout), generator=g)
+    elif rm == 2:
+        res = torch.randn((N, To, Ho // 2, Wo // 2, Cout), generator=g)
+    dtype = cv.BF16 if mode == 'bf16' else cv.TF32
+    if mode == 'bf16':
+        x = x.bfloat16().float(); w = w.bfloat16().float()
+        xd = x.bfloat16().cuda()
+        tol = 2e-4
+    else:
+        xd = x.cuda()
+        tol = 1e-3
+    wp = cv.pack_weight(w, dtype)
+    y = cv.conv3d(xd.contiguous(), wp, k, s, p,
+                  scale.cuda() if scale is not None else None, bias.cuda() if bias is not None else None,
+                  res.cuda().contiguous() if res is not None else None, rm, bool(c.get('relu')),
+                  out_f32=True, dtype=dtype, cin=Cin)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, s, p, scale, bias, res, rm, bool(c.get('relu')))
+    err = (y.cpu() - ref).abs().max().item()
+    den = ref.abs().max().item()
+    assert y.shape == ref.shape
+    assert err <= tol * den, (err, den, err / den)
+
+
+def test_conv_bf16_output_and_channel_slices():
+    """bf16 output path, reading a channel slice (in_ld > Cin) and writing into a slice of a
+    wider tensor (out_ld > Cout), as the engine does for concatenations."""
+    import torch
+    from detectandtrack_b200.ops import conv as cv
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn((1, 1, 12, 20, 128), generator=g).bfloat16()
+    w = (torch.randn((64, 64, 1, 3, 3), generator=g) * 0.05).bfloat16()
+    out = torch.zeros((1, 1, 12, 20, 192), dtype=torch.bfloat16, device='cuda')
+    wp = cv.pack_weight(w.float(), cv.BF16)
+    cv.conv3d(x.cuda(), wp, (1, 3, 3), (1, 1, 1), (0, 1, 1), relu=True, out_f32=False, dtype=cv.BF16, cin=64, out=out)
+    ref = _ref_conv(x[..., :64].float(), w.float(), (1, 1, 1), (0, 1, 1), None, None, None, 0, True)
+    got = out.cpu().float()
+    assert torch.all(got[..., 64:] == 0)
+    assert (got[..., :64] - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()     # bf16 output rounding (2^-8)
+
+
+def test_conv_rejects_bad_arguments():
+    import torch
+    from detectandtrack_b200.ops import conv as cv
+    x = torch.zeros((1, 1, 8, 8, 12), dtype=torch.bfloat16, device='cuda')     # 24-byte rows
+    wp = torch.zeros((1, 16, 16), dtype=torch.bfloat16, device='cuda')
+    with pytest.raises(RuntimeError, match='16 bytes'):
+        cv.conv3d(x, wp, (1, 1, 1), cin=12)
