@@ -1,0 +1,414 @@
+// HBM-bound NDHWC kernels around the tensor-core convolutions (channels innermost, 16-byte vector
+// accesses, one thread per 8 bf16 / 4 fp32 channels so every warp touches whole 128-byte lines):
+//   dt_prep_clip        lib/utils/blob.py:40-90 + lib/core/test.py:43-74: mean-subtract, cv2
+//                       INTER_LINEAR resize, zero pad to the /32 blob, BGR u8 -> NDHWC (C padded)
+//   dt_maxpool2d        Caffe2 MaxPool [1,k,k] (lib/modeling/ResNet3D.py:264-265; FPN P6 subsample
+//                       lib/modeling/FPN3D.py:157-160)
+//   dt_roi_align        Caffe2 RoIAlign (Detectron module; lib/modeling/detector.py:216-310) incl.
+//                       the FPN level routing, tube -> per-frame boxes (lib/ops/roi_blob_transforms.py:
+//                       25-36) and the BatchPermutation un-shuffle (rows are written in RoI order)
+//   dt_keypoint_decode  fixed bilinear 2x ConvTranspose (lib/modeling/detector.py:348-380) applied to
+//                       the sub-pixel-packed low-res scores + lib/utils/keypoints.py:94-149 heatmap ->
+//                       (x, y, logit, prob) with the cv2 INTER_CUBIC resize evaluated on the fly
+#include "common.cuh"
+#include "../../include/dt_b200.h"
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+namespace dt {
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) { const float4 q = *reinterpret_cast<const float4*>(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+  __device__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* v) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* v) {
+    uint4 q; uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]); w[e] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+};
+
+// ------------------------------------------------------------------- image prep
+// frames [F, H, W, 3] u8 (BGR).  out [F, Hp, Wp, Cp]: channels 0..2 = resized (pixel - mean), rest 0;
+// rows/cols beyond the resized image are 0 (blob.py:40-62).  cv2.resize(INTER_LINEAR) on float32:
+// sx = (dx + 0.5) * (1/fx) - 0.5, floor, clamp, weights in float (parity unpinned).
+template <typename OT>
+__global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F, int H, int W, float m0, float m1,
+                                 float m2, double inv_scale, int Hr, int Wr, int Hp, int Wp, int Cp,
+                                 OT* __restrict__ out) {
+  const long long total = (long long)F * Hp * Wp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % Wp);
+    const int y = (int)((idx / Wp) % Hp);
+    const int f = (int)(idx / ((long long)Wp * Hp));
+    float v[3] = {0.f, 0.f, 0.f};
+    if (y < Hr && x < Wr) {
+      const unsigned char* src = frames + (size_t)f * H * W * 3;
+      const float mean[3] = {m0, m1, m2};
+      if (Hr == H && Wr == W) {
+        const unsigned char* p = src + ((size_t)y * W + x) * 3;
+        for (int c = 0; c < 3; ++c) v[c] = (float)p[c] - mean[c];
+      } else {
+        float fy = (float)((y + 0.5) * inv_scale - 0.5), fx = (float)((x + 0.5) * inv_scale - 0.5);
+        int sy = (int)floorf(fy), sx = (int)floorf(fx);
+        fy -= sy; fx -= sx;
+        if (sy < 0) { sy = 0; fy = 0.f; }
+        if (sy >= H - 1) { sy = H - 1 > 0 ? H - 2 : 0; fy = H > 1 ? 1.f : 0.f; if (H == 1) { sy = 0; } }
+        if (sx < 0) { sx = 0; fx = 0.f; }
+        if (sx >= W - 1) { sx = W - 1 > 0 ? W - 2 : 0; fx = W > 1 ? 1.f : 0.f; if (W == 1) { sx = 0; } }
+        const int sy1 = min(sy + 1, H - 1), sx1 = min(sx + 1, W - 1);
+        for (int c = 0; c < 3; ++c) {
+          const float p00 = (float)src[((size_t)sy * W + sx) * 3 + c] - mean[c];
+          const float p01 = (float)src[((size_t)sy * W + sx1) * 3 + c] - mean[c];
+          const float p10 = (float)src[((size_t)sy1 * W + sx) * 3 + c] - mean[c];
+          const float p11 = (float)src[((size_t)sy1 * W + sx1) * 3 + c] - mean[c];
+          const float r0 = p00 * (1.f - fx) + p01 * fx;      // horizontal pass first (cv2 hresize)
+          const float r1 = p10 * (1.f - fx) + p11 * fx;
+          v[c] = r0 * (1.f - fy) + r1 * fy;                  // then vertical
+        }
+      }
+    }
+    OT* o = out + (size_t)idx * Cp;
+    for (int c = 0; c < Cp; ++c) o[c] = (OT)(c < 3 ? v[c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------- max pooling (NHWC)
+template <typename ET>
+__global__ void maxpool_kernel(const ET* __restrict__ x, int N, int H, int W, int C, int ldx, int k, int s, int p,
+                               int Ho, int Wo, ET* __restrict__ y, int ldy) {
+  constexpr int V = Vec<ET>::N;
+  const int cv = C / V;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V;
+    long long r = idx / cv;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float m[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) m[e] = -CUDART_INF_F;
+    for (int kh = 0; kh < k; ++kh) {
+      const int hi = ho * s - p + kh;
+      if (hi < 0 || hi >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int wi = wo * s - p + kw;
+        if (wi < 0 || wi >= W) continue;
+        float v[V];
+        Vec<ET>::load(x + (((size_t)n * H + hi) * W + wi) * ldx + c, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    }
+    Vec<ET>::store(y + (((size_t)n * Ho + ho) * Wo + wo) * ldy + c, m);
+  }
+}
+
+// ------------------------------------------------------------------- RoIAlign (multi-level, tubes)
+struct RoiLevels {
+  const void* feat[8];
+  int H[8], W[8];
+  float scale[8];
+};
+
+template <typename ET>
+__device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, int W, int ld, float y, float x, float* acc) {
+  constexpr int V = Vec<ET>::N;
+  if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return;      // contributes 0
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+  const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+  float v1[V], v2[V], v3[V], v4[V];
+  Vec<ET>::load(f + ((size_t)yl * W + xl) * ld, v1);
+  Vec<ET>::load(f + ((size_t)yl * W + xh) * ld, v2);
+  Vec<ET>::load(f + ((size_t)yh * W + xl) * ld, v3);
+  Vec<ET>::load(f + ((size_t)yh * W + xh) * ld, v4);
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] += w1 * v1[e] + w2 * v2[e] + w3 * v3[e] + w4 * v4[e];
+}
+
+// rois [R, ldr]: col 0 batch idx, then 4*T box columns.  out [R, T, P, P, C].
+// grid: (R*T, P) blocks; threads over (pw, channel vectors).
+template <typename ET>
+__global__ void roi_align_kernel(RoiLevels lv, int kmin, const float* __restrict__ rois, int ldr,
+                                 const int* __restrict__ n_dev, int R, int T, const int* __restrict__ levels, int C,
+                                 int ldf, int P, int sampling, ET* __restrict__ out) {
+  constexpr int V = Vec<ET>::N;
+  const int rt = blockIdx.x, ph = blockIdx.y;
+  const int r = rt / T, t = rt - r * T;
+  const int n = n_dev ? min(*n_dev, R) : R;
+  const int cv = C / V;
+  ET* obase = out + (((size_t)r * T + t) * P + ph) * P * C;
+  if (r >= n) {          // rows beyond the live count are zero-filled (keeps downstream GEMMs finite)
+    for (int i = threadIdx.x; i < P * cv; i += blockDim.x) {
+      float z[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) z[e] = 0.f;
+      Vec<ET>::store(obase + (size_t)(i / cv) * C + (i % cv) * V, z);
+    }
+    return;
+  }
+  const float* roi = rois + (size_t)r * ldr;
+  const int l = levels ? (levels[r] - kmin) : 0;
+  const int H = lv.H[l], W = lv.W[l];
+  const float sc = lv.scale[l];
+  const int img = (int)roi[0] * T + t;                 // RoIToBatchFormat: b*T + t
+  const ET* f = reinterpret_cast<const ET*>(lv.feat[l]) + (size_t)img * H * W * ldf;
+  const float x1 = roi[1 + 4 * t] * sc, y1 = roi[2 + 4 * t] * sc, x2 = roi[3 + 4 * t] * sc, y2 = roi[4 + 4 * t] * sc;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bh = rh / (float)P, bw = rw / (float)P;
+  const int gh = sampling > 0 ? sampling : (int)ceilf(rh / P), gw = sampling > 0 ? sampling : (int)ceilf(rw / P);
+  const float cnt = (float)(gh * gw);
+  for (int i = threadIdx.x; i < P * cv; i += blockDim.x) {
+    const int pw = i / cv, c = (i - pw * cv) * V;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int iy = 0; iy < gh; ++iy) {
+      const float y = y1 + ph * bh + (iy + 0.5f) * bh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float x = x1 + pw * bw + (ix + 0.5f) * bw / (float)gw;
+        bilinear_acc<ET>(f + c, H, W, ldf, y, x, acc);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] /= cnt;
+    Vec<ET>::store(obase + (size_t)pw * C + c, acc);
+  }
+}
+
+// ------------------------------------------------------------------- keypoint decode
+// lowres [D, S, S, ldl]: channel (py*2+px)*K + k holds kps_score_lowres[k] at output pixel
+// (2*y+py, 2*x+px) (the k4 s2 p1 ConvTranspose evaluated as four 2x2 sub-pixel filters by the
+// conv kernel).  Step 1: fixed bilinear 2x ConvTranspose (filter [.25,.75,.75,.25]) -> M x M map in
+// shared memory (M = 4*S = 56).  Step 2: cv2.resize(INTER_CUBIC, A=-0.75, replicate border) to
+// (ceil(w), ceil(h)) evaluated per output pixel, first-occurrence argmax, softmax prob at the max.
+// One CTA per (detection, keypoint, frame).
+__device__ __forceinline__ void cubic_coeffs(float x, float* c) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+  c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+  c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+__global__ void __launch_bounds__(256)
+keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, int T,
+                       const float* __restrict__ boxes /*[D, ldb] image coords*/, int ldb,
+                       const int* __restrict__ n_dev, int D, int min_size,
+                       float* __restrict__ heat /*[D, T*K, M, M] or null*/,
+                       float* __restrict__ xy /*[D, 4, T*K]*/) {
+  extern __shared__ float sm[];
+  const int M2 = 2 * S, M = 4 * S;
+  float* low = sm;                 // [M2*M2]  kps_score_lowres for this (d, k)
+  float* map = sm + M2 * M2;       // [M*M]    kps_score
+  __shared__ float s_red[32];
+  __shared__ int s_redi[32];
+  __shared__ float s_max;
+  __shared__ int s_arg;
+  const int d = blockIdx.x, k = blockIdx.y, t = blockIdx.z;
+  const int n = n_dev ? min(*n_dev, D) : D;
+  if (d >= n) return;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  // un-pack the sub-pixel channels of frame t (row d*T + t of the time-in-batch lowres tensor)
+  const float* src = lowres + (size_t)(d * T + t) * S * S * ldl;
+  for (int i = tid; i < M2 * M2; i += nth) {
+    const int oy = i / M2, ox = i - oy * M2;
+    low[i] = src[((size_t)(oy >> 1) * S + (ox >> 1)) * ldl + ((oy & 1) * 2 + (ox & 1)) * K + k];
+  }
+  __syncthreads();
+  // bilinear ConvTranspose k=4 s=2 p=1: out[o] = sum_i in[i] * f[o - 2i + 1]
+  for (int i = tid; i < M * M; i += nth) {
+    const int oy = i / M, ox = i - oy * M;
+    const int iy0 = (oy + 1) >> 1, ix0 = (ox + 1) >> 1;          // taps i = iy0 (ky = o-2i+1) and iy0-1 (ky+2)
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int iy = iy0 - a, ky = oy - 2 * iy + 1;
+      if (iy < 0 || iy >= M2 || ky < 0 || ky > 3) continue;
+      const float fy = 1.f - fabsf(ky - 1.5f) / 2.f;
+#pragma unroll
+      for (int bq = 0; bq < 2; ++bq) {
+        const int ix = ix0 - bq, kx = ox - 2 * ix + 1;
+        if (ix < 0 || ix >= M2 || kx < 0 || kx > 3) continue;
+        const float fx = 1.f - fabsf(kx - 1.5f) / 2.f;
+        acc += low[iy * M2 + ix] * (fy * fx);
+      }
+    }
+    map[i] = acc;
+    if (heat) heat[(((size_t)d * T + t) * K + k) * M * M + i] = acc;   // channel t*K + k (model_builder.py:865-868)
+  }
+  __syncthreads();
+  // ---- heatmaps_to_keypoints (keypoints.py:94-149) for this (roi, keypoint) ----
+  const float* bx = boxes + (size_t)d * ldb + 4 * t;
+  const float ofx = bx[0], ofy = bx[1];
+  const float bw = fmaxf(bx[2] - bx[0], 1.f), bh = fmaxf(bx[3] - bx[1], 1.f);
+  int rw = (int)ceilf(bw), rh = (int)ceilf(bh);
+  if (min_size > 0) { rw = max(rw, min_size); rh = max(rh, min_size); }
+  const float wcorr = bw / (float)rw, hcorr = bh / (float)rh;
+  const double sclx = 1.0 / ((double)rw / M), scly = 1.0 / ((double)rh / M);   // cv2: scale = 1 / (dsize / ssize)
+  // pass 1: max + first argmax.  pass 2: sum exp(v - max).
+  float best = -CUDART_INF_F; int besti = 0x7fffffff;
+  const long long total = (long long)rw * rh;
+  auto sample = [&](int oy, int ox) -> float {
+    float fy = (float)((oy + 0.5) * scly - 0.5), fx = (float)((ox + 0.5) * sclx - 0.5);
+    const int sy = (int)floorf(fy), sx = (int)floorf(fx);
+    fy -= sy; fx -= sx;
+    float cy[4], cx[4];
+    cubic_coeffs(fy, cy); cubic_coeffs(fx, cx);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(sy - 1 + a, 0), M - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const int xx = min(max(sx - 1 + bq, 0), M - 1);
+        row += map[yy * M + xx] * cx[bq];
+      }
+      acc += row * cy[a];
+    }
+    return acc;
+  };
+  for (long long i = tid; i < total; i += nth) {
+    const int oy = (int)(i / rw), ox = (int)(i - (long long)oy * rw);
+    const float v = sample(oy, ox);
+    if (v > best) { best = v; besti = (int)i; }
+  }
+  // block argmax (max value, then lowest index)
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if ((tid & 31) == 0) { s_red[tid >> 5] = best; s_redi[tid >> 5] = besti; }
+  __syncthreads();
+  if (tid == 0) {
+    float b2 = s_red[0]; int i2 = s_redi[0];
+    for (int w = 1; w < (nth >> 5); ++w)
+      if (s_red[w] > b2 || (s_red[w] == b2 && s_redi[w] < i2)) { b2 = s_red[w]; i2 = s_redi[w]; }
+    s_max = b2; s_arg = i2;
+  }
+  __syncthreads();
+  const float mx = s_max;
+  float sum = 0.f;
+  for (long long i = tid; i < total; i += nth) {
+    const int oy = (int)(i / rw), ox = (int)(i - (long long)oy * rw);
+    sum += expf(sample(oy, ox) - mx);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (nth >> 5); ++w) tot += s_red[w];
+    const int pos = s_arg;
+    const int x_int = pos % rw, y_int = (pos - x_int) / rw;
+    const int KT = K * T, col = t * K + k;
+    float* o = xy + (size_t)d * 4 * KT;
+    // keypoints.py:140-145: python floats (fp64) until the store into the fp32 result
+    o[0 * KT + col] = (float)((x_int + 0.5) * (double)wcorr + (double)ofx);
+    o[1 * KT + col] = (float)((y_int + 0.5) * (double)hcorr + (double)ofy);
+    o[2 * KT + col] = mx;
+    o[3 * KT + col] = 1.f / tot;           // exp(max - max) / sum
+  }
+}
+
+}  // namespace dt
+
+using namespace dt;
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3 /*host*/,
+                            double im_scale, int Hr, int Wr, int Hp, int Wp, int Cp, int out_f32, void* out,
+                            void* stream) {
+  DT_CHECK_ARG(F >= 0 && H >= 1 && W >= 1 && Hr >= 1 && Wr >= 1 && Hp >= Hr && Wp >= Wr && Cp >= 3 && im_scale > 0,
+               "dt_prep_clip: bad shape F=%d H=%d W=%d Hr=%d Wr=%d Hp=%d Wp=%d Cp=%d", F, H, W, Hr, Wr, Hp, Wp, Cp);
+  if (F == 0) return 0;
+  DT_CHECK_ARG(frames && mean3 && out, "dt_prep_clip: null pointer");
+  const long long total = (long long)F * Hp * Wp;
+  if (out_f32)
+    prep_clip_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, F, H, W, mean3[0], mean3[1], mean3[2],
+                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, (float*)out);
+  else
+    prep_clip_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32, void* y,
+                            int ldy, void* stream) {
+  const int V = f32 ? 4 : 8;
+  DT_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && C >= 1 && k >= 1 && s >= 1 && p >= 0 && p < k, "dt_maxpool2d: bad shape");
+  DT_CHECK_ARG(C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C, "dt_maxpool2d: C/ld must be multiples of %d", V);
+  if (N == 0) return 0;
+  DT_CHECK_ARG(x && y, "dt_maxpool2d: null pointer");
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;      // Caffe2 legacy (floor) pooling
+  const long long total = (long long)N * Ho * Wo * (C / V);
+  if (f32)
+    maxpool_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (float*)y, ldy);
+  else
+    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (__nv_bfloat16*)y, ldy);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_roi_align(const void* const* feats /*host array [nlevels] of device ptrs*/, const int* Hs, const int* Ws,
+                            const float* scales /*host arrays*/, int nlevels, int k_min, int C, int ldf, int f32,
+                            const float* rois, int ldr, const int* n_dev, int R, int T, const int* levels, int P,
+                            int sampling_ratio, void* out, void* stream) {
+  const int V = f32 ? 4 : 8;
+  DT_CHECK_ARG(nlevels >= 1 && nlevels <= 8 && C >= 1 && C % V == 0 && ldf % V == 0 && R >= 0 && T >= 1 && P >= 1 && ldr >= 4 * T + 1,
+               "dt_roi_align: bad shape (C=%d must be a multiple of %d)", C, V);
+  DT_CHECK_ARG(nlevels == 1 || levels, "dt_roi_align: multi-level pooling needs the per-RoI level array");
+  if (R == 0) return 0;
+  DT_CHECK_ARG(feats && Hs && Ws && scales && rois && out, "dt_roi_align: null pointer");
+  RoiLevels lv;
+  for (int l = 0; l < nlevels; ++l) { lv.feat[l] = feats[l]; lv.H[l] = Hs[l]; lv.W[l] = Ws[l]; lv.scale[l] = scales[l]; }
+  dim3 grid(R * T, P);
+  const int threads = 256;
+  if (f32)
+    roi_align_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, (float*)out);
+  else
+    roi_align_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, int T, const float* boxes, int ldb,
+                                  const int* n_dev, int D, int min_size, float* heatmaps, float* xy_preds, void* stream) {
+  DT_CHECK_ARG(S >= 1 && S <= 32 && K >= 1 && T >= 1 && T <= DT_MAX_T && D >= 0 && ldl >= 4 * K && ldb >= 4 * T,
+               "dt_keypoint_decode: bad shape S=%d K=%d T=%d D=%d ldl=%d ldb=%d", S, K, T, D, ldl, ldb);
+  if (D == 0) return 0;
+  DT_CHECK_ARG(lowres && boxes && xy_preds, "dt_keypoint_decode: null pointer");
+  const size_t smem = (size_t)(4 * S * S + 16 * S * S) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  dim3 grid(D, K, T);
+  keypoint_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, ldl, S, K, T, boxes, ldb, n_dev, D, min_size, heatmaps, xy_preds);
+  DT_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,533 @@
+// RPN proposal generation and detection post-processing on the device (no host round trips).
+//
+//   dt_rpn_proposals      lib/ops/generate_proposals.py:40-196 up to (not including) NMS:
+//                         sigmoid, top-k, anchor enumeration, bbox/tube decode, clip, min-size filter
+//   dt_collect_rpn        lib/ops/collect_and_distribute_fpn_rpn_proposals.py:44-62
+//   dt_distribute_fpn     same file :65-87 + lib/modeling/FPN.py:349-360 (level per RoI, restore index)
+//   dt_box_decode         lib/core/test.py:211-252 (unscale, bbox_transform, clip) + :750-766 score filter
+//   dt_limit_detections   lib/core/test.py:790-800 (DETECTIONS_PER_IM threshold) and gather of kept rows
+// NMS itself is dt_nms_batched (boxes.cu).
+//
+// Arithmetic follows the reference's dtype promotions (see oracle/boxes.py): the 2-D decode is
+// fp32 op by op (lib/utils/boxes.py:141-183); the tube decode (T > 1) runs in fp64 and is rounded
+// once to fp32 (boxes.py:26-57 promotes the parts to float64).  exp() of the fp32 path may differ
+// from numpy's by an ulp (tolerance 1e-3 relative, stated in the tests); everything integer
+// (selection, ordering, filtering, levels, indices) is exact given the same float inputs.
+// Score ties: the reference's order is undefined; here: descending score, then ascending index.
+#include "common.cuh"
+#include "../../include/dt_b200.h"
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+namespace dt {
+
+__device__ __forceinline__ uint32_t sort_key_f32(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) {      // Caffe2 Sigmoid: 1 / (1 + exp(-x))
+  return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+}
+
+// In-place bitonic sort (descending) of n = power-of-two u64 keys in shared memory.
+__device__ void bitonic_desc(unsigned long long* keys, int npow2) {
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], c = keys[ixj];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Ordered block compaction helper: returns the exclusive rank of `flag` among all threads'
+// flags in thread order, adds the block total to *running (shared).  All threads must call.
+__device__ int block_rank(bool flag, int* s_warp, int* running) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  int off = *running;
+  for (int x = 0; x < wid; ++x) off += s_warp[x];
+  off += __popc(bal & ((1u << lane) - 1));
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int x = 0; x < nwarp; ++x) t += s_warp[x]; *running += t; }
+  __syncthreads();
+  return off;
+}
+
+// boxes.py:141-183 for one box / one 4-vector of deltas, fp32 op order.
+__device__ __forceinline__ void decode_f32(const float* bx, const float* dl, float wx, float wy, float ww, float wh,
+                                           float clipv, float* o) {
+  const float w = __fadd_rn(__fsub_rn(bx[2], bx[0]), 1.f);
+  const float h = __fadd_rn(__fsub_rn(bx[3], bx[1]), 1.f);
+  const float cx = __fadd_rn(bx[0], __fmul_rn(0.5f, w));
+  const float cy = __fadd_rn(bx[1], __fmul_rn(0.5f, h));
+  const float dx = __fdiv_rn(dl[0], wx), dy = __fdiv_rn(dl[1], wy);
+  const float dw = fminf(__fdiv_rn(dl[2], ww), clipv), dh = fminf(__fdiv_rn(dl[3], wh), clipv);
+  const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+  o[0] = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  o[1] = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  o[2] = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+  o[3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+}
+// Same in fp64 (tube path), rounded to fp32 on store.
+__device__ __forceinline__ void decode_f64(const double* bx, const float* dl, double wx, double wy, double ww,
+                                           double wh, double clipv, float* o) {
+  const double w = __dadd_rn(__dsub_rn(bx[2], bx[0]), 1.0);
+  const double h = __dadd_rn(__dsub_rn(bx[3], bx[1]), 1.0);
+  const double cx = __dadd_rn(bx[0], __dmul_rn(0.5, w));
+  const double cy = __dadd_rn(bx[1], __dmul_rn(0.5, h));
+  const double dx = __ddiv_rn((double)dl[0], wx), dy = __ddiv_rn((double)dl[1], wy);
+  const double dw = fmin(__ddiv_rn((double)dl[2], ww), clipv), dh = fmin(__ddiv_rn((double)dl[3], wh), clipv);
+  const double pcx = __dadd_rn(__dmul_rn(dx, w), cx), pcy = __dadd_rn(__dmul_rn(dy, h), cy);
+  const double pw = __dmul_rn(exp(dw), w), ph = __dmul_rn(exp(dh), h);
+  o[0] = (float)__dsub_rn(pcx, __dmul_rn(0.5, pw));
+  o[1] = (float)__dsub_rn(pcy, __dmul_rn(0.5, ph));
+  o[2] = (float)__dadd_rn(pcx, __dmul_rn(0.5, pw));
+  o[3] = (float)__dadd_rn(pcy, __dmul_rn(0.5, ph));
+}
+
+__device__ __forceinline__ float load_act(const void* p, size_t i, int f32) {
+  return f32 ? reinterpret_cast<const float*>(p)[i]
+             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+// ------------------------------------------------------------------- RPN top-k + decode
+// One CTA per image.  logits [B, H*W, ld_s] (first A channels), deltas [B, H*W, ld_d] (first 4*A*T).
+// Flat anchor index i = (h*W + w)*A + a  (generate_proposals.py:58-70 ordering).
+__global__ void __launch_bounds__(1024, 1)
+rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __restrict__ deltas, int ld_d,
+                     int act_f32, int H, int W, int A, int T, const double* __restrict__ anchors /*[A,4T]*/,
+                     double feat_stride, const float* __restrict__ im_info /*[B,3]*/, int pre_topn,
+                     float min_size, float clipv_f, double clipv_d,
+                     float* __restrict__ out /*[B, out_bstride] rows of 4T+1*/, long long out_bstride,
+                     int* __restrict__ counts, int counts_stride, int kcap /*pow2 >= K*/) {
+  extern __shared__ unsigned long long skeys[];          // [kcap] selected (key<<32 | ~idx)
+  __shared__ int hist[4096];
+  __shared__ int s_warp[32];
+  __shared__ int s_run, s_bin, s_need;
+  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int n = H * W * A;
+  const int K = (pre_topn <= 0 || pre_topn > n) ? n : pre_topn;
+  const size_t sbase = (size_t)b * H * W * ld_s;
+  auto score_at = [&](int i) -> float {
+    const int pos = i / A, a = i - pos * A;
+    return sigmoidf_ref(load_act(logits, sbase + (size_t)pos * ld_s + a, act_f32));
+  };
+  // ---- exact K-th largest key by 12/12/8-bit radix select --------------------------------
+  uint32_t prefix = 0, mask = 0;
+  int need = K;
+  const int shifts[3] = {20, 8, 0};
+  const int bits[3] = {12, 12, 8};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int nb = 1 << bits[pass];
+    for (int x = tid; x < nb; x += nth) hist[x] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nth) {
+      const uint32_t key = sort_key_f32(score_at(i));
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shifts[pass]) & (nb - 1)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int cum = 0, bin = nb - 1;
+      for (; bin >= 0; --bin) { if (cum + hist[bin] >= need) break; cum += hist[bin]; }
+      s_bin = bin; s_need = need - cum;
+    }
+    __syncthreads();
+    prefix |= (uint32_t)s_bin << shifts[pass];
+    mask |= (uint32_t)(nb - 1) << shifts[pass];
+    need = s_need;
+    __syncthreads();
+  }
+  const uint32_t kth = prefix;          // keys > kth are all selected; `need` keys == kth, lowest index first
+  // ---- gather the K selected (ordered compaction keeps index order among equals) ------------
+  if (tid == 0) s_run = 0;
+  for (int x = tid; x < kcap; x += nth) skeys[x] = 0ull;
+  __syncthreads();
+  int eq_taken_base = 0;                 // number of == kth elements seen so far (uniform)
+  for (int start = 0; start < n; start += nth) {
+    const int i = start + tid;
+    uint32_t key = 0; bool gt = false, eq = false;
+    if (i < n) { key = sort_key_f32(score_at(i)); gt = key > kth; eq = key == kth; }
+    // rank among equals (ordered)
+    const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    int eoff = eq_taken_base;
+    for (int x = 0; x < wid; ++x) eoff += s_warp[x];
+    eoff += __popc(bal & ((1u << lane) - 1));
+    int etot = 0;
+    for (int x = 0; x < nwarp; ++x) etot += s_warp[x];
+    __syncthreads();
+    const bool take = gt || (eq && eoff < need);
+    eq_taken_base += etot;
+    const int slot = block_rank(take, s_warp, &s_run);
+    if (take) skeys[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+  }
+  __syncthreads();
+  bitonic_desc(skeys, kcap);             // descending score, ascending index on ties
+  // ---- decode / clip / filter the K candidates in order --------------------------------------
+  const float imh = im_info[3 * b], imw = im_info[3 * b + 1], imscale = im_info[3 * b + 2];
+  const float hmax = __fsub_rn(imh, 1.f), wmax = __fsub_rn(imw, 1.f);
+  const float msz = __fmul_rn(min_size, imscale);
+  const size_t dbase = (size_t)b * H * W * ld_d;
+  const int ldo = 4 * T + 1;
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int start = 0; start < K; start += nth) {
+    const int r = start + tid;
+    bool ok = false;
+    float box[DT_MAX_T * 4];
+    float sc = 0.f;
+    if (r < K) {
+      const unsigned long long kk = skeys[r];
+      const int i = (int)(0xffffffffu - (uint32_t)(kk & 0xffffffffull));
+      const int pos = i / A, a = i - pos * A;
+      const int hh = pos / W, ww = pos - hh * W;
+      sc = score_at(i);
+      const double shx = (double)ww * feat_stride, shy = (double)hh * feat_stride;
+      ok = true;
+      for (int t = 0; t < T; ++t) {
+        double an[4];
+        an[0] = anchors[(size_t)a * 4 * T + 4 * t + 0] + shx; an[1] = anchors[(size_t)a * 4 * T + 4 * t + 1] + shy;
+        an[2] = anchors[(size_t)a * 4 * T + 4 * t + 2] + shx; an[3] = anchors[(size_t)a * 4 * T + 4 * t + 3] + shy;
+        float dl[4];
+        for (int k = 0; k < 4; ++k) dl[k] = load_act(deltas, dbase + (size_t)pos * ld_d + (size_t)a * 4 * T + 4 * t + k, act_f32);
+        float* o = box + 4 * t;
+        if (T == 1) {
+          const float af[4] = {(float)an[0], (float)an[1], (float)an[2], (float)an[3]};
+          decode_f32(af, dl, 1.f, 1.f, 1.f, 1.f, clipv_f, o);
+        } else {
+          decode_f64(an, dl, 1.0, 1.0, 1.0, 1.0, clipv_d, o);
+        }
+        // clip_tiled_boxes (boxes.py:243-253)
+        o[0] = fmaxf(fminf(o[0], wmax), 0.f); o[1] = fmaxf(fminf(o[1], hmax), 0.f);
+        o[2] = fmaxf(fminf(o[2], wmax), 0.f); o[3] = fmaxf(fminf(o[3], hmax), 0.f);
+        // _filter_boxes (generate_proposals.py:184-196), AND over frames
+        const float ws = __fadd_rn(__fsub_rn(o[2], o[0]), 1.f), hs = __fadd_rn(__fsub_rn(o[3], o[1]), 1.f);
+        const float xc = __fadd_rn(o[0], __fdiv_rn(ws, 2.f)), yc = __fadd_rn(o[1], __fdiv_rn(hs, 2.f));
+        ok = ok && (ws >= msz) && (hs >= msz) && (xc < imw) && (yc < imh);
+      }
+    }
+    const int slot = block_rank(ok, s_warp, &s_run);
+    if (ok) {
+      float* o = out + (size_t)b * out_bstride + (size_t)slot * ldo;
+      for (int c = 0; c < 4 * T; ++c) o[c] = box[c];
+      o[4 * T] = sc;
+    }
+  }
+  if (tid == 0) counts[(size_t)b * counts_stride] = s_run;
+}
+
+// ------------------------------------------------------------------- collect across levels
+// One CTA per image.  props [B, L, K, ldo], keep [B*L, K] (indices into the level's rows),
+// nkeep [B*L].  Output rois [B, R, ldo+1] = (batch idx, box(es)) + scores [B, R]; count [B].
+__global__ void __launch_bounds__(1024, 1)
+collect_kernel(const float* __restrict__ props, const int* __restrict__ keep, const int* __restrict__ nkeep,
+               int L, int K, int T, int post_topn, float* __restrict__ rois, float* __restrict__ roi_scores,
+               int* __restrict__ roi_counts, int R, int cap /*pow2 >= L*K*/) {
+  extern __shared__ unsigned long long skeys[];
+  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int ldo = 4 * T + 1;
+  __shared__ int s_off[16];
+  if (tid == 0) { int o = 0; for (int l = 0; l < L; ++l) { s_off[l] = o; o += min(nkeep[b * L + l], K); } s_off[L] = o; }
+  __syncthreads();
+  const int total = s_off[L];
+  for (int x = tid; x < cap; x += nth) skeys[x] = 0ull;
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const int nk = s_off[l + 1] - s_off[l];
+    for (int j = tid; j < nk; j += nth) {
+      const int row = keep[(size_t)(b * L + l) * K + j];
+      const float sc = props[(((size_t)b * L + l) * K + row) * ldo + 4 * T];
+      const uint32_t cidx = (uint32_t)(s_off[l] + j);                 // position in the concatenation
+      // payload: concat position (for the stable tie rule) in the low word; (level,row) recovered below
+      skeys[s_off[l] + j] = ((unsigned long long)sort_key_f32(sc) << 32) | (unsigned long long)(0xffffffffu - cidx);
+    }
+  }
+  __syncthreads();
+  bitonic_desc(skeys, cap);
+  const int nout = min(total, min(post_topn > 0 ? post_topn : total, R));
+  for (int r = tid; r < nout; r += nth) {
+    const uint32_t cidx = 0xffffffffu - (uint32_t)(skeys[r] & 0xffffffffull);
+    int l = 0;
+    while (l + 1 < L && (int)cidx >= s_off[l + 1]) ++l;
+    const int j = (int)cidx - s_off[l];
+    const int row = keep[(size_t)(b * L + l) * K + j];
+    const float* src = props + (((size_t)b * L + l) * K + row) * ldo;
+    float* dst = rois + ((size_t)b * R + r) * (ldo);
+    dst[0] = (float)b;
+    for (int c = 0; c < 4 * T; ++c) dst[1 + c] = src[c];
+    roi_scores[(size_t)b * R + r] = src[4 * T];
+  }
+  if (tid == 0) roi_counts[b] = nout;
+}
+
+// ------------------------------------------------------------------- FPN level per RoI
+// FPN.py:349-360 on rois [n, ld] (box columns start at col0).  One CTA; also emits the
+// reference's restore permutation (argsort of the level-bucketed order).
+__global__ void distribute_kernel(const float* __restrict__ rois, int n_max, const int* __restrict__ n_dev, int ld,
+                                  int col0, int T, int kmin, int kmax, float s0, float lvl0,
+                                  int* __restrict__ levels, int* __restrict__ idx_restore,
+                                  int* __restrict__ level_counts) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  for (int i = tid; i < n; i += nth) {
+    const float* r = rois + (size_t)i * ld + col0;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) {      // boxes_area: mean over frames of (w+1)(h+1), sequential fp32
+      const float w = __fadd_rn(__fsub_rn(r[4 * t + 2], r[4 * t]), 1.f), h = __fadd_rn(__fsub_rn(r[4 * t + 3], r[4 * t + 1]), 1.f);
+      const float a = __fmul_rn(w, h);
+      acc = (t == 0) ? a : __fadd_rn(acc, a);
+    }
+    const float area = __fdiv_rn(acc, (float)T);
+    const float s = __fsqrt_rn(area);
+    float lv = floorf(__fadd_rn(lvl0, log2f(__fadd_rn(__fdiv_rn(s, s0), 1e-6f))));
+    lv = fminf(fmaxf(lv, (float)kmin), (float)kmax);
+    levels[i] = (int)lv;
+  }
+  __syncthreads();
+  if (idx_restore) {
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    for (int lvl = kmin; lvl <= kmax; ++lvl) {
+      const int before = s_run;
+      for (int start = 0; start < n; start += nth) {
+        const int i = start + tid;
+        const bool f = (i < n) && levels[i] == lvl;
+        const int slot = block_rank(f, s_warp, &s_run);
+        if (f) idx_restore[i] = slot;     // position of roi i in the level-bucketed concatenation
+      }
+      if (tid == 0 && level_counts) level_counts[lvl - kmin] = s_run - before;
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------- box head post-processing
+// test.py:211-252: boxes = rois / im_scale; bbox_transform(weights); clip to the ORIGINAL image;
+// :760-766: per class j >= 1 keep score > thresh.  One CTA per (image, class-1).
+// rois [B, R, 4T+1] (col 0 = batch idx); cls_prob from logits [B*R, ld_c] via softmax;
+// deltas [B*R, ld_b] with class-major blocks j*4T (test.py:772).
+__global__ void box_decode_kernel(const float* __restrict__ rois, const int* __restrict__ roi_counts, int R, int T,
+                                  const float* __restrict__ cls_logits, int ld_c, const float* __restrict__ bbox_deltas,
+                                  int ld_b, int num_classes, const float* __restrict__ im_info /*[B,3] blob h,w,scale*/,
+                                  const float* __restrict__ im_hw /*[B,2] original image h,w*/, float wx, float wy,
+                                  float ww, float wh, float clipv_f, double clipv_d, float score_thresh,
+                                  float* __restrict__ dets /*[B, C-1, R, 4T+1]*/, int* __restrict__ det_counts) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int b = blockIdx.x, j = blockIdx.y + 1, tid = threadIdx.x, nth = blockDim.x;
+  const int n = min(roi_counts[b], R);
+  const int ldr = 4 * T + 1, ldo = 4 * T + 1;
+  const float scale = im_info[3 * b + 2];
+  const float hmax = __fsub_rn(im_hw[2 * b], 1.f), wmax = __fsub_rn(im_hw[2 * b + 1], 1.f);
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int start = 0; start < n; start += nth) {
+    const int i = start + tid;
+    bool ok = false;
+    float box[DT_MAX_T * 4];
+    float sc = 0.f;
+    if (i < n) {
+      const size_t row = (size_t)b * R + i;
+      // softmax over classes (Caffe2 Softmax: subtract max, exp, normalise)
+      float m = -CUDART_INF_F;
+      for (int c = 0; c < num_classes; ++c) m = fmaxf(m, cls_logits[row * ld_c + c]);
+      float sum = 0.f, ej = 0.f;
+      for (int c = 0; c < num_classes; ++c) { const float e = expf(cls_logits[row * ld_c + c] - m); sum += e; if (c == j) ej = e; }
+      sc = ej / sum;
+      ok = sc > score_thresh;
+      const float* r = rois + row * ldr + 1;
+      const float* dl = bbox_deltas + row * ld_b + (size_t)j * 4 * T;
+      for (int t = 0; t < T; ++t) {
+        float* o = box + 4 * t;
+        if (T == 1) {
+          const float bx[4] = {__fdiv_rn(r[0], scale), __fdiv_rn(r[1], scale), __fdiv_rn(r[2], scale), __fdiv_rn(r[3], scale)};
+          decode_f32(bx, dl, wx, wy, ww, wh, clipv_f, o);
+        } else {
+          const double bx[4] = {(double)__fdiv_rn(r[4 * t], scale), (double)__fdiv_rn(r[4 * t + 1], scale),
+                                (double)__fdiv_rn(r[4 * t + 2], scale), (double)__fdiv_rn(r[4 * t + 3], scale)};
+          decode_f64(bx, dl + 4 * t, (double)wx, (double)wy, (double)ww, (double)wh, clipv_d, o);
+        }
+        o[0] = fmaxf(fminf(o[0], wmax), 0.f); o[1] = fmaxf(fminf(o[1], hmax), 0.f);
+        o[2] = fmaxf(fminf(o[2], wmax), 0.f); o[3] = fmaxf(fminf(o[3], hmax), 0.f);
+      }
+    }
+    const int slot = block_rank(ok, s_warp, &s_run);
+    if (ok) {
+      float* o = dets + (((size_t)b * (num_classes - 1) + (j - 1)) * R + slot) * ldo;
+      for (int c = 0; c < 4 * T; ++c) o[c] = box[c];
+      o[4 * T] = sc;
+    }
+  }
+  if (tid == 0) det_counts[b * (num_classes - 1) + (j - 1)] = s_run;
+}
+
+// test.py:768-800: nms_dets = dets_j[keep]; if more than max_per_im over all classes, keep
+// score >= the max_per_im-th largest score.  One CTA per image.
+__global__ void __launch_bounds__(1024, 1)
+limit_kernel(const float* __restrict__ dets, const int* __restrict__ keep, const int* __restrict__ nkeep, int ncls1,
+             int R, int T, int max_per_im, float* __restrict__ out /*[B, C-1, cap, 4T+1]*/,
+             int* __restrict__ out_counts, int cap, int sortcap) {
+  extern __shared__ unsigned long long skeys[];
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  __shared__ float s_thresh;
+  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int ld = 4 * T + 1;
+  int total = 0;
+  for (int c = 0; c < ncls1; ++c) total += min(nkeep[b * ncls1 + c], R);
+  if (tid == 0) s_thresh = -CUDART_INF_F;
+  __syncthreads();
+  if (max_per_im > 0 && total > max_per_im) {
+    for (int x = tid; x < sortcap; x += nth) skeys[x] = 0ull;
+    __syncthreads();
+    int off = 0;
+    for (int c = 0; c < ncls1; ++c) {
+      const int nk = min(nkeep[b * ncls1 + c], R);
+      for (int q = tid; q < nk; q += nth) {
+        const int row = keep[(size_t)(b * ncls1 + c) * R + q];
+        const float sc = dets[(((size_t)b * ncls1 + c) * R + row) * ld + 4 * T];
+        skeys[off + q] = ((unsigned long long)sort_key_f32(sc) << 32) | 1ull;
+      }
+      off += nk;
+    }
+    __syncthreads();
+    bitonic_desc(skeys, sortcap);
+    if (tid == 0) {
+      uint32_t k = (uint32_t)(skeys[max_per_im - 1] >> 32);      // np.sort(scores)[-max_per_im]
+      k = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+      s_thresh = __uint_as_float(k);
+    }
+    __syncthreads();
+  }
+  const float th = s_thresh;
+  for (int c = 0; c < ncls1; ++c) {
+    if (tid == 0) s_run = 0;
+    __syncthreads();
+    const int nk = min(nkeep[b * ncls1 + c], R);
+    for (int start = 0; start < nk; start += nth) {
+      const int q = start + tid;
+      bool f = false; int row = 0;
+      if (q < nk) {
+        row = keep[(size_t)(b * ncls1 + c) * R + q];
+        f = dets[(((size_t)b * ncls1 + c) * R + row) * ld + 4 * T] >= th;
+      }
+      const int slot = block_rank(f, s_warp, &s_run);
+      if (f && slot < cap) {
+        const float* src = dets + (((size_t)b * ncls1 + c) * R + row) * ld;
+        float* dst = out + (((size_t)b * ncls1 + c) * cap + slot) * ld;
+        for (int x = 0; x < ld; ++x) dst[x] = src[x];
+      }
+    }
+    if (tid == 0) out_counts[b * ncls1 + c] = min(s_run, cap);
+    __syncthreads();
+  }
+}
+
+static int next_pow2i(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace dt
+
+using namespace dt;
+
+extern "C" int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas, int ld_d, int act_f32, int B, int H,
+                                int W, int A, int T, const double* anchors, double feat_stride, const float* im_info,
+                                int pre_nms_topn, float min_size, double bbox_xform_clip, float* out,
+                                long long out_batch_stride, int* counts, int counts_stride, void* stream) {
+  DT_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && A >= 1 && T >= 1 && T <= DT_MAX_T, "dt_rpn_proposals: bad shape B=%d H=%d W=%d A=%d T=%d", B, H, W, A, T);
+  DT_CHECK_ARG(ld_s >= A && ld_d >= 4 * A * T, "dt_rpn_proposals: leading dims too small (ld_s=%d, ld_d=%d)", ld_s, ld_d);
+  if (B == 0) return 0;
+  DT_CHECK_ARG(logits && deltas && anchors && im_info && out && counts, "dt_rpn_proposals: null pointer");
+  const long long n = (long long)H * W * A;
+  DT_CHECK_ARG(n < (1ll << 31), "dt_rpn_proposals: too many anchors");
+  const int K = (pre_nms_topn <= 0 || pre_nms_topn > n) ? (int)n : pre_nms_topn;
+  const int kcap = next_pow2i(K);
+  DT_CHECK_ARG(kcap <= 16384, "dt_rpn_proposals: pre-NMS top-N %d exceeds 16384", K);
+  DT_CHECK_ARG(out_batch_stride >= (long long)K * (4 * T + 1), "dt_rpn_proposals: out_batch_stride too small");
+  static size_t attr = 0;
+  const size_t smem = (size_t)kcap * sizeof(unsigned long long);
+  if (smem > attr) {
+    DT_CHECK_CUDA(cudaFuncSetAttribute(rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    attr = 16384 * 8;
+  }
+  rpn_proposals_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(logits, ld_s, deltas, ld_d, act_f32, H, W, A, T, anchors,
+                                                               feat_stride, im_info, pre_nms_topn, min_size,
+                                                               (float)bbox_xform_clip, bbox_xform_clip, out,
+                                                               out_batch_stride, counts, counts_stride, kcap);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_collect_rpn(const float* props, const int* keep, const int* nkeep, int B, int L, int K, int T,
+                              int post_nms_topn, float* rois, float* roi_scores, int* roi_counts, int R, void* stream) {
+  DT_CHECK_ARG(B >= 0 && L >= 1 && L <= 15 && K >= 1 && T >= 1 && T <= DT_MAX_T && R >= 1, "dt_collect_rpn: bad shape");
+  if (B == 0) return 0;
+  DT_CHECK_ARG(props && keep && nkeep && rois && roi_scores && roi_counts, "dt_collect_rpn: null pointer");
+  const int cap = next_pow2i(L * K);
+  DT_CHECK_ARG(cap <= 16384, "dt_collect_rpn: L*K=%d exceeds 16384", L * K);
+  static bool attr = false;
+  if (!attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8)); attr = true; }
+  collect_kernel<<<B, 1024, (size_t)cap * 8, (cudaStream_t)stream>>>(props, keep, nkeep, L, K, T, post_nms_topn, rois,
+                                                                     roi_scores, roi_counts, R, cap);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_distribute_fpn(const float* rois, int n_max, const int* n_dev, int ld, int col0, int T, int k_min,
+                                 int k_max, float canonical_scale, float canonical_level, int* levels,
+                                 int* idx_restore, int* level_counts, void* stream) {
+  DT_CHECK_ARG(n_max >= 0 && T >= 1 && T <= DT_MAX_T && ld >= col0 + 4 * T && k_max >= k_min, "dt_distribute_fpn: bad shape");
+  if (n_max == 0) return 0;
+  DT_CHECK_ARG(rois && levels, "dt_distribute_fpn: null pointer");
+  distribute_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rois, n_max, n_dev, ld, col0, T, k_min, k_max, canonical_scale,
+                                                          canonical_level, levels, idx_restore, level_counts);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_box_decode(const float* rois, const int* roi_counts, int B, int R, int T, const float* cls_logits,
+                             int ld_c, const float* bbox_deltas, int ld_b, int num_classes, const float* im_info,
+                             const float* im_hw, const float* weights4 /*host*/, double bbox_xform_clip,
+                             float score_thresh, float* dets, int* det_counts, void* stream) {
+  DT_CHECK_ARG(B >= 0 && R >= 1 && T >= 1 && T <= DT_MAX_T && num_classes >= 2, "dt_box_decode: bad shape");
+  DT_CHECK_ARG(ld_c >= num_classes && ld_b >= 4 * T * num_classes, "dt_box_decode: leading dims too small");
+  if (B == 0) return 0;
+  DT_CHECK_ARG(rois && roi_counts && cls_logits && bbox_deltas && im_info && im_hw && weights4 && dets && det_counts,
+               "dt_box_decode: null pointer");
+  dim3 grid(B, num_classes - 1);
+  box_decode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rois, roi_counts, R, T, cls_logits, ld_c, bbox_deltas, ld_b,
+                                                            num_classes, im_info, im_hw, weights4[0], weights4[1],
+                                                            weights4[2], weights4[3], (float)bbox_xform_clip,
+                                                            bbox_xform_clip, score_thresh, dets, det_counts);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes, int R,
+                                   int T, int max_per_im, float* out, int* out_counts, int cap, void* stream) {
+  DT_CHECK_ARG(B >= 0 && num_classes >= 2 && R >= 1 && T >= 1 && T <= DT_MAX_T && cap >= 1, "dt_limit_detections: bad shape");
+  if (B == 0) return 0;
+  DT_CHECK_ARG(dets && keep && nkeep && out && out_counts, "dt_limit_detections: null pointer");
+  const int sortcap = next_pow2i((num_classes - 1) * R);
+  DT_CHECK_ARG(sortcap <= 16384, "dt_limit_detections: (C-1)*R=%d exceeds 16384", (num_classes - 1) * R);
+  static bool attr = false;
+  if (!attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(limit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8)); attr = true; }
+  limit_kernel<<<B, 1024, (size_t)sortcap * 8, (cudaStream_t)stream>>>(dets, keep, nkeep, num_classes - 1, R, T, max_per_im,
+                                                                       out, out_counts, cap, sortcap);
+  DT_CHECK_LAUNCH();
+  return 0;
+}

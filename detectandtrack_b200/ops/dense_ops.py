@@ -1,0 +1,63 @@
+"""Device-tensor API over csrc/dense_ops.cu (image prep, max-pool, RoIAlign, keypoint decode)."""
+import ctypes as C
+
+from .. import _lib as L
+
+
+def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=False):
+    """frames [F,H,W,3] uint8 cuda (BGR) -> [F,Hp,Wp,cpad] (pixel - mean), resized, zero padded."""
+    torch = L.require_cuda()
+    F, H, W, _ = frames_u8.shape
+    Hr, Wr = out_hw
+    Hp, Wp = pad_hw
+    out = torch.empty((F, Hp, Wp, cpad), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
+    m = (C.c_float * 3)(*[float(v) for v in pixel_means])
+    L.call('dt_prep_clip', L.ptr(frames_u8.contiguous()), F, H, W, m, float(im_scale), Hr, Wr, Hp, Wp, cpad,
+           int(out_f32), L.ptr(out), L.stream_ptr())
+    return out
+
+
+def maxpool2d(x, k, s, p):
+    """x [N,H,W,C] -> [N,Ho,Wo,C] (floor mode)."""
+    torch = L.require_cuda()
+    N, H, W, Cc = x.shape
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    y = torch.empty((N, Ho, Wo, Cc), dtype=x.dtype, device='cuda')
+    L.call('dt_maxpool2d', L.ptr(x), N, H, W, Cc, Cc, k, s, p, int(x.dtype == torch.float32), L.ptr(y), Cc, L.stream_ptr())
+    return y
+
+
+def roi_align(feats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_dev=None, channels=None):
+    """feats: list of [Nimg*T, H_l, W_l, C] (finest first, level k_min + i); rois [R, 4T+1] fp32
+    (col 0 = image index); levels [R] int32 or None for a single level -> [R, T, P, P, C]."""
+    torch = L.require_cuda()
+    nl = len(feats)
+    ldf = feats[0].shape[-1]
+    Cc = channels or ldf
+    R = rois.shape[0]
+    out = torch.empty((R, T, P, P, Cc), dtype=feats[0].dtype, device='cuda')
+    fp = (C.c_void_p * nl)(*[f.data_ptr() for f in feats])
+    Hs = (C.c_int * nl)(*[f.shape[1] for f in feats])
+    Ws = (C.c_int * nl)(*[f.shape[2] for f in feats])
+    sc = (C.c_float * nl)(*[float(s) for s in scales])
+    for f in feats:
+        assert f.is_contiguous() and f.dtype == feats[0].dtype and f.shape[-1] == ldf
+    rois = rois.contiguous()
+    L.call('dt_roi_align', fp, Hs, Ws, sc, nl, k_min, Cc, ldf, int(feats[0].dtype == torch.float32), L.ptr(rois),
+           rois.shape[1], L.ptr(n_dev), R, T, L.ptr(levels), P, sampling_ratio, L.ptr(out), L.stream_ptr())
+    return out
+
+
+def keypoint_decode(lowres, boxes, K=17, T=1, n_dev=None, min_size=0, want_heatmaps=False):
+    """lowres [D*T, S, S, >=4K] fp32 (sub-pixel packed), boxes [D, >=4T] image space.
+    Returns (xy_preds [D,4,T*K], heatmaps [D,T*K,4S,4S] or None)."""
+    torch = L.require_cuda()
+    DT_, S, _, ldl = lowres.shape
+    D = DT_ // T
+    xy = torch.zeros((D, 4, T * K), dtype=torch.float32, device='cuda')
+    heat = torch.zeros((D, T * K, 4 * S, 4 * S), dtype=torch.float32, device='cuda') if want_heatmaps else None
+    boxes = boxes.contiguous()
+    assert lowres.dtype == torch.float32 and lowres.is_contiguous()
+    L.call('dt_keypoint_decode', L.ptr(lowres), ldl, S, K, T, L.ptr(boxes), boxes.shape[1], L.ptr(n_dev), D, int(min_size),
+           L.ptr(heat), L.ptr(xy), L.stream_ptr())
+    return xy, heat

@@ -135,6 +135,77 @@ typedef struct dt_conv_desc {
 int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
               const float* bias, const void* residual, void* y, void* stream);
 
+/* ---- proposals.cu -------------------------------------------------------- */
+
+/* GenerateProposalsOp up to NMS (lib/ops/generate_proposals.py:40-106,116-161): sigmoid,
+ * top pre_nms_topn by score, shifted (tube) anchors, bbox/tube decode (weights 1), clip to
+ * im_info, min-size filter (AND over frames).  One level, all images.
+ * logits [B, H, W, ld_s] (first A channels), deltas [B, H, W, ld_d] (first 4*A*T; channel
+ * a*4T + t*4 + k) — the NHWC order IS the reference's (H, W, A) enumeration; act_f32: 1 fp32,
+ * 0 bf16.  anchors [A, 4T] fp64 device (generate_anchors.py).  out rows [4T+1] (boxes, score) in
+ * descending score, batch image b at out + b*out_batch_stride; counts[b*counts_stride] rows. */
+int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas, int ld_d, int act_f32, int B,
+                     int H, int W, int A, int T, const double* anchors, double feat_stride,
+                     const float* im_info, int pre_nms_topn, float min_size, double bbox_xform_clip,
+                     float* out, long long out_batch_stride, int* counts, int counts_stride,
+                     void* stream);
+
+/* collect (lib/ops/collect_and_distribute_fpn_rpn_proposals.py:44-62): props [B, L, K, 4T+1],
+ * keep [B*L, K] / nkeep [B*L] from dt_nms_batched -> rois [B, R, 4T+1] (col 0 = image index),
+ * roi_scores [B, R], roi_counts [B]; top post_nms_topn by score over the level concatenation. */
+int dt_collect_rpn(const float* props, const int* keep, const int* nkeep, int B, int L, int K, int T,
+                   int post_nms_topn, float* rois, float* roi_scores, int* roi_counts, int R,
+                   void* stream);
+
+/* distribute (same file :65-87; lib/modeling/FPN.py:349-360): levels[i] in [k_min, k_max] from the
+ * mean-over-frames '+1' area of rois[i, col0 : col0+4T]; idx_restore (may be NULL) is the
+ * reference's rois_idx_restore_int32; level_counts [k_max-k_min+1] (may be NULL). n_dev may be NULL. */
+int dt_distribute_fpn(const float* rois, int n_max, const int* n_dev, int ld, int col0, int T, int k_min,
+                      int k_max, float canonical_scale, float canonical_level, int* levels,
+                      int* idx_restore, int* level_counts, void* stream);
+
+/* lib/core/test.py:211-252 + :760-766: softmax(cls_logits), boxes = rois / im_scale,
+ * bbox_transform(weights4 [host]), clip to the original image (im_hw [B,2] = h, w), keep
+ * score > score_thresh per class j >= 1.  dets [B, C-1, R, 4T+1] compacted, det_counts [B*(C-1)]. */
+int dt_box_decode(const float* rois, const int* roi_counts, int B, int R, int T, const float* cls_logits,
+                  int ld_c, const float* bbox_deltas, int ld_b, int num_classes, const float* im_info,
+                  const float* im_hw, const float* weights4, double bbox_xform_clip, float score_thresh,
+                  float* dets, int* det_counts, void* stream);
+
+/* lib/core/test.py:768-800: gather dets[keep] per class and apply the DETECTIONS_PER_IM score
+ * threshold over all classes.  out [B, C-1, cap, 4T+1], out_counts [B*(C-1)]. */
+int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes, int R,
+                        int T, int max_per_im, float* out, int* out_counts, int cap, void* stream);
+
+/* ---- dense_ops.cu -------------------------------------------------------- */
+
+/* lib/utils/blob.py:40-90 + lib/core/test.py:43-74.  frames [F, H, W, 3] u8 BGR ->
+ * out [F, Hp, Wp, Cp] (bf16 or fp32): (pixel - mean3) bilinearly resized by im_scale to Hr x Wr,
+ * zero padded (Cp >= 3 channels, spatially to Hp x Wp). */
+int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3, double im_scale,
+                 int Hr, int Wr, int Hp, int Wp, int Cp, int out_f32, void* out, void* stream);
+
+/* Caffe2 MaxPool kernels [1,k,k] strides [1,s,s] pads [0,p,p] on NHWC (N = B*T frames). */
+int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32,
+                 void* y, int ldy, void* stream);
+
+/* RoIFeatureTransform (lib/modeling/detector.py:216-310): RoIAlign (Detectron semantics,
+ * non-"aligned") over FPN levels with tube -> frame routing and the un-shuffle fused.
+ * feats/Hs/Ws/scales: host arrays [nlevels] (feature l is [n_images*T, Hs[l], Ws[l], ldf]);
+ * rois [R, ldr] (col 0 image index, then 4*T), levels [R] (NULL if nlevels == 1);
+ * out [R, T, P, P, C]; rows >= *n_dev are zero-filled. */
+int dt_roi_align(const void* const* feats, const int* Hs, const int* Ws, const float* scales, int nlevels,
+                 int k_min, int C, int ldf, int f32, const float* rois, int ldr, const int* n_dev, int R,
+                 int T, const int* levels, int P, int sampling_ratio, void* out, void* stream);
+
+/* BilinearInterpolation (lib/modeling/detector.py:348-380) + heatmaps_to_keypoints
+ * (lib/utils/keypoints.py:94-149).  lowres [D*T, S, S, ldl] fp32 with channel (py*2+px)*K + k =
+ * kps_score_lowres[k] at pixel (2y+py, 2x+px); boxes [D, ldb] image-space (4*T columns);
+ * heatmaps (may be NULL) [D, T*K, 4S, 4S]; xy_preds [D, 4, T*K] = (x, y, logit, prob). */
+int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, int T, const float* boxes, int ldb,
+                       const int* n_dev, int D, int min_size, float* heatmaps, float* xy_preds,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
