@@ -32,7 +32,7 @@ SIGNATURES = {
     'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_maxpool2d': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_roi_align': [C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _p, _i, _p, _i,
-                     _i, _p, _i, _i, _p, _p],
+                     _i, _p, _i, _i, _i, _p, _p],
     'dt_keypoint_decode': [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p],
 }
 
@@ -42,7 +42,7 @@ class ConvDesc(C.Structure):
     """dt_conv_desc (include/dt_b200.h)."""
     _fields_ = [(n, C.c_int) for n in (
         'N', 'Ti', 'Hi', 'Wi', 'Cin', 'Cout', 'kT', 'kH', 'kW', 'sT', 'sH', 'sW', 'pT', 'pH', 'pW',
-        'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode')]
+        'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode', 'out_round_tf32')]
 _RESTYPE = {'dt_last_error': C.c_char_p}
 
 

@@ -51,7 +51,15 @@ struct ConvKernelParams {
   void* out;
   int out_ld;                  // elements between consecutive positions
   int out_f32;                 // 1: fp32 output, 0: bf16
+  int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
+                               // which TRUNCATES its 32-bit operands, sees exactly representable values
 };
+
+__device__ __forceinline__ float round_to_tf32(float v) {
+  uint32_t u = __float_as_uint(v);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
 
 template <int BN>
 struct ConvCfg {
@@ -229,6 +237,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (p.out_f32) {
+            if (p.round_tf32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = round_to_tf32(v[j]);
+            }
             float* op = reinterpret_cast<float*>(p.out) + pos * p.out_ld + cbase;
             if (ncols == 32) {
 #pragma unroll
@@ -382,7 +394,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   p.TH = TH; p.TW = TW; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW);
   p.a_bytes = (uint32_t)TH * TW * 128u;
   p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = d->res_mode; p.res_ld = res_ld;
-  p.relu = d->relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32;
+  p.relu = d->relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32; p.round_tf32 = d->out_round_tf32;
 
   int BN = d->Cout >= 256 ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32));
   if (d->Cout > 128 && d->Cout < 256) BN = 128;

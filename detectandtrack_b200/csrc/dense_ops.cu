@@ -18,6 +18,15 @@
 namespace dt {
 
 template <typename T> struct Vec;
+__device__ __forceinline__ float round_to_tf32(float v) {   // see conv_tc.cu: kind::tf32 truncates operands
+  uint32_t u = __float_as_uint(v);
+  u += 0xFFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+template <typename T> __device__ __forceinline__ T to_act(float v);
+template <> __device__ __forceinline__ float to_act<float>(float v) { return round_to_tf32(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_act<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
 template <> struct Vec<float> {
   static constexpr int N = 4;
   __device__ static void load(const float* p, float* v) { const float4 q = *reinterpret_cast<const float4*>(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
@@ -80,7 +89,7 @@ __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F
       }
     }
     OT* o = out + (size_t)idx * Cp;
-    for (int c = 0; c < Cp; ++c) o[c] = (OT)(c < 3 ? v[c] : 0.f);
+    for (int c = 0; c < Cp; ++c) o[c] = to_act<OT>(c < 3 ? v[c] : 0.f);
   }
 }
 
@@ -148,7 +157,7 @@ __device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, in
 template <typename ET>
 __global__ void roi_align_kernel(RoiLevels lv, int kmin, const float* __restrict__ rois, int ldr,
                                  const int* __restrict__ n_dev, int R, int T, const int* __restrict__ levels, int C,
-                                 int ldf, int P, int sampling, ET* __restrict__ out) {
+                                 int ldf, int P, int sampling, int round_out, ET* __restrict__ out) {
   constexpr int V = Vec<ET>::N;
   const int rt = blockIdx.x, ph = blockIdx.y;
   const int r = rt / T, t = rt - r * T;
@@ -189,6 +198,10 @@ __global__ void roi_align_kernel(RoiLevels lv, int kmin, const float* __restrict
     }
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e] /= cnt;
+    if (round_out) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = round_to_tf32(acc[e]);
+    }
     Vec<ET>::store(obase + (size_t)pw * C + c, acc);
   }
 }
@@ -379,7 +392,7 @@ extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, 
 extern "C" int dt_roi_align(const void* const* feats /*host array [nlevels] of device ptrs*/, const int* Hs, const int* Ws,
                             const float* scales /*host arrays*/, int nlevels, int k_min, int C, int ldf, int f32,
                             const float* rois, int ldr, const int* n_dev, int R, int T, const int* levels, int P,
-                            int sampling_ratio, void* out, void* stream) {
+                            int sampling_ratio, int round_tf32, void* out, void* stream) {
   const int V = f32 ? 4 : 8;
   DT_CHECK_ARG(nlevels >= 1 && nlevels <= 8 && C >= 1 && C % V == 0 && ldf % V == 0 && R >= 0 && T >= 1 && P >= 1 && ldr >= 4 * T + 1,
                "dt_roi_align: bad shape (C=%d must be a multiple of %d)", C, V);
@@ -391,9 +404,9 @@ extern "C" int dt_roi_align(const void* const* feats /*host array [nlevels] of d
   dim3 grid(R * T, P);
   const int threads = 256;
   if (f32)
-    roi_align_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, (float*)out);
+    roi_align_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, round_tf32, (float*)out);
   else
-    roi_align_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, (__nv_bfloat16*)out);
+    roi_align_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, 0, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -234,7 +234,8 @@ class DetectionEngine(object):
         levels, _, _ = rpn_ops.distribute(rois_flat, None, col0=1, T=1, k_min=s.roi_levels[0], k_max=s.roi_levels[-1],
                                           s0=float(self.cfg.FPN.ROI_CANONICAL_SCALE), lvl0=float(self.cfg.FPN.ROI_CANONICAL_LEVEL),
                                           want_restore=False)
-        return dense_ops.roi_align(fl, scales, rois_flat, levels, resolution, sampling, T=1, k_min=s.roi_levels[0])
+        return dense_ops.roi_align(fl, scales, rois_flat, levels, resolution, sampling, T=1, k_min=s.roi_levels[0],
+                                   round_tf32=(self.dtype == cv.TF32))
 
     def box_head(self, feats2d, rois, roi_counts, im_info, im_hw):
         torch, cfg, s = self.torch, self.cfg, self.spec

@@ -26,11 +26,23 @@ def pack_weight(w, dtype=BF16):
     Cp = (Cin + mult - 1) // mult * mult
     out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=_dt(dtype, torch), device='cuda')
     out[:, :, :Cin] = w.to('cuda').permute(2, 3, 4, 0, 1).reshape(kT * kH * kW, Cout, Cin).to(out.dtype)
+    if dtype == TF32:
+        out = round_tf32(out)
     return out
 
 
+def round_tf32(t):
+    """Round an fp32 tensor to the nearest (even) tf32-representable value.  tcgen05 kind::tf32
+    truncates the low 13 mantissa bits of its operands; feeding it pre-rounded values makes the
+    truncation exact instead of a one-sided error."""
+    torch = L.require_cuda()
+    u = t.contiguous().view(torch.int32)
+    u = u + 0xFFF + ((u >> 13) & 1)
+    return (u & ~0x1FFF).view(torch.float32)
+
+
 def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias=None,
-           residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None):
+           residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None, round_tf32=None):
     """x [N,T,H,W,Cx] (first `cin` channels are the conv input); returns y [N,To,Ho,Wo,Cout]."""
     torch = L.require_cuda()
     assert x.is_cuda and x.dim() == 5 and x.is_contiguous()
@@ -47,6 +59,8 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     Wo = (Wi + 2 * pW - kW) // sW + 1
     if out_f32 is None:
         out_f32 = dtype == TF32
+    if round_tf32 is None:
+        round_tf32 = bool(out_f32) and dtype == TF32 and out is None      # intermediate activations
     odt = torch.float32 if out_f32 else torch.bfloat16
     if out is None:
         out = torch.empty((N, To, Ho, Wo, Cout), dtype=odt, device='cuda')
@@ -54,7 +68,7 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     d = L.ConvDesc(N=N, Ti=Ti, Hi=Hi, Wi=Wi, Cin=cin, Cout=Cout, kT=kT, kH=kH, kW=kW, sT=sT, sH=sH, sW=sW,
                    pT=pT, pH=pH, pW=pW, in_ld=Cx, w_ld=w_ld, out_ld=out.shape[-1],
                    res_ld=(residual.shape[-1] if residual is not None else 0), dtype=dtype,
-                   out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode))
+                   out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode), out_round_tf32=int(bool(round_tf32)))
     if residual is not None:
         assert residual.dtype == odt and residual.is_contiguous()
     if scale is not None:

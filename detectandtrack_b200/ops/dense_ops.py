@@ -27,7 +27,8 @@ def maxpool2d(x, k, s, p):
     return y
 
 
-def roi_align(feats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_dev=None, channels=None):
+def roi_align(feats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_dev=None, channels=None,
+              round_tf32=False):
     """feats: list of [Nimg*T, H_l, W_l, C] (finest first, level k_min + i); rois [R, 4T+1] fp32
     (col 0 = image index); levels [R] int32 or None for a single level -> [R, T, P, P, C]."""
     torch = L.require_cuda()
@@ -44,7 +45,8 @@ def roi_align(feats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_de
         assert f.is_contiguous() and f.dtype == feats[0].dtype and f.shape[-1] == ldf
     rois = rois.contiguous()
     L.call('dt_roi_align', fp, Hs, Ws, sc, nl, k_min, Cc, ldf, int(feats[0].dtype == torch.float32), L.ptr(rois),
-           rois.shape[1], L.ptr(n_dev), R, T, L.ptr(levels), P, sampling_ratio, L.ptr(out), L.stream_ptr())
+           rois.shape[1], L.ptr(n_dev), R, T, L.ptr(levels), P, sampling_ratio, int(bool(round_tf32)), L.ptr(out),
+           L.stream_ptr())
     return out
 
 

@@ -130,6 +130,9 @@ typedef struct dt_conv_desc {
   int out_f32;    /* 1: y/residual fp32, 0: bf16 */
   int relu;
   int res_mode;
+  int out_round_tf32; /* fp32 output rounded (nearest-even) to tf32: set when the consumer is another
+                         DT_DTYPE_TF32 conv, because kind::tf32 truncates its operands (a one-sided
+                         error that otherwise compounds to percents over ~50 layers) */
 } dt_conv_desc;
 
 int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
@@ -193,10 +196,11 @@ int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int 
  * non-"aligned") over FPN levels with tube -> frame routing and the un-shuffle fused.
  * feats/Hs/Ws/scales: host arrays [nlevels] (feature l is [n_images*T, Hs[l], Ws[l], ldf]);
  * rois [R, ldr] (col 0 image index, then 4*T), levels [R] (NULL if nlevels == 1);
- * out [R, T, P, P, C]; rows >= *n_dev are zero-filled. */
+ * out [R, T, P, P, C]; rows >= *n_dev are zero-filled.  round_tf32: round fp32 outputs to tf32
+ * (when they feed a DT_DTYPE_TF32 GEMM; prep_clip does the same for its fp32 output). */
 int dt_roi_align(const void* const* feats, const int* Hs, const int* Ws, const float* scales, int nlevels,
                  int k_min, int C, int ldf, int f32, const float* rois, int ldr, const int* n_dev, int R,
-                 int T, const int* levels, int P, int sampling_ratio, void* out, void* stream);
+                 int T, const int* levels, int P, int sampling_ratio, int round_tf32, void* out, void* stream);
 
 /* BilinearInterpolation (lib/modeling/detector.py:348-380) + heatmaps_to_keypoints
  * (lib/utils/keypoints.py:94-149).  lowres [D*T, S, S, ldl] fp32 with channel (py*2+px)*K + k =
