@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — clips/sec of the per-clip detect path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[3] — 3-D ResNet-50-FPN (T=3, time kernel 3)
+keypoint R-CNN inference, 800x1333 frames (blob 800x1344), per-clip data parallel: FPN3D body,
+BODY_HEAD_LINK slice-center, 2mlp box head, 8-conv keypoint head (the reference's runnable FPN
+semantics, lib/modeling/FPN3D.py:228), R = 1000 proposals, D <= 100 detections, synthetic uint8
+frames, seeded random weights.  A step = `--clips` clips per GPU through
+DetectionEngine.detect; weak scaling (clips are independent: no data-path collective).
+
+  value      clips/s with the uint8 frames already resident in HBM (CUDA events, max over ranks)
+  e2e        same through the public call with PINNED HOST frames: H2D of the frames and D2H of
+             boxes + keypoints inside the timed region
+  roofline   tensor-core roofline of the dominant kernel (conv_tc_kernel): algorithmic conv/FC
+             FLOPs of a step / summed CUDA-event time of those launches, vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the torch-fp32 CPU restatement of the reference graph
+             (oracle/, test infrastructure) on the host cores, one bounded clip per step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def bench_cfg(h=800, w=1333):
+    from detectandtrack_b200.core.config import cfg, reset_cfg, assert_and_infer_cfg
+    reset_cfg()
+    cfg.MODEL.TYPE = 'keypoint_rcnn'
+    cfg.MODEL.CONV_BODY = 'FPN3D.add_fpn_ResNet50_conv5_body'
+    cfg.MODEL.ROI_HEAD = 'head_builder.add_roi_2mlp_head'
+    cfg.MODEL.NUM_CLASSES = 2
+    cfg.MODEL.FASTER_RCNN = True
+    cfg.MODEL.KEYPOINTS_ON = True
+    cfg.MODEL.VIDEO_ON = True
+    cfg.FPN.FPN_ON = True; cfg.FPN.MULTILEVEL_ROIS = True; cfg.FPN.MULTILEVEL_RPN = True
+    cfg.FAST_RCNN.ROI_XFORM_METHOD = 'RoIAlign'; cfg.FAST_RCNN.ROI_XFORM_RESOLUTION = 7
+    cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO = 2
+    cfg.KRCNN.ROI_KEYPOINTS_HEAD = 'keypoint_rcnn_heads.add_roi_pose_head_v1convX'
+    cfg.KRCNN.NUM_STACKED_CONVS = 8; cfg.KRCNN.NUM_KEYPOINTS = 17; cfg.KRCNN.USE_DECONV_OUTPUT = True
+    cfg.KRCNN.CONV_HEAD_DIM = 512; cfg.KRCNN.UP_SCALE = 2; cfg.KRCNN.HEATMAP_SIZE = 56
+    cfg.KRCNN.ROI_XFORM_RESOLUTION = 14; cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO = 2
+    cfg.VIDEO.NUM_FRAMES = 3; cfg.VIDEO.TIME_INTERVAL = 1
+    for k in ('BODY', 'HEAD_RPN', 'HEAD_KPS', 'HEAD_DET'):
+        cfg.VIDEO.TIME_KERNEL_DIM[k] = 3
+    cfg.VIDEO.BODY_HEAD_LINK = 'slice-center'; cfg.VIDEO.NUM_FRAMES_MID = 1
+    cfg.TEST.SCALES = (min(h, w),); cfg.TEST.MAX_SIZE = max(h, w)
+    cfg.TEST.NMS = 0.5; cfg.TEST.RPN_PRE_NMS_TOP_N = 1000; cfg.TEST.RPN_POST_NMS_TOP_N = 1000
+    cfg.TEST.COMPETITION_MODE = False
+    assert_and_infer_cfg()
+    return cfg
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1413.7))), src='measured (MEASURED_PEAKS.json, bf16 sustained)')
+    return dict(tflops=1400.0, src='fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def synth_frames(B, T, H, W, seed):
+    rng = np.random.RandomState(seed)
+    return rng.randint(0, 256, (B, T, H, W, 3)).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------ reference / CPU arm
+def reference_clip(cfg, blobs, spec, frames, R=1000, D=100):
+    """One clip through the torch-fp32 CPU restatement of the reference graph with the reference's
+    host ops (oracle/; TEST INFRASTRUCTURE used here only as the measured CPU baseline)."""
+    import torch
+    from oracle import net as onet, proposals as oprop, detections as odet, keypoints as okp
+    from oracle.proposals import generate_anchors
+    H, W = frames.shape[2:4]
+    hp, wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    means = np.asarray(cfg.PIXEL_MEANS, np.float32).reshape(1, 1, 1, 1, 3)
+    blob = np.zeros((1, frames.shape[1], hp, wp, 3), np.float32)
+    blob[:, :, :H, :W] = frames.astype(np.float32) - means
+    data = torch.from_numpy(blob).permute(0, 4, 1, 2, 3).contiguous()
+    im_info = np.array([hp, wp, 1.0], np.float32)
+    with torch.no_grad():
+        pyr = onet.fpn(blobs, spec, onet.conv_body(blobs, spec, data))
+        feats = [onet.time_pool(p, 'slice-center', 1) for p in pyr][::-1]          # P2..P6
+        rois_l, sc_l = [], []
+        for l, (lg, dl) in enumerate(onet.rpn_heads_fpn(blobs, spec, feats[::-1])):
+            lvl = spec.rpn_levels[l]
+            anchors = generate_anchors(2. ** lvl, (cfg.FPN.RPN_ANCHOR_START_SIZE * 2. ** (lvl - 2),), cfg.FPN.RPN_ASPECT_RATIOS)
+            probs = torch.sigmoid(lg)[0].numpy()
+            p, s = oprop.generate_proposals(probs, dl[0].numpy(), im_info, anchors, 2. ** lvl,
+                                            cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N, cfg.TEST.RPN_NMS_THRESH, 0)
+            rois_l.append(np.hstack([np.zeros((p.shape[0], 1), np.float32), p])); sc_l.append(s)
+        rois = oprop.collect(rois_l, sc_l, R)
+        scales = [1. / 2 ** l for l in spec.roi_levels]
+        cls, bbox = onet.box_head_2mlp(blobs, onet.roi_features(feats[:4], scales, rois, 7, 2))
+        scores = odet.softmax(cls.numpy())
+        boxes = odet.decode_boxes(rois, bbox.numpy(), 1.0, (H, W))
+        _, det_boxes, cls_boxes = odet.box_results_with_nms_and_limit(scores, boxes, 2, cfg.TEST.SCORE_THRESH, cfg.TEST.NMS, D)
+        kr = np.hstack([np.zeros((det_boxes.shape[0], 1), np.float32), det_boxes]).astype(np.float32)
+        n_kp = 0
+        if kr.shape[0]:
+            heat, _ = onet.keypoint_head_2d(blobs, onet.roi_features(feats[:4], scales, kr, 14, 2))
+            okp.keypoint_results(heat.numpy(), det_boxes, 17)
+            n_kp = kr.shape[0]
+    return cls_boxes[1].shape[0], n_kp
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    from detectandtrack_b200.modeling import params as P
+    cfg = bench_cfg(args.height, args.width)
+    blobs, spec = P.random_blobs(cfg)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = synth_frames(1, 3, args.height, args.width, 7)
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    # bounded sample: ONE clip per step; cap the run at ~5 minutes
+    t_first = None
+    done, t_total = 0, 0.0
+    for i in range(warm + steps):
+        t0 = time.time()
+        nd, nk = reference_clip(cfg, blobs, spec, frames)
+        dt = time.time() - t0
+        if t_first is None:
+            t_first = dt
+        if i >= warm:
+            done += 1; t_total += dt
+        if (i + 1 < warm + steps) and (time.time() - T_START + dt > 300):
+            break
+    if done == 0:
+        done, t_total = 1, t_first
+    v = done / t_total
+    line = dict(impl='reference', metric='clips/sec (T=3, 800x1333)', value=v, unit='clips/s', n_gpus=args.gpus,
+                steps=done, warmup=min(warm, 1), ms_per_step=1000.0 * t_total / done, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload='R50-FPN-3D (T=3, tk=3) keypoint R-CNN inference, slice-center + 2-D heads, %dx%d, R=1000, D<=100' % (args.height, args.width),
+                            clips_per_step=1, note='torch-fp32 CPU restatement of the reference graph + reference host ops (oracle/); '
+                                                   'the reference Caffe2/cuDNN build cannot be produced here (BASELINE.md §2)'),
+                cpu_baseline=dict(value=v, unit='clips/s', cores=cores, kind='port', sample='%d clip(s), full graph, batch 1' % done),
+                e2e=dict(value=v, unit='clips/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ our arm
+class ConvMeter(object):
+    """CUDA-event timing of every conv_tc launch + its algorithmic FLOPs (2*MACs)."""
+
+    def __init__(self, torch):
+        self.torch, self.ev, self.flops, self.on = torch, [], 0.0, False
+
+    def install(self):
+        from detectandtrack_b200.ops import conv as cv
+        meter, orig = self, cv.conv3d
+
+        def timed(x, w_packed, ksize, *a, **kw):
+            if not meter.on:
+                return orig(x, w_packed, ksize, *a, **kw)
+            e0 = meter.torch.cuda.Event(enable_timing=True); e1 = meter.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = orig(x, w_packed, ksize, *a, **kw)
+            e1.record()
+            cin = kw.get('cin') or min(x.shape[-1], w_packed.shape[-1])
+            cout = w_packed.shape[1]
+            meter.flops += 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3] * cout * cin * ksize[0] * ksize[1] * ksize[2]
+            meter.ev.append((e0, e1))
+            return y
+        cv.conv3d = timed
+        import detectandtrack_b200.modeling.engine as eng
+        eng.cv.conv3d = timed
+
+    def result(self):
+        ms = sum(a.elapsed_time(b) for a, b in self.ev)
+        return ms, self.flops, len(self.ev)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from detectandtrack_b200 import _lib as L
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    cfg = bench_cfg(args.height, args.width)
+    blobs, spec = P.random_blobs(cfg)
+    eng = DetectionEngine(cfg, blobs, spec, dtype=args.dtype)
+    eng.skip_dead_frames = bool(args.dce)
+    B, T, H, W = args.clips, 3, args.height, args.width
+    host = torch.from_numpy(synth_frames(B, T, H, W, 100 + rank)).pin_memory()
+    dev = host.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    meter = ConvMeter(torch)
+    meter.install()
+    ncalls = {'n': 0}
+    orig_call = L.call
+
+    def counting_call(name, *a):
+        ncalls['n'] += 3 if name == 'dt_nms_batched' else 1
+        return orig_call(name, *a)
+    L.call = counting_call
+    for m in ('box_ops', 'rpn_ops', 'dense_ops', 'conv'):
+        mod = __import__('detectandtrack_b200.ops.' + m, fromlist=['x'])
+        mod.L.call = counting_call
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        flush.zero_()                       # L2 flush between iterations (256 MiB > 126 MB L2)
+        return eng.detect(dev)
+
+    def step_e2e():
+        flush.zero_()
+        d = host.cuda(non_blocking=True)
+        res = eng.detect(d)
+        out = [(r['boxes'].cpu(), r['keyps'].cpu() if r['keyps'] is not None else None) for r in res]
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        res = step_resident()
+    barrier()
+    ndet = [int(r['boxes'].shape[0]) for r in res]
+    # ---- timed: resident inputs -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ncalls['n'] = 0
+    meter.on = True
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    meter.on = False
+    launches = ncalls['n'] + args.steps          # + the flush fill per step (torch kernel, not counted as ours)
+    launches = ncalls['n']
+    ms = e0.elapsed_time(e1)
+    conv_ms, conv_flops, conv_n = meter.result()
+    # ---- timed: end to end (pinned host -> device -> host) --------------------------------------
+    for _ in range(2):
+        out = step_e2e()
+    barrier()
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        out = step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    d2h = sum(int(b.numel() * 4 + (k.numel() * 4 if k is not None else 0)) for b, k in out)
+    t = torch.tensor([ms, ms_e2e, conv_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, conv_ms_max = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        value = world * B * args.steps / (ms / 1000.0)
+        e2e = world * B * args.steps / (ms_e2e / 1000.0)
+        achieved = conv_flops / (conv_ms / 1000.0) / 1e12
+        line = dict(metric='clips/sec (T=3, 800x1333)', value=value, unit='clips/s', n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype=args.dtype, data='synthetic',
+                    config=dict(workload='R50-FPN-3D (T=3, tk=3) keypoint R-CNN inference, slice-center + 2-D heads, %dx%d, R=1000, D<=100 (BASELINE.json configs[3])' % (H, W),
+                                clips_per_step_per_gpu=B, parallelism='clips sharded over %d GPU(s), no collective' % world,
+                                detections_per_clip=ndet, l2='flushed between iterations (256 MiB fill)',
+                                dead_frame_elimination=bool(args.dce),
+                                conv_gflop_per_clip=conv_flops / 1e9 / (B * args.steps), conv_launches_per_step=conv_n // args.steps,
+                                conv_share_of_step=conv_ms / ms),
+                    e2e=dict(value=e2e, unit='clips/s', h2d_bytes_per_step=int(host.numel()), d2h_bytes_per_step=d2h),
+                    gpu_launches=launches, clocks=clocks,
+                    roofline=dict(bound='tensor', kernel='conv_tc_kernel (all conv/FC launches of the step)', achieved=achieved,
+                                  peak=pk['tflops'], unit='TFLOP/s', frac=achieved / pk['tflops'], traffic=None,
+                                  peak_source=pk['src']))
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline(cfg, blobs, spec, args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, blobs, spec, args):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = synth_frames(1, 3, args.height, args.width, 7)
+    t0 = time.time()
+    nd, nk = reference_clip(cfg, blobs, spec, frames)
+    dt = time.time() - t0
+    return dict(value=1.0 / dt, unit='clips/s', cores=cores, kind='port',
+                sample='1 clip, full graph incl. host NMS/decoding, torch fp32 CPU (oracle/), %d detections' % nd)
+
+
+T_START = time.time()
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'tf32'])
+    ap.add_argument('--clips', type=int, default=2, help='clips per GPU per step')
+    ap.add_argument('--height', type=int, default=800)
+    ap.add_argument('--width', type=int, default=1333)
+    ap.add_argument('--dce', type=int, default=0, help='1: compute only the consumed centre frame of the post-hoc FPN convs')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        if a.steps == 10 and a.warmup == 3:
+            a.steps, a.warmup = 2, 1
+        run_reference(a)
+    else:
+        run_ours(a)
