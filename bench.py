@@ -195,7 +195,7 @@ class ConvMeter(object):
     """CUDA-event timing of every conv_tc launch + its algorithmic FLOPs (2*MACs)."""
 
     def __init__(self, torch):
-        self.torch, self.ev, self.flops, self.on = torch, [], 0.0, False
+        self.torch, self.ev, self.flops, self.on, self.meta = torch, [], 0.0, False, []
 
     def install(self):
         from detectandtrack_b200.ops import conv as cv
@@ -212,6 +212,7 @@ class ConvMeter(object):
             cout = w_packed.shape[1]
             meter.flops += 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3] * cout * cin * ksize[0] * ksize[1] * ksize[2]
             meter.ev.append((e0, e1))
+            meter.meta.append((tuple(x.shape), cin, cout, tuple(ksize), tuple(y.shape)))
             return y
         cv.conv3d = timed
         import detectandtrack_b200.modeling.engine as eng
@@ -220,6 +221,19 @@ class ConvMeter(object):
     def result(self):
         ms = sum(a.elapsed_time(b) for a, b in self.ev)
         return ms, self.flops, len(self.ev)
+
+    def layers(self, nsteps):
+        """Per-layer median time over the timed steps (layer = position in the launch sequence)."""
+        n = len(self.ev) // nsteps
+        rows = []
+        for i in range(n):
+            ts = sorted(self.ev[s * n + i][0].elapsed_time(self.ev[s * n + i][1]) for s in range(nsteps))
+            xs, cin, cout, k, ys = self.meta[i]
+            fl = 2.0 * ys[0] * ys[1] * ys[2] * ys[3] * cout * cin * k[0] * k[1] * k[2]
+            ms = ts[len(ts) // 2]
+            rows.append(dict(i=i, x=list(xs), cin=cin, cout=cout, k=list(k), ms=round(ms, 4), gflop=round(fl / 1e9, 2),
+                             tflops=round(fl / ms / 1e9, 1)))
+        return rows
 
 
 def run_ours(args):
@@ -329,6 +343,9 @@ def run_ours(args):
                     roofline=dict(bound='tensor', kernel='conv_tc_kernel (all conv/FC launches of the step)', achieved=achieved,
                                   peak=pk['tflops'], unit='TFLOP/s', frac=achieved / pk['tflops'], traffic=None,
                                   peak_source=pk['src']))
+        if args.layers:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            json.dump(meter.layers(args.steps), open(os.path.join(ROOT, 'gpurun_out', 'conv_layers.json'), 'w'), indent=0)
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(cfg, blobs, spec, args)
         print(json.dumps(line))
@@ -362,6 +379,7 @@ if __name__ == '__main__':
     ap.add_argument('--width', type=int, default=1333)
     ap.add_argument('--dce', type=int, default=0, help='1: compute only the consumed centre frame of the post-hoc FPN convs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layers', action='store_true', help='dump per-conv timings to gpurun_out/conv_layers.json')
     a = ap.parse_args()
     if a.impl == 'reference':
         if a.steps == 10 and a.warmup == 3:

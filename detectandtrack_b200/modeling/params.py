@@ -203,27 +203,38 @@ def param_shapes(cfg):
 
 
 def random_blobs(cfg, seed=None):
-    """seeded N(0, sqrt(2/fan_in)) filters, affine s~U(0.5,1.5), b~N(0,0.1),
-    conv/FC biases N(0, 0.01).  Heads get the reference's small stds so scores stay finite."""
+    """Seeded synthetic weights (He-normal filters, affine s~U(0.5,1.5), b~N(0,0.1))
+    conditioned like a trained network so the synthetic workload is the one BASELINE.json names
+    (R = 1000 proposals, D = DETECTIONS_PER_IM detections per clip):
+      * conv1 absorbs the un-normalised pixel scale (He std / 64);
+      * the last affine of every residual branch is damped (s~U(0.2,0.4)) so activations stay O(1);
+      * FPN convs Xavier, heads with the reference's own init stds (GaussianFill 0.01 for RPN /
+        cls_score, 0.001 for bbox_pred: FPN.py:223-262, model_builder.py:431-478; MSRAFill for the
+        keypoint convs, keypoint_rcnn_heads.py:53-65), biases 0."""
     shapes, spec = param_shapes(cfg)
     rng = np.random.RandomState(cfg.RNG_SEED if seed is None else seed)
     blobs = OrderedDict()
     for name, shp in shapes.items():
+        fan_in = int(np.prod(shp[1:])) if len(shp) > 1 else 1
         if name.endswith('_bn_s'):
-            v = rng.uniform(0.5, 1.5, shp)
+            last = name.endswith('_branch2c_bn_s') or (spec.block == 'basic' and name.endswith('_branch2b_bn_s'))
+            v = rng.uniform(0.2, 0.4, shp) if last else rng.uniform(0.5, 1.5, shp)
         elif name.endswith('_bn_b'):
             v = rng.normal(0, 0.1, shp)
         elif name.endswith('_b'):
+            v = np.zeros(shp)
+        elif name == 'conv1_w':
+            v = rng.normal(0, np.sqrt(2.0 / fan_in) / 64.0, shp)
+        elif name.startswith('fpn_') or name.startswith(('fc6', 'fc7')):
+            v = rng.uniform(-np.sqrt(3.0 / fan_in), np.sqrt(3.0 / fan_in), shp)          # XavierFill
+        elif name.startswith(('conv_rpn', 'rpn_cls', 'rpn_bbox', 'cls_score')):
             v = rng.normal(0, 0.01, shp)
+        elif name.startswith('bbox_pred'):
+            v = rng.normal(0, 0.001, shp)
+        elif name.startswith('kps_score_lowres'):
+            v = rng.normal(0, np.sqrt(2.0 / (shp[0] * shp[2] * shp[3] / 4.0)), shp)      # ConvTranspose: Cin first
         else:
-            if name.startswith('kps_score_lowres'):
-                fan_in = shp[0] * shp[2] * shp[3] / 4.0
-            else:
-                fan_in = int(np.prod(shp[1:]))
-            std = np.sqrt(2.0 / fan_in)
-            if name.startswith(('rpn_cls', 'rpn_bbox', 'cls_score', 'bbox_pred')):
-                std = min(std, 0.01)
-            v = rng.normal(0, std, shp)
+            v = rng.normal(0, np.sqrt(2.0 / fan_in), shp)                                # MSRAFill
         blobs[name] = v.astype(np.float32)
     return blobs, spec
 
