@@ -29,7 +29,8 @@ SIGNATURES = {
     'dt_distribute_fpn': [_p, _i, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     'dt_box_decode': [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, C.POINTER(_f), C.c_double, _f, _p, _p, _p],
     'dt_limit_detections': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],
-    'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_conv1_7x7s2': [_p, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p],
     'dt_maxpool2d': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_roi_align': [C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _p, _i, _p, _i,
                      _i, _p, _i, _i, _i, _p, _p],

@@ -446,3 +446,68 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   }
 #undef DT_LAUNCH
 }
+
+
+// conv1 of the ResNet bodies: 7x7 stride 2 pad 3 on a 3-channel image (lib/modeling/ResNet3D.py:258-261,
+// ResNet.py).  With Cin = 3 a per-tap k-block would waste 61/64 of every MMA, so the taps of one filter
+// ROW are packed into K instead: the image blob is channel-padded to Cp (8 bf16 / 4 fp32 = 16 bytes per
+// pixel) and carries physical zero borders (3 rows top/bottom, 4 pixels left/right, written by
+// dt_prep_clip), so the 7-pixel window of output column wo is ONE contiguous 112-byte run starting at
+// padded pixel 2*wo + 1.  The A tensor map is an overlapping strided view
+//   dim0 = 8 pixels x Cp (128 B, the 8th pixel meets zero weights), dim1 = wo (stride 2 pixels = 32 B),
+//   dim2 = padded rows (element stride 2), dim4 = frames
+// and the conv is 7 k-blocks (one per filter row) of K = 128 bytes: 3*7/ (8*8) = 33 % useful MACs instead
+// of 4.7 %.  w [7][Cout][8*Cp] (kw-major, channel-minor).  y [F, Hp/2, Wp/2, out_ld].
+extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
+                              const float* scale, const float* bias, int relu, int dtype, int out_f32,
+                              int out_round_tf32, void* y, int out_ld, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DT_CHECK_ARG(dtype == DT_DTYPE_BF16 || dtype == DT_DTYPE_TF32, "dt_conv1_7x7s2: bad dtype %d", dtype);
+  const bool tf32 = dtype == DT_DTYPE_TF32;
+  const int esz = tf32 ? 4 : 2;
+  DT_CHECK_ARG(Cp * esz == 16, "dt_conv1_7x7s2: the blob must carry 16 bytes per pixel (Cp=%d, %d B/elem)", Cp, esz);
+  DT_CHECK_ARG(F >= 1 && Hp >= 2 && Wp >= 2 && Hp % 2 == 0 && Wp % 2 == 0 && Cout >= 1 && Cout <= 64,
+               "dt_conv1_7x7s2: bad shape F=%d Hp=%d Wp=%d Cout=%d", F, Hp, Wp, Cout);
+  DT_CHECK_ARG(x_padded && w && y, "dt_conv1_7x7s2: null pointer");
+  const int oesz = out_f32 ? 4 : 2;
+  if (out_ld <= 0) out_ld = Cout;
+  DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && out_ld >= Cout, "dt_conv1_7x7s2: bad out_ld %d", out_ld);
+  const int Ho = Hp / 2, Wo = Wp / 2;
+  const int BKe = 128 / esz;                       // elements per k-block
+  int TH, TW;
+  pick_tile(Ho, Wo, &TH, &TW);
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = F; p.To = 1; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.kT = 1; p.kH = 7; p.kW = 1; p.sT = 1; p.sH = 2; p.sW = 1; p.pT = 0; p.pH = 0; p.pW = 0;
+  p.kchunks = 1;
+  p.TH = TH; p.TW = TW; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_n = 1;
+  p.a_bytes = (uint32_t)TH * TW * 128u;
+  p.scale = scale; p.bias = bias; p.relu = relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32;
+  p.round_tf32 = out_round_tf32;
+  const long long total = (long long)F * p.tiles_h * p.tiles_w;
+  DT_CHECK_ARG(total < (1ll << 31), "dt_conv1_7x7s2: too many tiles");
+  p.total_tiles = (int)total;
+  const uint64_t pix = 16, row = (uint64_t)(Wp + 8) * pix, frame = row * (Hp + 6);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)BKe, (uint64_t)Wo, (uint64_t)(Hp + 6), 1, (uint64_t)F};
+    uint64_t strides[4] = {2 * pix, row, frame, frame};
+    uint32_t box[5] = {(uint32_t)BKe, (uint32_t)TW, (uint32_t)(2 * TH), 1, 1};
+    uint32_t estr[5] = {1, 1, 2, 1, 1};
+    DT_CHECK_ARG(box[2] <= 256, "dt_conv1_7x7s2: tile too tall");
+    if (encode_map(&tmA, tf32, 5, (const char*)x_padded + pix, dims, strides, box, estr)) return 1;
+  }
+  {
+    uint64_t wd[3] = {(uint64_t)BKe, (uint64_t)Cout, 7};
+    uint64_t ws[2] = {128, (uint64_t)128 * Cout};
+    uint32_t wb[3] = {(uint32_t)BKe, 64, 1};
+    uint32_t we[3] = {1, 1, 1};
+    if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
+  }
+  int dev = 0, sms = 148;
+  DT_CHECK_CUDA(cudaGetDevice(&dev));
+  DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  return tf32 ? launch_conv<64, true>(tmA, tmB, p, grid, stream) : launch_conv<64, false>(tmA, tmB, p, grid, stream);
+}

@@ -55,14 +55,16 @@ template <> struct Vec<__nv_bfloat16> {
 template <typename OT>
 __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F, int H, int W, float m0, float m1,
                                  float m2, double inv_scale, int Hr, int Wr, int Hp, int Wp, int Cp,
-                                 OT* __restrict__ out) {
-  const long long total = (long long)F * Hp * Wp;
+                                 int by, int bx, OT* __restrict__ out) {
+  // the output buffer is [F, Hp + 2*by, Wp + 2*bx, Cp]: `by` zero rows above/below, `bx` zero pixels left/right
+  const int Ht = Hp + 2 * by, Wt = Wp + 2 * bx;
+  const long long total = (long long)F * Ht * Wt;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(idx % Wp);
-    const int y = (int)((idx / Wp) % Hp);
-    const int f = (int)(idx / ((long long)Wp * Hp));
+    const int x = (int)(idx % Wt) - bx;
+    const int y = (int)((idx / Wt) % Ht) - by;
+    const int f = (int)(idx / ((long long)Wt * Ht));
     float v[3] = {0.f, 0.f, 0.f};
-    if (y < Hr && x < Wr) {
+    if (y >= 0 && x >= 0 && y < Hr && x < Wr) {
       const unsigned char* src = frames + (size_t)f * H * W * 3;
       const float mean[3] = {m0, m1, m2};
       if (Hr == H && Wr == W) {
@@ -355,19 +357,20 @@ static int grid_for(long long total, int block) {
 }
 
 extern "C" int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3 /*host*/,
-                            double im_scale, int Hr, int Wr, int Hp, int Wp, int Cp, int out_f32, void* out,
-                            void* stream) {
+                            double im_scale, int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x,
+                            int out_f32, void* out, void* stream) {
   DT_CHECK_ARG(F >= 0 && H >= 1 && W >= 1 && Hr >= 1 && Wr >= 1 && Hp >= Hr && Wp >= Wr && Cp >= 3 && im_scale > 0,
                "dt_prep_clip: bad shape F=%d H=%d W=%d Hr=%d Wr=%d Hp=%d Wp=%d Cp=%d", F, H, W, Hr, Wr, Hp, Wp, Cp);
   if (F == 0) return 0;
   DT_CHECK_ARG(frames && mean3 && out, "dt_prep_clip: null pointer");
-  const long long total = (long long)F * Hp * Wp;
+  DT_CHECK_ARG(border_y >= 0 && border_x >= 0, "dt_prep_clip: negative border");
+  const long long total = (long long)F * (Hp + 2 * border_y) * (Wp + 2 * border_x);
   if (out_f32)
     prep_clip_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, F, H, W, mean3[0], mean3[1], mean3[2],
-                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, (float*)out);
+                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, (float*)out);
   else
     prep_clip_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, (__nv_bfloat16*)out);
+        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -134,7 +134,12 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
     __syncthreads();
     for (int i = tid; i < n; i += nth) {
       const uint32_t key = sort_key_f32(score_at(i));
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shifts[pass]) & (nb - 1)], 1);
+      if ((key & mask) == prefix) {
+        // warp-aggregated histogram update: RPN scores cluster, so most lanes hit the same bin
+        const int bin = (key >> shifts[pass]) & (nb - 1);
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[bin], __popc(peers));
+      }
     }
     __syncthreads();
     if (tid == 0) {

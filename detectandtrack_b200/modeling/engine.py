@@ -77,7 +77,10 @@ class DetectionEngine(object):
 
     def _build(self, blobs):
         s, cfg, torch = self.spec, self.cfg, self.torch
-        self.conv1 = self._c(blobs, 'conv1', 'res_conv1_bn', stride=(1, 2, 2), pad=(0, 3, 3), relu=True)
+        # conv1: 7x7/2 on the 3-channel blob with the filter row packed into K (dt_conv1_7x7s2)
+        self.conv1_w = cv.pack_conv1_weight(torch.from_numpy(np.ascontiguousarray(blobs['conv1_w'])), self.dtype)
+        self.conv1_s = torch.from_numpy(np.ascontiguousarray(blobs['res_conv1_bn_s'], dtype=np.float32)).cuda()
+        self.conv1_b = torch.from_numpy(np.ascontiguousarray(blobs['res_conv1_bn_b'], dtype=np.float32)).cuda()
         self.stages = []
         dim_in = s.dims[0]
         for si, n in enumerate(s.counts):
@@ -150,11 +153,13 @@ class DetectionEngine(object):
 
     # ------------------------------------------------------------------ backbone
     def body(self, x):
-        """x [B,T,H,W,cin_pad] -> stage outputs (finest first)."""
+        """x [B,T,Hp+6,Wp+8,cin_pad] (zero-bordered blob) -> stage outputs (finest first)."""
         torch = self.torch
         B, T = x.shape[:2]
-        y = self.conv1(x, cin=self.cin_pad)
-        y = dense_ops.maxpool2d(y.view((B * T,) + tuple(y.shape[2:])), 3, 2, 1)
+        hp, wp = x.shape[2] - 6, x.shape[3] - 8
+        y = cv.conv1_7x7s2(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, (hp, wp), self.conv1_s, self.conv1_b,
+                           relu=True, dtype=self.dtype)
+        y = dense_ops.maxpool2d(y, 3, 2, 1)
         y = y.view((B, T) + tuple(y.shape[1:]))
         outs = []
         for blocks in self.stages:
@@ -295,8 +300,8 @@ class DetectionEngine(object):
         B, T, H, W, _ = frames_u8.shape
         scale, (hr, wr), (hp, wp) = self.blob_geometry(H, W)
         x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
-                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32))
-        x = x.view(B, T, hp, wp, self.cin_pad)
+                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
+        x = x.view(B, T, hp + 6, wp + 8, self.cin_pad)
         feats = self.link(self.fpn(self.body(x)))
         im_info = torch.tensor([[hp, wp, scale]] * B, dtype=torch.float32, device='cuda')
         return feats, im_info, scale

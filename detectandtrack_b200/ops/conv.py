@@ -78,3 +78,33 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     L.call('dt_conv3d', C.byref(d), L.ptr(x), L.ptr(w_packed), L.ptr(scale), L.ptr(bias), L.ptr(residual),
            L.ptr(out), L.stream_ptr())
     return out
+
+
+def pack_conv1_weight(w, dtype=BF16):
+    """conv1 filter (Cout, 3, [1,] 7, 7) -> [7 (kh)][Cout][8 pixels x Cp] with element kw*Cp + c
+    (dt_conv1_7x7s2); Cp = 8 (bf16) / 4 (tf32) channels per 16-byte pixel, zeros elsewhere."""
+    torch = L.require_cuda()
+    if w.dim() == 5:
+        w = w[:, :, 0]
+    Cout, Cin, kh, kw = w.shape
+    assert (kh, kw) == (7, 7) and Cin <= 3 + 1
+    Cp = 4 if dtype == TF32 else 8
+    out = torch.zeros((7, Cout, 8, Cp), dtype=_dt(dtype, torch), device='cuda')
+    out[:, :, :7, :Cin] = w.to('cuda').permute(2, 0, 3, 1).to(out.dtype)          # (kh, Cout, kw, c)
+    out = out.reshape(7, Cout, 8 * Cp)
+    return round_tf32(out) if dtype == TF32 else out
+
+
+def conv1_7x7s2(x_padded, w_packed, hw, scale=None, bias=None, relu=True, dtype=BF16, out_f32=None):
+    """x_padded [F, Hp+6, Wp+8, Cp] (dense_ops.prep_clip(border=(3, 4))) -> [F, Hp/2, Wp/2, Cout]."""
+    torch = L.require_cuda()
+    F, Ht, Wt, Cp = x_padded.shape
+    Hp, Wp = hw
+    assert Ht == Hp + 6 and Wt == Wp + 8 and x_padded.is_contiguous()
+    Cout = w_packed.shape[1]
+    if out_f32 is None:
+        out_f32 = dtype == TF32
+    y = torch.empty((F, Hp // 2, Wp // 2, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
+    L.call('dt_conv1_7x7s2', L.ptr(x_padded), F, Hp, Wp, Cp, L.ptr(w_packed), Cout, L.ptr(scale), L.ptr(bias), int(relu),
+           dtype, int(out_f32), int(bool(out_f32) and dtype == TF32), L.ptr(y), Cout, L.stream_ptr())
+    return y

@@ -4,15 +4,17 @@ import ctypes as C
 from .. import _lib as L
 
 
-def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=False):
-    """frames [F,H,W,3] uint8 cuda (BGR) -> [F,Hp,Wp,cpad] (pixel - mean), resized, zero padded."""
+def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=False, border=(0, 0)):
+    """frames [F,H,W,3] uint8 cuda (BGR) -> [F,Hp+2by,Wp+2bx,cpad] (pixel - mean), resized, zero padded,
+    with `border` = (by, bx) physical zero rows / pixels on every side."""
     torch = L.require_cuda()
     F, H, W, _ = frames_u8.shape
     Hr, Wr = out_hw
     Hp, Wp = pad_hw
-    out = torch.empty((F, Hp, Wp, cpad), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
+    by, bx = border
+    out = torch.empty((F, Hp + 2 * by, Wp + 2 * bx, cpad), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
     m = (C.c_float * 3)(*[float(v) for v in pixel_means])
-    L.call('dt_prep_clip', L.ptr(frames_u8.contiguous()), F, H, W, m, float(im_scale), Hr, Wr, Hp, Wp, cpad,
+    L.call('dt_prep_clip', L.ptr(frames_u8.contiguous()), F, H, W, m, float(im_scale), Hr, Wr, Hp, Wp, cpad, by, bx,
            int(out_f32), L.ptr(out), L.stream_ptr())
     return out
 

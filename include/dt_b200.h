@@ -138,6 +138,14 @@ typedef struct dt_conv_desc {
 int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
               const float* bias, const void* residual, void* y, void* stream);
 
+/* conv1 of the ResNet bodies (lib/modeling/ResNet3D.py:258-261): 7x7 stride 2 pad 3 on the 3-channel
+ * image + AffineChannel + ReLU, with the 7 taps of a filter row packed into one 128-byte k-block.
+ * x_padded [F, Hp+6, Wp+8, Cp] from dt_prep_clip(border 3, 4), Cp*elemsize == 16;
+ * w [7 (kh)][Cout <= 64][8*Cp] with w[kh][o][kw*Cp + c]; y [F, Hp/2, Wp/2, out_ld]. */
+int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
+                   const float* scale, const float* bias, int relu, int dtype, int out_f32,
+                   int out_round_tf32, void* y, int out_ld, void* stream);
+
 /* ---- proposals.cu -------------------------------------------------------- */
 
 /* GenerateProposalsOp up to NMS (lib/ops/generate_proposals.py:40-106,116-161): sigmoid,
@@ -184,9 +192,11 @@ int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, in
 
 /* lib/utils/blob.py:40-90 + lib/core/test.py:43-74.  frames [F, H, W, 3] u8 BGR ->
  * out [F, Hp, Wp, Cp] (bf16 or fp32): (pixel - mean3) bilinearly resized by im_scale to Hr x Wr,
- * zero padded (Cp >= 3 channels, spatially to Hp x Wp). */
+ * zero padded (Cp >= 3 channels, spatially to Hp x Wp) and framed by border_y zero rows / border_x
+ * zero pixels on every side: out is [F, Hp + 2*border_y, Wp + 2*border_x, Cp] (dt_conv1_7x7s2 wants 3 / 4). */
 int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3, double im_scale,
-                 int Hr, int Wr, int Hp, int Wp, int Cp, int out_f32, void* out, void* stream);
+                 int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x, int out_f32,
+                 void* out, void* stream);
 
 /* Caffe2 MaxPool kernels [1,k,k] strides [1,s,s] pads [0,p,p] on NHWC (N = B*T frames). */
 int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32,

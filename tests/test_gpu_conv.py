@@ -119,3 +119,31 @@ def test_conv_rejects_bad_arguments():
     wp = torch.zeros((1, 16, 16), dtype=torch.bfloat16, device='cuda')
     with pytest.raises(RuntimeError, match='16 bytes'):
         cv.conv3d(x, wp, (1, 1, 1), cin=12)
+
+
+@pytest.mark.parametrize('mode', ['bf16', 'tf32'])
+def test_conv1_packed_rows_vs_torch(mode):
+    """dt_conv1_7x7s2 (filter row packed into K over a zero-bordered blob) == conv 7x7 s2 p3 + affine + relu."""
+    import torch
+    import torch.nn.functional as F
+    from detectandtrack_b200.ops import conv as cv, dense_ops
+    g = torch.Generator().manual_seed(11)
+    Fr, H, W = 3, 64, 96
+    frames = torch.randint(0, 256, (Fr, H, W, 3), generator=g, dtype=torch.uint8)
+    means = (102.9801, 115.9465, 122.7717)
+    w = torch.randn((64, 3, 1, 7, 7), generator=g) * 0.01
+    sc = torch.rand(64, generator=g) + 0.5
+    bi = torch.randn(64, generator=g) * 0.1
+    dtype = cv.BF16 if mode == 'bf16' else cv.TF32
+    cp = 8 if mode == 'bf16' else 4
+    x = dense_ops.prep_clip(frames.cuda(), means, 1.0, (H, W), (H, W), cpad=cp, out_f32=(mode == 'tf32'), border=(3, 4))
+    assert x.shape == (Fr, H + 6, W + 8, cp)
+    wp = cv.pack_conv1_weight(w, dtype)
+    y = cv.conv1_7x7s2(x, wp, (H, W), sc.cuda(), bi.cuda(), relu=True, dtype=dtype, out_f32=True).cpu()
+    xin = x[:, 3:3 + H, 4:4 + W, :3].float().cpu().permute(0, 3, 1, 2)          # what the kernel saw (rounded blob)
+    wr = w[:, :, 0].bfloat16().float() if mode == 'bf16' else w[:, :, 0]
+    ref = F.conv2d(xin.double(), wr.double(), None, 2, 3) * sc.double().view(1, -1, 1, 1) + bi.double().view(1, -1, 1, 1)
+    ref = ref.clamp_min(0).permute(0, 2, 3, 1).float()
+    tol = 2e-4 if mode == 'bf16' else 1.5e-3
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= tol * ref.abs().max().item()

@@ -22,6 +22,10 @@ def test_prep_clip_identity_scale_and_padding():
     np.testing.assert_allclose(out, ref, rtol=2.0 ** -11, atol=0)
     out_bf = dense_ops.prep_clip(torch.from_numpy(fr).cuda(), means, 1.0, (H, W), (64, 96), cpad=8, out_f32=False).float().cpu().numpy()
     assert np.array_equal(out_bf, torch.from_numpy(ref).bfloat16().float().numpy())
+    # physical zero border (conv1 wants 3 rows / 4 pixels)
+    ob = dense_ops.prep_clip(torch.from_numpy(fr).cuda(), means, 1.0, (H, W), (64, 96), cpad=8, out_f32=False, border=(3, 4)).float().cpu().numpy()
+    assert ob.shape == (F, 70, 104, 8) and np.array_equal(ob[:, 3:67, 4:100], out_bf)
+    assert np.all(ob[:, :3] == 0) and np.all(ob[:, 67:] == 0) and np.all(ob[:, :, :4] == 0) and np.all(ob[:, :, 100:] == 0)
 
 
 @pytest.mark.parametrize('scale', [1.6, 0.53])
