@@ -68,25 +68,31 @@ struct ConvCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int C_BYTES = 128 * 128;            // one staged output chunk: 128 rows x 128 B
+  static constexpr int NCBUF = (BN >= 256) ? 1 : 2;    // output staging buffers (smem budget)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NCBUF * C_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    2 * BN * 4 /*scale, bias*/;
 };
 
 template <int BN, bool TF32>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvKernelParams p) {
+               const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using Cfg = ConvCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BK = TF32 ? 32 : 64;                 // elements per 128-byte k-block
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (required by SWIZZLE_128B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* cbuf = smem + STAGES * Cfg::STAGE_BYTES;                  // [NCBUF][128 rows][128 B], 128B-swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + Cfg::NCBUF * Cfg::C_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + STAGES;             // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [BN]
+  float* s_bias = s_scale + BN;                                                           // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     fence_barrier_init();
@@ -164,10 +171,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers -> fp32 epilogue -> 128B-swizzled smem chunk -> one TMA store per chunk.
+    // The TMA store writes whole 128-byte lines and clips rows / channels outside the tensor,
+    // so ragged tiles need no predication on the store side.
     const int lg = warp & 3;                   // TMEM lane group this warp may access
-    const int row = lg * 32 + lane;            // accumulator row == TMEM lane
+    const int row = lg * 32 + lane;            // accumulator row == TMEM lane == staging row
     const int th = row / p.TW, tw = row - th * p.TW;
+    const bool leader = (threadIdx.x == 64);   // warp 2, lane 0 issues the stores
+    const int ep_tid = threadIdx.x - 64;       // 0..127
+    const int CW = p.out_f32 ? 32 : 64;        // output columns per 128-byte staged row
+    const uint32_t row_smem = (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
     int as = 0; uint32_t aphase = 0;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
@@ -182,27 +198,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.res_mode == 2)
         rpos = ((size_t)(n * p.To + t) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
 
+      // per-tile scale / bias -> smem (previous tile's readers are past their last named barrier)
+      for (int j = ep_tid; j < BN; j += 128) {
+        const int c = nt * BN + j;
+        s_scale[j] = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
+        s_bias[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c0, r);
-        tmem_ld_wait();
-        const int cbase = nt * BN + c0;
-        if (valid && cbase < p.Cout) {
+      for (int cc = 0; cc < BN; cc += CW) {
+        const int cchunk = nt * BN + cc;
+        if (cchunk >= p.Cout) break;                                   // uniform: nothing left to write
+        uint8_t* buf = cbuf + (chunk_ctr % Cfg::NCBUF) * Cfg::C_BYTES;
+        ++chunk_ctr;
+        // the staging buffer must have been read out by the TMA store that used it last
+        if (leader) {
+          if (Cfg::NCBUF == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = cc; c0 < cc + CW; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          tmem_ld_wait();
+          const int cbase = nt * BN + c0;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            const bool cok = c < p.Cout;
-            const float s = (p.scale && cok) ? __ldg(p.scale + c) : 1.f;
-            const float b = (p.bias && cok) ? __ldg(p.bias + c) : 0.f;
-            v[j] = fmaf(__uint_as_float(r[j]), s, b);
-          }
-          const int ncols = min(32, p.Cout - cbase);
-          if (p.res_mode != 0) {
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]);
+          if (p.res_mode != 0 && valid && cbase < p.Cout) {
+            const int ncols = min(32, p.Cout - cbase);
             if (p.out_f32) {
               const float* rp = reinterpret_cast<const float*>(p.residual) + rpos * p.res_ld + cbase;
               if (ncols == 32) {
@@ -236,37 +265,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          const uint32_t dst = smem_u32(buf) + row_smem;
           if (p.out_f32) {
             if (p.round_tf32) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = round_to_tf32(v[j]);
             }
-            float* op = reinterpret_cast<float*>(p.out) + pos * p.out_ld + cbase;
-            if (ncols == 32) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < ncols; ++j) op[j] = v[j];
+            for (int q = 0; q < 8; ++q) {            // 8 x 16 B = the whole 128-byte row
+              const uint32_t a = dst + (((uint32_t)q ^ swz) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                           "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
             }
           } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.out_ld + cbase;
-            if (ncols == 32) {
+            const uint32_t q0 = (uint32_t)((c0 - cc) >> 3);     // 16-byte chunk index of this half row (0 or 4)
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 q;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-                q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(op + j) = q;
-              }
-            } else {
-              for (int j = 0; j < ncols; ++j) op[j] = __float2bfloat16_rn(v[j]);
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+              const uint32_t a = dst + (((q0 + (uint32_t)q) ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                           "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                           "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
             }
           }
+        }
+        // generic-proxy smem writes -> visible to the async proxy, then one thread stores the chunk
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          asm volatile(
+              "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                  reinterpret_cast<uint64_t>(&tmC)),
+              "r"(smem_u32(buf)), "r"(cchunk), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
+              : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tcgen05_fence_before();
@@ -274,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -330,9 +366,21 @@ static void pick_tile(int Ho, int Wo, int* TH, int* TW) {
   *TH = bh; *TW = bw;
 }
 
+// Output map: dims (Cout, Wo, Ho, To, N) of the NDHWC result, box = one staged chunk (128 B of channels x TW x TH).
+static int encode_out_map(CUtensorMap* m, void* y, int out_f32, int Cout, int Wo, int Ho, int To, int N, int out_ld,
+                          int TH, int TW) {
+  const uint64_t oesz = out_f32 ? 4 : 2;
+  uint64_t d[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)To, (uint64_t)N};
+  uint64_t st[4] = {(uint64_t)out_ld * oesz, (uint64_t)out_ld * oesz * Wo, (uint64_t)out_ld * oesz * Wo * Ho,
+                    (uint64_t)out_ld * oesz * Wo * Ho * To};
+  uint32_t b[5] = {(uint32_t)(128 / oesz), (uint32_t)TW, (uint32_t)TH, 1, 1};
+  uint32_t e[5] = {1, 1, 1, 1, 1};
+  return encode_map(m, out_f32 != 0, 5, y, d, st, b, e);
+}
+
 template <int BN, bool TF32>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, int grid,
-                       cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -340,7 +388,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
                                        Cfg::SMEM_BYTES));
     attr = true;
   }
-  conv_tc_kernel<BN, TF32><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  conv_tc_kernel<BN, TF32><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -432,12 +480,14 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
     uint32_t we[3] = {1, 1, 1};
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
+  CUtensorMap tmC;
+  if (encode_out_map(&tmC, y, out_f32, d->Cout, Wo, Ho, To, d->N, out_ld, TH, TW)) return 1;
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
 #define DT_LAUNCH(BNv)                                                                      \
-  return tf32 ? launch_conv<BNv, true>(tmA, tmB, p, grid, stream) : launch_conv<BNv, false>(tmA, tmB, p, grid, stream)
+  return tf32 ? launch_conv<BNv, true>(tmA, tmB, tmC, p, grid, stream) : launch_conv<BNv, false>(tmA, tmB, tmC, p, grid, stream)
   switch (BN) {
     case 256: DT_LAUNCH(256);
     case 128: DT_LAUNCH(128);
@@ -505,9 +555,11 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
     uint32_t we[3] = {1, 1, 1};
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
+  CUtensorMap tmC;
+  if (encode_out_map(&tmC, y, out_f32, Cout, Wo, Ho, 1, F, out_ld, TH, TW)) return 1;
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  return tf32 ? launch_conv<64, true>(tmA, tmB, p, grid, stream) : launch_conv<64, false>(tmA, tmB, p, grid, stream);
+  return tf32 ? launch_conv<64, true>(tmA, tmB, tmC, p, grid, stream) : launch_conv<64, false>(tmA, tmB, tmC, p, grid, stream);
 }

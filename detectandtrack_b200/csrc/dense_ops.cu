@@ -223,6 +223,8 @@ __device__ __forceinline__ void cubic_coeffs(float x, float* c) {
   c[3] = 1.f - c[0] - c[1] - c[2];
 }
 
+#define KD_SW 256   // output columns per strip of the separable cubic resize
+
 __global__ void __launch_bounds__(256)
 keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, int T,
                        const float* __restrict__ boxes /*[D, ldb] image coords*/, int ldb,
@@ -234,9 +236,7 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   float* low = sm;                 // [M2*M2]  kps_score_lowres for this (d, k)
   float* map = sm + M2 * M2;       // [M*M]    kps_score
   __shared__ float s_red[32];
-  __shared__ int s_redi[32];
   __shared__ float s_max;
-  __shared__ int s_arg;
   const int d = blockIdx.x, k = blockIdx.y, t = blockIdx.z;
   const int n = n_dev ? min(*n_dev, D) : D;
   if (d >= n) return;
@@ -271,6 +271,10 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   }
   __syncthreads();
   // ---- heatmaps_to_keypoints (keypoints.py:94-149) for this (roi, keypoint) ----
+  // cv2.resize(INTER_CUBIC) is separable and cv2 evaluates it in this order too: horizontal pass on
+  // the source rows (float), then a 4-tap vertical combination.  Work is done in strips of KD_SW output
+  // columns: H-pass of all M source rows into smem, then each thread walks its column top to bottom
+  // keeping (max, first argmax, online sum of exp(v - max)).
   const float* bx = boxes + (size_t)d * ldb + 4 * t;
   const float ofx = bx[0], ofy = bx[1];
   const float bw = fmaxf(bx[2] - bx[0], 1.f), bh = fmaxf(bx[3] - bx[1], 1.f);
@@ -278,64 +282,70 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   if (min_size > 0) { rw = max(rw, min_size); rh = max(rh, min_size); }
   const float wcorr = bw / (float)rw, hcorr = bh / (float)rh;
   const double sclx = 1.0 / ((double)rw / M), scly = 1.0 / ((double)rh / M);   // cv2: scale = 1 / (dsize / ssize)
-  // pass 1: max + first argmax.  pass 2: sum exp(v - max).
-  float best = -CUDART_INF_F; int besti = 0x7fffffff;
-  const long long total = (long long)rw * rh;
-  auto sample = [&](int oy, int ox) -> float {
-    float fy = (float)((oy + 0.5) * scly - 0.5), fx = (float)((ox + 0.5) * sclx - 0.5);
-    const int sy = (int)floorf(fy), sx = (int)floorf(fx);
-    fy -= sy; fx -= sx;
-    float cy[4], cx[4];
-    cubic_coeffs(fy, cy); cubic_coeffs(fx, cx);
-    float acc = 0.f;
+  float* tmp = map + M * M;        // [M][KD_SW] horizontally resized strip
+  float best = -CUDART_INF_F; long long besti = 0x7fffffffffffffffll;
+  float run_max = -CUDART_INF_F, run_sum = 0.f;
+  for (int x0 = 0; x0 < rw; x0 += KD_SW) {
+    const int sw = min(KD_SW, rw - x0);
+    for (int i = tid; i < M * sw; i += nth) {
+      const int y = i / sw, xl = i - y * sw;
+      float fx = (float)((x0 + xl + 0.5) * sclx - 0.5);
+      const int sx = (int)floorf(fx);
+      fx -= sx;
+      float cx[4];
+      cubic_coeffs(fx, cx);
+      float rowv = 0.f;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int yy = min(max(sy - 1 + a, 0), M - 1);
-      float row = 0.f;
-#pragma unroll
-      for (int bq = 0; bq < 4; ++bq) {
-        const int xx = min(max(sx - 1 + bq, 0), M - 1);
-        row += map[yy * M + xx] * cx[bq];
-      }
-      acc += row * cy[a];
+      for (int bq = 0; bq < 4; ++bq) rowv += map[y * M + min(max(sx - 1 + bq, 0), M - 1)] * cx[bq];
+      tmp[y * KD_SW + xl] = rowv;
     }
-    return acc;
-  };
-  for (long long i = tid; i < total; i += nth) {
-    const int oy = (int)(i / rw), ox = (int)(i - (long long)oy * rw);
-    const float v = sample(oy, ox);
-    if (v > best) { best = v; besti = (int)i; }
+    __syncthreads();
+    for (int xl = tid; xl < sw; xl += nth) {
+      for (int oy = 0; oy < rh; ++oy) {
+        float fy = (float)((oy + 0.5) * scly - 0.5);
+        const int sy = (int)floorf(fy);
+        fy -= sy;
+        float cy[4];
+        cubic_coeffs(fy, cy);
+        float v = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) v += tmp[min(max(sy - 1 + a, 0), M - 1) * KD_SW + xl] * cy[a];
+        const long long lin = (long long)oy * rw + (x0 + xl);
+        if (v > best || (v == best && lin < besti)) { best = v; besti = lin; }
+        if (v > run_max) { run_sum = run_sum * expf(run_max - v) + 1.f; run_max = v; }
+        else run_sum += expf(v - run_max);
+      }
+    }
+    __syncthreads();
   }
-  // block argmax (max value, then lowest index)
+  // block reduction: (max value, lowest linear index) and the softmax denominator at the global max
+  __shared__ long long s_redl[32];
+  float bm = best; long long bi = besti;
   for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    const float ob = __shfl_xor_sync(0xffffffffu, bm, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > bm || (ob == bm && oi < bi)) { bm = ob; bi = oi; }
   }
-  if ((tid & 31) == 0) { s_red[tid >> 5] = best; s_redi[tid >> 5] = besti; }
+  if ((tid & 31) == 0) { s_red[tid >> 5] = bm; s_redl[tid >> 5] = bi; }
   __syncthreads();
   if (tid == 0) {
-    float b2 = s_red[0]; int i2 = s_redi[0];
+    float b2 = s_red[0]; long long i2 = s_redl[0];
     for (int w = 1; w < (nth >> 5); ++w)
-      if (s_red[w] > b2 || (s_red[w] == b2 && s_redi[w] < i2)) { b2 = s_red[w]; i2 = s_redi[w]; }
-    s_max = b2; s_arg = i2;
+      if (s_red[w] > b2 || (s_red[w] == b2 && s_redl[w] < i2)) { b2 = s_red[w]; i2 = s_redl[w]; }
+    s_max = b2; s_redl[0] = i2;
   }
   __syncthreads();
   const float mx = s_max;
-  float sum = 0.f;
-  for (long long i = tid; i < total; i += nth) {
-    const int oy = (int)(i / rw), ox = (int)(i - (long long)oy * rw);
-    sum += expf(sample(oy, ox) - mx);
-  }
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const long long pos = s_redl[0];
   __syncthreads();
+  float sum = (run_max == -CUDART_INF_F) ? 0.f : run_sum * expf(run_max - mx);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((tid & 31) == 0) s_red[tid >> 5] = sum;
   __syncthreads();
   if (tid == 0) {
     float tot = 0.f;
     for (int w = 0; w < (nth >> 5); ++w) tot += s_red[w];
-    const int pos = s_arg;
-    const int x_int = pos % rw, y_int = (pos - x_int) / rw;
+    const int x_int = (int)(pos % rw), y_int = (int)(pos / rw);
     const int KT = K * T, col = t * K + k;
     float* o = xy + (size_t)d * 4 * KT;
     // keypoints.py:140-145: python floats (fp64) until the store into the fp32 result
@@ -420,7 +430,7 @@ extern "C" int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, in
                "dt_keypoint_decode: bad shape S=%d K=%d T=%d D=%d ldl=%d ldb=%d", S, K, T, D, ldl, ldb);
   if (D == 0) return 0;
   DT_CHECK_ARG(lowres && boxes && xy_preds, "dt_keypoint_decode: null pointer");
-  const size_t smem = (size_t)(4 * S * S + 16 * S * S) * sizeof(float);
+  const size_t smem = (size_t)(4 * S * S + 16 * S * S + 4 * S * KD_SW) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   dim3 grid(D, K, T);

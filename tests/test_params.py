@@ -1,0 +1,68 @@
+"""CPU: parameter inventory, pkl wire format and 2-D -> 3-D weight inflation
+(lib/utils/net.py:95-161,164-294)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg3d():
+    from test_gpu_engine import _cfg
+    return _cfg()
+
+
+def test_param_inventory_names_and_shapes():
+    from detectandtrack_b200.modeling import params as P
+    cfg = _cfg3d()
+    shapes, spec = P.param_shapes(cfg)
+    assert shapes['conv1_w'] == (64, 3, 1, 7, 7)
+    assert shapes['res2_0_branch2b_w'] == (64, 64, 1, 3, 3)              # res2: no temporal kernel
+    assert shapes['res3_0_branch2b_w'] == (128, 128, 3, 3, 3)            # TIME_KERNEL_DIM.BODY
+    assert shapes['res3_0_branch1_w'] == (512, 256, 1, 1, 1)
+    assert shapes['fpn_inner_res5_2_sum_w'] == (256, 2048, 1, 1, 1)
+    assert shapes['fpn_inner_res4_5_sum_lateral_w'] == (256, 1024, 1, 1, 1)
+    assert shapes['fpn_res2_2_sum_w'] == (256, 256, 3, 3, 3)
+    assert shapes['conv_rpn_fpn2_w'] == (256, 256, 3, 3) and shapes['rpn_bbox_pred_fpn2_w'] == (12, 256, 1, 1)
+    assert shapes['fc6_w'] == (1024, 256 * 7 * 7) and shapes['bbox_pred_w'] == (8, 1024)
+    assert shapes['conv_fcn1_w'] == (512, 256, 3, 3) and shapes['kps_score_lowres_w'] == (512, 17, 4, 4)
+    assert sum(int(np.prod(s)) for s in shapes.values()) > 80e6
+    assert spec.stage_blobs == ['res2_2_sum', 'res3_3_sum', 'res4_5_sum', 'res5_2_sum']
+
+
+def test_inflate_modes():
+    from detectandtrack_b200.modeling import params as P
+    w2 = np.arange(2 * 3 * 3 * 3, dtype=np.float32).reshape(2, 3, 3, 3)
+    for mode in ('center-only', 'mean-repeat', 'repeat'):
+        w3 = P.inflate_weights(w2, (2, 3, 3, 3, 3), mode)
+        assert w3.shape == (2, 3, 3, 3, 3)
+        if mode == 'center-only':
+            assert np.array_equal(w3[:, :, 1], w2) and not w3[:, :, 0].any() and not w3[:, :, 2].any()
+        elif mode == 'mean-repeat':
+            np.testing.assert_allclose(w3.sum(2), w2, rtol=1e-6)
+        else:
+            assert all(np.array_equal(w3[:, :, t], w2) for t in range(3))
+    with pytest.raises(ValueError):
+        P.inflate_weights(w2, (2, 3, 3, 3, 3), 'nope')
+
+
+def test_weights_file_roundtrip_with_inflation(tmp_path):
+    """A 2-D (COCO-style) pkl loads into the 3-D graph through center-only inflation; unknown blobs keep init."""
+    from detectandtrack_b200.modeling import params as P
+    cfg = _cfg3d()
+    cfg.VIDEO.WEIGHTS_INFLATE_MODE = 'center-only'
+    blobs, _ = P.random_blobs(cfg, seed=1)
+    two_d = {}
+    for k, v in blobs.items():
+        if k.startswith(('res3_0', 'conv1', 'fc7')):
+            two_d[k] = v[:, :, v.shape[2] // 2] if v.ndim == 5 else v          # 4-D filters as a 2-D model stores them
+    path = str(tmp_path / 'w.pkl')
+    P.save_weights_file(two_d, 'cfg: yaml', path)
+    loaded, _ = P.load_weights_file(cfg, path)
+    w = loaded['res3_0_branch2b_w']
+    assert w.shape == (128, 128, 3, 3, 3)
+    assert np.array_equal(w[:, :, 1], two_d['res3_0_branch2b_w']) and not w[:, :, 0].any()
+    assert np.array_equal(loaded['fc7_w'], blobs['fc7_w'])
+    assert loaded['res4_0_branch2a_w'].shape == blobs['res4_0_branch2a_w'].shape      # missing in file: kept
