@@ -51,6 +51,7 @@ struct ConvKernelParams {
   void* out;
   int out_ld;                  // elements between consecutive positions
   int out_f32;                 // 1: fp32 output, 0: bf16
+  int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
 };
@@ -66,12 +67,20 @@ struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;            // 128 rows x 128 B
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int MAX_STAGES = 8;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int C_BYTES = 128 * 128;            // one staged output chunk: 128 rows x 128 B
-  static constexpr int NCBUF = (BN >= 256) ? 1 : 2;    // output staging buffers (smem budget)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NCBUF * C_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    2 * BN * 4 /*scale, bias*/;
+  static constexpr int FIXED_BYTES = 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*scale, bias*/;
+  static constexpr int BUDGET = 227 * 1024;
+  // K-heavy layers want a deep operand ring; K-light (HBM-bound) layers want output staging buffers so the
+  // epilogue never waits for a TMA store to drain.
+  static void split(int kiters, int* stages, int* ncbuf) {
+    const int c = (kiters >= 12) ? ((BN >= 256) ? 1 : 2) : 4;
+    int st = (BUDGET - FIXED_BYTES - c * C_BYTES) / STAGE_BYTES;
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    *stages = st; *ncbuf = c;
+  }
+  static int smem_bytes(int stages, int ncbuf) { return stages * STAGE_BYTES + ncbuf * C_BYTES + FIXED_BYTES; }
 };
 
 template <int BN, bool TF32>
@@ -79,13 +88,13 @@ __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using Cfg = ConvCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.nstages;
   constexpr int BK = TF32 ? 32 : 64;                 // elements per 128-byte k-block
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned operand ring (required by SWIZZLE_128B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* cbuf = smem + STAGES * Cfg::STAGE_BYTES;                  // [NCBUF][128 rows][128 B], 128B-swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + Cfg::NCBUF * Cfg::C_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + p.ncbuf * Cfg::C_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + STAGES;             // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
@@ -213,12 +222,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int cc = 0; cc < BN; cc += CW) {
         const int cchunk = nt * BN + cc;
         if (cchunk >= p.Cout) break;                                   // uniform: nothing left to write
-        uint8_t* buf = cbuf + (chunk_ctr % Cfg::NCBUF) * Cfg::C_BYTES;
+        uint8_t* buf = cbuf + (chunk_ctr % (uint32_t)p.ncbuf) * Cfg::C_BYTES;
         ++chunk_ctr;
         // the staging buffer must have been read out by the TMA store that used it last
         if (leader) {
-          if (Cfg::NCBUF == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (p.ncbuf == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else if (p.ncbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
@@ -385,10 +395,14 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   static bool attr = false;
   if (!attr) {
     DT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+                                       Cfg::BUDGET));
     attr = true;
   }
-  conv_tc_kernel<BN, TF32><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  ConvKernelParams q = p;
+  Cfg::split(p.kT * p.kH * p.kW * p.kchunks, &q.nstages, &q.ncbuf);
+  const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf);
+  DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
+  conv_tc_kernel<BN, TF32><<<grid, 192, smem, stream>>>(tmA, tmB, tmC, q);
   DT_CHECK_LAUNCH();
   return 0;
 }
