@@ -24,7 +24,7 @@ SIGNATURES = {
     'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
     'dt_conv3d': [_p, _p, _p, _p, _p, _p, _p, _p],
     'dt_rpn_proposals': [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_double, _p, _i, _f, C.c_double, _p,
-                         C.c_longlong, _p, _i, _p],
+                         C.c_longlong, _p, _i, _i, _p],
     'dt_collect_rpn': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     'dt_distribute_fpn': [_p, _i, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     'dt_box_decode': [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, C.POINTER(_f), C.c_double, _f, _p, _p, _p],
@@ -35,6 +35,8 @@ SIGNATURES = {
     'dt_roi_align': [C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _p, _i, _p, _i,
                      _i, _p, _i, _i, _i, _p, _p],
     'dt_keypoint_decode': [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p],
+    'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    'dt_fold_tube_heads': [_p, _i, _i, _i, _i, _p, _p, _p],
 }
 
 

@@ -17,12 +17,12 @@
 //           zero-filled by the TMA unit, so padding costs no instructions and no branches.
 //   W tile: 3-D TMA box (C=128B, BLOCK_N, 1) of the pre-packed [tap][Cout][Cin] weights.
 //   Both land in the 128B-swizzled K-major layout tcgen05.mma reads directly.
-// Roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0   : TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
 //   warp 1   : TMEM allocator + MMA issuer (one lane)   tcgen05.mma -> TMEM, tcgen05.commit
-//   warps 2-5: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32,
-//              16-byte stores to NDHWC.  Two TMEM accumulator stages overlap it with the next
-//              tile's MMAs.
+//   warps 2-9: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32, staged in
+//              128B-swizzled smem chunks and written with TMA stores.  Two TMEM accumulator stages
+//              overlap it with the next tile's MMAs.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/dt_b200.h"
@@ -84,7 +84,7 @@ struct ConvCfg {
 };
 
 template <int BN, bool TF32>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using Cfg = ConvCfg<BN>;
@@ -111,7 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
@@ -179,15 +179,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     // TMEM -> registers -> fp32 epilogue -> 128B-swizzled smem chunk -> one TMA store per chunk.
-    // The TMA store writes whole 128-byte lines and clips rows / channels outside the tensor,
-    // so ragged tiles need no predication on the store side.
+    // Eight warps (two per scheduler) so that TMEM / shared / global latencies of one warp hide behind
+    // the other: warp w reads TMEM lane group (w & 3) and the column half ((w - 2) >> 2) of each chunk.
+    // The TMA store writes whole 128-byte lines and clips rows / channels outside the tensor, so ragged
+    // tiles need no predication on the store side.
     const int lg = warp & 3;                   // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;          // which half of the staged 128-byte row this warp fills
     const int row = lg * 32 + lane;            // accumulator row == TMEM lane == staging row
     const int th = row / p.TW, tw = row - th * p.TW;
     const bool leader = (threadIdx.x == 64);   // warp 2, lane 0 issues the stores
-    const int ep_tid = threadIdx.x - 64;       // 0..127
+    const int ep_tid = threadIdx.x - 64;       // 0..255
     const int CW = p.out_f32 ? 32 : 64;        // output columns per 128-byte staged row
     const uint32_t row_smem = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
@@ -208,12 +211,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rpos = ((size_t)(n * p.To + t) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
 
       // per-tile scale / bias -> smem (previous tile's readers are past their last named barrier)
-      for (int j = ep_tid; j < BN; j += 128) {
+      for (int j = ep_tid; j < BN; j += 256) {
         const int c = nt * BN + j;
         s_scale[j] = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
         s_bias[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
@@ -230,81 +233,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else if (p.ncbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
-        for (int c0 = cc; c0 < cc + CW; c0 += 32) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t dst = smem_u32(buf) + row_smem;
+        if (p.out_f32) {
+          // ---- fp32 output: this warp owns 16 columns = 64 bytes = 16-byte chunks [4*half, 4*half+4)
+          const int c0 = cc + 16 * half;
+          const int cbase = nt * BN + c0;
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(taddr + c0, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]);
+          if (p.res_mode != 0 && valid) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + rpos * p.res_ld + cbase;
+            if (cbase + 16 <= p.Cout) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j));
+                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cbase + j < p.Cout) v[j] += __ldg(rp + j);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (p.relu) v[j] = fmaxf(v[j], 0.f);
+            if (p.round_tf32) v[j] = round_to_tf32(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t a = dst + ((((uint32_t)(4 * half + q)) ^ swz) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                         "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+          }
+        } else {
+          // ---- bf16 output: this warp owns 32 columns = 64 bytes
+          const int c0 = cc + 32 * half;
+          const int cbase = nt * BN + c0;
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           tmem_ld_wait();
-          const int cbase = nt * BN + c0;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]);
-          if (p.res_mode != 0 && valid && cbase < p.Cout) {
-            const int ncols = min(32, p.Cout - cbase);
-            if (p.out_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.residual) + rpos * p.res_ld + cbase;
-              if (ncols == 32) {
+          if (p.res_mode != 0 && valid) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
+            if (cbase + 32 <= p.Cout) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j));
-                  v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[j + 2 * e] += __uint_as_float(w4[e] << 16);
+                  v[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
                 }
-              } else {
-                for (int j = 0; j < ncols; ++j) v[j] += __ldg(rp + j);
               }
             } else {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
-              if (ncols == 32) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
-                  const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    v[j + 2 * e] += __uint_as_float(w4[e] << 16);
-                    v[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
-                  }
-                }
-              } else {
-                for (int j = 0; j < ncols; ++j) v[j] += __bfloat162float(rp[j]);
-              }
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.Cout) v[j] += __bfloat162float(rp[j]);
             }
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          const uint32_t dst = smem_u32(buf) + row_smem;
-          if (p.out_f32) {
-            if (p.round_tf32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = round_to_tf32(v[j]);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {            // 8 x 16 B = the whole 128-byte row
-              const uint32_t a = dst + (((uint32_t)q ^ swz) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
-                           "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
-            }
-          } else {
-            const uint32_t q0 = (uint32_t)((c0 - cc) >> 3);     // 16-byte chunk index of this half row (0 or 4)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-              const uint32_t a = dst + (((q0 + (uint32_t)q) ^ swz) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)),
-                           "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
-                           "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
-            }
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            const uint32_t a = dst + ((((uint32_t)(4 * half + q)) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
           }
         }
         // generic-proxy smem writes -> visible to the async proxy, then one thread stores the chunk
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (leader) {
           asm volatile(
               "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
@@ -402,7 +415,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   Cfg::split(p.kT * p.kH * p.kW * p.kchunks, &q.nstages, &q.ncbuf);
   const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
-  conv_tc_kernel<BN, TF32><<<grid, 192, smem, stream>>>(tmA, tmB, tmC, q);
+  conv_tc_kernel<BN, TF32><<<grid, 320, smem, stream>>>(tmA, tmB, tmC, q);
   DT_CHECK_LAUNCH();
   return 0;
 }

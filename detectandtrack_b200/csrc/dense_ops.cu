@@ -356,6 +356,57 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   }
 }
 
+// ------------------------------------------------------------------- 3-D box head glue
+// ReduceBackMean over W then over H (lib/modeling/ResNet3D.py:321-322): x [N, H, W, ldx] -> y [N, C]
+template <typename ET>
+__global__ void spatial_mean_kernel(const ET* __restrict__ x, int N, int H, int W, int C, int ldx, ET* __restrict__ y,
+                                    int ldy, int round_out) {
+  constexpr int V = Vec<ET>::N;
+  const int cv = C / V;
+  const long long total = (long long)N * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V;
+    const int n = (int)(idx / cv);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int h = 0; h < H; ++h) {
+      float row[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) row[e] = 0.f;
+      for (int w = 0; w < W; ++w) {
+        float v[V];
+        Vec<ET>::load(x + (((size_t)n * H + h) * W + w) * ldx + c, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) row[e] += v[e];
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += row[e] / (float)W;
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) { acc[e] /= (float)H; if (round_out) acc[e] = round_to_tf32(acc[e]); }
+    Vec<ET>::store(y + (size_t)n * ldy + c, acc);
+  }
+}
+
+// add_fast_rcnn_outputs, 3-D head (lib/modeling/model_builder.py:427-473): per-frame outputs
+// in [R*T, ld] = [cls logits (C) | bbox (4C, channel c*4+k)] -> cls [R, C] = mean over T,
+// bbox [R, C*T*4] with channel c*4T + t*4 + k.
+__global__ void fold_tube_heads_kernel(const float* __restrict__ in, int ld, int R, int T, int C,
+                                       float* __restrict__ cls, float* __restrict__ bbox) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  for (int c = 0; c < C; ++c) {
+    float acc = in[((size_t)r * T) * ld + c];
+    for (int t = 1; t < T; ++t) acc += in[((size_t)r * T + t) * ld + c];
+    cls[(size_t)r * C + c] = acc / (float)T;
+  }
+  for (int c = 0; c < C; ++c)
+    for (int t = 0; t < T; ++t)
+      for (int k = 0; k < 4; ++k)
+        bbox[(size_t)r * C * T * 4 + (size_t)c * 4 * T + 4 * t + k] = in[((size_t)r * T + t) * ld + C + c * 4 + k];
+}
+
 }  // namespace dt
 
 using namespace dt;
@@ -435,6 +486,31 @@ extern "C" int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, in
   if (smem > attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   dim3 grid(D, K, T);
   keypoint_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, ldl, S, K, T, boxes, ldb, n_dev, D, min_size, heatmaps, xy_preds);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, void* y, int ldy,
+                               void* stream) {
+  const int V = f32 ? 4 : 8;
+  DT_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && C >= 1 && C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C,
+               "dt_spatial_mean: bad shape (C/ld must be multiples of %d)", V);
+  if (N == 0) return 0;
+  DT_CHECK_ARG(x && y, "dt_spatial_mean: null pointer");
+  const long long total = (long long)N * (C / V);
+  if (f32)
+    spatial_mean_kernel<float><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, (float*)y, ldy, round_tf32);
+  else
+    spatial_mean_kernel<__nv_bfloat16><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, (__nv_bfloat16*)y, ldy, 0);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, float* cls, float* bbox, void* stream) {
+  DT_CHECK_ARG(R >= 0 && T >= 1 && T <= DT_MAX_T && C >= 1 && ld >= 5 * C, "dt_fold_tube_heads: bad shape");
+  if (R == 0) return 0;
+  DT_CHECK_ARG(in && cls && bbox, "dt_fold_tube_heads: null pointer");
+  fold_tube_heads_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, ld, R, T, C, cls, bbox);
   DT_CHECK_LAUNCH();
   return 0;
 }

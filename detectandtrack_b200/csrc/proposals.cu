@@ -110,7 +110,7 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
                      double feat_stride, const float* __restrict__ im_info /*[B,3]*/, int pre_topn,
                      float min_size, float clipv_f, double clipv_d,
                      float* __restrict__ out /*[B, out_bstride] rows of 4T+1*/, long long out_bstride,
-                     int* __restrict__ counts, int counts_stride, int kcap /*pow2 >= K*/) {
+                     int* __restrict__ counts, int counts_stride, int kcap /*pow2 >= K*/, int time_major) {
   extern __shared__ unsigned long long skeys[];          // [kcap] selected (key<<32 | ~idx)
   __shared__ int hist[4096];
   __shared__ int s_warp[32];
@@ -118,10 +118,17 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = H * W * A;
   const int K = (pre_topn <= 0 || pre_topn > n) ? n : pre_topn;
-  const size_t sbase = (size_t)b * H * W * ld_s;
+  // time_major (3-D RPN head, model_builder.py:509-563): logits / deltas are [B, T, H*W, ld] with A / 4A
+  // channels per frame; the tube score is the mean over frames of the per-frame logits (TimePool 'avg',
+  // sequential fp32 sum then / T) and delta (a, t, k) lives at frame t, channel a*4 + k.
+  const size_t HW = (size_t)H * W;
+  const size_t sbase = (size_t)b * HW * ld_s * (time_major ? T : 1);
   auto score_at = [&](int i) -> float {
     const int pos = i / A, a = i - pos * A;
-    return sigmoidf_ref(load_act(logits, sbase + (size_t)pos * ld_s + a, act_f32));
+    if (!time_major) return sigmoidf_ref(load_act(logits, sbase + (size_t)pos * ld_s + a, act_f32));
+    float acc = load_act(logits, sbase + (size_t)pos * ld_s + a, act_f32);
+    for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, load_act(logits, sbase + ((size_t)t * HW + pos) * ld_s + a, act_f32));
+    return sigmoidf_ref(__fdiv_rn(acc, (float)T));
   };
   // ---- exact K-th largest key by 12/12/8-bit radix select --------------------------------
   uint32_t prefix = 0, mask = 0;
@@ -185,7 +192,7 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
   const float imh = im_info[3 * b], imw = im_info[3 * b + 1], imscale = im_info[3 * b + 2];
   const float hmax = __fsub_rn(imh, 1.f), wmax = __fsub_rn(imw, 1.f);
   const float msz = __fmul_rn(min_size, imscale);
-  const size_t dbase = (size_t)b * H * W * ld_d;
+  const size_t dbase = (size_t)b * HW * ld_d * (time_major ? T : 1);
   const int ldo = 4 * T + 1;
   if (tid == 0) s_run = 0;
   __syncthreads();
@@ -207,7 +214,9 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
         an[0] = anchors[(size_t)a * 4 * T + 4 * t + 0] + shx; an[1] = anchors[(size_t)a * 4 * T + 4 * t + 1] + shy;
         an[2] = anchors[(size_t)a * 4 * T + 4 * t + 2] + shx; an[3] = anchors[(size_t)a * 4 * T + 4 * t + 3] + shy;
         float dl[4];
-        for (int k = 0; k < 4; ++k) dl[k] = load_act(deltas, dbase + (size_t)pos * ld_d + (size_t)a * 4 * T + 4 * t + k, act_f32);
+        for (int k = 0; k < 4; ++k)
+          dl[k] = time_major ? load_act(deltas, dbase + ((size_t)t * HW + pos) * ld_d + (size_t)a * 4 + k, act_f32)
+                             : load_act(deltas, dbase + (size_t)pos * ld_d + (size_t)a * 4 * T + 4 * t + k, act_f32);
         float* o = box + 4 * t;
         if (T == 1) {
           const float af[4] = {(float)an[0], (float)an[1], (float)an[2], (float)an[3]};
@@ -438,7 +447,7 @@ limit_kernel(const float* __restrict__ dets, const int* __restrict__ keep, const
         for (int x = 0; x < ld; ++x) dst[x] = src[x];
       }
     }
-    if (tid == 0) out_counts[b * ncls1 + c] = min(s_run, cap);
+    if (tid == 0) out_counts[b * ncls1 + c] = s_run;      // may exceed cap (score ties at the threshold): caller checks
     __syncthreads();
   }
 }
@@ -452,9 +461,10 @@ using namespace dt;
 extern "C" int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas, int ld_d, int act_f32, int B, int H,
                                 int W, int A, int T, const double* anchors, double feat_stride, const float* im_info,
                                 int pre_nms_topn, float min_size, double bbox_xform_clip, float* out,
-                                long long out_batch_stride, int* counts, int counts_stride, void* stream) {
+                                long long out_batch_stride, int* counts, int counts_stride, int time_major,
+                                void* stream) {
   DT_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && A >= 1 && T >= 1 && T <= DT_MAX_T, "dt_rpn_proposals: bad shape B=%d H=%d W=%d A=%d T=%d", B, H, W, A, T);
-  DT_CHECK_ARG(ld_s >= A && ld_d >= 4 * A * T, "dt_rpn_proposals: leading dims too small (ld_s=%d, ld_d=%d)", ld_s, ld_d);
+  DT_CHECK_ARG(ld_s >= A && ld_d >= 4 * A * (time_major ? 1 : T), "dt_rpn_proposals: leading dims too small (ld_s=%d, ld_d=%d)", ld_s, ld_d);
   if (B == 0) return 0;
   DT_CHECK_ARG(logits && deltas && anchors && im_info && out && counts, "dt_rpn_proposals: null pointer");
   const long long n = (long long)H * W * A;
@@ -472,7 +482,7 @@ extern "C" int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas
   rpn_proposals_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(logits, ld_s, deltas, ld_d, act_f32, H, W, A, T, anchors,
                                                                feat_stride, im_info, pre_nms_topn, min_size,
                                                                (float)bbox_xform_clip, bbox_xform_clip, out,
-                                                               out_batch_stride, counts, counts_stride, kcap);
+                                                               out_batch_stride, counts, counts_stride, kcap, time_major);
   DT_CHECK_LAUNCH();
   return 0;
 }

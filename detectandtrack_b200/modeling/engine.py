@@ -58,15 +58,17 @@ class DetectionEngine(object):
         self.cfg = cfg
         self.spec = spec or P.GraphSpec(cfg)
         s = self.spec
-        if not s.fpn or s.head3d:
-            raise NotImplementedError('engine: FPN bodies with 2-D heads only this round (got %s, link %r)'
-                                      % (cfg.MODEL.CONV_BODY, cfg.VIDEO.BODY_HEAD_LINK))
-        if s.link not in ('slice-center', 'none2d'):
+        if s.fpn and s.head3d:
+            raise NotImplementedError('3-D FPN heads are unimplemented in the reference too (FPN3D.py:228)')
+        if not s.fpn and not s.head3d:
+            raise NotImplementedError('engine: single-level bodies are wired for 3-D heads (BODY_HEAD_LINK \'\') only')
+        if s.link not in ('slice-center', 'none2d', ''):
             raise NotImplementedError('engine: BODY_HEAD_LINK %r' % s.link)
         self.dtype = cv.BF16 if dtype == 'bf16' else cv.TF32
         self.act_dtype = torch.bfloat16 if dtype == 'bf16' else torch.float32
         self.cin_pad = 8 if dtype == 'bf16' else 4
         self.skip_dead_frames = False       # compute only the consumed (centre) frame of the post-hoc FPN convs
+        self._geom = {}
         self._build(blobs)
 
     # ------------------------------------------------------------------ weights
@@ -74,6 +76,28 @@ class DetectionEngine(object):
         scale = blobs[affine + '_s'] if affine else None
         b = blobs[affine + '_b'] if affine else (blobs[name + '_b'] if bias else None)
         return _Conv(self.torch, blobs[name + '_w'], self.dtype, scale, b, **kw)
+
+    def _block(self, blobs, pre, dim_in, dim_out, st, tk):
+        """One residual block (ResNet3D.py:21-152); the last conv carries the fused shortcut add + ReLU."""
+        s = self.spec
+        sc = self._c(blobs, pre + '_branch1', pre + '_branch1_bn', stride=st) if dim_in != dim_out else None
+        if s.block == 'bottleneck':
+            s1, s3 = (st, (1, 1, 1)) if s.stride_1x1 else ((1, 1, 1), st)
+            return dict(sc=sc, convs=[
+                self._c(blobs, pre + '_branch2a', pre + '_branch2a_bn', stride=s1, relu=True),
+                self._c(blobs, pre + '_branch2b', pre + '_branch2b_bn', stride=s3, pad=(tk // 2, 1, 1), relu=True),
+                self._c(blobs, pre + '_branch2c', pre + '_branch2c_bn', relu=True)])
+        return dict(sc=sc, convs=[
+            self._c(blobs, pre + '_branch2a', pre + '_branch2a_bn', stride=st, pad=(tk // 2, 1, 1), relu=True),
+            self._c(blobs, pre + '_branch2b', pre + '_branch2b_bn', pad=(tk // 2, 1, 1), relu=True)])
+
+    @staticmethod
+    def _run_block(blk, y):
+        sc = blk['sc'](y) if blk['sc'] is not None else y
+        h = y
+        for c in blk['convs'][:-1]:
+            h = c(h)
+        return blk['convs'][-1](h, residual=sc, res_mode=1)
 
     def _build(self, blobs):
         s, cfg, torch = self.spec, self.cfg, self.torch
@@ -91,16 +115,18 @@ class DetectionEngine(object):
                 pre = 'res%d_%d' % (si + 2, i)
                 stride = 2 if (dim_in != dim_out and si != 0) else 1
                 st = (1, stride, stride)
-                assert s.block == 'bottleneck'
-                s1, s3 = (st, (1, 1, 1)) if s.stride_1x1 else ((1, 1, 1), st)
-                blk = dict(
-                    a=self._c(blobs, pre + '_branch2a', pre + '_branch2a_bn', stride=s1, relu=True),
-                    b=self._c(blobs, pre + '_branch2b', pre + '_branch2b_bn', stride=s3, pad=(tk // 2, 1, 1), relu=True),
-                    c=self._c(blobs, pre + '_branch2c', pre + '_branch2c_bn', relu=True),     # relu after the fused sum
-                    sc=self._c(blobs, pre + '_branch1', pre + '_branch1_bn', stride=st) if dim_in != dim_out else None)
-                blocks.append(blk)
+                blocks.append(self._block(blobs, pre, dim_in, dim_out, st, tk))
                 dim_in = dim_out
             self.stages.append(blocks)
+        self.pixel_means = np.asarray(cfg.PIXEL_MEANS, dtype=np.float32).ravel()
+        if s.fpn:
+            self._build_fpn_heads(blobs)
+        else:
+            self._build_tube_heads(blobs, dim_in)
+        self._build_keypoint_head(blobs)
+
+    def _build_fpn_heads(self, blobs):
+        s, cfg, torch = self.spec, self.cfg, self.torch
         names = s.stage_blobs[::-1]
         self.fpn_inner = [self._c(blobs, 'fpn_inner_' + names[0], bias=True)]
         for i in range(1, len(names)):
@@ -128,12 +154,44 @@ class DetectionEngine(object):
         bcb = np.concatenate([blobs['cls_score_b'], blobs['bbox_pred_b']], 0)
         self.cls_bbox = _Conv(torch, wcb, self.dtype, None, bcb)
         self.cls_bbox_ld = (5 * s.num_classes + 3) // 4 * 4
-        # keypoint head
+
+    def _build_tube_heads(self, blobs, dim_conv):
+        """Single-level 3-D RPN (model_builder.py:500-609) and the res5 RoI head + 3-D outputs
+        (ResNet3D.py:301-327, model_builder.py:427-473)."""
+        s, cfg, torch = self.spec, self.cfg, self.torch
+        T = s.T_head
+        tk = cfg.VIDEO.TIME_KERNEL_DIM.HEAD_RPN
+        A = s.num_anchors
+        self.feat_stride = 16.0
+        self.rpn_conv = self._c(blobs, 'conv_rpn', bias=True, pad=(tk // 2, 1, 1), relu=True)
+        w = np.concatenate([blobs['rpn_cls_logits_1_w'], blobs['rpn_bbox_pred_1_w']], 0)
+        b = np.concatenate([blobs['rpn_cls_logits_1_b'], blobs['rpn_bbox_pred_1_b']], 0)
+        self.rpn_out = _Conv(torch, w, self.dtype, None, b)
+        self.rpn_out_ld = (5 * A + 3) // 4 * 4
+        self.anchors = [torch.from_numpy(generate_anchors(stride=self.feat_stride, sizes=cfg.RPN.SIZES,
+                                                          aspect_ratios=cfg.RPN.ASPECT_RATIOS, time_dim=T)).cuda()]
+        arch = s.roi_head.split('add_')[1].split('_')[0]
+        n5, dout = P._BLOCKS[arch][0][3], P._BLOCKS[arch][2][4]
+        stride_init = int(cfg.FAST_RCNN.ROI_XFORM_RESOLUTION / 7)
+        self.res5 = []
+        din = dim_conv
+        for i in range(n5):
+            st = stride_init if din != dout else 1              # add_bottleneck_block: stage_id 4, dim change
+            self.res5.append(self._block(blobs, 'res5_%d' % i, din, dout, (1, st, st), 1))
+            din = dout
+        wcb = np.concatenate([blobs['cls_score_1_w'], blobs['bbox_pred_1_w']], 0).reshape(-1, dout)
+        bcb = np.concatenate([blobs['cls_score_1_b'], blobs['bbox_pred_1_b']], 0)
+        self.cls_bbox = _Conv(torch, wcb, self.dtype, None, bcb)
+        self.cls_bbox_ld = (5 * s.num_classes + 3) // 4 * 4
+
+    def _build_keypoint_head(self, blobs):
+        s, cfg, torch = self.spec, self.cfg, self.torch
         self.kps_convs = []
         if cfg.MODEL.KEYPOINTS_ON:
+            tkk = cfg.VIDEO.TIME_KERNEL_DIM.HEAD_KPS if s.kps_head.endswith('_3d') else 1
             for i in range(cfg.KRCNN.NUM_STACKED_CONVS):
                 ks = cfg.KRCNN.CONV_HEAD_KERNEL
-                self.kps_convs.append(self._c(blobs, 'conv_fcn%d' % (i + 1), bias=True, pad=(0, ks // 2, ks // 2), relu=True))
+                self.kps_convs.append(self._c(blobs, 'conv_fcn%d' % (i + 1), bias=True, pad=(tkk // 2, ks // 2, ks // 2), relu=True))
             wt = blobs['kps_score_lowres_w']                 # ConvTranspose (Cin, K, 4, 4), stride 2, pad 1
             cin, K = wt.shape[0], wt.shape[1]
             w3 = np.zeros((4 * K, cin, 3, 3), np.float32)     # four 2x2 sub-pixel filters on a 3x3 footprint
@@ -149,7 +207,6 @@ class DetectionEngine(object):
                                 continue
                             w3[(py * 2 + px) * K:(py * 2 + px + 1) * K, :, dy + 1, dx + 1] = wt[:, :, ky, kx].T
             self.kps_lowres = _Conv(torch, w3, self.dtype, None, np.tile(blobs['kps_score_lowres_b'], 4), pad=(0, 1, 1))
-        self.pixel_means = np.asarray(cfg.PIXEL_MEANS, dtype=np.float32).ravel()
 
     # ------------------------------------------------------------------ backbone
     def body(self, x):
@@ -164,10 +221,7 @@ class DetectionEngine(object):
         outs = []
         for blocks in self.stages:
             for blk in blocks:
-                sc = blk['sc'](y) if blk['sc'] is not None else y
-                h = blk['a'](y)
-                h = blk['b'](h)
-                y = blk['c'](h, residual=sc, res_mode=1)
+                y = self._run_block(blk, y)
             outs.append(y)
         return outs
 
@@ -199,6 +253,8 @@ class DetectionEngine(object):
     def link(self, feats):
         """model_builder.time_pool_blobs (:1024-1042): centre-frame slice -> [B, 1, h, w, C]."""
         s = self.spec
+        if s.head3d:
+            return feats
         out = []
         for f in feats:
             if f.shape[1] == 1:
@@ -257,25 +313,79 @@ class DetectionEngine(object):
                                        cfg.MODEL.BBOX_REG_WEIGHTS, cfg.TEST.SCORE_THRESH, 1)
         keep, nkeep = box_ops.nms_batched(dets.view(B * (C - 1), R, 5), cnt, cfg.TEST.NMS, box_ops.NMS_2D_GE,
                                           box_ops.ORDER_INDEX)
-        cap = max(cfg.TEST.DETECTIONS_PER_IM, 1) if cfg.TEST.DETECTIONS_PER_IM > 0 else R
-        return rpn_ops.limit_detections(dets, keep, nkeep, cfg.TEST.DETECTIONS_PER_IM, cap=min(R, 2 * cap))
+        return rpn_ops.limit_detections(dets, keep, nkeep, cfg.TEST.DETECTIONS_PER_IM, cap=min(R, self.det_cap))
 
-    def keypoint_head(self, feats2d, boxes, batch_idx, im_scale, want_heatmaps=False):
-        """boxes [D, 4] image space (fp32 cuda), batch_idx [D] -> xy_preds [D, 4, K]."""
+    def keypoint_head(self, feats, boxes, batch_idx, im_scale, want_heatmaps=False):
+        """boxes [D, 4*Th] image space (fp32 cuda), batch_idx [D] -> xy_preds [D, 4, Th*K].
+        2-D heads: feats = per-level centre-frame maps; tube heads: feats = [conv feature 5-D]."""
         torch, cfg, s = self.torch, self.cfg, self.spec
         D = boxes.shape[0]
+        Th = s.T_head
         # _get_rois_blob (test.py:76-113): float64 product, stored fp32, image index in col 0
         rois = torch.cat([batch_idx.double()[:, None], boxes.double() * float(im_scale)], 1).float().contiguous()
-        x = self._roi_feats(feats2d, rois, cfg.KRCNN.ROI_XFORM_RESOLUTION, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO)
-        x = x.view((D, 1) + tuple(x.shape[2:]))
+        res, samp = cfg.KRCNN.ROI_XFORM_RESOLUTION, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO
+        if s.head3d:
+            x = self._roi_feats_tube(feats[0], rois, res, samp)               # [D, Th, S, S, C]
+        else:
+            x = self._roi_feats(feats, rois, res, samp)
+            x = x.view((D, 1) + tuple(x.shape[2:]))
         for c in self.kps_convs:
             x = c(x)
         S = x.shape[2]
         ld = (4 * s.K + 3) // 4 * 4
-        low = torch.empty((D, 1, S, S, ld), dtype=torch.float32, device='cuda')
-        self.kps_lowres(x, out_f32=True, out=low)
-        return dense_ops.keypoint_decode(low.view(D, S, S, ld), boxes, s.K, 1, min_size=cfg.KRCNN.INFERENCE_MIN_SIZE,
-                                         want_heatmaps=want_heatmaps)
+        low = torch.empty((D, Th, S, S, ld), dtype=torch.float32, device='cuda')
+        self.kps_lowres(x, out_f32=True, out=low)                             # per-frame (kT = 1): time in batch
+        return dense_ops.keypoint_decode(low.view(D * Th, S, S, ld), boxes, s.K, Th,
+                                         min_size=cfg.KRCNN.INFERENCE_MIN_SIZE, want_heatmaps=want_heatmaps)
+
+    # ------------------------------------------------------------------ tube (3-D) heads
+    def _roi_feats_tube(self, feat5d, rois, resolution, sampling):
+        """RoIFeatureTransform for 3-D heads (detector.py:216-254): tube -> per-frame boxes with image
+        index b*T + t, 2-D RoIAlign, back to [R, T, P, P, C]."""
+        B, T = feat5d.shape[:2]
+        f = feat5d.view((B * T,) + tuple(feat5d.shape[2:]))
+        return dense_ops.roi_align([f], [1.0 / self.feat_stride], rois, None, resolution, sampling, T=T,
+                                   round_tf32=(self.dtype == cv.TF32))
+
+    def rpn_tube(self, feat5d, im_info):
+        """Single-level 3-D RPN -> rois [B, R, 4T+1], roi_counts [B]."""
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        B, T, H, W, _ = feat5d.shape
+        A, K = s.num_anchors, cfg.TEST.RPN_PRE_NMS_TOP_N
+        h = self.rpn_conv(feat5d)
+        o = torch.empty((B, T, H, W, self.rpn_out_ld), dtype=torch.float32, device='cuda')
+        self.rpn_out(h, out_f32=True, out=o)
+        n = H * W * A
+        Kc = n if (K <= 0 or K > n) else K
+        props = torch.zeros((B, 1, Kc, 4 * T + 1), dtype=torch.float32, device='cuda')
+        counts = torch.zeros((B, 1), dtype=torch.int32, device='cuda')
+        rpn_ops.rpn_proposals(o[..., :A], o[..., A:5 * A], self.anchors[0], self.feat_stride, im_info, K,
+                              float(cfg.TEST.RPN_MIN_SIZE), T, out=props[:, 0], counts=counts[:, 0], time_major=True)
+        keep, nkeep = box_ops.nms_batched(props.view(B, Kc, 4 * T + 1), counts.view(-1), cfg.TEST.RPN_NMS_THRESH,
+                                          box_ops.NMS_TUBE_GT if T > 1 else box_ops.NMS_2D_GE,
+                                          box_ops.ORDER_SCORE if T > 1 else box_ops.ORDER_INDEX,
+                                          max_keep=cfg.TEST.RPN_POST_NMS_TOP_N)
+        return rpn_ops.collect(props, keep, nkeep, cfg.TEST.RPN_POST_NMS_TOP_N)
+
+    def box_head_tube(self, feat5d, rois, roi_counts, im_info, im_hw):
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        B, R, ldr = rois.shape
+        T, C = s.T_head, s.num_classes
+        x = self._roi_feats_tube(feat5d, rois.view(B * R, ldr), cfg.FAST_RCNN.ROI_XFORM_RESOLUTION,
+                                 cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO)                 # [BR, T, 7, 7, C]
+        for blk in self.res5:
+            x = self._run_block(blk, x)
+        n, _, hh, ww, ch = x.shape
+        x = dense_ops.spatial_mean(x.view(n * T, hh, ww, ch), round_tf32=(self.dtype == cv.TF32))    # [BR*T, C]
+        o = torch.empty((1, 1, 1, n * T, self.cls_bbox_ld), dtype=torch.float32, device='cuda')
+        self.cls_bbox(x.view(1, 1, 1, n * T, ch), out_f32=True, out=o)
+        cls, bbox = dense_ops.fold_tube_heads(o.view(n * T, self.cls_bbox_ld), n, T, C)
+        dets, cnt = rpn_ops.box_decode(rois, roi_counts, cls, bbox, C, im_info, im_hw, cfg.MODEL.BBOX_REG_WEIGHTS,
+                                       cfg.TEST.SCORE_THRESH, T)
+        keep, nkeep = box_ops.nms_batched(dets.view(B * (C - 1), R, 4 * T + 1), cnt, cfg.TEST.NMS,
+                                          box_ops.NMS_TUBE_GT if T > 1 else box_ops.NMS_2D_GE,
+                                          box_ops.ORDER_SCORE if T > 1 else box_ops.ORDER_INDEX)
+        return rpn_ops.limit_detections(dets, keep, nkeep, cfg.TEST.DETECTIONS_PER_IM, cap=min(R, self.det_cap))
 
     # ------------------------------------------------------------------ end to end
     def blob_geometry(self, h, w):
@@ -302,32 +412,94 @@ class DetectionEngine(object):
         x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
                                 cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
         x = x.view(B, T, hp + 6, wp + 8, self.cin_pad)
-        feats = self.link(self.fpn(self.body(x)))
+        feats = self.link(self.fpn(self.body(x))) if self.spec.fpn else [self.body(x)[-1]]
         im_info = torch.tensor([[hp, wp, scale]] * B, dtype=torch.float32, device='cuda')
         return feats, im_info, scale
 
-    def detect(self, frames_u8, want_heatmaps=False):
-        """Whole path for a batch of clips.  Returns per clip (cls_boxes [n, 5], xy_preds [n, 4, K])
-        as device tensors plus the raw device outputs (no host sync except the detection counts)."""
+    def _geom_tensors(self, B, H, W):
+        """im_info / im_hw / batch indices for a (B, H, W) batch, created once (no H2D in the hot loop)."""
+        key = (B, H, W)
+        g = self._geom.get(key)
+        if g is None:
+            torch = self.torch
+            scale, (hr, wr), (hp, wp) = self.blob_geometry(H, W)
+            cap = self.det_cap
+            g = dict(scale=scale, hr=hr, wr=wr, hp=hp, wp=wp,
+                     im_info=torch.tensor([[hp, wp, scale]] * B, dtype=torch.float32, device='cuda'),
+                     im_hw=torch.tensor([[H, W]] * B, dtype=torch.float32, device='cuda'),
+                     bidx=torch.arange(B, dtype=torch.float32, device='cuda').repeat_interleave(cap))
+            self._geom[key] = g
+        return g
+
+    @property
+    def det_cap(self):
+        """Detection slots per clip: DETECTIONS_PER_IM (+ a few for exact score ties at the threshold,
+        lib/core/test.py:796-800 keeps all of them)."""
+        d = self.cfg.TEST.DETECTIONS_PER_IM
+        return (d + 4 + 7) // 8 * 8 if d > 0 else self.cfg.TEST.RPN_POST_NMS_TOP_N
+
+    def detect_static(self, frames_u8, want_heatmaps=False):
+        """The whole path with NO host synchronisation (CUDA-graph capturable): fixed-capacity outputs
+        plus device-side counts.  dets [B, C-1, cap, 5], det_counts [B*(C-1)], xy [B*cap, 4, K]."""
         torch, s = self.torch, self.spec
         B, T, H, W, _ = frames_u8.shape
-        feats, im_info, scale = self.forward_features(frames_u8)
-        im_hw = torch.tensor([[H, W]] * B, dtype=torch.float32, device='cuda')
-        rois, _, roi_counts = self.rpn(feats, im_info)
-        dets, det_counts = self.box_head(feats, rois, roi_counts, im_info, im_hw)
-        cnt = det_counts.view(B, s.num_classes - 1)[:, 0].tolist()       # the one small D2H of the path
-        results = []
-        boxes_l, bidx_l = [], []
+        g = self._geom_tensors(B, H, W)
+        x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, g['scale'], (g['hr'], g['wr']),
+                                (g['hp'], g['wp']), cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
+        x = x.view(B, T, g['hp'] + 6, g['wp'] + 8, self.cin_pad)
+        if s.fpn:
+            feats = self.link(self.fpn(self.body(x)))
+            rois, _, roi_counts = self.rpn(feats, g['im_info'])
+            dets, det_counts = self.box_head(feats, rois, roi_counts, g['im_info'], g['im_hw'])
+        else:
+            feats = [self.body(x)[-1]]
+            rois, _, roi_counts = self.rpn_tube(feats[0], g['im_info'])
+            dets, det_counts = self.box_head_tube(feats[0], rois, roi_counts, g['im_info'], g['im_hw'])
+        out = dict(dets=dets, det_counts=det_counts, xy=None, heat=None)
+        if self.kps_convs:
+            cap = dets.shape[2]
+            boxes = dets[:, 0, :, :4 * s.T_head].reshape(B * cap, 4 * s.T_head)
+            out['xy'], out['heat'] = self.keypoint_head(feats, boxes, g['bidx'], g['scale'], want_heatmaps)
+        return out
+
+    def gather(self, out):
+        """Host side of detect_static: per clip (boxes [n,5], keyps [n,4,K]) as device tensor views."""
+        s = self.spec
+        dets = out['dets']
+        B, _, cap, _ = dets.shape
+        cnt = out['det_counts'].view(B, s.num_classes - 1)[:, 0].tolist()
+        if max(cnt) > cap:
+            raise RuntimeError('more than %d detections tie at the DETECTIONS_PER_IM threshold (%s)' % (cap, cnt))
+        res = []
         for b in range(B):
-            d = dets[b, 0, :cnt[b]]
-            boxes_l.append(d[:, :4])
-            bidx_l.append(torch.full((cnt[b],), b, dtype=torch.float32, device='cuda'))
-        xy = heat = None
-        if self.kps_convs and sum(cnt) > 0:
-            xy, heat = self.keypoint_head(feats, torch.cat(boxes_l).contiguous(), torch.cat(bidx_l), scale, want_heatmaps)
-        off = 0
-        for b in range(B):
-            results.append(dict(boxes=dets[b, 0, :cnt[b]], keyps=(xy[off:off + cnt[b]] if xy is not None else None),
-                                heatmaps=(heat[off:off + cnt[b]] if heat is not None else None)))
-            off += cnt[b]
-        return results
+            n = cnt[b]
+            res.append(dict(boxes=dets[b, 0, :n],
+                            keyps=(out['xy'][b * cap:b * cap + n] if out['xy'] is not None else None),
+                            heatmaps=(out['heat'][b * cap:b * cap + n] if out['heat'] is not None else None)))
+        return res
+
+    def detect(self, frames_u8, want_heatmaps=False):
+        """Per clip dict(boxes [n,5], keyps [n,4,K], heatmaps) — the public per-batch call."""
+        return self.gather(self.detect_static(frames_u8, want_heatmaps))
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, B, T, H, W):
+        """Capture detect_static for a fixed batch geometry.  Returns (static_input, run) where run()
+        replays the graph and returns the static output dict."""
+        torch = self.torch
+        static_in = torch.zeros((B, T, H, W, 3), dtype=torch.uint8, device='cuda')
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                                     # warm-up: lazy attribute / workspace setup
+                self.detect_static(static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.detect_static(static_in)
+
+        def run():
+            graph.replay()
+            return static_out
+        return static_in, run

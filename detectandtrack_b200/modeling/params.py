@@ -133,15 +133,14 @@ def param_shapes(cfg):
         dim_conv = dim_in
         A, Th = spec.num_anchors, spec.T_head
         tk = cfg.VIDEO.TIME_KERNEL_DIM.HEAD_RPN if spec.head3d else 1
-        if spec.head3d:
-            P['conv_rpn_w'] = (dim_conv, dim_conv, tk, 3, 3)
-            P['rpn_cls_logits_w'] = (A, dim_conv, 1, 1, 1)
-            P['rpn_bbox_pred_w'] = (4 * A, dim_conv, 1, 1, 1)      # -> (A*T*4) after the time fold (model_builder.py:553-563)
+        if spec.head3d:                                   # blob names of model_builder.py:509-547
+            P['conv_rpn_w'] = (dim_conv, dim_conv, tk, 3, 3); P['conv_rpn_b'] = (dim_conv,)
+            P['rpn_cls_logits_1_w'] = (A, dim_conv, 1, 1, 1); P['rpn_cls_logits_1_b'] = (A,)
+            P['rpn_bbox_pred_1_w'] = (4 * A, dim_conv, 1, 1, 1); P['rpn_bbox_pred_1_b'] = (4 * A,)   # time fold :553-563
         else:
-            P['conv_rpn_w'] = (dim_conv, dim_conv, 3, 3)
-            P['rpn_cls_logits_w'] = (A, dim_conv, 1, 1)
-            P['rpn_bbox_pred_w'] = (4 * A, dim_conv, 1, 1)
-        P['conv_rpn_b'] = (dim_conv,); P['rpn_cls_logits_b'] = (A,); P['rpn_bbox_pred_b'] = (4 * A,)
+            P['conv_rpn_w'] = (dim_conv, dim_conv, 3, 3); P['conv_rpn_b'] = (dim_conv,)
+            P['rpn_cls_logits_w'] = (A, dim_conv, 1, 1); P['rpn_cls_logits_b'] = (A,)
+            P['rpn_bbox_pred_w'] = (4 * A, dim_conv, 1, 1); P['rpn_bbox_pred_b'] = (4 * A,)
     # ---- box head ----
     C = spec.num_classes
     if spec.roi_head.endswith('add_roi_2mlp_head'):
@@ -196,7 +195,10 @@ def param_shapes(cfg):
             din = hd
         assert not cfg.KRCNN.USE_DECONV and cfg.KRCNN.USE_DECONV_OUTPUT and cfg.KRCNN.UP_SCALE == 2, \
             'only the shipped keypoint output stack (deconv output + 2x bilinear) is implemented'
-        kt = spec.T_head if (nd and not cfg.KRCNN.NO_3D_DECONV_TIME_TO_CH) else 1
+        if nd and not cfg.KRCNN.NO_3D_DECONV_TIME_TO_CH:
+            raise NotImplementedError('time-in-channel keypoint deconv (KRCNN.NO_3D_DECONV_TIME_TO_CH False) is not '
+                                      'used by any shipped config')
+        kt = 1
         P['kps_score_lowres_w'] = (din * kt, spec.K * kt, cfg.KRCNN.DECONV_KERNEL, cfg.KRCNN.DECONV_KERNEL)
         P['kps_score_lowres_b'] = (spec.K * kt,)
     return P, spec

@@ -65,3 +65,24 @@ def keypoint_decode(lowres, boxes, K=17, T=1, n_dev=None, min_size=0, want_heatm
     L.call('dt_keypoint_decode', L.ptr(lowres), ldl, S, K, T, L.ptr(boxes), boxes.shape[1], L.ptr(n_dev), D, int(min_size),
            L.ptr(heat), L.ptr(xy), L.stream_ptr())
     return xy, heat
+
+
+def spatial_mean(x, round_tf32=False):
+    """x [N, H, W, C] -> [N, C]: mean over W, then over H (ReduceBackMean twice)."""
+    torch = L.require_cuda()
+    N, H, W, Cc = x.shape
+    y = torch.empty((N, Cc), dtype=x.dtype, device='cuda')
+    L.call('dt_spatial_mean', L.ptr(x), N, H, W, Cc, Cc, int(x.dtype == torch.float32), int(bool(round_tf32)), L.ptr(y), Cc,
+           L.stream_ptr())
+    return y
+
+
+def fold_tube_heads(o, R, T, C):
+    """o [R*T, ld] fp32 = per-frame [cls | bbox] -> (cls [R, C], bbox [R, C*T*4])."""
+    torch = L.require_cuda()
+    cls = torch.empty((R, C), dtype=torch.float32, device='cuda')
+    bbox = torch.empty((R, C * T * 4), dtype=torch.float32, device='cuda')
+    assert o.dtype == torch.float32 and o.stride(1) == 1
+    L.call('dt_fold_tube_heads', L.ptr(o), o.stride(0), R, T, C, L.ptr(cls), L.ptr(bbox),
+           L.stream_ptr())
+    return cls, bbox

@@ -20,13 +20,19 @@ def _nhwc_ld(t):
 
 
 def rpn_proposals(logits, deltas, anchors, feat_stride, im_info, pre_nms_topn, min_size=0.0,
-                  T=1, out=None, counts=None, clip=BBOX_XFORM_CLIP):
+                  T=1, out=None, counts=None, clip=BBOX_XFORM_CLIP, time_major=False):
     """logits [B,H,W,A], deltas [B,H,W,4AT] (fp32 or bf16; channel slices of a wider NHWC tensor
     are fine), anchors [A,4T] fp64 cuda, im_info [B,3] fp32 cuda.
     Returns (props [B,K,4T+1] fp32, counts [B] int32)."""
     torch = L.require_cuda()
-    B, H, W, _ = logits.shape
-    ld_s, ld_d = _nhwc_ld(logits), _nhwc_ld(deltas)
+    if time_major:          # [B, T, H, W, C'] channel slices of contiguous 5-D tensors
+        B, Tt, H, W, _ = logits.shape
+        assert Tt == T and deltas.shape[:4] == logits.shape[:4]
+        ld_s, ld_d = logits.stride(3), deltas.stride(3)
+        assert logits.stride(4) == 1 and deltas.stride(4) == 1 and logits.stride(1) == H * W * ld_s
+    else:
+        B, H, W, _ = logits.shape
+        ld_s, ld_d = _nhwc_ld(logits), _nhwc_ld(deltas)
     A = anchors.shape[0]
     assert logits.dtype == deltas.dtype
     act_f32 = int(logits.dtype == torch.float32)
@@ -40,7 +46,7 @@ def rpn_proposals(logits, deltas, anchors, feat_stride, im_info, pre_nms_topn, m
     L.call('dt_rpn_proposals', C.c_void_p(logits.data_ptr()), ld_s, C.c_void_p(deltas.data_ptr()), ld_d, act_f32,
            B, H, W, A, T, L.ptr(anchors), float(feat_stride), L.ptr(im_info), int(pre_nms_topn), float(min_size),
            float(clip), C.c_void_p(out.data_ptr()), out.stride(0), C.c_void_p(counts.data_ptr()), counts.stride(0),
-           L.stream_ptr())
+           int(bool(time_major)), L.stream_ptr())
     return out, counts
 
 

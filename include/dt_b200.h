@@ -154,12 +154,14 @@ int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const vo
  * logits [B, H, W, ld_s] (first A channels), deltas [B, H, W, ld_d] (first 4*A*T; channel
  * a*4T + t*4 + k) — the NHWC order IS the reference's (H, W, A) enumeration; act_f32: 1 fp32,
  * 0 bf16.  anchors [A, 4T] fp64 device (generate_anchors.py).  out rows [4T+1] (boxes, score) in
- * descending score, batch image b at out + b*out_batch_stride; counts[b*counts_stride] rows. */
+ * descending score, batch image b at out + b*out_batch_stride; counts[b*counts_stride] rows.
+ * time_major != 0 (3-D RPN head, lib/modeling/model_builder.py:509-563): logits [B, T, H, W, ld_s] with A
+ * channels per frame are averaged over T (TimePool 'avg'), deltas [B, T, H, W, ld_d] hold channel a*4+k per frame. */
 int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas, int ld_d, int act_f32, int B,
                      int H, int W, int A, int T, const double* anchors, double feat_stride,
                      const float* im_info, int pre_nms_topn, float min_size, double bbox_xform_clip,
                      float* out, long long out_batch_stride, int* counts, int counts_stride,
-                     void* stream);
+                     int time_major, void* stream);
 
 /* collect (lib/ops/collect_and_distribute_fpn_rpn_proposals.py:44-62): props [B, L, K, 4T+1],
  * keep [B*L, K] / nkeep [B*L] from dt_nms_batched -> rois [B, R, 4T+1] (col 0 = image index),
@@ -184,7 +186,8 @@ int dt_box_decode(const float* rois, const int* roi_counts, int B, int R, int T,
                   float* dets, int* det_counts, void* stream);
 
 /* lib/core/test.py:768-800: gather dets[keep] per class and apply the DETECTIONS_PER_IM score
- * threshold over all classes.  out [B, C-1, cap, 4T+1], out_counts [B*(C-1)]. */
+ * threshold over all classes.  out [B, C-1, cap, 4T+1]; out_counts [B*(C-1)] is the reference's count and
+ * may exceed cap when scores tie at the threshold (rows beyond cap are not written). */
 int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, int B, int num_classes, int R,
                         int T, int max_per_im, float* out, int* out_counts, int cap, void* stream);
 
@@ -219,6 +222,15 @@ int dt_roi_align(const void* const* feats, const int* Hs, const int* Ws, const f
 int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, int T, const float* boxes, int ldb,
                        const int* n_dev, int D, int min_size, float* heatmaps, float* xy_preds,
                        void* stream);
+
+/* 3-D box head glue.  dt_spatial_mean: ReduceBackMean over W then H
+ * (lib/modeling/ResNet3D.py:321-322), x [N, H, W, ldx] -> y [N, ldy] (first C channels).
+ * dt_fold_tube_heads: per-frame head outputs in [R*T, ld] = [C cls logits | 4C deltas (c*4+k)] ->
+ * cls [R, C] = mean over T, bbox [R, C*T*4] with channel c*4T + t*4 + k
+ * (lib/modeling/model_builder.py:427-473). */
+int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, void* y,
+                    int ldy, void* stream);
+int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, float* cls, float* bbox, void* stream);
 
 #ifdef __cplusplus
 }

@@ -160,3 +160,74 @@ def keypoint_head_2d(blobs, roi_feat, num_convs=8):
         x = torch.relu(F.conv2d(x, _t(blobs, 'conv_fcn%d_w' % (i + 1)), _t(blobs, 'conv_fcn%d_b' % (i + 1)), 1, 1))
     low = okp.deconv_k4s2p1(x, _t(blobs, 'kps_score_lowres_w'), _t(blobs, 'kps_score_lowres_b'))
     return okp.bilinear_upsample2x(low), low
+
+
+# ------------------------------------------------------------------ 3-D (tube) heads
+def rpn_heads_3d(blobs, spec, feat):
+    """model_builder.py:500-563.  feat (B,C,T,H,W) -> logits (B,A,H,W) [TimePool avg of the per-frame
+    logits], deltas (B, A*T*4, H, W) with channel a*4T + t*4 + k."""
+    import torch
+    import torch.nn.functional as F
+    w = _t(blobs, 'conv_rpn_w')
+    tk = w.shape[2]
+    h = torch.relu(F.conv3d(feat, w, _t(blobs, 'conv_rpn_b'), 1, (tk // 2, 1, 1)))
+    lg = F.conv3d(h, _t(blobs, 'rpn_cls_logits_1_w'), _t(blobs, 'rpn_cls_logits_1_b')).mean(dim=2)
+    d = F.conv3d(h, _t(blobs, 'rpn_bbox_pred_1_w'), _t(blobs, 'rpn_bbox_pred_1_b'))        # (B, 4A, T, H, W)
+    B, A4, T, H, W = d.shape
+    d = d.view(B, A4 // 4, 4, T, H, W).permute(0, 1, 3, 2, 4, 5).reshape(B, -1, H, W)
+    return lg, d
+
+
+def roi_features_tube(feat, scale, rois, resolution, sampling_ratio):
+    """detector.py:216-254 for 3-D heads: RoIToBatchFormat + time->batch + RoIAlign + inverse.
+    feat (B,C,T,H,W), rois (R, 4T+1) -> (R, C, T, res, res)."""
+    import torch
+    from torchvision.ops import roi_align
+    B, C, T, H, W = feat.shape
+    f = feat.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+    bt = oprop.roi_to_batch_format(np.asarray(rois, dtype=np.float32)).astype(np.float32)       # rows n*T + t
+    out = roi_align(f, torch.from_numpy(bt), (resolution, resolution), scale, sampling_ratio, aligned=False)
+    R = rois.shape[0]
+    return out.view(R, T, C, resolution, resolution).permute(0, 2, 1, 3, 4).contiguous()
+
+
+def _basic_block_3d(blobs, x, pre, has_sc):
+    import torch
+    y = torch.relu(_affine(_conv(x, blobs, pre + '_branch2a', (1, 1, 1), (0, 1, 1)), blobs, pre + '_branch2a_bn'))
+    y = _affine(_conv(y, blobs, pre + '_branch2b', (1, 1, 1), (0, 1, 1)), blobs, pre + '_branch2b_bn')
+    sc = _affine(_conv(x, blobs, pre + '_branch1', (1, 1, 1), (0, 0, 0)), blobs, pre + '_branch1_bn') if has_sc else x
+    return torch.relu(y + sc)
+
+
+def box_head_conv5_3d(blobs, roi_feat, n_blocks=2):
+    """ResNet3D.add_ResNet18_roi_conv5_head (:301-327, stride_init 1, time kernel 1) +
+    add_fast_rcnn_outputs 3-D (:427-473).  roi_feat (R,C,T,7,7) -> cls (R,Cls), bbox (R, Cls*T*4)."""
+    import torch.nn.functional as F
+    x = roi_feat
+    for i in range(n_blocks):
+        x = _basic_block_3d(blobs, x, 'res5_%d' % i, i == 0)
+    x = x.mean(dim=4).mean(dim=3)                                   # ReduceBackMean W then H -> (R, C, T)
+    x = x[..., None, None]
+    cls = F.conv3d(x, _t(blobs, 'cls_score_1_w'), _t(blobs, 'cls_score_1_b')).mean(4).mean(3).mean(2)
+    bb = F.conv3d(x, _t(blobs, 'bbox_pred_1_w'), _t(blobs, 'bbox_pred_1_b'))                   # (R, 4C, T, 1, 1)
+    R, C4, T = bb.shape[:3]
+    bb = bb.view(R, C4 // 4, 4, T, 1, 1).permute(0, 1, 3, 2, 4, 5).reshape(R, -1, 1, 1).mean(3).mean(2)
+    return cls, bb
+
+
+def keypoint_head_3d(blobs, roi_feat, num_convs=8):
+    """keypoint_rcnn_heads.add_roi_pose_head_v1convX_3d + add_heatmap_outputs with
+    NO_3D_DECONV_TIME_TO_CH (time -> batch for the deconv, back to channel t*K + k).
+    roi_feat (D,C,T,14,14) -> kps_score (D, T*K, 56, 56)."""
+    import torch
+    import torch.nn.functional as F
+    x = roi_feat
+    for i in range(num_convs):
+        w = _t(blobs, 'conv_fcn%d_w' % (i + 1))
+        x = torch.relu(F.conv3d(x, w, _t(blobs, 'conv_fcn%d_b' % (i + 1)), 1, (w.shape[2] // 2, 1, 1)))
+    D, C, T, H, W = x.shape
+    xb = x.permute(0, 2, 1, 3, 4).reshape(D * T, C, H, W)
+    low = okp.deconv_k4s2p1(xb, _t(blobs, 'kps_score_lowres_w'), _t(blobs, 'kps_score_lowres_b'))
+    up = okp.bilinear_upsample2x(low)                                # (D*T, K, 56, 56)
+    K = up.shape[1]
+    return up.view(D, T * K, up.shape[2], up.shape[3])
