@@ -345,6 +345,9 @@ def run_ours(args):
     g0.record()
     for _ in range(args.steps):
         flush.zero_()
+        # keep the GPU busy while the CPU enqueues the step, so the per-conv events bracket kernel
+        # execution back to back instead of CPU launch latency (eager mode is launch-bound)
+        torch.cuda._sleep(int(40e6))
         eng.detect_static(dev)
     g1.record()
     barrier()
@@ -370,8 +373,8 @@ def run_ours(args):
                                 detections_per_clip=ndet, l2='flushed between iterations (256 MiB fill)',
                                 dead_frame_elimination=bool(args.dce),
                                 conv_gflop_per_clip=conv_flops / 1e9 / (B * args.steps), conv_launches_per_step=conv_n // args.steps,
-                                conv_share_of_step=conv_ms / ms_eager, cuda_graph=bool(args.graph),
-                                roofline_pass='same step run eagerly with CUDA events around every conv_tc launch (%.3f ms/step eager)' % (ms_eager / args.steps)),
+                                conv_share_of_step=conv_ms / ms, cuda_graph=bool(args.graph),
+                                roofline_pass='same step run eagerly behind a GPU-side delay, CUDA events around every conv_tc launch'),
                     e2e=dict(value=e2e, unit='clips/s', h2d_bytes_per_step=int(host.numel()), d2h_bytes_per_step=d2h),
                     gpu_launches=launches, clocks=clocks,
                     roofline=dict(bound='tensor', kernel='conv_tc_kernel (all conv/FC launches of the step)', achieved=achieved,

@@ -1,0 +1,97 @@
+"""GPU: the reference's two entry points end to end on a synthetic dataset:
+tools/test_net.py (detections.pkl schema) -> tools/compute_tracks.py (detections_withTracks.pkl)."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+YAML = '''
+MODEL:
+  TYPE: keypoint_rcnn
+  CONV_BODY: FPN3D.add_fpn_ResNet50_conv5_body
+  ROI_HEAD: head_builder.add_roi_2mlp_head
+  NUM_CLASSES: 2
+  FASTER_RCNN: True
+  KEYPOINTS_ON: True
+  VIDEO_ON: True
+FPN:
+  FPN_ON: True
+  MULTILEVEL_ROIS: True
+  MULTILEVEL_RPN: True
+FAST_RCNN:
+  ROI_XFORM_METHOD: RoIAlign
+  ROI_XFORM_RESOLUTION: 7
+  ROI_XFORM_SAMPLING_RATIO: 2
+KRCNN:
+  ROI_KEYPOINTS_HEAD: keypoint_rcnn_heads.add_roi_pose_head_v1convX
+  NUM_STACKED_CONVS: 8
+  NUM_KEYPOINTS: 17
+  USE_DECONV_OUTPUT: True
+  CONV_HEAD_DIM: 512
+  UP_SCALE: 2
+  HEATMAP_SIZE: 56
+  ROI_XFORM_RESOLUTION: 14
+  ROI_XFORM_SAMPLING_RATIO: 2
+VIDEO:
+  NUM_FRAMES: 3
+  TIME_INTERVAL: 1
+  WEIGHTS_INFLATE_MODE: center-only
+  TIME_KERNEL_DIM: 3
+  BODY_HEAD_LINK: 'slice-center'
+  NUM_FRAMES_MID: 1
+TEST:
+  DATASET: synthetic_2x3_96x128
+  WEIGHTS: random
+  SCALES: (96,)
+  MAX_SIZE: 128
+  NMS: 0.5
+  RPN_PRE_NMS_TOP_N: 1000
+  RPN_POST_NMS_TOP_N: 300
+  COMPETITION_MODE: False
+TRACKING:
+  CONF_FILTER_INITIAL_DETS: 0.3
+  DISTANCE_METRICS: ('bbox-overlap', 'cnn-cosdist')
+  DISTANCE_METRIC_WTS: (1.0, 0.0)
+  BIPARTITE_MATCHING_ALGO: 'hungarian'
+NUM_GPUS: 1
+'''
+
+
+def test_test_net_then_compute_tracks(tmp_path):
+    cfg = tmp_path / 'cfg.yaml'
+    cfg.write_text(YAML)
+    out = str(tmp_path / 'out')
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'test_net.py'), '--cfg', str(cfg), 'OUTPUT_DIR', out],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ddir = os.path.join(out, 'test', 'synthetic_2x3_96x128', 'keypoint_rcnn')
+    det = pickle.load(open(os.path.join(ddir, 'detections.pkl'), 'rb'))
+    assert set(det) >= {'all_boxes', 'all_segms', 'all_keyps', 'cfg'}
+    assert len(det['all_boxes']) == 2 and len(det['all_boxes'][1]) == 6
+    for i in range(6):
+        b = det['all_boxes'][1][i]
+        assert b.dtype == np.float32 and b.ndim == 2 and b.shape[1] == 5
+        assert len(det['all_keyps'][1][i]) == b.shape[0]
+        if b.shape[0]:
+            assert det['all_keyps'][1][i][0].shape == (4, 17)
+    # test_net on a posetrack-like dataset runs tracking itself (test_engine.py:326-328)
+    trk = pickle.load(open(os.path.join(ddir, 'detections_withTracks.pkl'), 'rb'))
+    assert len(trk['all_tracks'][1]) == 6
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'compute_tracks.py'), '--cfg', str(cfg), 'OUTPUT_DIR', out],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    trk2 = pickle.load(open(os.path.join(ddir, 'detections_withTracks.pkl'), 'rb'))
+    assert trk2['all_tracks'][1] == trk['all_tracks'][1]
+    for i in range(6):
+        assert len(trk2['all_tracks'][1][i]) == trk2['all_boxes'][1][i].shape[0]
+    # ids restart per video (2 videos x 3 frames): first frame of each video starts at FIRST_TRACK_ID
+    for first in (0, 3):
+        ids = trk2['all_tracks'][1][first]
+        assert ids == list(range(len(ids)))
