@@ -23,29 +23,37 @@ SIGNATURES = {
     'dt_assign_track_ids': [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p],
     'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
     'dt_conv3d': [_p, _p, _p, _p, _p, _p, _p, _p],
-    'dt_rpn_proposals': [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, C.c_double, _p, _i, _f, C.c_double, _p,
-                         C.c_longlong, _p, _i, _i, _p],
+    'dt_rpn_workspace_bytes': [_i, _i, C.POINTER(_i), C.POINTER(_i), _i, C.POINTER(_sz)],
+    'dt_rpn_proposals_multi': [_p, _i, _i, _i, _i, _i, _p, _i, _f, C.c_double, C.c_longlong, _i, _i, _p, _sz, _p],
     'dt_collect_rpn': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
     'dt_distribute_fpn': [_p, _i, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     'dt_box_decode': [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, C.POINTER(_f), C.c_double, _f, _p, _p, _p],
     'dt_limit_detections': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_conv1_7x7s2': [_p, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p],
-    'dt_maxpool2d': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    'dt_maxpool2d': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_roi_align': [C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _p, _i, _p, _i,
-                     _i, _p, _i, _i, _i, _p, _p],
+                     _i, _p, _i, _i, _i, _i, _p, _p],
     'dt_keypoint_decode': [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p],
-    'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    'dt_conv1_7x7s2_f32': [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_fold_tube_heads': [_p, _i, _i, _i, _i, _p, _p, _p],
 }
 
+
+
+class RpnLevel(C.Structure):
+    """dt_rpn_level (include/dt_b200.h)."""
+    _fields_ = [('logits', C.c_void_p), ('deltas', C.c_void_p), ('anchors', C.c_void_p), ('ld_s', C.c_int), ('ld_d', C.c_int),
+                ('H', C.c_int), ('W', C.c_int), ('feat_stride', C.c_double), ('out', C.c_void_p), ('counts', C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
     """dt_conv_desc (include/dt_b200.h)."""
     _fields_ = [(n, C.c_int) for n in (
         'N', 'Ti', 'Hi', 'Wi', 'Cin', 'Cout', 'kT', 'kH', 'kW', 'sT', 'sH', 'sW', 'pT', 'pH', 'pW',
-        'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode', 'out_round_tf32')]
+        'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode', 'x3', 'in_lo_off', 'out_lo_off',
+        'res_lo_off', 'out_round_tf32')]
 _RESTYPE = {'dt_last_error': C.c_char_p}
 
 

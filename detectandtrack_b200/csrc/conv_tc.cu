@@ -51,6 +51,12 @@ struct ConvKernelParams {
   void* out;
   int out_ld;                  // elements between consecutive positions
   int out_f32;                 // 1: fp32 output, 0: bf16
+  // 3xTF32 ("fp32-accurate") mode: activations / weights are stored as [hi | lo] tf32 pairs along the
+  // channel axis; D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the lo*lo term is below fp32 resolution).
+  int split_in;                // 1: three k-blocks per (tap, channel chunk) with the offsets below
+  int a_lo_off, b_lo_off;      // element offsets of the lo halves in the x rows / packed weight rows
+  int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
+  int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
@@ -121,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_base_smem;
 
   const int taps = p.kT * p.kH * p.kW;
-  const int kiters = taps * p.kchunks;
+  const int kiters = taps * p.kchunks * (p.split_in ? 3 : 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -142,13 +148,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kh = 0; kh < p.kH; ++kh)
             for (int kw = 0; kw < p.kW; ++kw, ++tap)
               for (int kc = 0; kc < p.kchunks; ++kc) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                mbar_expect_tx(&full[stage], p.a_bytes + Cfg::B_BYTES);
-                tma_load_5d(a_dst, &tmA, &full[stage], kc * BK, w_base + kw, h_base + kh, t_base + kt, n);
-                tma_load_3d(b_dst, &tmB, &full[stage], kc * BK, nt * BN, tap);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                const int nsub = p.split_in ? 3 : 1;
+                for (int sub = 0; sub < nsub; ++sub) {
+                  // sub 0: A_hi x B_hi, 1: A_lo x B_hi, 2: A_hi x B_lo
+                  const int ca = kc * BK + (sub == 1 ? p.a_lo_off : 0);
+                  const int cb = kc * BK + (sub == 2 ? p.b_lo_off : 0);
+                  mbar_wait(&empty[stage], phase ^ 1);
+                  uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+                  uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                  mbar_expect_tx(&full[stage], p.a_bytes + Cfg::B_BYTES);
+                  tma_load_5d(a_dst, &tmA, &full[stage], ca, w_base + kw, h_base + kh, t_base + kt, n);
+                  tma_load_3d(b_dst, &tmB, &full[stage], cb, nt * BN, tap);
+                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
               }
       }
     }
@@ -225,12 +237,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int cc = 0; cc < BN; cc += CW) {
         const int cchunk = nt * BN + cc;
         if (cchunk >= p.Cout) break;                                   // uniform: nothing left to write
-        uint8_t* buf = cbuf + (chunk_ctr % (uint32_t)p.ncbuf) * Cfg::C_BYTES;
+        // split output: buffers (2i, 2i+1) of a 4-buffer ring hold the hi / lo chunk, committed as ONE group
+        uint8_t* buf = p.split_out ? cbuf + ((chunk_ctr & 1u) * 2u) * Cfg::C_BYTES
+                                   : cbuf + (chunk_ctr % (uint32_t)p.ncbuf) * Cfg::C_BYTES;
         ++chunk_ctr;
         // the staging buffer must have been read out by the TMA store that used it last
         if (leader) {
           if (p.ncbuf == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else if (p.ncbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else if (p.ncbuf == 2 || p.split_out) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -252,17 +266,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 16; j += 4) {
                 const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j));
                 v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                if (p.split_out) {                                   // residual = hi + lo
+                  const float4 ql = __ldg(reinterpret_cast<const float4*>(rp + p.res_lo_off + j));
+                  v[j] += ql.x; v[j + 1] += ql.y; v[j + 2] += ql.z; v[j + 3] += ql.w;
+                }
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (cbase + j < p.Cout) v[j] += __ldg(rp + j);
+                if (cbase + j < p.Cout) v[j] += __ldg(rp + j) + (p.split_out ? __ldg(rp + p.res_lo_off + j) : 0.f);
             }
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 16; ++j)
             if (p.relu) v[j] = fmaxf(v[j], 0.f);
-            if (p.round_tf32) v[j] = round_to_tf32(v[j]);
+          if (p.split_out) {
+            float lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float hi = round_to_tf32(v[j]); lo[j] = round_to_tf32(v[j] - hi); v[j] = hi; }
+            const uint32_t dst_lo = dst + Cfg::C_BYTES;               // the lo chunk uses the next staging buffer
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t a = dst_lo + ((((uint32_t)(4 * half + q)) ^ swz) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(lo[4 * q]), "f"(lo[4 * q + 1]),
+                           "f"(lo[4 * q + 2]), "f"(lo[4 * q + 3]) : "memory");
+            }
+          } else if (p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = round_to_tf32(v[j]);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -324,6 +355,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   reinterpret_cast<uint64_t>(&tmC)),
               "r"(smem_u32(buf)), "r"(cchunk), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
               : "memory");
+          if (p.split_out)
+            asm volatile(
+                "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tmC)),
+                "r"(smem_u32(buf) + Cfg::C_BYTES), "r"(cchunk + p.out_lo_off), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
+                : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -412,7 +449,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr = true;
   }
   ConvKernelParams q = p;
-  Cfg::split(p.kT * p.kH * p.kW * p.kchunks, &q.nstages, &q.ncbuf);
+  Cfg::split(p.split_out ? 1 : p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1), &q.nstages, &q.ncbuf);
   const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
   conv_tc_kernel<BN, TF32><<<grid, 320, smem, stream>>>(tmA, tmB, tmC, q);
@@ -470,6 +507,17 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   p.a_bytes = (uint32_t)TH * TW * 128u;
   p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = d->res_mode; p.res_ld = res_ld;
   p.relu = d->relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32; p.round_tf32 = d->out_round_tf32;
+  // 3xTF32 split operands / outputs
+  p.split_in = (d->x3 & 1) ? 1 : 0;
+  p.split_out = (d->x3 & 2) ? 1 : 0;
+  DT_CHECK_ARG(!p.split_in || (tf32 && d->Cin % BK == 0), "dt_conv3d: x3 inputs need DT_DTYPE_TF32 and Cin %% %d == 0 (Cin=%d)", BK, d->Cin);
+  DT_CHECK_ARG(!p.split_out || (out_f32 && d->Cout % 32 == 0), "dt_conv3d: x3 outputs need fp32 and Cout %% 32 == 0 (Cout=%d)", d->Cout);
+  p.a_lo_off = d->in_lo_off > 0 ? d->in_lo_off : in_ld / 2;
+  p.b_lo_off = w_ld / 2;
+  p.out_lo_off = d->out_lo_off > 0 ? d->out_lo_off : out_ld / 2;
+  p.res_lo_off = d->res_lo_off > 0 ? d->res_lo_off : res_ld / 2;
+  DT_CHECK_ARG(!p.split_in || (p.a_lo_off + d->Cin <= in_ld && p.b_lo_off >= d->Cin), "dt_conv3d: x3 lo halves do not fit the rows");
+  DT_CHECK_ARG(!p.split_out || p.out_lo_off + d->Cout <= out_ld, "dt_conv3d: x3 output lo half does not fit the row");
 
   int BN = d->Cout >= 256 ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32));
   if (d->Cout > 128 && d->Cout < 256) BN = 128;
@@ -486,13 +534,14 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   const bool pointwise = d->kT == 1 && d->kH == 1 && d->kW == 1 && d->pT == 0 && d->pH == 0 && d->pW == 0;
   uint64_t dims[5], strides[4]; uint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   const uint64_t sC = (uint64_t)in_ld * esz, sW = sC * d->Wi, sH = sW * d->Hi, sT = sH * d->Ti;
+  const uint64_t cdim = p.split_in ? (uint64_t)in_ld : (uint64_t)d->Cin;
   if (pointwise) {
-    dims[0] = d->Cin; dims[1] = Wo; dims[2] = Ho; dims[3] = To; dims[4] = d->N;
+    dims[0] = cdim; dims[1] = Wo; dims[2] = Ho; dims[3] = To; dims[4] = d->N;
     strides[0] = sC * d->sW; strides[1] = sW * d->sH; strides[2] = sH * d->sT; strides[3] = sT;
     box[0] = BK; box[1] = TW; box[2] = TH; box[3] = 1; box[4] = 1;
     p.sT = p.sH = p.sW = 1;
   } else {
-    dims[0] = d->Cin; dims[1] = d->Wi; dims[2] = d->Hi; dims[3] = d->Ti; dims[4] = d->N;
+    dims[0] = cdim; dims[1] = d->Wi; dims[2] = d->Hi; dims[3] = d->Ti; dims[4] = d->N;
     strides[0] = sC; strides[1] = sW; strides[2] = sH; strides[3] = sT;
     box[0] = BK; box[1] = (uint32_t)TW * d->sW; box[2] = (uint32_t)TH * d->sH; box[3] = 1; box[4] = 1;
     estr[1] = d->sW; estr[2] = d->sH;
@@ -501,14 +550,14 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   if (encode_map(&tmA, tf32, 5, x, dims, strides, box, estr)) return 1;
   {
     const int taps = d->kT * d->kH * d->kW;
-    uint64_t wd[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)taps};
+    uint64_t wd[3] = {p.split_in ? (uint64_t)w_ld : (uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)taps};
     uint64_t ws[2] = {(uint64_t)w_ld * esz, (uint64_t)w_ld * esz * d->Cout};
     uint32_t wb[3] = {(uint32_t)BK, (uint32_t)BN, 1};
     uint32_t we[3] = {1, 1, 1};
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC;
-  if (encode_out_map(&tmC, y, out_f32, d->Cout, Wo, Ho, To, d->N, out_ld, TH, TW)) return 1;
+  if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, TH, TW)) return 1;
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -24,7 +24,7 @@ __device__ __forceinline__ float round_to_tf32(float v) {   // see conv_tc.cu: k
   return __uint_as_float(u & 0xFFFFE000u);
 }
 template <typename T> __device__ __forceinline__ T to_act(float v);
-template <> __device__ __forceinline__ float to_act<float>(float v) { return round_to_tf32(v); }
+template <> __device__ __forceinline__ float to_act<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 to_act<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 template <> struct Vec<float> {
@@ -48,6 +48,29 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
+// 3xTF32 storage: a value is kept as hi + lo with hi = tf32(v), lo = tf32(v - hi), the two halves `lo_off`
+// elements apart in the channel row (fp32 tensors only; lo_off == 0 means plain storage).
+template <typename ET>
+__device__ __forceinline__ void load_vals(const ET* p, int lo_off, float* v) {
+  Vec<ET>::load(p, v);
+  if (lo_off) {
+    float l[Vec<ET>::N];
+    Vec<ET>::load(p + lo_off, l);
+#pragma unroll
+    for (int e = 0; e < Vec<ET>::N; ++e) v[e] += l[e];
+  }
+}
+template <typename ET>
+__device__ __forceinline__ void store_vals(ET* p, int lo_off, float* v) {
+  if (lo_off) {
+    float l[Vec<ET>::N];
+#pragma unroll
+    for (int e = 0; e < Vec<ET>::N; ++e) { const float h = round_to_tf32(v[e]); l[e] = round_to_tf32(v[e] - h); v[e] = h; }
+    Vec<ET>::store(p + lo_off, l);
+  }
+  Vec<ET>::store(p, v);
+}
+
 // ------------------------------------------------------------------- image prep
 // frames [F, H, W, 3] u8 (BGR).  out [F, Hp, Wp, Cp]: channels 0..2 = resized (pixel - mean), rest 0;
 // rows/cols beyond the resized image are 0 (blob.py:40-62).  cv2.resize(INTER_LINEAR) on float32:
@@ -55,7 +78,7 @@ template <> struct Vec<__nv_bfloat16> {
 template <typename OT>
 __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F, int H, int W, float m0, float m1,
                                  float m2, double inv_scale, int Hr, int Wr, int Hp, int Wp, int Cp,
-                                 int by, int bx, OT* __restrict__ out) {
+                                 int by, int bx, int round_out, OT* __restrict__ out) {
   // the output buffer is [F, Hp + 2*by, Wp + 2*bx, Cp]: `by` zero rows above/below, `bx` zero pixels left/right
   const int Ht = Hp + 2 * by, Wt = Wp + 2 * bx;
   const long long total = (long long)F * Ht * Wt;
@@ -91,14 +114,14 @@ __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F
       }
     }
     OT* o = out + (size_t)idx * Cp;
-    for (int c = 0; c < Cp; ++c) o[c] = to_act<OT>(c < 3 ? v[c] : 0.f);
+    for (int c = 0; c < Cp; ++c) o[c] = to_act<OT>(c < 3 ? (round_out ? round_to_tf32(v[c]) : v[c]) : 0.f);
   }
 }
 
 // ------------------------------------------------------------------- max pooling (NHWC)
 template <typename ET>
 __global__ void maxpool_kernel(const ET* __restrict__ x, int N, int H, int W, int C, int ldx, int k, int s, int p,
-                               int Ho, int Wo, ET* __restrict__ y, int ldy) {
+                               int Ho, int Wo, ET* __restrict__ y, int ldy, int lo_in, int lo_out) {
   constexpr int V = Vec<ET>::N;
   const int cv = C / V;
   const long long total = (long long)N * Ho * Wo * cv;
@@ -118,12 +141,12 @@ __global__ void maxpool_kernel(const ET* __restrict__ x, int N, int H, int W, in
         const int wi = wo * s - p + kw;
         if (wi < 0 || wi >= W) continue;
         float v[V];
-        Vec<ET>::load(x + (((size_t)n * H + hi) * W + wi) * ldx + c, v);
+        load_vals<ET>(x + (((size_t)n * H + hi) * W + wi) * ldx + c, lo_in, v);
 #pragma unroll
         for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], v[e]);
       }
     }
-    Vec<ET>::store(y + (((size_t)n * Ho + ho) * Wo + wo) * ldy + c, m);
+    store_vals<ET>(y + (((size_t)n * Ho + ho) * Wo + wo) * ldy + c, lo_out, m);
   }
 }
 
@@ -135,7 +158,7 @@ struct RoiLevels {
 };
 
 template <typename ET>
-__device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, int W, int ld, float y, float x, float* acc) {
+__device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, int W, int ld, int lo_in, float y, float x, float* acc) {
   constexpr int V = Vec<ET>::N;
   if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return;      // contributes 0
   if (y <= 0.f) y = 0.f;
@@ -146,10 +169,10 @@ __device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, in
   const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
   const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
   float v1[V], v2[V], v3[V], v4[V];
-  Vec<ET>::load(f + ((size_t)yl * W + xl) * ld, v1);
-  Vec<ET>::load(f + ((size_t)yl * W + xh) * ld, v2);
-  Vec<ET>::load(f + ((size_t)yh * W + xl) * ld, v3);
-  Vec<ET>::load(f + ((size_t)yh * W + xh) * ld, v4);
+  load_vals<ET>(f + ((size_t)yl * W + xl) * ld, lo_in, v1);
+  load_vals<ET>(f + ((size_t)yl * W + xh) * ld, lo_in, v2);
+  load_vals<ET>(f + ((size_t)yh * W + xl) * ld, lo_in, v3);
+  load_vals<ET>(f + ((size_t)yh * W + xh) * ld, lo_in, v4);
 #pragma unroll
   for (int e = 0; e < V; ++e) acc[e] += w1 * v1[e] + w2 * v2[e] + w3 * v3[e] + w4 * v4[e];
 }
@@ -159,19 +182,22 @@ __device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, in
 template <typename ET>
 __global__ void roi_align_kernel(RoiLevels lv, int kmin, const float* __restrict__ rois, int ldr,
                                  const int* __restrict__ n_dev, int R, int T, const int* __restrict__ levels, int C,
-                                 int ldf, int P, int sampling, int round_out, ET* __restrict__ out) {
+                                 int ldf, int P, int sampling, int round_out, int lo_in, long long o_row, int o_pos,
+                                 int o_lo, ET* __restrict__ out) {
+  // output addressing: roi r starts at r*o_row, position (t, ph, pw) at ((t*P + ph)*P + pw)*o_pos, the lo
+  // half (3xTF32 storage) o_lo elements further (0 = plain).
   constexpr int V = Vec<ET>::N;
   const int rt = blockIdx.x, ph = blockIdx.y;
   const int r = rt / T, t = rt - r * T;
   const int n = n_dev ? min(*n_dev, R) : R;
   const int cv = C / V;
-  ET* obase = out + (((size_t)r * T + t) * P + ph) * P * C;
+  ET* obase = out + (size_t)r * o_row + ((size_t)t * P + ph) * P * o_pos;
   if (r >= n) {          // rows beyond the live count are zero-filled (keeps downstream GEMMs finite)
     for (int i = threadIdx.x; i < P * cv; i += blockDim.x) {
       float z[V];
 #pragma unroll
       for (int e = 0; e < V; ++e) z[e] = 0.f;
-      Vec<ET>::store(obase + (size_t)(i / cv) * C + (i % cv) * V, z);
+      store_vals<ET>(obase + (size_t)(i / cv) * o_pos + (i % cv) * V, o_lo, z);
     }
     return;
   }
@@ -195,16 +221,16 @@ __global__ void roi_align_kernel(RoiLevels lv, int kmin, const float* __restrict
       const float y = y1 + ph * bh + (iy + 0.5f) * bh / (float)gh;
       for (int ix = 0; ix < gw; ++ix) {
         const float x = x1 + pw * bw + (ix + 0.5f) * bw / (float)gw;
-        bilinear_acc<ET>(f + c, H, W, ldf, y, x, acc);
+        bilinear_acc<ET>(f + c, H, W, ldf, lo_in, y, x, acc);
       }
     }
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e] /= cnt;
-    if (round_out) {
+    if (round_out && !o_lo) {
 #pragma unroll
       for (int e = 0; e < V; ++e) acc[e] = round_to_tf32(acc[e]);
     }
-    Vec<ET>::store(obase + (size_t)pw * C + c, acc);
+    store_vals<ET>(obase + (size_t)pw * o_pos + c, o_lo, acc);
   }
 }
 
@@ -360,7 +386,7 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
 // ReduceBackMean over W then over H (lib/modeling/ResNet3D.py:321-322): x [N, H, W, ldx] -> y [N, C]
 template <typename ET>
 __global__ void spatial_mean_kernel(const ET* __restrict__ x, int N, int H, int W, int C, int ldx, ET* __restrict__ y,
-                                    int ldy, int round_out) {
+                                    int ldy, int round_out, int lo_in, int lo_out) {
   constexpr int V = Vec<ET>::N;
   const int cv = C / V;
   const long long total = (long long)N * cv;
@@ -376,7 +402,7 @@ __global__ void spatial_mean_kernel(const ET* __restrict__ x, int N, int H, int 
       for (int e = 0; e < V; ++e) row[e] = 0.f;
       for (int w = 0; w < W; ++w) {
         float v[V];
-        Vec<ET>::load(x + (((size_t)n * H + h) * W + w) * ldx + c, v);
+        load_vals<ET>(x + (((size_t)n * H + h) * W + w) * ldx + c, lo_in, v);
 #pragma unroll
         for (int e = 0; e < V; ++e) row[e] += v[e];
       }
@@ -384,8 +410,8 @@ __global__ void spatial_mean_kernel(const ET* __restrict__ x, int N, int H, int 
       for (int e = 0; e < V; ++e) acc[e] += row[e] / (float)W;
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) { acc[e] /= (float)H; if (round_out) acc[e] = round_to_tf32(acc[e]); }
-    Vec<ET>::store(y + (size_t)n * ldy + c, acc);
+    for (int e = 0; e < V; ++e) { acc[e] /= (float)H; if (round_out && !lo_out) acc[e] = round_to_tf32(acc[e]); }
+    store_vals<ET>(y + (size_t)n * ldy + c, lo_out, acc);
   }
 }
 
@@ -405,6 +431,51 @@ __global__ void fold_tube_heads_kernel(const float* __restrict__ in, int ld, int
     for (int t = 0; t < T; ++t)
       for (int k = 0; k < 4; ++k)
         bbox[(size_t)r * C * T * 4 + (size_t)c * 4 * T + 4 * t + k] = in[((size_t)r * T + t) * ld + C + c * 4 + k];
+}
+
+// ------------------------------------------------------------------- conv1, exact fp32 (3xTF32 mode)
+// 7x7 stride 2 pad 3 conv + AffineChannel + ReLU in plain fp32 FMAs (lib/modeling/ResNet3D.py:258-263);
+// output stored as [hi | lo] tf32 pairs for the 3xTF32 consumers.  blob [F, Hp, Wp, Cp] raw fp32.
+// One CTA = 32 output pixels x 64 channels; thread = (pixel, 8 channels); weights [147][64] in smem.
+__global__ void __launch_bounds__(256)
+conv1_f32_kernel(const float* __restrict__ blob, int F, int Hp, int Wp, int Cp, const float* __restrict__ w /*[7][7][3][64]*/,
+                 const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ y /*[F,Ho,Wo,128]*/) {
+  __shared__ float sw[147 * 64];
+  for (int i = threadIdx.x; i < 147 * 64; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int Ho = Hp / 2, Wo = Wp / 2;
+  const long long total = (long long)F * Ho * Wo;
+  const long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int cg = (threadIdx.x & 7) * 8;
+  if (pix >= total) return;
+  const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), f = (int)(pix / ((long long)Wo * Ho));
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int kh = 0; kh < 7; ++kh) {
+    const int hi = 2 * ho - 3 + kh;
+    if (hi < 0 || hi >= Hp) continue;
+    for (int kw = 0; kw < 7; ++kw) {
+      const int wi = 2 * wo - 3 + kw;
+      if (wi < 0 || wi >= Wp) continue;
+      const float* px = blob + (((size_t)f * Hp + hi) * Wp + wi) * Cp;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xv = px[c];
+        const float* wr = sw + ((kh * 7 + kw) * 3 + c) * 64 + cg;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, wr[e], acc[e]);
+      }
+    }
+  }
+  float* o = y + (size_t)pix * 128 + cg;
+#pragma unroll
+  for (int e = 0; e < 8; e += 4) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = fmaxf(fmaf(acc[e + q], scale[cg + e + q], bias[cg + e + q]), 0.f);
+    store_vals<float>(o + e, 64, v);
+  }
 }
 
 }  // namespace dt
@@ -428,27 +499,29 @@ extern "C" int dt_prep_clip(const unsigned char* frames, int F, int H, int W, co
   const long long total = (long long)F * (Hp + 2 * border_y) * (Wp + 2 * border_x);
   if (out_f32)
     prep_clip_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, F, H, W, mean3[0], mean3[1], mean3[2],
-                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, (float*)out);
+                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, out_f32 == 1, (float*)out);
   else
     prep_clip_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, (__nv_bfloat16*)out);
+        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, 0, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32, void* y,
-                            int ldy, void* stream) {
+extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32, int x3,
+                            void* y, int ldy, void* stream) {
   const int V = f32 ? 4 : 8;
   DT_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && C >= 1 && k >= 1 && s >= 1 && p >= 0 && p < k, "dt_maxpool2d: bad shape");
   DT_CHECK_ARG(C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C, "dt_maxpool2d: C/ld must be multiples of %d", V);
+  DT_CHECK_ARG(!x3 || (f32 && ldx >= 2 * C && ldy >= 2 * C), "dt_maxpool2d: x3 storage needs fp32 rows of 2*C");
   if (N == 0) return 0;
   DT_CHECK_ARG(x && y, "dt_maxpool2d: null pointer");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;      // Caffe2 legacy (floor) pooling
   const long long total = (long long)N * Ho * Wo * (C / V);
   if (f32)
-    maxpool_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (float*)y, ldy);
+    maxpool_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (float*)y, ldy,
+                                                                                   x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   else
-    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (__nv_bfloat16*)y, ldy);
+    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (__nv_bfloat16*)y, ldy, 0, 0);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -456,7 +529,7 @@ extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, 
 extern "C" int dt_roi_align(const void* const* feats /*host array [nlevels] of device ptrs*/, const int* Hs, const int* Ws,
                             const float* scales /*host arrays*/, int nlevels, int k_min, int C, int ldf, int f32,
                             const float* rois, int ldr, const int* n_dev, int R, int T, const int* levels, int P,
-                            int sampling_ratio, int round_tf32, void* out, void* stream) {
+                            int sampling_ratio, int round_tf32, int x3_mode, void* out, void* stream) {
   const int V = f32 ? 4 : 8;
   DT_CHECK_ARG(nlevels >= 1 && nlevels <= 8 && C >= 1 && C % V == 0 && ldf % V == 0 && R >= 0 && T >= 1 && P >= 1 && ldr >= 4 * T + 1,
                "dt_roi_align: bad shape (C=%d must be a multiple of %d)", C, V);
@@ -468,9 +541,20 @@ extern "C" int dt_roi_align(const void* const* feats /*host array [nlevels] of d
   dim3 grid(R * T, P);
   const int threads = 256;
   if (f32)
-    roi_align_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, round_tf32, (float*)out);
+  {
+    // x3_mode 0: plain; 1: [hi | lo] per position (rows of 2C); 2: planar [R][hi block | lo block] (for the FC head)
+    DT_CHECK_ARG(x3_mode == 0 || (f32 && ldf >= 2 * C), "dt_roi_align: x3 storage needs fp32 feature rows of 2*C");
+    const long long blk = (long long)T * P * P * C;
+    const int lo_in = x3_mode ? ldf / 2 : 0;
+    const long long o_row = x3_mode ? 2 * blk : blk;
+    const int o_pos = (x3_mode == 1) ? 2 * C : C;
+    const int o_lo = (x3_mode == 1) ? C : (x3_mode == 2 ? (int)blk : 0);
+    roi_align_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio,
+                                                                        round_tf32, lo_in, o_row, o_pos, o_lo, (float*)out);
+  }
   else
-    roi_align_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, 0, (__nv_bfloat16*)out);
+    roi_align_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, 0,
+                                                                                0, (long long)T * P * P * C, C, 0, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -490,8 +574,8 @@ extern "C" int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, in
   return 0;
 }
 
-extern "C" int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, void* y, int ldy,
-                               void* stream) {
+extern "C" int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, int x3, void* y,
+                               int ldy, void* stream) {
   const int V = f32 ? 4 : 8;
   DT_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && C >= 1 && C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C,
                "dt_spatial_mean: bad shape (C/ld must be multiples of %d)", V);
@@ -499,9 +583,9 @@ extern "C" int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ld
   DT_CHECK_ARG(x && y, "dt_spatial_mean: null pointer");
   const long long total = (long long)N * (C / V);
   if (f32)
-    spatial_mean_kernel<float><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, (float*)y, ldy, round_tf32);
+    spatial_mean_kernel<float><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, (float*)y, ldy, round_tf32, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   else
-    spatial_mean_kernel<__nv_bfloat16><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, (__nv_bfloat16*)y, ldy, 0);
+    spatial_mean_kernel<__nv_bfloat16><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, (__nv_bfloat16*)y, ldy, 0, 0, 0);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -511,6 +595,16 @@ extern "C" int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, 
   if (R == 0) return 0;
   DT_CHECK_ARG(in && cls && bbox, "dt_fold_tube_heads: null pointer");
   fold_tube_heads_kernel<<<(R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, ld, R, T, C, cls, bbox);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_conv1_7x7s2_f32(const float* blob, int F, int Hp, int Wp, int Cp, const float* w, const float* scale,
+                                  const float* bias, float* y, void* stream) {
+  DT_CHECK_ARG(F >= 1 && Hp >= 2 && Wp >= 2 && Hp % 2 == 0 && Wp % 2 == 0 && Cp >= 3, "dt_conv1_7x7s2_f32: bad shape");
+  DT_CHECK_ARG(blob && w && scale && bias && y, "dt_conv1_7x7s2_f32: null pointer");
+  const long long total = (long long)F * (Hp / 2) * (Wp / 2);
+  conv1_f32_kernel<<<(unsigned)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(blob, F, Hp, Wp, Cp, w, scale, bias, y);
   DT_CHECK_LAUNCH();
   return 0;
 }

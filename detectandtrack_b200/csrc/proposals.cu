@@ -102,22 +102,37 @@ __device__ __forceinline__ float load_act(const void* p, size_t i, int f32) {
 }
 
 // ------------------------------------------------------------------- RPN top-k + decode
-// One CTA per image.  logits [B, H*W, ld_s] (first A channels), deltas [B, H*W, ld_d] (first 4*A*T).
+// One CTA per (image, level): all FPN levels of a clip batch run in ONE launch.
+// logits [B, H*W, ld_s] (first A channels), deltas [B, H*W, ld_d] (first 4*A*T).
 // Flat anchor index i = (h*W + w)*A + a  (generate_proposals.py:58-70 ordering).
+struct RpnLevel {
+  const void* logits; const void* deltas; const double* anchors;
+  int ld_s, ld_d, H, W;
+  double feat_stride;
+  float* out; int* counts;            // out rows [4T+1] per image at out + b*out_bstride; counts[b*counts_stride]
+  uint32_t* keys;                     // scratch [B, H*W*A] sortable score keys
+};
+struct RpnLevels { RpnLevel lv[8]; };
+
 __global__ void __launch_bounds__(1024, 1)
-rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __restrict__ deltas, int ld_d,
-                     int act_f32, int H, int W, int A, int T, const double* __restrict__ anchors /*[A,4T]*/,
-                     double feat_stride, const float* __restrict__ im_info /*[B,3]*/, int pre_topn,
-                     float min_size, float clipv_f, double clipv_d,
-                     float* __restrict__ out /*[B, out_bstride] rows of 4T+1*/, long long out_bstride,
-                     int* __restrict__ counts, int counts_stride, int kcap /*pow2 >= K*/, int time_major) {
+rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* __restrict__ im_info /*[B,3]*/,
+                     int pre_topn, float min_size, float clipv_f, double clipv_d, long long out_bstride,
+                     int counts_stride, int kcap /*pow2 >= K*/, int time_major) {
   extern __shared__ unsigned long long skeys[];          // [kcap] selected (key<<32 | ~idx)
   __shared__ int hist[4096];
   __shared__ int s_warp[32];
-  __shared__ int s_run, s_bin, s_need;
+  __shared__ int s_run, s_bin, s_need, s_cnt;
+  __shared__ uint32_t s_lo, s_hi;
+  const RpnLevel& lv = L.lv[blockIdx.y];
+  const void* __restrict__ logits = lv.logits;
+  const void* __restrict__ deltas = lv.deltas;
+  const double* __restrict__ anchors = lv.anchors;
+  const int ld_s = lv.ld_s, ld_d = lv.ld_d, H = lv.H, W = lv.W;
+  const double feat_stride = lv.feat_stride;
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = H * W * A;
   const int K = (pre_topn <= 0 || pre_topn > n) ? n : pre_topn;
+  uint32_t* __restrict__ keys = lv.keys + (size_t)b * n;
   // time_major (3-D RPN head, model_builder.py:509-563): logits / deltas are [B, T, H*W, ld] with A / 4A
   // channels per frame; the tube score is the mean over frames of the per-frame logits (TimePool 'avg',
   // sequential fp32 sum then / T) and delta (a, t, k) lives at frame t, channel a*4 + k.
@@ -130,63 +145,97 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
     for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, load_act(logits, sbase + ((size_t)t * HW + pos) * ld_s + a, act_f32));
     return sigmoidf_ref(__fdiv_rn(acc, (float)T));
   };
-  // ---- exact K-th largest key by 12/12/8-bit radix select --------------------------------
-  uint32_t prefix = 0, mask = 0;
+  // ---- pass 0: scores -> sortable keys (stored once), global min / max --------------------------
+  if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; }
+  __syncthreads();
+  uint32_t tlo = 0xffffffffu, thi = 0u;
+  for (int i = tid; i < n; i += nth) {
+    const uint32_t key = sort_key_f32(score_at(i));
+    keys[i] = key;
+    tlo = min(tlo, key); thi = max(thi, key);
+  }
+  for (int o = 16; o > 0; o >>= 1) { tlo = min(tlo, __shfl_xor_sync(0xffffffffu, tlo, o)); thi = max(thi, __shfl_xor_sync(0xffffffffu, thi, o)); }
+  if ((tid & 31) == 0) { atomicMin(&s_lo, tlo); atomicMax(&s_hi, thi); }
+  __syncthreads();
+  // ---- exact K-th largest key: iterative range refinement with 4096 adaptive-width bins ----------
+  // invariant: `need` of the elements with key in [lo, hi] belong to the top K (all keys > hi already do)
+  uint32_t lo = s_lo, hi = s_hi;
   int need = K;
-  const int shifts[3] = {20, 8, 0};
-  const int bits[3] = {12, 12, 8};
-  for (int pass = 0; pass < 3; ++pass) {
-    const int nb = 1 << bits[pass];
-    for (int x = tid; x < nb; x += nth) hist[x] = 0;
+  while (lo < hi) {
+    const unsigned long long range = (unsigned long long)hi - lo + 1ull;
+    int shift = 0;
+    while ((range >> shift) > 4096ull) ++shift;
+    for (int x = tid; x < 4096; x += nth) hist[x] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += nth) {
-      const uint32_t key = sort_key_f32(score_at(i));
-      if ((key & mask) == prefix) {
-        // warp-aggregated histogram update: RPN scores cluster, so most lanes hit the same bin
-        const int bin = (key >> shifts[pass]) & (nb - 1);
+      const uint32_t key = keys[i];
+      if (key >= lo && key <= hi) {
+        // warp-aggregated histogram update: RPN scores cluster, so many lanes hit the same bin
+        const int bin = (int)((key - lo) >> shift);
         const unsigned peers = __match_any_sync(__activemask(), bin);
         if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&hist[bin], __popc(peers));
       }
     }
     __syncthreads();
     if (tid == 0) {
-      int cum = 0, bin = nb - 1;
+      int cum = 0, bin = 4095;
       for (; bin >= 0; --bin) { if (cum + hist[bin] >= need) break; cum += hist[bin]; }
       s_bin = bin; s_need = need - cum;
     }
     __syncthreads();
-    prefix |= (uint32_t)s_bin << shifts[pass];
-    mask |= (uint32_t)(nb - 1) << shifts[pass];
+    const uint32_t nlo = lo + ((uint32_t)s_bin << shift);
+    const unsigned long long nhi64 = (unsigned long long)nlo + ((1ull << shift) - 1ull);
+    hi = (nhi64 > hi) ? hi : (uint32_t)nhi64;
+    lo = nlo;
     need = s_need;
     __syncthreads();
   }
-  const uint32_t kth = prefix;          // keys > kth are all selected; `need` keys == kth, lowest index first
-  // ---- gather the K selected (ordered compaction keeps index order among equals) ------------
-  if (tid == 0) s_run = 0;
+  const uint32_t kth = lo;              // keys > kth are all selected; `need` keys == kth, lowest index first
+  // ---- gather the K selected.  Order is fixed by the sort below, so keys > kth are appended unordered;
+  // keys == kth must be the `need` LOWEST indices: unordered too when every equal key is taken (the usual
+  // case: a unique K-th score), otherwise an ordered compaction.
+  if (tid == 0) { s_run = 0; s_cnt = 0; }
   for (int x = tid; x < kcap; x += nth) skeys[x] = 0ull;
   __syncthreads();
-  int eq_taken_base = 0;                 // number of == kth elements seen so far (uniform)
-  for (int start = 0; start < n; start += nth) {
-    const int i = start + tid;
-    uint32_t key = 0; bool gt = false, eq = false;
-    if (i < n) { key = sort_key_f32(score_at(i)); gt = key > kth; eq = key == kth; }
-    // rank among equals (ordered)
-    const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
-    const unsigned bal = __ballot_sync(0xffffffffu, eq);
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
-    int eoff = eq_taken_base;
-    for (int x = 0; x < wid; ++x) eoff += s_warp[x];
-    eoff += __popc(bal & ((1u << lane) - 1));
-    int etot = 0;
-    for (int x = 0; x < nwarp; ++x) etot += s_warp[x];
-    __syncthreads();
-    const bool take = gt || (eq && eoff < need);
-    eq_taken_base += etot;
-    const int slot = block_rank(take, s_warp, &s_run);
-    if (take) skeys[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+  int my_eq = 0;
+  for (int i = tid; i < n; i += nth) {
+    const uint32_t key = keys[i];
+    if (key > kth) {
+      const int slot = atomicAdd(&s_run, 1);
+      skeys[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    } else if (key == kth) ++my_eq;
   }
+  if (my_eq) atomicAdd(&s_cnt, my_eq);
   __syncthreads();
+  const int total_eq = s_cnt;
+  if (total_eq == need) {
+    for (int i = tid; i < n; i += nth)
+      if (keys[i] == kth) {
+        const int slot = atomicAdd(&s_run, 1);
+        skeys[slot] = ((unsigned long long)kth << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+      }
+    __syncthreads();
+  } else {
+    int eq_base = 0;                     // == kth elements seen so far (uniform)
+    for (int start = 0; start < n && eq_base < need; start += nth) {
+      const int i = start + tid;
+      const bool eq = (i < n) && keys[i] == kth;
+      const int lane = tid & 31, wid = tid >> 5, nwarp = nth >> 5;
+      const unsigned bal = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s_warp[wid] = __popc(bal);
+      __syncthreads();
+      int eoff = eq_base, etot = 0;
+      for (int x = 0; x < nwarp; ++x) { if (x < wid) eoff += s_warp[x]; etot += s_warp[x]; }
+      eoff += __popc(bal & ((1u << lane) - 1));
+      if (eq && eoff < need) {
+        const int slot = atomicAdd(&s_run, 1);
+        skeys[slot] = ((unsigned long long)kth << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+      }
+      eq_base += etot;
+      __syncthreads();
+    }
+    __syncthreads();
+  }
   bitonic_desc(skeys, kcap);             // descending score, ascending index on ties
   // ---- decode / clip / filter the K candidates in order --------------------------------------
   const float imh = im_info[3 * b], imw = im_info[3 * b + 1], imscale = im_info[3 * b + 2];
@@ -194,6 +243,7 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
   const float msz = __fmul_rn(min_size, imscale);
   const size_t dbase = (size_t)b * HW * ld_d * (time_major ? T : 1);
   const int ldo = 4 * T + 1;
+  float* __restrict__ out = lv.out;
   if (tid == 0) s_run = 0;
   __syncthreads();
   for (int start = 0; start < K; start += nth) {
@@ -240,7 +290,7 @@ rpn_proposals_kernel(const void* __restrict__ logits, int ld_s, const void* __re
       o[4 * T] = sc;
     }
   }
-  if (tid == 0) counts[(size_t)b * counts_stride] = s_run;
+  if (tid == 0) lv.counts[(size_t)b * counts_stride] = s_run;
 }
 
 // ------------------------------------------------------------------- collect across levels
@@ -458,31 +508,55 @@ static int next_pow2i(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 using namespace dt;
 
-extern "C" int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas, int ld_d, int act_f32, int B, int H,
-                                int W, int A, int T, const double* anchors, double feat_stride, const float* im_info,
-                                int pre_nms_topn, float min_size, double bbox_xform_clip, float* out,
-                                long long out_batch_stride, int* counts, int counts_stride, int time_major,
-                                void* stream) {
-  DT_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && A >= 1 && T >= 1 && T <= DT_MAX_T, "dt_rpn_proposals: bad shape B=%d H=%d W=%d A=%d T=%d", B, H, W, A, T);
-  DT_CHECK_ARG(ld_s >= A && ld_d >= 4 * A * (time_major ? 1 : T), "dt_rpn_proposals: leading dims too small (ld_s=%d, ld_d=%d)", ld_s, ld_d);
+extern "C" int dt_rpn_workspace_bytes(int B, int nlevels, const int* Hs, const int* Ws, int A, size_t* bytes) {
+  DT_CHECK_ARG(B >= 0 && nlevels >= 1 && nlevels <= 8 && Hs && Ws && A >= 1 && bytes, "dt_rpn_workspace_bytes: bad args");
+  size_t b = 0;
+  for (int l = 0; l < nlevels; ++l) b += align_up((size_t)B * Hs[l] * Ws[l] * A * sizeof(uint32_t), 256);
+  *bytes = b;
+  return 0;
+}
+
+extern "C" int dt_rpn_proposals_multi(const dt_rpn_level* levels, int nlevels, int act_f32, int B, int A, int T,
+                                      const float* im_info, int pre_nms_topn, float min_size, double bbox_xform_clip,
+                                      long long out_batch_stride, int counts_stride, int time_major, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  DT_CHECK_ARG(levels && nlevels >= 1 && nlevels <= 8, "dt_rpn_proposals_multi: 1..8 levels");
+  DT_CHECK_ARG(B >= 0 && A >= 1 && T >= 1 && T <= DT_MAX_T, "dt_rpn_proposals_multi: bad shape B=%d A=%d T=%d", B, A, T);
   if (B == 0) return 0;
-  DT_CHECK_ARG(logits && deltas && anchors && im_info && out && counts, "dt_rpn_proposals: null pointer");
-  const long long n = (long long)H * W * A;
-  DT_CHECK_ARG(n < (1ll << 31), "dt_rpn_proposals: too many anchors");
-  const int K = (pre_nms_topn <= 0 || pre_nms_topn > n) ? (int)n : pre_nms_topn;
-  const int kcap = next_pow2i(K);
-  DT_CHECK_ARG(kcap <= 16384, "dt_rpn_proposals: pre-NMS top-N %d exceeds 16384", K);
-  DT_CHECK_ARG(out_batch_stride >= (long long)K * (4 * T + 1), "dt_rpn_proposals: out_batch_stride too small");
-  static size_t attr = 0;
-  const size_t smem = (size_t)kcap * sizeof(unsigned long long);
-  if (smem > attr) {
-    DT_CHECK_CUDA(cudaFuncSetAttribute(rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    attr = 16384 * 8;
+  DT_CHECK_ARG(im_info && workspace, "dt_rpn_proposals_multi: null pointer");
+  RpnLevels L;
+  memset(&L, 0, sizeof(L));
+  int kmax = 1;
+  char* ws = (char*)workspace;
+  size_t used = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    const dt_rpn_level& v = levels[l];
+    DT_CHECK_ARG(v.H >= 1 && v.W >= 1 && v.ld_s >= A && v.ld_d >= 4 * A * (time_major ? 1 : T),
+                 "dt_rpn_proposals_multi: level %d bad shape / leading dims", l);
+    DT_CHECK_ARG(v.logits && v.deltas && v.anchors && v.out && v.counts, "dt_rpn_proposals_multi: level %d null pointer", l);
+    const long long n = (long long)v.H * v.W * A;
+    DT_CHECK_ARG(n < (1ll << 31), "dt_rpn_proposals_multi: too many anchors");
+    const int K = (pre_nms_topn <= 0 || pre_nms_topn > n) ? (int)n : pre_nms_topn;
+    DT_CHECK_ARG(out_batch_stride >= (long long)K * (4 * T + 1) || B == 1, "dt_rpn_proposals_multi: out_batch_stride too small");
+    if (K > kmax) kmax = K;
+    RpnLevel& d = L.lv[l];
+    d.logits = v.logits; d.deltas = v.deltas; d.anchors = v.anchors; d.ld_s = v.ld_s; d.ld_d = v.ld_d; d.H = v.H; d.W = v.W;
+    d.feat_stride = v.feat_stride; d.out = v.out; d.counts = v.counts;
+    d.keys = (uint32_t*)(ws + used);
+    used += align_up((size_t)B * n * sizeof(uint32_t), 256);
   }
-  rpn_proposals_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(logits, ld_s, deltas, ld_d, act_f32, H, W, A, T, anchors,
-                                                               feat_stride, im_info, pre_nms_topn, min_size,
-                                                               (float)bbox_xform_clip, bbox_xform_clip, out,
-                                                               out_batch_stride, counts, counts_stride, kcap, time_major);
+  DT_CHECK_ARG(used <= workspace_bytes, "dt_rpn_proposals_multi: workspace %zu < %zu bytes", workspace_bytes, used);
+  const int kcap = next_pow2i(kmax);
+  DT_CHECK_ARG(kcap <= 16384, "dt_rpn_proposals_multi: pre-NMS top-N %d exceeds 16384", kmax);
+  static bool attr = false;
+  if (!attr) {
+    DT_CHECK_CUDA(cudaFuncSetAttribute(rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    attr = true;
+  }
+  dim3 grid(B, nlevels);
+  rpn_proposals_kernel<<<grid, 1024, (size_t)kcap * sizeof(unsigned long long), (cudaStream_t)stream>>>(
+      L, act_f32, A, T, im_info, pre_nms_topn, min_size, (float)bbox_xform_clip, bbox_xform_clip, out_batch_stride,
+      counts_stride, kcap, time_major);
   DT_CHECK_LAUNCH();
   return 0;
 }

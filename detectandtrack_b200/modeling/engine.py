@@ -64,7 +64,10 @@ class DetectionEngine(object):
             raise NotImplementedError('engine: single-level bodies are wired for 3-D heads (BODY_HEAD_LINK \'\') only')
         if s.link not in ('slice-center', 'none2d', ''):
             raise NotImplementedError('engine: BODY_HEAD_LINK %r' % s.link)
-        self.dtype = cv.BF16 if dtype == 'bf16' else cv.TF32
+        # 'bf16': fast path; 'tf32': fp32 storage, tf32 MMAs (1e-3 per layer); 'tf32x3': fp32-accurate
+        # parity mode (activations / weights as [hi | lo] tf32 pairs, 3 MMAs per k-block)
+        self.dtype = {'bf16': cv.BF16, 'tf32': cv.TF32, 'tf32x3': cv.TF32X3}[dtype]
+        self.x3 = self.dtype == cv.TF32X3
         self.act_dtype = torch.bfloat16 if dtype == 'bf16' else torch.float32
         self.cin_pad = 8 if dtype == 'bf16' else 4
         self.skip_dead_frames = False       # compute only the consumed (centre) frame of the post-hoc FPN convs
@@ -102,7 +105,8 @@ class DetectionEngine(object):
     def _build(self, blobs):
         s, cfg, torch = self.spec, self.cfg, self.torch
         # conv1: 7x7/2 on the 3-channel blob with the filter row packed into K (dt_conv1_7x7s2)
-        self.conv1_w = cv.pack_conv1_weight(torch.from_numpy(np.ascontiguousarray(blobs['conv1_w'])), self.dtype)
+        w1 = torch.from_numpy(np.ascontiguousarray(blobs['conv1_w']))
+        self.conv1_w = cv.pack_conv1_weight_f32(w1) if self.x3 else cv.pack_conv1_weight(w1, self.dtype)
         self.conv1_s = torch.from_numpy(np.ascontiguousarray(blobs['res_conv1_bn_s'], dtype=np.float32)).cuda()
         self.conv1_b = torch.from_numpy(np.ascontiguousarray(blobs['res_conv1_bn_b'], dtype=np.float32)).cuda()
         self.stages = []
@@ -213,10 +217,13 @@ class DetectionEngine(object):
         """x [B,T,Hp+6,Wp+8,cin_pad] (zero-bordered blob) -> stage outputs (finest first)."""
         torch = self.torch
         B, T = x.shape[:2]
-        hp, wp = x.shape[2] - 6, x.shape[3] - 8
-        y = cv.conv1_7x7s2(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, (hp, wp), self.conv1_s, self.conv1_b,
-                           relu=True, dtype=self.dtype)
-        y = dense_ops.maxpool2d(y, 3, 2, 1)
+        if self.x3:      # exact fp32 conv1 on the raw (un-bordered) blob
+            y = cv.conv1_7x7s2_f32(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, self.conv1_s, self.conv1_b)
+        else:
+            hp, wp = x.shape[2] - 6, x.shape[3] - 8
+            y = cv.conv1_7x7s2(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, (hp, wp), self.conv1_s, self.conv1_b,
+                               relu=True, dtype=self.dtype)
+        y = dense_ops.maxpool2d(y, 3, 2, 1, x3=self.x3)
         y = y.view((B, T) + tuple(y.shape[1:]))
         outs = []
         for blocks in self.stages:
@@ -246,7 +253,7 @@ class DetectionEngine(object):
             outs.append(y)
         p5 = outs[0]
         B, T = p5.shape[:2]
-        p6 = dense_ops.maxpool2d(p5.view((B * T,) + tuple(p5.shape[2:])), 1, 2, 0)
+        p6 = dense_ops.maxpool2d(p5.view((B * T,) + tuple(p5.shape[2:])), 1, 2, 0, x3=self.x3)
         outs.insert(0, p6.view((B, T) + tuple(p6.shape[1:])))
         return outs[::-1]
 
@@ -275,19 +282,21 @@ class DetectionEngine(object):
         A = s.num_anchors
         props = torch.zeros((B, Lv, K, 5), dtype=torch.float32, device='cuda')
         counts = torch.zeros((B, Lv), dtype=torch.int32, device='cuda')
+        levels = []
         for l, f in enumerate(feats2d):
             h = self.rpn_conv(f)
             Bq, _, H, W, _ = h.shape
             o = torch.empty((Bq, 1, H, W, self.rpn_out_ld), dtype=torch.float32, device='cuda')
             self.rpn_out(h, out_f32=True, out=o)
             o4 = o.view(Bq, H, W, self.rpn_out_ld)
-            rpn_ops.rpn_proposals(o4[..., :A], o4[..., A:5 * A], self.anchors[l], 2. ** s.rpn_levels[l], im_info, K,
-                                  float(cfg.TEST.RPN_MIN_SIZE), 1, out=props[:, l], counts=counts[:, l])
+            levels.append(dict(logits=o4[..., :A], deltas=o4[..., A:5 * A], anchors=self.anchors[l],
+                               feat_stride=2. ** s.rpn_levels[l], out=props[:, l], counts=counts[:, l]))
+        rpn_ops.rpn_proposals_levels(levels, im_info, K, A, float(cfg.TEST.RPN_MIN_SIZE), 1)      # all levels, one launch
         keep, nkeep = box_ops.nms_batched(props.view(B * Lv, K, 5), counts.view(-1), cfg.TEST.RPN_NMS_THRESH,
                                           box_ops.NMS_2D_GE, box_ops.ORDER_INDEX, max_keep=cfg.TEST.RPN_POST_NMS_TOP_N)
         return rpn_ops.collect(props, keep, nkeep, cfg.TEST.RPN_POST_NMS_TOP_N)
 
-    def _roi_feats(self, feats2d, rois_flat, resolution, sampling):
+    def _roi_feats(self, feats2d, rois_flat, resolution, sampling, planar=False):
         s = self.spec
         nl = len(s.roi_levels)
         fl = [f.view((f.shape[0] * f.shape[1],) + tuple(f.shape[2:])) for f in feats2d[:nl]]
@@ -296,14 +305,14 @@ class DetectionEngine(object):
                                           s0=float(self.cfg.FPN.ROI_CANONICAL_SCALE), lvl0=float(self.cfg.FPN.ROI_CANONICAL_LEVEL),
                                           want_restore=False)
         return dense_ops.roi_align(fl, scales, rois_flat, levels, resolution, sampling, T=1, k_min=s.roi_levels[0],
-                                   round_tf32=(self.dtype == cv.TF32))
+                                   round_tf32=(self.dtype == cv.TF32), x3_mode=(2 if planar else 1) if self.x3 else 0)
 
     def box_head(self, feats2d, rois, roi_counts, im_info, im_hw):
         torch, cfg, s = self.torch, self.cfg, self.spec
         B, R, _ = rois.shape
         C = s.num_classes
         x = self._roi_feats(feats2d, rois.view(B * R, 5), cfg.FAST_RCNN.ROI_XFORM_RESOLUTION,
-                            cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO)
+                            cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO, planar=True)      # x3: [hi block | lo block] rows for the FC
         x = x.view(1, 1, 1, B * R, -1)
         x = self.fc7(self.fc6(x))
         o = torch.empty((1, 1, 1, B * R, self.cls_bbox_ld), dtype=torch.float32, device='cuda')
@@ -345,7 +354,7 @@ class DetectionEngine(object):
         B, T = feat5d.shape[:2]
         f = feat5d.view((B * T,) + tuple(feat5d.shape[2:]))
         return dense_ops.roi_align([f], [1.0 / self.feat_stride], rois, None, resolution, sampling, T=T,
-                                   round_tf32=(self.dtype == cv.TF32))
+                                   round_tf32=(self.dtype == cv.TF32), x3_mode=1 if self.x3 else 0)
 
     def rpn_tube(self, feat5d, im_info):
         """Single-level 3-D RPN -> rois [B, R, 4T+1], roi_counts [B]."""
@@ -376,7 +385,7 @@ class DetectionEngine(object):
         for blk in self.res5:
             x = self._run_block(blk, x)
         n, _, hh, ww, ch = x.shape
-        x = dense_ops.spatial_mean(x.view(n * T, hh, ww, ch), round_tf32=(self.dtype == cv.TF32))    # [BR*T, C]
+        x = dense_ops.spatial_mean(x.view(n * T, hh, ww, ch), round_tf32=(self.dtype == cv.TF32), x3=self.x3)    # [BR*T, C]
         o = torch.empty((1, 1, 1, n * T, self.cls_bbox_ld), dtype=torch.float32, device='cuda')
         self.cls_bbox(x.view(1, 1, 1, n * T, ch), out_f32=True, out=o)
         cls, bbox = dense_ops.fold_tube_heads(o.view(n * T, self.cls_bbox_ld), n, T, C)
@@ -404,14 +413,28 @@ class DetectionEngine(object):
         hp, wp = int(np.ceil(hr / stride) * stride), int(np.ceil(wr / stride) * stride)
         return scale, (hr, wr), (hp, wp)
 
+    def plain(self, t):
+        """Activation tensor as plain values (joins the [hi | lo] pairs of the 3xTF32 mode)."""
+        return cv.join_tf32(t) if self.x3 else t
+
+    def _blob(self, frames_u8, scale, hr, wr, hp, wp):
+        """uint8 frames -> network input: zero-bordered bf16 / tf32 blob for the packed-row conv1, or the raw
+        fp32 blob for the exact conv1 of the 3xTF32 mode."""
+        B, T, H, W, _ = frames_u8.shape
+        if self.x3:
+            x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
+                                    cpad=4, out_f32=2)
+            return x.view(B, T, hp, wp, 4)
+        x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
+                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
+        return x.view(B, T, hp + 6, wp + 8, self.cin_pad)
+
     def forward_features(self, frames_u8):
         """frames [B, T, H, W, 3] uint8 cuda -> (feats2d finest first, im_info [B,3], scale)."""
         torch = self.torch
         B, T, H, W, _ = frames_u8.shape
         scale, (hr, wr), (hp, wp) = self.blob_geometry(H, W)
-        x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
-                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
-        x = x.view(B, T, hp + 6, wp + 8, self.cin_pad)
+        x = self._blob(frames_u8, scale, hr, wr, hp, wp)
         feats = self.link(self.fpn(self.body(x))) if self.spec.fpn else [self.body(x)[-1]]
         im_info = torch.tensor([[hp, wp, scale]] * B, dtype=torch.float32, device='cuda')
         return feats, im_info, scale
@@ -444,9 +467,7 @@ class DetectionEngine(object):
         torch, s = self.torch, self.spec
         B, T, H, W, _ = frames_u8.shape
         g = self._geom_tensors(B, H, W)
-        x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, g['scale'], (g['hr'], g['wr']),
-                                (g['hp'], g['wp']), cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
-        x = x.view(B, T, g['hp'] + 6, g['wp'] + 8, self.cin_pad)
+        x = self._blob(frames_u8, g['scale'], g['hr'], g['wr'], g['hp'], g['wp'])
         if s.fpn:
             feats = self.link(self.fpn(self.body(x)))
             rois, _, roi_counts = self.rpn(feats, g['im_info'])

@@ -30,12 +30,12 @@ def bbox_overlaps(boxes, query, T=None):
 _ws_cache = {}
 
 
-def _workspace(nbytes, torch):
-    dev = torch.cuda.current_device()
-    ws = _ws_cache.get(dev)
+def _workspace(nbytes, torch, slot='nms'):
+    key = (torch.cuda.current_device(), slot)
+    ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device='cuda')
-        _ws_cache[dev] = ws
+        _ws_cache[key] = ws
     return ws
 
 

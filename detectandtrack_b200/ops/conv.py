@@ -6,10 +6,11 @@ import ctypes as C
 from .. import _lib as L
 
 BF16, TF32 = 0, 1
+TF32X3 = 2      # host-level mode: DT_DTYPE_TF32 kernels on [hi | lo] tf32 pairs (3 MMAs per k-block, ~fp32 accuracy)
 
 
 def _dt(dtype, torch):
-    return torch.float32 if dtype == TF32 else torch.bfloat16
+    return torch.bfloat16 if dtype == BF16 else torch.float32
 
 
 def pack_weight(w, dtype=BF16):
@@ -22,13 +23,29 @@ def pack_weight(w, dtype=BF16):
     elif w.dim() == 4:
         w = w[:, :, None, :, :]
     Cout, Cin, kT, kH, kW = w.shape
-    mult = 4 if dtype == TF32 else 8
+    mult = 8 if dtype == BF16 else 4
     Cp = (Cin + mult - 1) // mult * mult
     out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=_dt(dtype, torch), device='cuda')
     out[:, :, :Cin] = w.to('cuda').permute(2, 3, 4, 0, 1).reshape(kT * kH * kW, Cout, Cin).to(out.dtype)
     if dtype == TF32:
         out = round_tf32(out)
+    elif dtype == TF32X3:
+        out = split_tf32(out)                         # [taps, Cout, 2*Cp] = [hi | lo]
     return out
+
+
+def split_tf32(t):
+    """fp32 [..., C] -> [..., 2C] = [hi | lo] with hi = tf32(t), lo = tf32(t - hi) (3xTF32 storage)."""
+    torch = L.require_cuda()
+    hi = round_tf32(t)
+    lo = round_tf32(t - hi)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def join_tf32(t):
+    """Inverse of split_tf32 (exact: hi + lo fits fp32)."""
+    c = t.shape[-1] // 2
+    return t[..., :c] + t[..., c:]
 
 
 def round_tf32(t):
@@ -42,7 +59,8 @@ def round_tf32(t):
 
 
 def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias=None,
-           residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None, round_tf32=None):
+           residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None, round_tf32=None,
+           split_out=None):
     """x [N,T,H,W,Cx] (first `cin` channels are the conv input); returns y [N,To,Ho,Wo,Cout]."""
     torch = L.require_cuda()
     assert x.is_cuda and x.dim() == 5 and x.is_contiguous()
@@ -51,6 +69,16 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     taps, Cout, w_ld = w_packed.shape
     kT, kH, kW = ksize
     assert taps == kT * kH * kW
+    x3 = dtype == TF32X3
+    if x3:
+        cin = cin if cin is not None else min(Cx // 2, w_ld // 2)
+        if split_out is None:
+            split_out = out is None                  # intermediate activations stay split; given buffers are final
+        if out_f32 is None:
+            out_f32 = True
+        assert out_f32, '3xTF32 outputs are fp32'
+    else:
+        split_out = False
     cin = cin if cin is not None else min(Cx, w_ld)
     sT, sH, sW = stride
     pT, pH, pW = pad
@@ -61,14 +89,18 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
         out_f32 = dtype == TF32
     if round_tf32 is None:
         round_tf32 = bool(out_f32) and dtype == TF32 and out is None      # intermediate activations
+    if x3:
+        round_tf32 = False
     odt = torch.float32 if out_f32 else torch.bfloat16
     if out is None:
-        out = torch.empty((N, To, Ho, Wo, Cout), dtype=odt, device='cuda')
+        out = torch.empty((N, To, Ho, Wo, 2 * Cout if split_out else Cout), dtype=odt, device='cuda')
     assert out.dtype == odt and out.is_contiguous()
     d = L.ConvDesc(N=N, Ti=Ti, Hi=Hi, Wi=Wi, Cin=cin, Cout=Cout, kT=kT, kH=kH, kW=kW, sT=sT, sH=sH, sW=sW,
                    pT=pT, pH=pH, pW=pW, in_ld=Cx, w_ld=w_ld, out_ld=out.shape[-1],
-                   res_ld=(residual.shape[-1] if residual is not None else 0), dtype=dtype,
-                   out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode), out_round_tf32=int(bool(round_tf32)))
+                   res_ld=(residual.shape[-1] if residual is not None else 0), dtype=(TF32 if x3 else dtype),
+                   out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode),
+                   x3=(1 if x3 else 0) | (2 if split_out else 0), in_lo_off=0, out_lo_off=0, res_lo_off=0,
+                   out_round_tf32=int(bool(round_tf32)))
     if residual is not None:
         assert residual.dtype == odt and residual.is_contiguous()
     if scale is not None:
@@ -108,3 +140,22 @@ def conv1_7x7s2(x_padded, w_packed, hw, scale=None, bias=None, relu=True, dtype=
     L.call('dt_conv1_7x7s2', L.ptr(x_padded), F, Hp, Wp, Cp, L.ptr(w_packed), Cout, L.ptr(scale), L.ptr(bias), int(relu),
            dtype, int(out_f32), int(bool(out_f32) and dtype == TF32), L.ptr(y), Cout, L.stream_ptr())
     return y
+
+
+def conv1_7x7s2_f32(blob, w, scale, bias):
+    """3xTF32 mode conv1: exact fp32 (dt_conv1_7x7s2_f32).  blob [F, Hp, Wp, Cp] raw fp32;
+    w (64, 3, [1,] 7, 7) -> [F, Hp/2, Wp/2, 128] as [hi | lo]."""
+    torch = L.require_cuda()
+    F, Hp, Wp, Cp = blob.shape
+    y = torch.empty((F, Hp // 2, Wp // 2, 128), dtype=torch.float32, device='cuda')
+    L.call('dt_conv1_7x7s2_f32', L.ptr(blob), F, Hp, Wp, Cp, L.ptr(w), L.ptr(scale), L.ptr(bias), L.ptr(y), L.stream_ptr())
+    return y
+
+
+def pack_conv1_weight_f32(w):
+    """(64, 3, [1,] 7, 7) -> [7][7][3][64] fp32 for dt_conv1_7x7s2_f32."""
+    torch = L.require_cuda()
+    if w.dim() == 5:
+        w = w[:, :, 0]
+    assert tuple(w.shape) == (64, 3, 7, 7)
+    return w.to('cuda').float().permute(2, 3, 1, 0).contiguous()

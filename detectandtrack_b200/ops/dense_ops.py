@@ -12,6 +12,7 @@ def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=
     Hr, Wr = out_hw
     Hp, Wp = pad_hw
     by, bx = border
+    # out_f32: False/0 bf16, True/1 fp32 rounded to tf32, 2 raw fp32
     out = torch.empty((F, Hp + 2 * by, Wp + 2 * bx, cpad), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
     m = (C.c_float * 3)(*[float(v) for v in pixel_means])
     L.call('dt_prep_clip', L.ptr(frames_u8.contiguous()), F, H, W, m, float(im_scale), Hr, Wr, Hp, Wp, cpad, by, bx,
@@ -19,26 +20,30 @@ def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=
     return out
 
 
-def maxpool2d(x, k, s, p):
-    """x [N,H,W,C] -> [N,Ho,Wo,C] (floor mode)."""
+def maxpool2d(x, k, s, p, x3=False):
+    """x [N,H,W,C] -> [N,Ho,Wo,C] (floor mode).  x3: rows are [hi | lo] tf32 pairs (C = row / 2)."""
     torch = L.require_cuda()
-    N, H, W, Cc = x.shape
+    N, H, W, ld = x.shape
+    Cc = ld // 2 if x3 else ld
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
-    y = torch.empty((N, Ho, Wo, Cc), dtype=x.dtype, device='cuda')
-    L.call('dt_maxpool2d', L.ptr(x), N, H, W, Cc, Cc, k, s, p, int(x.dtype == torch.float32), L.ptr(y), Cc, L.stream_ptr())
+    y = torch.empty((N, Ho, Wo, ld), dtype=x.dtype, device='cuda')
+    L.call('dt_maxpool2d', L.ptr(x), N, H, W, Cc, ld, k, s, p, int(x.dtype == torch.float32), int(bool(x3)), L.ptr(y), ld,
+           L.stream_ptr())
     return y
 
 
 def roi_align(feats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_dev=None, channels=None,
-              round_tf32=False):
+              round_tf32=False, x3_mode=0):
     """feats: list of [Nimg*T, H_l, W_l, C] (finest first, level k_min + i); rois [R, 4T+1] fp32
     (col 0 = image index); levels [R] int32 or None for a single level -> [R, T, P, P, C]."""
     torch = L.require_cuda()
     nl = len(feats)
     ldf = feats[0].shape[-1]
-    Cc = channels or ldf
+    Cc = channels or (ldf // 2 if x3_mode else ldf)
     R = rois.shape[0]
-    out = torch.empty((R, T, P, P, Cc), dtype=feats[0].dtype, device='cuda')
+    # x3_mode 1: [R,T,P,P,2C] per-position [hi | lo]; 2: [R, 2*T*P*P*C] planar hi block | lo block
+    oshape = (R, T, P, P, 2 * Cc) if x3_mode == 1 else ((R, 2 * T * P * P * Cc) if x3_mode == 2 else (R, T, P, P, Cc))
+    out = torch.empty(oshape, dtype=feats[0].dtype, device='cuda')
     fp = (C.c_void_p * nl)(*[f.data_ptr() for f in feats])
     Hs = (C.c_int * nl)(*[f.shape[1] for f in feats])
     Ws = (C.c_int * nl)(*[f.shape[2] for f in feats])
@@ -47,8 +52,8 @@ def roi_align(feats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_de
         assert f.is_contiguous() and f.dtype == feats[0].dtype and f.shape[-1] == ldf
     rois = rois.contiguous()
     L.call('dt_roi_align', fp, Hs, Ws, sc, nl, k_min, Cc, ldf, int(feats[0].dtype == torch.float32), L.ptr(rois),
-           rois.shape[1], L.ptr(n_dev), R, T, L.ptr(levels), P, sampling_ratio, int(bool(round_tf32)), L.ptr(out),
-           L.stream_ptr())
+           rois.shape[1], L.ptr(n_dev), R, T, L.ptr(levels), P, sampling_ratio, int(bool(round_tf32)), int(x3_mode),
+           L.ptr(out), L.stream_ptr())
     return out
 
 
@@ -67,13 +72,14 @@ def keypoint_decode(lowres, boxes, K=17, T=1, n_dev=None, min_size=0, want_heatm
     return xy, heat
 
 
-def spatial_mean(x, round_tf32=False):
+def spatial_mean(x, round_tf32=False, x3=False):
     """x [N, H, W, C] -> [N, C]: mean over W, then over H (ReduceBackMean twice)."""
     torch = L.require_cuda()
-    N, H, W, Cc = x.shape
-    y = torch.empty((N, Cc), dtype=x.dtype, device='cuda')
-    L.call('dt_spatial_mean', L.ptr(x), N, H, W, Cc, Cc, int(x.dtype == torch.float32), int(bool(round_tf32)), L.ptr(y), Cc,
-           L.stream_ptr())
+    N, H, W, ld = x.shape
+    Cc = ld // 2 if x3 else ld
+    y = torch.empty((N, ld), dtype=x.dtype, device='cuda')
+    L.call('dt_spatial_mean', L.ptr(x), N, H, W, Cc, ld, int(x.dtype == torch.float32), int(bool(round_tf32)), int(bool(x3)),
+           L.ptr(y), ld, L.stream_ptr())
     return y
 
 

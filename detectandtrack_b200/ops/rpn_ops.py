@@ -19,34 +19,62 @@ def _nhwc_ld(t):
     return ld
 
 
+def rpn_proposals_levels(levels, im_info, pre_nms_topn, A, min_size=0.0, T=1, clip=BBOX_XFORM_CLIP, time_major=False):
+    """All levels of a clip batch in ONE launch.  levels: list of dicts(logits, deltas, anchors, feat_stride,
+    out [B, >=K, 4T+1] (may be a strided view), counts [B] (may be a strided view))."""
+    torch = L.require_cuda()
+    nl = len(levels)
+    arr = (L.RpnLevel * nl)()
+    Hs, Ws = (C.c_int * nl)(), (C.c_int * nl)()
+    B = None
+    out_bs = cnt_s = None
+    for i, lv in enumerate(levels):
+        lg, dl = lv['logits'], lv['deltas']
+        assert lg.dtype == dl.dtype
+        if time_major:
+            Bq, Tt, H, W, _ = lg.shape
+            assert Tt == T and dl.shape[:4] == lg.shape[:4]
+            ld_s, ld_d = lg.stride(3), dl.stride(3)
+            assert lg.stride(4) == 1 and dl.stride(4) == 1 and lg.stride(1) == H * W * ld_s
+        else:
+            Bq, H, W, _ = lg.shape
+            ld_s, ld_d = _nhwc_ld(lg), _nhwc_ld(dl)
+        B = Bq if B is None else B
+        assert Bq == B and lv['anchors'].shape[0] == A
+        o, c = lv['out'], lv['counts']
+        assert o.dtype == torch.float32 and o.shape[-1] == 4 * T + 1 and o.stride(-1) == 1 and o.stride(-2) == 4 * T + 1
+        if out_bs is None:
+            out_bs, cnt_s = o.stride(0), c.stride(0)
+        assert (o.stride(0) == out_bs and c.stride(0) == cnt_s) or B == 1
+        arr[i] = L.RpnLevel(lg.data_ptr(), dl.data_ptr(), lv['anchors'].data_ptr(), ld_s, ld_d, H, W,
+                            float(lv['feat_stride']), o.data_ptr(), c.data_ptr())
+        Hs[i], Ws[i] = H, W
+    act_f32 = int(levels[0]['logits'].dtype == torch.float32)
+    need = C.c_size_t(0)
+    L.call('dt_rpn_workspace_bytes', B, nl, Hs, Ws, A, C.byref(need))
+    ws = box_ops._workspace(need.value, torch, slot='rpn')
+    L.call('dt_rpn_proposals_multi', arr, nl, act_f32, B, A, T, L.ptr(im_info), int(pre_nms_topn), float(min_size), float(clip),
+           out_bs, cnt_s, int(bool(time_major)), L.ptr(ws), ws.numel(), L.stream_ptr())
+
+
 def rpn_proposals(logits, deltas, anchors, feat_stride, im_info, pre_nms_topn, min_size=0.0,
                   T=1, out=None, counts=None, clip=BBOX_XFORM_CLIP, time_major=False):
-    """logits [B,H,W,A], deltas [B,H,W,4AT] (fp32 or bf16; channel slices of a wider NHWC tensor
-    are fine), anchors [A,4T] fp64 cuda, im_info [B,3] fp32 cuda.
+    """One level.  logits [B,H,W,A], deltas [B,H,W,4AT] (fp32 or bf16; channel slices of a wider NHWC tensor
+    are fine; [B,T,H,W,.] when time_major), anchors [A,4T] fp64 cuda, im_info [B,3] fp32 cuda.
     Returns (props [B,K,4T+1] fp32, counts [B] int32)."""
     torch = L.require_cuda()
-    if time_major:          # [B, T, H, W, C'] channel slices of contiguous 5-D tensors
-        B, Tt, H, W, _ = logits.shape
-        assert Tt == T and deltas.shape[:4] == logits.shape[:4]
-        ld_s, ld_d = logits.stride(3), deltas.stride(3)
-        assert logits.stride(4) == 1 and deltas.stride(4) == 1 and logits.stride(1) == H * W * ld_s
-    else:
-        B, H, W, _ = logits.shape
-        ld_s, ld_d = _nhwc_ld(logits), _nhwc_ld(deltas)
+    B = logits.shape[0]
+    H, W = (logits.shape[2], logits.shape[3]) if time_major else (logits.shape[1], logits.shape[2])
     A = anchors.shape[0]
-    assert logits.dtype == deltas.dtype
-    act_f32 = int(logits.dtype == torch.float32)
     n = H * W * A
     K = n if (pre_nms_topn <= 0 or pre_nms_topn > n) else pre_nms_topn
     if out is None:
         out = torch.zeros((B, K, 4 * T + 1), dtype=torch.float32, device='cuda')
     if counts is None:
         counts = torch.zeros((B,), dtype=torch.int32, device='cuda')
-    assert out.shape[-1] == 4 * T + 1 and out.shape[-2] >= K
-    L.call('dt_rpn_proposals', C.c_void_p(logits.data_ptr()), ld_s, C.c_void_p(deltas.data_ptr()), ld_d, act_f32,
-           B, H, W, A, T, L.ptr(anchors), float(feat_stride), L.ptr(im_info), int(pre_nms_topn), float(min_size),
-           float(clip), C.c_void_p(out.data_ptr()), out.stride(0), C.c_void_p(counts.data_ptr()), counts.stride(0),
-           int(bool(time_major)), L.stream_ptr())
+    assert out.shape[-2] >= K
+    rpn_proposals_levels([dict(logits=logits, deltas=deltas, anchors=anchors, feat_stride=feat_stride, out=out, counts=counts)],
+                         im_info, pre_nms_topn, A, min_size, T, clip, time_major)
     return out, counts
 
 

@@ -130,6 +130,10 @@ typedef struct dt_conv_desc {
   int out_f32;    /* 1: y/residual fp32, 0: bf16 */
   int relu;
   int res_mode;
+  int x3;             /* 3xTF32 mode (DT_DTYPE_TF32 only), bit 0: x and w rows are [hi | lo] tf32 pairs
+                         (lo half at in_lo_off / w_ld/2) and D = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo;
+                         bit 1: y (and the residual) rows are written / read as [hi | lo] pairs */
+  int in_lo_off, out_lo_off, res_lo_off;  /* element offsets of the lo halves (0 => ld / 2) */
   int out_round_tf32; /* fp32 output rounded (nearest-even) to tf32: set when the consumer is another
                          DT_DTYPE_TF32 conv, because kind::tf32 truncates its operands (a one-sided
                          error that otherwise compounds to percents over ~50 layers) */
@@ -148,20 +152,27 @@ int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const vo
 
 /* ---- proposals.cu -------------------------------------------------------- */
 
-/* GenerateProposalsOp up to NMS (lib/ops/generate_proposals.py:40-106,116-161): sigmoid,
- * top pre_nms_topn by score, shifted (tube) anchors, bbox/tube decode (weights 1), clip to
- * im_info, min-size filter (AND over frames).  One level, all images.
- * logits [B, H, W, ld_s] (first A channels), deltas [B, H, W, ld_d] (first 4*A*T; channel
- * a*4T + t*4 + k) — the NHWC order IS the reference's (H, W, A) enumeration; act_f32: 1 fp32,
- * 0 bf16.  anchors [A, 4T] fp64 device (generate_anchors.py).  out rows [4T+1] (boxes, score) in
- * descending score, batch image b at out + b*out_batch_stride; counts[b*counts_stride] rows.
+/* GenerateProposalsOp up to NMS (lib/ops/generate_proposals.py:40-106,116-161) for ALL levels of a clip
+ * batch in one launch: sigmoid, exact top pre_nms_topn by score (ties: ascending anchor index), shifted
+ * (tube) anchors, bbox/tube decode (weights 1), clip to im_info, min-size filter (AND over frames).
+ * Per level: logits [B, H, W, ld_s] (first A channels), deltas [B, H, W, ld_d] (first 4*A*T; channel
+ * a*4T + t*4 + k) — the NHWC order IS the reference's (H, W, A) enumeration; anchors [A, 4T] fp64 device
+ * (generate_anchors.py); out rows [4T+1] (boxes, score) in descending score, image b at
+ * out + b*out_batch_stride, count at counts[b*counts_stride].  act_f32: 1 fp32, 0 bf16.
  * time_major != 0 (3-D RPN head, lib/modeling/model_builder.py:509-563): logits [B, T, H, W, ld_s] with A
- * channels per frame are averaged over T (TimePool 'avg'), deltas [B, T, H, W, ld_d] hold channel a*4+k per frame. */
-int dt_rpn_proposals(const void* logits, int ld_s, const void* deltas, int ld_d, int act_f32, int B,
-                     int H, int W, int A, int T, const double* anchors, double feat_stride,
-                     const float* im_info, int pre_nms_topn, float min_size, double bbox_xform_clip,
-                     float* out, long long out_batch_stride, int* counts, int counts_stride,
-                     int time_major, void* stream);
+ * channels per frame are averaged over T (TimePool 'avg'), deltas [B, T, H, W, ld_d] hold a*4+k per frame.
+ * workspace: dt_rpn_workspace_bytes (one u32 key per anchor). */
+typedef struct dt_rpn_level {
+  const void* logits; const void* deltas; const double* anchors;
+  int ld_s, ld_d, H, W;
+  double feat_stride;
+  float* out; int* counts;
+} dt_rpn_level;
+int dt_rpn_workspace_bytes(int B, int nlevels, const int* Hs, const int* Ws, int A, size_t* bytes /*host out*/);
+int dt_rpn_proposals_multi(const dt_rpn_level* levels /*host*/, int nlevels, int act_f32, int B, int A, int T,
+                           const float* im_info, int pre_nms_topn, float min_size, double bbox_xform_clip,
+                           long long out_batch_stride, int counts_stride, int time_major, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* collect (lib/ops/collect_and_distribute_fpn_rpn_proposals.py:44-62): props [B, L, K, 4T+1],
  * keep [B*L, K] / nkeep [B*L] from dt_nms_batched -> rois [B, R, 4T+1] (col 0 = image index),
@@ -196,13 +207,15 @@ int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, in
 /* lib/utils/blob.py:40-90 + lib/core/test.py:43-74.  frames [F, H, W, 3] u8 BGR ->
  * out [F, Hp, Wp, Cp] (bf16 or fp32): (pixel - mean3) bilinearly resized by im_scale to Hr x Wr,
  * zero padded (Cp >= 3 channels, spatially to Hp x Wp) and framed by border_y zero rows / border_x
- * zero pixels on every side: out is [F, Hp + 2*border_y, Wp + 2*border_x, Cp] (dt_conv1_7x7s2 wants 3 / 4). */
+ * zero pixels on every side: out is [F, Hp + 2*border_y, Wp + 2*border_x, Cp] (dt_conv1_7x7s2 wants 3 / 4).
+ * out_f32: 0 bf16, 1 fp32 rounded to tf32 (kind::tf32 consumer), 2 raw fp32 (dt_conv1_7x7s2_f32). */
 int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3, double im_scale,
                  int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x, int out_f32,
                  void* out, void* stream);
 
-/* Caffe2 MaxPool kernels [1,k,k] strides [1,s,s] pads [0,p,p] on NHWC (N = B*T frames). */
-int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32,
+/* Caffe2 MaxPool kernels [1,k,k] strides [1,s,s] pads [0,p,p] on NHWC (N = B*T frames).
+ * x3 != 0: 3xTF32 storage, rows are [hi(C) | lo(C)] tf32 pairs at ld/2 (fp32 only). */
+int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32, int x3,
                  void* y, int ldy, void* stream);
 
 /* RoIFeatureTransform (lib/modeling/detector.py:216-310): RoIAlign (Detectron semantics,
@@ -210,10 +223,13 @@ int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int 
  * feats/Hs/Ws/scales: host arrays [nlevels] (feature l is [n_images*T, Hs[l], Ws[l], ldf]);
  * rois [R, ldr] (col 0 image index, then 4*T), levels [R] (NULL if nlevels == 1);
  * out [R, T, P, P, C]; rows >= *n_dev are zero-filled.  round_tf32: round fp32 outputs to tf32
- * (when they feed a DT_DTYPE_TF32 GEMM; prep_clip does the same for its fp32 output). */
+ * (when they feed a DT_DTYPE_TF32 GEMM; prep_clip does the same for its fp32 output).
+ * x3_mode (3xTF32 storage, features are [hi | lo] rows): 1 = out [R,T,P,P,2C] per-position pairs,
+ * 2 = out [R, 2, T*P*P*C] planar hi / lo blocks (input of the FC head). */
 int dt_roi_align(const void* const* feats, const int* Hs, const int* Ws, const float* scales, int nlevels,
                  int k_min, int C, int ldf, int f32, const float* rois, int ldr, const int* n_dev, int R,
-                 int T, const int* levels, int P, int sampling_ratio, int round_tf32, void* out, void* stream);
+                 int T, const int* levels, int P, int sampling_ratio, int round_tf32, int x3_mode, void* out,
+                 void* stream);
 
 /* BilinearInterpolation (lib/modeling/detector.py:348-380) + heatmaps_to_keypoints
  * (lib/utils/keypoints.py:94-149).  lowres [D*T, S, S, ldl] fp32 with channel (py*2+px)*K + k =
@@ -223,13 +239,18 @@ int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, int T, const 
                        const int* n_dev, int D, int min_size, float* heatmaps, float* xy_preds,
                        void* stream);
 
+/* 3xTF32 mode conv1: exact fp32 7x7/2 conv + AffineChannel + ReLU on the raw fp32 blob [F, Hp, Wp, Cp];
+ * w [7][7][3][64] fp32; y [F, Hp/2, Wp/2, 128] = [hi(64) | lo(64)] tf32 pairs. */
+int dt_conv1_7x7s2_f32(const float* blob, int F, int Hp, int Wp, int Cp, const float* w, const float* scale,
+                       const float* bias, float* y, void* stream);
+
 /* 3-D box head glue.  dt_spatial_mean: ReduceBackMean over W then H
  * (lib/modeling/ResNet3D.py:321-322), x [N, H, W, ldx] -> y [N, ldy] (first C channels).
  * dt_fold_tube_heads: per-frame head outputs in [R*T, ld] = [C cls logits | 4C deltas (c*4+k)] ->
  * cls [R, C] = mean over T, bbox [R, C*T*4] with channel c*4T + t*4 + k
  * (lib/modeling/model_builder.py:427-473). */
-int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, void* y,
-                    int ldy, void* stream);
+int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, int x3,
+                    void* y, int ldy, void* stream);
 int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, float* cls, float* bbox, void* stream);
 
 #ifdef __cplusplus

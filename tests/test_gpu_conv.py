@@ -52,7 +52,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('mode', ['bf16', 'tf32'])
+@pytest.mark.parametrize('mode', ['bf16', 'tf32', 'tf32x3'])
 @pytest.mark.parametrize('case', range(len(CASES)))
 def test_conv_parity(case, mode):
     import torch
@@ -74,8 +74,13 @@ def test_conv_parity(case, mode):
         res = torch.randn((N, To, Ho, Wo, Cout), generator=g)
     elif rm == 2:
         res = torch.randn((N, To, Ho // 2, Wo // 2, Cout), generator=g)
-    dtype = cv.BF16 if mode == 'bf16' else cv.TF32
-    if mode == 'bf16':
+    dtype = {'bf16': cv.BF16, 'tf32': cv.TF32, 'tf32x3': cv.TF32X3}[mode]
+    if mode == 'tf32x3':
+        if Cin % 32 or Cout % 32:
+            pytest.skip('3xTF32 storage needs channel counts that are multiples of 32 (true for every layer that uses it)')
+        xd = cv.split_tf32(x.cuda())
+        tol = 2e-5
+    elif mode == 'bf16':
         x = x.bfloat16().float(); w = w.bfloat16().float()
         xd = x.bfloat16().cuda()
         tol = 2e-4
@@ -83,10 +88,14 @@ def test_conv_parity(case, mode):
         xd = x.cuda()
         tol = 1e-3
     wp = cv.pack_weight(w, dtype)
+    resd = res.cuda().contiguous() if res is not None else None
+    if mode == 'tf32x3' and resd is not None:
+        resd = cv.split_tf32(resd)
     y = cv.conv3d(xd.contiguous(), wp, k, s, p,
                   scale.cuda() if scale is not None else None, bias.cuda() if bias is not None else None,
-                  res.cuda().contiguous() if res is not None else None, rm, bool(c.get('relu')),
-                  out_f32=True, dtype=dtype, cin=Cin, round_tf32=False)
+                  resd, rm, bool(c.get('relu')), out_f32=True, dtype=dtype, cin=Cin, round_tf32=False)
+    if mode == 'tf32x3':
+        y = cv.join_tf32(y)
     torch.cuda.synchronize()
     ref = _ref_conv(x, w, s, p, scale, bias, res, rm, bool(c.get('relu')))
     err = (y.cpu() - ref).abs().max().item()
