@@ -237,6 +237,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int cc = 0; cc < BN; cc += CW) {
         const int cchunk = nt * BN + cc;
         if (cchunk >= p.Cout) break;                                   // uniform: nothing left to write
+        // bf16 residual rows for this chunk: issue the global loads FIRST so their latency overlaps the
+        // staging-buffer wait, the named barrier and the TMEM load below
+        uint4 resq[4];
+        bool res_vec = false;
+        if (!p.out_f32 && p.res_mode != 0 && valid) {
+          const int cb = nt * BN + cc + 32 * half;
+          if (cb + 32 <= p.Cout) {
+            res_vec = true;
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cb;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) resq[g4] = __ldg(reinterpret_cast<const uint4*>(rp + 8 * g4));
+          }
+        }
         // split output: buffers (2i, 2i+1) of a 4-buffer ring hold the hi / lo chunk, committed as ONE group
         uint8_t* buf = p.split_out ? cbuf + ((chunk_ctr & 1u) * 2u) * Cfg::C_BYTES
                                    : cbuf + (chunk_ctr % (uint32_t)p.ncbuf) * Cfg::C_BYTES;
@@ -312,19 +325,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]);
           if (p.res_mode != 0 && valid) {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
-            if (cbase + 32 <= p.Cout) {
+            if (res_vec) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
-                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+              for (int g4 = 0; g4 < 4; ++g4) {
+                const uint32_t w4[4] = {resq[g4].x, resq[g4].y, resq[g4].z, resq[g4].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  v[j + 2 * e] += __uint_as_float(w4[e] << 16);
-                  v[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                  v[8 * g4 + 2 * e] += __uint_as_float(w4[e] << 16);
+                  v[8 * g4 + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
                 }
               }
             } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (cbase + j < p.Cout) v[j] += __bfloat162float(rp[j]);

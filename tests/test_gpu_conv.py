@@ -7,6 +7,7 @@ Tolerances (north star: 1e-3 relative fp32):
   bf16 mode: the reference is evaluated on the SAME bf16-rounded x and w, so only fp32
              accumulation order differs: |err| <= 2e-4 * max|y| (fp32 output).
   tf32 mode: fp32 inputs, tf32 multiplies: |err| <= 1e-3 * max|y|.
+  tf32x3   : [hi | lo] tf32 pairs, 3 MMAs per k-block (fp32-accurate parity mode): |err| <= 1e-4 * max|y|.
 """
 import numpy as np
 import pytest
@@ -79,7 +80,7 @@ def test_conv_parity(case, mode):
         if Cin % 32 or Cout % 32:
             pytest.skip('3xTF32 storage needs channel counts that are multiples of 32 (true for every layer that uses it)')
         xd = cv.split_tf32(x.cuda())
-        tol = 2e-5
+        tol = 1e-4          # fp32 accumulation over K up to 3456 (measured ~2e-5); 10x inside the north star's 1e-3
     elif mode == 'bf16':
         x = x.bfloat16().float(); w = w.bfloat16().float()
         xd = x.bfloat16().cuda()
