@@ -410,8 +410,8 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'tf32'])
-    ap.add_argument('--clips', type=int, default=2, help='clips per GPU per step')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'tf32', 'tf32x3'])
+    ap.add_argument('--clips', type=int, default=8, help='clips per GPU per step')
     ap.add_argument('--height', type=int, default=800)
     ap.add_argument('--width', type=int, default=1333)
     ap.add_argument('--dce', type=int, default=0, help='1: compute only the consumed centre frame of the post-hoc FPN convs')
