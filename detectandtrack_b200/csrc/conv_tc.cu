@@ -58,6 +58,7 @@ struct ConvKernelParams {
   int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
   int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
+  int cgroup;                  // output chunks staged per named-barrier pair / TMA commit group (divides ncbuf)
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
 };
@@ -207,7 +208,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t row_smem = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
     int as = 0; uint32_t aphase = 0;
-    uint32_t chunk_ctr = 0;
+    uint32_t chunk_ctr = 0, grp_ctr = 0;
+    int grp_cc = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
@@ -253,14 +255,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // split output: buffers (2i, 2i+1) of a 4-buffer ring hold the hi / lo chunk, committed as ONE group
         uint8_t* buf = p.split_out ? cbuf + ((chunk_ctr & 1u) * 2u) * Cfg::C_BYTES
                                    : cbuf + (chunk_ctr % (uint32_t)p.ncbuf) * Cfg::C_BYTES;
+        const int gi = (int)(chunk_ctr % (uint32_t)p.cgroup);       // position inside the barrier group
+        if (gi == 0) { grp_cc = cc; grp_ctr = chunk_ctr; }
         ++chunk_ctr;
-        // the staging buffer must have been read out by the TMA store that used it last
-        if (leader) {
-          if (p.ncbuf == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          else if (p.ncbuf == 2 || p.split_out) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        if (gi == 0) {
+          // the staging buffers of this group must have been read out by the TMA stores that used them last
+          if (leader) {
+            const int inflight = p.split_out ? 1 : p.ncbuf / p.cgroup - 1;   // commit groups that may stay pending
+            if (inflight <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else if (inflight == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
         const uint32_t dst = smem_u32(buf) + row_smem;
         if (p.out_f32) {
           // ---- fp32 output: this warp owns 16 columns = 64 bytes = 16-byte chunks [4*half, 4*half+4)
@@ -358,22 +365,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                          "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
           }
         }
-        // generic-proxy smem writes -> visible to the async proxy, then one thread stores the chunk
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (leader) {
-          asm volatile(
-              "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                  reinterpret_cast<uint64_t>(&tmC)),
-              "r"(smem_u32(buf)), "r"(cchunk), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
-              : "memory");
-          if (p.split_out)
-            asm volatile(
-                "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                    reinterpret_cast<uint64_t>(&tmC)),
-                "r"(smem_u32(buf) + Cfg::C_BYTES), "r"(cchunk + p.out_lo_off), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
-                : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // group complete (or last chunk of the tile): generic-proxy smem writes -> visible to the async
+        // proxy, one barrier, then one thread stores every chunk of the group and commits them together
+        const bool last_in_group = (gi == p.cgroup - 1) || (cc + CW >= BN) || (nt * BN + cc + CW >= p.Cout);
+        if (last_in_group) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (leader) {
+            if (p.split_out) {
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmC)),
+                  "r"(smem_u32(buf)), "r"(cchunk), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
+                  : "memory");
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&tmC)),
+                  "r"(smem_u32(buf) + Cfg::C_BYTES), "r"(cchunk + p.out_lo_off), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
+                  : "memory");
+            } else {
+              for (int g = 0; g <= gi; ++g) {
+                const uint32_t sb = smem_u32(cbuf + ((grp_ctr + (uint32_t)g) % (uint32_t)p.ncbuf) * Cfg::C_BYTES);
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                        reinterpret_cast<uint64_t>(&tmC)),
+                    "r"(sb), "r"(nt * BN + grp_cc + g * CW), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
+                    : "memory");
+              }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          // keep groups aligned in the buffer ring when a tile ends with a short group
+          chunk_ctr = (chunk_ctr + (uint32_t)p.cgroup - 1u) / (uint32_t)p.cgroup * (uint32_t)p.cgroup;
         }
       }
       tcgen05_fence_before();
@@ -462,6 +485,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   ConvKernelParams q = p;
   Cfg::split(p.split_out ? 1 : p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1), &q.nstages, &q.ncbuf);
+  q.cgroup = (q.ncbuf >= 4 && !p.split_out) ? 4 : 1;
   const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
   conv_tc_kernel<BN, TF32><<<grid, 320, smem, stream>>>(tmA, tmB, tmC, q);

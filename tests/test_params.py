@@ -66,3 +66,76 @@ def test_weights_file_roundtrip_with_inflation(tmp_path):
     assert np.array_equal(w[:, :, 1], two_d['res3_0_branch2b_w']) and not w[:, :, 0].any()
     assert np.array_equal(loaded['fc7_w'], blobs['fc7_w'])
     assert loaded['res4_0_branch2a_w'].shape == blobs['res4_0_branch2a_w'].shape      # missing in file: kept
+
+
+SHIPPED_3D = '''
+MODEL:
+  TYPE: keypoint_rcnn
+  CONV_BODY: ResNet3D.add_ResNet18_conv4_body
+  ROI_HEAD: ResNet3D.add_ResNet18_roi_conv5_head
+  NUM_CLASSES: 2
+  FASTER_RCNN: True
+  KEYPOINTS_ON: True
+  VIDEO_ON: True
+NUM_GPUS: 8
+FAST_RCNN:
+  ROI_XFORM_METHOD: RoIAlign
+  ROI_XFORM_RESOLUTION: 7
+  ROI_XFORM_SAMPLING_RATIO: 2
+KRCNN:
+  ROI_KEYPOINTS_HEAD: keypoint_rcnn_heads.add_roi_pose_head_v1convX_3d
+  NUM_STACKED_CONVS: 8
+  NUM_KEYPOINTS: 17
+  USE_DECONV_OUTPUT: True
+  CONV_INIT: MSRAFill
+  CONV_HEAD_DIM: 512
+  UP_SCALE: 2
+  HEATMAP_SIZE: 56
+  ROI_XFORM_METHOD: RoIAlign
+  ROI_XFORM_RESOLUTION: 14
+  ROI_XFORM_SAMPLING_RATIO: 2
+  KEYPOINT_CONFIDENCE: bbox
+  NO_3D_DECONV_TIME_TO_CH: True
+VIDEO:
+  NUM_FRAMES: 3
+  TIME_INTERVAL: 1
+  WEIGHTS_INFLATE_MODE: center-only
+  TIME_KERNEL_DIM: 3
+  BODY_HEAD_LINK: ''
+  PREDICT_RPN_BOX_VIS: False
+TEST:
+  DATASET: posetrack_v1.0_val
+  SCALES: (256,)
+  MAX_SIZE: 333
+  NMS: 0.5
+  RPN_PRE_NMS_TOP_N: 1000
+  RPN_POST_NMS_TOP_N: 1000
+  COMPETITION_MODE: False
+TRACKING:
+  CONF_FILTER_INITIAL_DETS: 0.95
+  DISTANCE_METRICS: ('bbox-overlap', 'cnn-cosdist')
+  DISTANCE_METRIC_WTS: (1.0, 0.0)
+  BIPARTITE_MATCHING_ALGO: 'hungarian'
+EVAL:
+  EVAL_MPII_KPT_THRESHOLD: 1.95
+USE_NCCL: False
+OUTPUT_DIR: .
+'''
+
+
+def test_shipped_style_3d_yaml_builds_the_tube_graph(tmp_path):
+    """The option set of the reference's shipped 3-D config (configs/video/3d/03_R-18-3D_PTFromCOCO.yaml,
+    restated here because /root/reference does not exist on the GPU box) resolves to the tube graph:
+    basic-block conv4 body, single-level 3-D RPN with 12 tube anchors, res5 RoI head, 3-D keypoint head."""
+    from detectandtrack_b200.core.config import cfg, reset_cfg, cfg_from_file, assert_and_infer_cfg
+    from detectandtrack_b200.modeling import params as P
+    y = tmp_path / 'c.yaml'
+    y.write_text(SHIPPED_3D)
+    reset_cfg(); cfg_from_file(str(y)); assert_and_infer_cfg()
+    shapes, spec = P.param_shapes(cfg)
+    assert spec.block == 'basic' and spec.counts == (2, 2, 2) and not spec.fpn and spec.head3d
+    assert spec.T_head == 3 and spec.num_anchors == 12
+    assert shapes['conv_rpn_w'] == (256, 256, 3, 3, 3) and shapes['rpn_bbox_pred_1_w'] == (48, 256, 1, 1, 1)
+    assert shapes['res5_0_branch1_w'] == (512, 256, 1, 1, 1) and shapes['cls_score_1_w'] == (2, 512, 1, 1, 1)
+    assert shapes['conv_fcn1_w'] == (512, 256, 3, 3, 3) and shapes['kps_score_lowres_w'] == (512, 17, 4, 4)
+    reset_cfg()
