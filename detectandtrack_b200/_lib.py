@@ -18,8 +18,8 @@ SIGNATURES = {
     'dt_bbox_overlaps': [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p],
     'dt_nms_workspace_bytes': [_i, _i, C.POINTER(_sz)],
     'dt_nms_batched': [_p, _i, _i, _i, _i, _p, _f, _i, _i, _i, _p, _p, _p, _sz, _p],
-    'dt_lsa_batched': [_p, _i, _i, _i, _p, _p, _p, _p, _p],
-    'dt_match_frames': [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p],
+    'dt_lsa_batched': [_p, _i, _i, _i, _p, _p, _i, _p, _p, _p],
+    'dt_match_frames': [_p, _i, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p],
     'dt_assign_track_ids': [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p],
     'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
     'dt_conv3d': [_p, _p, _p, _p, _p, _p, _p, _p],

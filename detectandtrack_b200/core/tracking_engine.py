@@ -11,9 +11,9 @@ What changed underneath: instead of one python loop per frame pair
 into one [F, Dmax, 4T+1] tensor and three launches do the work
 (csrc/lsa.cu): fused (1 - IoU) cost + assignment for every consecutive pair
 (pairs are independent), then the sequential id scan, one thread per video.
-Only 'bbox-overlap' cost with 'hungarian' matching runs on the device (the
-configuration of every shipped yaml; weights of the other costs are 0,
-config.py:550-551); anything else raises NotImplementedError.
+Only the 'bbox-overlap' cost runs on the device (the configuration of every shipped yaml; the
+weights of the other costs are 0, config.py:550-551), with 'hungarian' or 'greedy' matching;
+anything else raises NotImplementedError.
 """
 import logging
 import os.path as osp
@@ -142,15 +142,15 @@ def _compute_matches(prev_frame_data, cur_frame_data, prev_boxes, cur_boxes,
                      bipart_match_algo, C=None):
     """:209-246.  Returns int32 matches[n_cur] = index into prev boxes, or -1."""
     import torch
-    if bipart_match_algo != 'hungarian':
-        raise NotImplementedError('device tracking implements hungarian matching only')
+    if bipart_match_algo not in box_ops.ALGOS:
+        raise NotImplementedError('Unknown matching algo: {}'.format(bipart_match_algo))
     if C is not None:
         C = np.ascontiguousarray(C, dtype=np.float32)
         P, Q = C.shape
         if P == 0 or Q == 0:
             return -np.ones((Q,), dtype=np.int32)
         m, status = box_ops.lsa_batched(torch.from_numpy(C).cuda().unsqueeze(0),
-                                        torch.tensor([P]), torch.tensor([Q]))
+                                        torch.tensor([P]), torch.tensor([Q]), bipart_match_algo)
         if int(status[0].item()) != 0:
             raise ValueError('cost matrix is infeasible')
         return m[0, :Q].cpu().numpy().astype(np.int32)
@@ -160,7 +160,8 @@ def _compute_matches(prev_frame_data, cur_frame_data, prev_boxes, cur_boxes,
         return -np.ones((nboxes,), dtype=np.int32)
     packed, counts = _pack([prev_boxes, cur_boxes])
     T = (packed.shape[2] - 1) // 4
-    m, _ = box_ops.match_frames(torch.from_numpy(packed).cuda(), torch.from_numpy(counts), None, T=T, weight=weight)
+    m, _ = box_ops.match_frames(torch.from_numpy(packed).cuda(), torch.from_numpy(counts), None, T=T, weight=weight,
+                                algo=bipart_match_algo)
     return m[1, :nboxes].cpu().numpy().astype(np.int32)
 
 
@@ -179,11 +180,12 @@ def _tracks_for_videos(videos_boxes):
     is_start = np.zeros(len(flat), dtype=np.uint8)
     is_start[np.array(first, dtype=np.int64)] = 1
     weight = _check_default_cost(cfg.TRACKING.DISTANCE_METRICS, cfg.TRACKING.DISTANCE_METRIC_WTS)
-    if cfg.TRACKING.BIPARTITE_MATCHING_ALGO != 'hungarian':
-        raise NotImplementedError('device tracking implements hungarian matching only')
+    algo = cfg.TRACKING.BIPARTITE_MATCHING_ALGO
+    if algo not in box_ops.ALGOS:
+        raise NotImplementedError('Unknown matching algo: {}'.format(algo))
     d_counts = torch.from_numpy(counts).cuda()
     d_start = torch.from_numpy(is_start).cuda()
-    matches, _ = box_ops.match_frames(torch.from_numpy(packed).cuda(), d_counts, d_start, T=T, weight=weight)
+    matches, _ = box_ops.match_frames(torch.from_numpy(packed).cuda(), d_counts, d_start, T=T, weight=weight, algo=algo)
     tracks = box_ops.assign_track_ids(matches, d_counts, torch.tensor(first, dtype=torch.int32), d_start)
     tracks = tracks.cpu().numpy()
     out = []

@@ -150,7 +150,40 @@ __device__ bool lsa_solve_warp(const LsaSmem& s, int nr, int nc) {
 
 // mode 0: cost given  [B, pmax, ldc] (rows = prev, cols = cur), per-problem (nprev, ncur)
 // mode 1: frames given [F, dmax, ld] boxes (+score col ignored); problem f = (frame f-1, frame f)
-__global__ void lsa_kernel(int mode, const float* __restrict__ src, int dmax, int ld, int T,
+// bipartite_matching_greedy (tracking_engine.py:184-206): repeatedly take the global argmin of the
+// remaining matrix (np.argmin: first occurrence in row-major order; deleting rows / columns keeps that
+// order, so ties go to the lowest remaining (row, col)).  s.C holds cost[p*Q + q]; SR / SC mark used rows / cols.
+__device__ void greedy_match_warp(const LsaSmem& s, int P, int Q, int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  for (int x = lane; x < P; x += 32) s.SR[x] = 0;
+  for (int x = lane; x < Q; x += 32) s.SC[x] = 0;
+  __syncwarp();
+  const int steps = min(P, Q);
+  for (int k = 0; k < steps; ++k) {
+    float bv = CUDART_INF_F; int bi = 0x7fffffff;
+    bool any = false;
+    for (int e = lane; e < P * Q; e += 32) {
+      const int p = e / Q, q = e - p * Q;
+      if (s.SR[p] || s.SC[q]) continue;
+      const float c = s.C[e];
+      if (!any || c < bv) { bv = c; bi = e; any = true; }          // strict '<': first occurrence per lane
+    }
+    if (!any) bi = 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(FULL, bv, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      const bool take = (oi != 0x7fffffff) && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi));
+      if (take) { bv = ov; bi = oi; }
+    }
+    const int p = bi / Q, q = bi - p * Q;
+    if (lane == 0) { s.SR[p] = 1; s.SC[q] = 1; out[q] = p; }
+    __syncwarp();
+  }
+}
+
+__global__ void lsa_kernel(int mode, int algo, const float* __restrict__ src, int dmax, int ld, int T,
                            const int* __restrict__ nrows, const int* __restrict__ ncols,
                            const unsigned char* __restrict__ is_start, float weight,
                            int* __restrict__ matches /*[B,dmax] cur -> prev or -1*/,
@@ -175,7 +208,7 @@ __global__ void lsa_kernel(int mode, const float* __restrict__ src, int dmax, in
   for (int q = lane; q < dmax; q += 32) out[q] = -1;
   if (lane == 0 && status) status[b] = 0;
   if (P == 0 || Q == 0) return;
-  const bool transpose = Q < P;                      // scipy: "tall matrix must be transposed"
+  const bool transpose = (algo == 0) && Q < P;       // scipy: "tall matrix must be transposed"
   const int nr = transpose ? Q : P, nc = transpose ? P : Q;
   // stage the internal matrix: internal(i, j) = cost(prev = transpose ? j : i, cur = transpose ? i : j)
   for (int e = lane; e < P * Q; e += 32) {
@@ -194,6 +227,7 @@ __global__ void lsa_kernel(int mode, const float* __restrict__ src, int dmax, in
     if (transpose) s.C[(size_t)q * nc + p] = c; else s.C[(size_t)p * nc + q] = c;
   }
   __syncwarp();
+  if (algo == 1) { greedy_match_warp(s, P, Q, out); return; }
   const bool ok = lsa_solve_warp(s, nr, nc);
   if (!ok) { if (lane == 0 && status) status[b] = 1; return; }
   __syncwarp();
@@ -290,7 +324,7 @@ __global__ void prune_kernel(const float* __restrict__ boxes, int nframes, int d
 
 using namespace dt;
 
-static int lsa_launch(int mode, const float* src, int batch, int dmax, int ld, int T,
+static int lsa_launch(int mode, int algo, const float* src, int batch, int dmax, int ld, int T,
                       const int* nrows, const int* ncols, const unsigned char* is_start, float weight,
                       int* matches, int* status, cudaStream_t stream) {
   const size_t smem = lsa_smem_bytes(dmax);
@@ -300,29 +334,31 @@ static int lsa_launch(int mode, const float* src, int batch, int dmax, int ld, i
     DT_CHECK_CUDA(cudaFuncSetAttribute(lsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
-  lsa_kernel<<<batch, 32, smem, stream>>>(mode, src, dmax, ld, T, nrows, ncols, is_start, weight, matches, status);
+  lsa_kernel<<<batch, 32, smem, stream>>>(mode, algo, src, dmax, ld, T, nrows, ncols, is_start, weight, matches, status);
   DT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int dt_lsa_batched(const float* cost, int batch, int dmax, int ldc, const int* nrows,
-                              const int* ncols, int* matches, int* status, void* stream) {
+                              const int* ncols, int algo, int* matches, int* status, void* stream) {
+  DT_CHECK_ARG(algo == DT_MATCH_HUNGARIAN || algo == DT_MATCH_GREEDY, "dt_lsa_batched: unknown algo %d", algo);
   DT_CHECK_ARG(batch >= 0 && dmax >= 1 && dmax <= DT_LSA_MAX_DIM && ldc >= 1,
                "dt_lsa_batched: bad shape batch=%d dmax=%d ldc=%d (dmax <= %d)", batch, dmax, ldc, DT_LSA_MAX_DIM);
   if (batch == 0) return 0;
   DT_CHECK_ARG(cost && nrows && ncols && matches, "dt_lsa_batched: null pointer");
-  return lsa_launch(0, cost, batch, dmax, ldc, 1, nrows, ncols, nullptr, 1.f, matches, status, (cudaStream_t)stream);
+  return lsa_launch(0, algo, cost, batch, dmax, ldc, 1, nrows, ncols, nullptr, 1.f, matches, status, (cudaStream_t)stream);
 }
 
 extern "C" int dt_match_frames(const float* frames, int nframes, int dmax, int ld, int T,
-                               const int* counts, const unsigned char* is_start, float weight,
+                               const int* counts, const unsigned char* is_start, float weight, int algo,
                                int* matches, int* status, void* stream) {
+  DT_CHECK_ARG(algo == DT_MATCH_HUNGARIAN || algo == DT_MATCH_GREEDY, "dt_match_frames: unknown algo %d", algo);
   DT_CHECK_ARG(T >= 1 && T <= DT_MAX_T, "dt_match_frames: T=%d outside [1,%d]", T, DT_MAX_T);
   DT_CHECK_ARG(nframes >= 0 && dmax >= 1 && dmax <= DT_LSA_MAX_DIM && ld >= 4 * T,
                "dt_match_frames: bad shape nframes=%d dmax=%d ld=%d T=%d (dmax <= %d)", nframes, dmax, ld, T, DT_LSA_MAX_DIM);
   if (nframes == 0) return 0;
   DT_CHECK_ARG(frames && counts && matches, "dt_match_frames: null pointer");
-  return lsa_launch(1, frames, nframes, dmax, ld, T, nullptr, counts, is_start, weight, matches, status, (cudaStream_t)stream);
+  return lsa_launch(1, algo, frames, nframes, dmax, ld, T, nullptr, counts, is_start, weight, matches, status, (cudaStream_t)stream);
 }
 
 extern "C" int dt_assign_track_ids(const int* matches, const int* counts, const unsigned char* is_start,

@@ -63,7 +63,10 @@ def nms_batched(dets, counts=None, thresh=0.5, cmp_mode=None, out_order=None, ma
     return keep, num
 
 
-def lsa_batched(cost, nrows, ncols):
+ALGOS = {'hungarian': 0, 'greedy': 1}
+
+
+def lsa_batched(cost, nrows, ncols, algo='hungarian'):
     """cost [B, D, D'] cuda fp32 (rows prev, cols cur); returns matches [B, dmax] int32."""
     torch = L.require_cuda()
     cost = _f32c(cost, torch)
@@ -77,12 +80,12 @@ def lsa_batched(cost, nrows, ncols):
     ncols = ncols.to(device='cuda', dtype=torch.int32).contiguous()
     matches = torch.empty((B, dmax), dtype=torch.int32, device='cuda')
     status = torch.empty((B,), dtype=torch.int32, device='cuda')
-    L.call('dt_lsa_batched', L.ptr(cost), B, dmax, dmax, L.ptr(nrows), L.ptr(ncols), L.ptr(matches),
+    L.call('dt_lsa_batched', L.ptr(cost), B, dmax, dmax, L.ptr(nrows), L.ptr(ncols), ALGOS[algo], L.ptr(matches),
            L.ptr(status), L.stream_ptr())
     return matches, status
 
 
-def match_frames(frames, counts, is_start=None, T=1, weight=1.0):
+def match_frames(frames, counts, is_start=None, T=1, weight=1.0, algo='hungarian'):
     """frames [F, Dmax, ld] cuda fp32, counts [F] int32 -> matches [F, Dmax] int32."""
     torch = L.require_cuda()
     frames = _f32c(frames, torch)
@@ -92,7 +95,7 @@ def match_frames(frames, counts, is_start=None, T=1, weight=1.0):
         is_start = is_start.to(device='cuda', dtype=torch.uint8).contiguous()
     matches = torch.empty((F, dmax), dtype=torch.int32, device='cuda')
     status = torch.empty((F,), dtype=torch.int32, device='cuda')
-    L.call('dt_match_frames', L.ptr(frames), F, dmax, ld, T, L.ptr(counts), L.ptr(is_start), float(weight),
+    L.call('dt_match_frames', L.ptr(frames), F, dmax, ld, T, L.ptr(counts), L.ptr(is_start), float(weight), ALGOS[algo],
            L.ptr(matches), L.ptr(status), L.stream_ptr())
     return matches, status
 

@@ -42,6 +42,10 @@ extern "C" {
 #define DT_NMS_ORDER_SCORE 0  /* survivors in descending-score order (py_cpu_nms_tubes) */
 #define DT_NMS_ORDER_INDEX 1  /* survivors in ascending input index (cython_nms np.where) */
 
+/* TRACKING.BIPARTITE_MATCHING_ALGO (lib/core/tracking_engine.py:236-242) */
+#define DT_MATCH_HUNGARIAN 0  /* scipy.optimize.linear_sum_assignment, :237        */
+#define DT_MATCH_GREEDY 1     /* bipartite_matching_greedy, :184-206 (argmin loop) */
+
 const char* dt_last_error(void);
 int dt_abi_version(void);
 
@@ -74,14 +78,14 @@ int dt_nms_batched(const float* dets, int batch, int nmax, int ld, int T, const 
  * (tracking_engine.py:229-246).  status [batch] (may be NULL): 1 = infeasible.
  * Indices equal scipy >= 1.6 bit-for-bit (see oracle/lsa.py). */
 int dt_lsa_batched(const float* cost, int batch, int dmax, int ldc, const int* nrows,
-                   const int* ncols, int* matches, int* status, void* stream);
+                   const int* ncols, int algo, int* matches, int* status, void* stream);
 
 /* lib/core/tracking_engine.py:158-246 fused: cost = weight * (1 - IoU) between
  * frame f-1 and frame f, then the assignment.  frames [nframes, dmax, ld]
  * (4*T box columns first), counts [nframes]; frame 0 and frames with
  * is_start[f] != 0 (may be NULL) get all -1 (first frame of a video, :283-285). */
 int dt_match_frames(const float* frames, int nframes, int dmax, int ld, int T, const int* counts,
-                    const unsigned char* is_start, float weight, int* matches, int* status,
+                    const unsigned char* is_start, float weight, int algo, int* matches, int* status,
                     void* stream);
 
 /* lib/core/tracking_engine.py:272-350 id propagation.  video_first [nvideos]

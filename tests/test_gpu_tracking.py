@@ -140,3 +140,30 @@ def test_assignment_properties_full_size():
         r, c = scipy.optimize.linear_sum_assignment(C[b])
         assert np.isclose(C[b][m[b], np.arange(D)].sum(), C[b][r, c].sum(), rtol=0, atol=1e-4)
         assert np.array_equal(m[b], _matches_from(r, c, D))
+
+
+def test_greedy_matching_vs_oracle():
+    """TRACKING.BIPARTITE_MATCHING_ALGO greedy (tracking_engine.py:184-206): identical pairs, incl. ties."""
+    import torch
+    from detectandtrack_b200.ops import box_ops
+    from detectandtrack_b200.core import tracking_engine as te
+    from oracle.lsa import bipartite_matching_greedy
+    rng = np.random.default_rng(31)
+    B, D = 60, 40
+    cost = np.zeros((B, D, D), np.float32)
+    nr = rng.integers(0, D + 1, B).astype(np.int32); nc = rng.integers(0, D + 1, B).astype(np.int32)
+    for b in range(B):
+        C = rng.random((nr[b], nc[b])) if b % 3 else np.round(rng.random((nr[b], nc[b])) * 4) / 4     # ties
+        cost[b, :nr[b], :nc[b]] = C
+    m, _ = box_ops.lsa_batched(_cuda(cost), torch.from_numpy(nr), torch.from_numpy(nc), algo='greedy')
+    m = m.cpu().numpy()
+    for b in range(B):
+        P, Q = nr[b], nc[b]
+        ref = -np.ones(Q, np.int32)
+        if P and Q:
+            pi, qi = bipartite_matching_greedy(cost[b, :P, :Q])
+            ref[qi] = pi
+        assert np.array_equal(m[b, :Q], ref), b
+    vid = ot.synth_video(rng, n_frames=3, n_dets=50)
+    got = te._compute_matches(None, None, vid[0], vid[1], None, None, ('bbox-overlap',), (1.0,), 'greedy')
+    assert np.array_equal(got, ot.compute_matches(vid[0], vid[1], algo='greedy'))
