@@ -339,6 +339,13 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     # ---- roofline pass: the same step, eager, with CUDA events around every conv_tc launch -------
+    # how long the CPU needs to enqueue one eager step -> GPU-side delay that covers it with margin
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.detect_static(dev)
+    enqueue_s = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    delay_cycles = int(max(40e6, 1.6 * enqueue_s * 2.0e9))
     meter.on = True
     barrier()
     g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
@@ -347,7 +354,7 @@ def run_ours(args):
         flush.zero_()
         # keep the GPU busy while the CPU enqueues the step, so the per-conv events bracket kernel
         # execution back to back instead of CPU launch latency (eager mode is launch-bound)
-        torch.cuda._sleep(int(40e6))
+        torch.cuda._sleep(delay_cycles)
         eng.detect_static(dev)
     g1.record()
     barrier()

@@ -17,10 +17,10 @@
 //           zero-filled by the TMA unit, so padding costs no instructions and no branches.
 //   W tile: 3-D TMA box (C=128B, BLOCK_N, 1) of the pre-packed [tap][Cout][Cin] weights.
 //   Both land in the 128B-swizzled K-major layout tcgen05.mma reads directly.
-// Roles (320 threads, 1 CTA / SM, persistent over tiles):
+// Roles (576 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0   : TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
 //   warp 1   : TMEM allocator + MMA issuer (one lane)   tcgen05.mma -> TMEM, tcgen05.commit
-//   warps 2-9: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32, staged in
+//   warps 2-17: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32, staged in
 //              128B-swizzled smem chunks and written with TMA stores.  Two TMEM accumulator stages
 //              overlap it with the next tile's MMAs.
 #include "common.cuh"
@@ -39,8 +39,9 @@ struct ConvKernelParams {
   int kT, kH, kW, sT, sH, sW, pT, pH, pW;
   int kchunks;                 // ceil(Cin / BK)
   // tiling
-  int TH, TW, tiles_h, tiles_w, tiles_n, total_tiles;
-  uint32_t a_bytes;            // TH*TW*128
+  int TH, TW, TT, TB;          // rows of one M tile = TB images x TT frames x TH x TW positions (<= 128)
+  int tiles_h, tiles_w, tiles_t, tiles_b, tiles_n, total_tiles;
+  uint32_t a_bytes;            // TB*TT*TH*TW*128
   // epilogue
   const float* scale;          // [Cout] or null (1)
   const float* bias;           // [Cout] or null (0)
@@ -58,6 +59,7 @@ struct ConvKernelParams {
   int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
   int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
+  int debug;                   // TUNING ONLY
   int cgroup;                  // output chunks staged per named-barrier pair / TMA commit group (divides ncbuf)
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
@@ -67,6 +69,14 @@ __device__ __forceinline__ float round_to_tf32(float v) {
   uint32_t u = __float_as_uint(v);
   u += 0xFFFu + ((u >> 13) & 1u);
   return __uint_as_float(u & 0xFFFFE000u);
+}
+
+constexpr int EPI_WARPS = 16;                         // 4 TMEM lane groups x 4 column quarters
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int CONV_THREADS = 64 + EPI_THREADS;        // + TMA producer warp + MMA issuer warp
+
+__device__ __forceinline__ void epi_bar_sync() {      // named barrier 1: the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
 
 template <int BN>
@@ -82,7 +92,8 @@ struct ConvCfg {
   // K-heavy layers want a deep operand ring; K-light (HBM-bound) layers want output staging buffers so the
   // epilogue never waits for a TMA store to drain.
   static void split(int kiters, int* stages, int* ncbuf) {
-    const int c = (kiters >= 12) ? ((BN >= 256) ? 1 : 2) : 4;
+    int c = (kiters >= 12) ? ((BN >= 256) ? 1 : 2) : 4;
+    if (const char* e = getenv("DT_CONV_NCBUF")) { const int g = atoi(e); if (kiters > 1 && kiters < 12 && (g == 1 || g == 2 || g == 4)) c = g; }   // TUNING ONLY
     int st = (BUDGET - FIXED_BYTES - c * C_BYTES) / STAGE_BYTES;
     if (st > MAX_STAGES) st = MAX_STAGES;
     *stages = st; *ncbuf = c;
@@ -91,7 +102,7 @@ struct ConvCfg {
 };
 
 template <int BN, bool TF32>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
   using Cfg = ConvCfg<BN>;
@@ -118,7 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
@@ -132,271 +143,292 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int mt = tile / p.tiles_n;
-        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-        const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-        const int t = mt % p.To;
-        const int n = mt / p.To;
-        const int w_base = twi * p.TW * p.sW - p.pW;
-        const int h_base = thi * p.TH * p.sH - p.pH;
-        const int t_base = t * p.sT - p.pT;
-        int tap = 0;
-        for (int kt = 0; kt < p.kT; ++kt)
-          for (int kh = 0; kh < p.kH; ++kh)
-            for (int kw = 0; kw < p.kW; ++kw, ++tap)
-              for (int kc = 0; kc < p.kchunks; ++kc) {
-                const int nsub = p.split_in ? 3 : 1;
-                for (int sub = 0; sub < nsub; ++sub) {
-                  // sub 0: A_hi x B_hi, 1: A_lo x B_hi, 2: A_hi x B_lo
-                  const int ca = kc * BK + (sub == 1 ? p.a_lo_off : 0);
-                  const int cb = kc * BK + (sub == 2 ? p.b_lo_off : 0);
-                  mbar_wait(&empty[stage], phase ^ 1);
-                  uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-                  uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                  mbar_expect_tx(&full[stage], p.a_bytes + Cfg::B_BYTES);
-                  tma_load_5d(a_dst, &tmA, &full[stage], ca, w_base + kw, h_base + kh, t_base + kt, n);
-                  tma_load_3d(b_dst, &tmB, &full[stage], cb, nt * BN, tap);
-                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-              }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, TF32 ? 2 : 1);
-      int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int ki = 0; ki < kiters; ++ki) {
-          mbar_wait(&full[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + Cfg::A_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)          // 4 x 32 B = one 128-byte swizzle row of K
-            umma<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&tmem_full[as]);           // accumulator ready for the epilogue
-        if (++as == 2) { as = 0; aphase ^= 1; }
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // TMEM -> registers -> fp32 epilogue -> 128B-swizzled smem chunk -> one TMA store per chunk.
-    // Eight warps (two per scheduler) so that TMEM / shared / global latencies of one warp hide behind
-    // the other: warp w reads TMEM lane group (w & 3) and the column half ((w - 2) >> 2) of each chunk.
-    // The TMA store writes whole 128-byte lines and clips rows / channels outside the tensor, so ragged
-    // tiles need no predication on the store side.
-    const int lg = warp & 3;                   // TMEM lane group this warp may access
-    const int half = (warp - 2) >> 2;          // which half of the staged 128-byte row this warp fills
-    const int row = lg * 32 + lane;            // accumulator row == TMEM lane == staging row
-    const int th = row / p.TW, tw = row - th * p.TW;
-    const bool leader = (threadIdx.x == 64);   // warp 2, lane 0 issues the stores
-    const int ep_tid = threadIdx.x - 64;       // 0..255
-    const int CW = p.out_f32 ? 32 : 64;        // output columns per 128-byte staged row
-    const uint32_t row_smem = (uint32_t)row * 128u;
-    const uint32_t swz = (uint32_t)(row & 7);
-    int as = 0; uint32_t aphase = 0;
-    uint32_t chunk_ctr = 0, grp_ctr = 0;
-    int grp_cc = 0;
+    // The whole warp runs the loop (warp-uniform control flow and addresses, so descriptors / coordinates
+    // stay in uniform registers); one elected lane issues.  A divergent `if (lane == 0)` around the loop
+    // makes the compiler wrap every UTMALDG / UTCHMMA in an elect-broadcast "waterfall" loop, which costs
+    // more than the MMAs of a narrow tile take to execute.
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t smem_u = smem_u32(smem);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
       const int twi = mt % p.tiles_w; mt /= p.tiles_w;
       const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-      const int t = mt % p.To;
-      const int n = mt / p.To;
+      const int tti = mt % p.tiles_t;
+      const int n = (mt / p.tiles_t) * p.TB;
+      const int w_base = twi * p.TW * p.sW - p.pW;
+      const int h_base = thi * p.TH * p.sH - p.pH;
+      const int t_base = tti * p.TT * p.sT - p.pT;
+      const int nsub = p.split_in ? 3 : 1;
+      int tap = 0;
+      for (int kt = 0; kt < p.kT; ++kt)
+        for (int kh = 0; kh < p.kH; ++kh)
+          for (int kw = 0; kw < p.kW; ++kw, ++tap)
+            for (int kc = 0; kc < p.kchunks; ++kc)
+              for (int sub = 0; sub < nsub; ++sub) {
+                // sub 0: A_hi x B_hi, 1: A_lo x B_hi, 2: A_hi x B_lo
+                const int ca = kc * BK + (sub == 1 ? p.a_lo_off : 0);
+                const int cb = kc * BK + (sub == 2 ? p.b_lo_off : 0);
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (elect_one()) {
+                  const uint32_t a_dst = smem_u + stage * Cfg::STAGE_BYTES;
+                  const uint32_t bar = smem_u32(&full[stage]);
+                  if (p.debug & 4) { mbar_arrive(&full[stage]); } else {
+                  mbar_expect_tx_u(bar, p.a_bytes + Cfg::B_BYTES);
+                  tma_load_5d_u(a_dst, &tmA, bar, ca, w_base + kw, h_base + kh, t_base + kt, n);
+                  tma_load_3d_u(a_dst + Cfg::A_BYTES, &tmB, bar, cb, nt * BN, tap); }
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc(128, BN, TF32 ? 2 : 1);
+    const uint32_t smem_u = smem_u32(smem);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_u + as * BN;
+      for (int ki = 0; ki < kiters; ++ki) {
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u + stage * Cfg::STAGE_BYTES;
+        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + Cfg::A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)          // 4 x 32 B = one 128-byte swizzle row of K
+            umma<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+          if (ki == kiters - 1) umma_commit(&tmem_full[as]);   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..17) =====================
+    // TMEM -> registers -> fp32 epilogue -> 128B-swizzled smem chunk -> one TMA store per chunk.
+    // The loop is latency-bound per warp (dependent address / convert / store chains, named barriers), so
+    // it runs on SIXTEEN warps (four per scheduler): warp w reads TMEM lane group (w & 3) and owns column
+    // quarter ((w - 2) >> 2) of every staged 128-byte row (32 bytes: 16 bf16 or 8 fp32 outputs).
+    // The TMA store writes whole 128-byte lines and clips rows / channels outside the tensor, so ragged
+    // tiles need no predication on the store side.  All layer constants live in registers, ring positions
+    // are counters (no divisions), scale/bias come from shared memory with explicit ld.shared.v4, ReLU rides
+    // on the bf16 pack (cvt.rn.relu), and the TMEM load of chunk c+1 is issued as soon as chunk c's
+    // accumulators have been consumed.
+    const int lg = warp & 3;                   // TMEM lane group this warp may access
+    const int part = (warp - 2) >> 2;          // which 32-byte quarter of the staged row this warp fills
+    const int row = lg * 32 + lane;            // accumulator row == TMEM lane == staging row
+    int rr = row;
+    const int tw = rr % p.TW; rr /= p.TW;
+    const int th = rr % p.TH; rr /= p.TH;
+    const int tl = rr % p.TT;
+    const int nl = rr / p.TT;                  // >= TB for the unused tail rows of a short tile
+    const bool store_warp = (warp == 2);       // one elected lane of warp 2 issues / tracks the TMA stores
+    const int ep_tid = threadIdx.x - 64;       // 0..511
+    const bool out_f32 = p.out_f32 != 0;
+    const bool split_out = p.split_out != 0;
+    const bool relu = p.relu != 0;
+    const int res_mode = p.res_mode;
+    const int Cout = p.Cout;
+    const int CW = out_f32 ? 32 : 64;          // output columns per 128-byte staged row
+    const int colw = out_f32 ? 8 : 16;         // columns this warp owns per chunk
+    const int ncbuf = p.ncbuf, cgroup = p.cgroup;
+    const int bstep = split_out ? 2 : 1;       // split output: buffers (2i, 2i+1) hold the hi / lo chunk
+    const int inflight = split_out ? 1 : ncbuf / cgroup - 1;   // commit groups that may stay pending
+    const uint32_t cbuf_u32 = smem_u32(cbuf);
+    const uint32_t row_smem = (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t q0 = (((uint32_t)(2 * part)) ^ swz) << 4, q1 = (((uint32_t)(2 * part + 1)) ^ swz) << 4;
+    const uint32_t sc_u32 = smem_u32(s_scale) + (uint32_t)(colw * part) * 4u;
+    const uint32_t bi_u32 = sc_u32 + BN * 4u;
+    int as = 0; uint32_t aphase = 0;
+    int buf_idx = 0, gi = 0, grp_buf = 0, grp_cc = 0;
+    int cur_nt = -1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int mt = tile / p.tiles_n;
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
+      const int tti = mt % p.tiles_t;
+      const int tbi = mt / p.tiles_t;
       const int ho = thi * p.TH + th, wo = twi * p.TW + tw;
-      const bool valid = (th < p.TH) && (ho < p.Ho) && (wo < p.Wo);
+      const int t = tti * p.TT + tl, n = tbi * p.TB + nl;
+      const bool valid = (nl < p.TB) && (ho < p.Ho) && (wo < p.Wo) && (t < p.To) && (n < p.N);
       const size_t pos = ((size_t)(n * p.To + t) * p.Ho + ho) * p.Wo + wo;
       size_t rpos = pos;
-      if (p.res_mode == 2)
+      if (res_mode == 2)
         rpos = ((size_t)(n * p.To + t) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
+      const int nbase = nt * BN;
+      const int ncols = min(BN, Cout - nbase);     // live output columns of this tile
 
-      // per-tile scale / bias -> smem (previous tile's readers are past their last named barrier)
-      for (int j = ep_tid; j < BN; j += 256) {
-        const int c = nt * BN + j;
-        s_scale[j] = (p.scale && c < p.Cout) ? __ldg(p.scale + c) : 1.f;
-        s_bias[j] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+      // scale / bias of this column tile -> smem (readers of the previous values are past their last
+      // named barrier); skipped while consecutive tiles share the column tile
+      if (nt != cur_nt) {
+        cur_nt = nt;
+        for (int j = ep_tid; j < BN; j += EPI_THREADS) {
+          const int c = nbase + j;
+          s_scale[j] = (p.scale && c < Cout) ? __ldg(p.scale + c) : 1.f;
+          s_bias[j] = (p.bias && c < Cout) ? __ldg(p.bias + c) : 0.f;
+        }
+        epi_bar_sync();
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
 
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)(colw * part);
+      uint32_t r[16];
+      if (out_f32) tmem_ld_32x32b_x8_lo(taddr, r); else tmem_ld_32x32b_x16(taddr, r);
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += CW) {
-        const int cchunk = nt * BN + cc;
-        if (cchunk >= p.Cout) break;                                   // uniform: nothing left to write
-        // bf16 residual rows for this chunk: issue the global loads FIRST so their latency overlaps the
-        // staging-buffer wait, the named barrier and the TMEM load below
-        uint4 resq[4];
-        bool res_vec = false;
-        if (!p.out_f32 && p.res_mode != 0 && valid) {
-          const int cb = nt * BN + cc + 32 * half;
-          if (cb + 32 <= p.Cout) {
-            res_vec = true;
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cb;
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) resq[g4] = __ldg(reinterpret_cast<const uint4*>(rp + 8 * g4));
-          }
-        }
-        // split output: buffers (2i, 2i+1) of a 4-buffer ring hold the hi / lo chunk, committed as ONE group
-        uint8_t* buf = p.split_out ? cbuf + ((chunk_ctr & 1u) * 2u) * Cfg::C_BYTES
-                                   : cbuf + (chunk_ctr % (uint32_t)p.ncbuf) * Cfg::C_BYTES;
-        const int gi = (int)(chunk_ctr % (uint32_t)p.cgroup);       // position inside the barrier group
-        if (gi == 0) { grp_cc = cc; grp_ctr = chunk_ctr; }
-        ++chunk_ctr;
-        if (gi == 0) {
-          // the staging buffers of this group must have been read out by the TMA stores that used them last
-          if (leader) {
-            const int inflight = p.split_out ? 1 : p.ncbuf / p.cgroup - 1;   // commit groups that may stay pending
-            if (inflight <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            else if (inflight == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-        const uint32_t dst = smem_u32(buf) + row_smem;
-        if (p.out_f32) {
-          // ---- fp32 output: this warp owns 16 columns = 64 bytes = 16-byte chunks [4*half, 4*half+4)
-          const int c0 = cc + 16 * half;
-          const int cbase = nt * BN + c0;
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(taddr + c0, r);
+      for (int cc = 0; cc < ncols; cc += CW) {
+        const int c0 = cc + colw * part;           // first column (inside the tile) this warp handles
+        const int cbase = nbase + c0;
+        const bool more = cc + CW < ncols;
+        float v[16];
+        if (out_f32) {
+          // ---- fp32 output: this warp owns 8 columns = 32 bytes
           tmem_ld_wait();
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]);
-          if (p.res_mode != 0 && valid) {
+          for (int q = 0; q < 2; ++q) {
+            const float4 s4 = lds_f4(sc_u32 + (uint32_t)(cc + 4 * q) * 4u), b4 = lds_f4(bi_u32 + (uint32_t)(cc + 4 * q) * 4u);
+            v[4 * q] = fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x);
+            v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y);
+            v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z);
+            v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w);
+          }
+          if (more) tmem_ld_32x32b_x8_lo(taddr + cc + CW, r);
+          if (res_mode != 0 && valid) {
             const float* rp = reinterpret_cast<const float*>(p.residual) + rpos * p.res_ld + cbase;
-            if (cbase + 16 <= p.Cout) {
+            if (cbase + 8 <= Cout) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
+              for (int j = 0; j < 8; j += 4) {
                 const float4 q = __ldg(reinterpret_cast<const float4*>(rp + j));
                 v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-                if (p.split_out) {                                   // residual = hi + lo
+                if (split_out) {                                     // residual = hi + lo
                   const float4 ql = __ldg(reinterpret_cast<const float4*>(rp + p.res_lo_off + j));
                   v[j] += ql.x; v[j + 1] += ql.y; v[j + 2] += ql.z; v[j + 3] += ql.w;
                 }
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cbase + j < p.Cout) v[j] += __ldg(rp + j) + (p.split_out ? __ldg(rp + p.res_lo_off + j) : 0.f);
+              for (int j = 0; j < 8; ++j)
+                if (cbase + j < Cout) v[j] += __ldg(rp + j) + (split_out ? __ldg(rp + p.res_lo_off + j) : 0.f);
             }
           }
+          if (relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-          if (p.split_out) {
-            float lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const float hi = round_to_tf32(v[j]); lo[j] = round_to_tf32(v[j] - hi); v[j] = hi; }
-            const uint32_t dst_lo = dst + Cfg::C_BYTES;               // the lo chunk uses the next staging buffer
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t a = dst_lo + ((((uint32_t)(4 * half + q)) ^ swz) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(lo[4 * q]), "f"(lo[4 * q + 1]),
-                           "f"(lo[4 * q + 2]), "f"(lo[4 * q + 3]) : "memory");
-            }
-          } else if (p.round_tf32) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = round_to_tf32(v[j]);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t a = dst + ((((uint32_t)(4 * half + q)) ^ swz) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * q]), "f"(v[4 * q + 1]),
-                         "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
           }
         } else {
-          // ---- bf16 output: this warp owns 32 columns = 64 bytes
-          const int c0 = cc + 32 * half;
-          const int cbase = nt * BN + c0;
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c0, r);
+          // ---- bf16 output: this warp owns 16 columns = 32 bytes
+          // residual rows first: the global loads overlap the TMEM wait and the scale/bias reads
+          uint4 resq[2];
+          const bool res_on = res_mode != 0 && valid;
+          const bool res_vec = res_on && (cbase + 16 <= Cout);
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
+          if (res_vec) {
+            resq[0] = __ldg(reinterpret_cast<const uint4*>(rp));
+            resq[1] = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+          }
           tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_bias[c0 + j]);
-          if (p.res_mode != 0 && valid) {
-            if (res_vec) {
-#pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4) {
-                const uint32_t w4[4] = {resq[g4].x, resq[g4].y, resq[g4].z, resq[g4].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[8 * g4 + 2 * e] += __uint_as_float(w4[e] << 16);
-                  v[8 * g4 + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
-                }
-              }
-            } else {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < p.Cout) v[j] += __bfloat162float(rp[j]);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-            const uint32_t a = dst + ((((uint32_t)(4 * half + q)) ^ swz) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+            const float4 s4 = lds_f4(sc_u32 + (uint32_t)(cc + 4 * q) * 4u), b4 = lds_f4(bi_u32 + (uint32_t)(cc + 4 * q) * 4u);
+            v[4 * q] = fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x);
+            v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y);
+            v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z);
+            v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w);
           }
+          if (more) tmem_ld_32x32b_x16(taddr + cc + CW, r);
+          if (res_vec) {
+#pragma unroll
+            for (int g4 = 0; g4 < 2; ++g4) {
+              const uint32_t w4[4] = {resq[g4].x, resq[g4].y, resq[g4].z, resq[g4].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[8 * g4 + 2 * e] += __uint_as_float(w4[e] << 16);
+                v[8 * g4 + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+              }
+            }
+          } else if (res_on) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cbase + j < Cout) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+
+        // staging buffers: the TMA stores that used this group's buffers last must have read them out
+        if (gi == 0) {
+          grp_buf = buf_idx; grp_cc = cc;
+          if (store_warp) {
+            if (elect_one()) {
+              if (inflight <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              else if (inflight == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            }
+            __syncwarp();
+          }
+          epi_bar_sync();
+        }
+        const uint32_t buf = cbuf_u32 + (uint32_t)buf_idx * Cfg::C_BYTES;
+        const uint32_t dst = buf + row_smem;
+        buf_idx += bstep;
+        if (buf_idx >= ncbuf) buf_idx = 0;
+        if (p.debug & 2) {} else
+        if (out_f32) {
+          if (split_out) {
+            float lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float hi = round_to_tf32(v[j]); lo[j] = round_to_tf32(v[j] - hi); v[j] = hi; }
+            const uint32_t dst_lo = dst + Cfg::C_BYTES;               // the lo chunk uses the next staging buffer
+            sts_f4(dst_lo + q0, lo[0], lo[1], lo[2], lo[3]);
+            sts_f4(dst_lo + q1, lo[4], lo[5], lo[6], lo[7]);
+          } else if (p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = round_to_tf32(v[j]);
+          }
+          sts_f4(dst + q0, v[0], v[1], v[2], v[3]);
+          sts_f4(dst + q1, v[4], v[5], v[6], v[7]);
+        } else {
+          uint32_t h[8];
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
+          sts_b4(dst + q0, h[0], h[1], h[2], h[3]);
+          sts_b4(dst + q1, h[4], h[5], h[6], h[7]);
         }
         // group complete (or last chunk of the tile): generic-proxy smem writes -> visible to the async
         // proxy, one barrier, then one thread stores every chunk of the group and commits them together
-        const bool last_in_group = (gi == p.cgroup - 1) || (cc + CW >= BN) || (nt * BN + cc + CW >= p.Cout);
-        if (last_in_group) {
+        if (gi == cgroup - 1 || !more) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (leader) {
-            if (p.split_out) {
-              asm volatile(
-                  "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                      reinterpret_cast<uint64_t>(&tmC)),
-                  "r"(smem_u32(buf)), "r"(cchunk), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
-                  : "memory");
-              asm volatile(
-                  "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                      reinterpret_cast<uint64_t>(&tmC)),
-                  "r"(smem_u32(buf) + Cfg::C_BYTES), "r"(cchunk + p.out_lo_off), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
-                  : "memory");
+          epi_bar_sync();
+          if (store_warp && elect_one() && !(p.debug & 1)) {
+            const int cw0 = twi * p.TW, ch0 = thi * p.TH, ct0 = tti * p.TT, cn0 = tbi * p.TB;
+            if (split_out) {
+              tma_store_5d(&tmC, buf, nbase + cc, cw0, ch0, ct0, cn0);
+              tma_store_5d(&tmC, buf + Cfg::C_BYTES, nbase + cc + p.out_lo_off, cw0, ch0, ct0, cn0);
             } else {
-              for (int g = 0; g <= gi; ++g) {
-                const uint32_t sb = smem_u32(cbuf + ((grp_ctr + (uint32_t)g) % (uint32_t)p.ncbuf) * Cfg::C_BYTES);
-                asm volatile(
-                    "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                        reinterpret_cast<uint64_t>(&tmC)),
-                    "r"(sb), "r"(nt * BN + grp_cc + g * CW), "r"(twi * p.TW), "r"(thi * p.TH), "r"(t), "r"(n)
-                    : "memory");
-              }
+              for (int g = 0; g <= gi; ++g)
+                tma_store_5d(&tmC, cbuf_u32 + (uint32_t)(grp_buf + g) * Cfg::C_BYTES, nbase + grp_cc + g * CW, cw0, ch0, ct0, cn0);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           // keep groups aligned in the buffer ring when a tile ends with a short group
-          chunk_ctr = (chunk_ctr + (uint32_t)p.cgroup - 1u) / (uint32_t)p.cgroup * (uint32_t)p.cgroup;
+          buf_idx = grp_buf + cgroup * bstep;
+          if (buf_idx >= ncbuf) buf_idx = 0;
+          gi = 0;
+        } else {
+          ++gi;
         }
       }
       tcgen05_fence_before();
@@ -404,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (store_warp && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -445,30 +477,42 @@ static int encode_map(CUtensorMap* m, bool f32, int rank, const void* base, cons
   return 0;
 }
 
-static void pick_tile(int Ho, int Wo, int* TH, int* TW) {
-  // maximise useful rows per 128-row MMA tile over a small candidate set
-  const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
-  double best = -1;
-  int bh = 8, bw = 16;
-  auto consider = [&](int th, int tw) {
-    if (th < 1 || tw < 1 || th * tw > 128 || tw > 256 || th > 256) return;
-    const double eff = (double)Ho * Wo / ((double)cdiv(Ho, th) * cdiv(Wo, tw) * 128.0);
-    if (eff > best + 1e-9) { best = eff; bh = th; bw = tw; }
-  };
-  for (auto& c : cand) consider(c[0], c[1]);
-  if (Wo <= 128) { consider(128 / Wo, Wo); for (int d = 2; d <= 4; ++d) { const int tw = cdiv(Wo, d); consider(128 / tw, tw); } }
-  if (Ho <= 128) { consider(Ho, 128 / Ho); for (int d = 2; d <= 4; ++d) { const int th = cdiv(Ho, d); consider(th, 128 / th); } }
-  *TH = bh; *TW = bw;
+// M tile = TB images x TT frames x TH x TW output positions (<= 128 rows).  Small feature maps (14x14 RoI
+// heads, 25x42 res5) would waste a quarter of every 128-row MMA with purely spatial tiles; stacking frames /
+// images fills the rows.  Among the shapes within 4 % of the best useful-row fraction a purely spatial tile
+// wins (the fullest, then the widest); otherwise the widest stacked tile (longest runs per TMA box).
+struct TileShape { int th, tw, tt, tb; };
+static TileShape pick_tile(int Ho, int Wo, int To, int N, int max_w, int max_h, bool stack_t) {
+  TileShape best = {8, 16, 1, 1};
+  double best_eff = -1;
+  long best_rank = -1;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int tw = 1; tw <= 128 && tw <= max_w && tw <= Wo; ++tw)
+      for (int th = 1; th * tw <= 128 && th <= max_h && th <= Ho; ++th) {
+        const int rem = 128 / (tw * th);
+        for (int tt = 1; tt <= rem && tt <= To && (tt == 1 || stack_t); ++tt)
+          for (int tb = 1; tb * tt <= rem && tb <= N; ++tb) {
+            const double tiles = (double)cdiv(Wo, tw) * cdiv(Ho, th) * cdiv(To, tt) * cdiv(N, tb);
+            const double eff = (double)Ho * Wo * To * N / (tiles * 128.0);
+            if (pass == 0) { if (eff > best_eff) best_eff = eff; continue; }
+            if (eff < best_eff - 0.04) continue;
+            const bool plain = tt == 1 && tb == 1;
+            const long e = (long)(eff * 1e6);
+            const long rank = plain ? (1L << 40) + e * 1000L + tw : (long)tw * 10000000L + e;
+            if (rank > best_rank) { best_rank = rank; best = {th, tw, tt, tb}; }
+          }
+      }
+  return best;
 }
 
-// Output map: dims (Cout, Wo, Ho, To, N) of the NDHWC result, box = one staged chunk (128 B of channels x TW x TH).
+// Output map: dims (Cout, Wo, Ho, To, N) of the NDHWC result, box = one staged chunk (128 B of channels x one M tile).
 static int encode_out_map(CUtensorMap* m, void* y, int out_f32, int Cout, int Wo, int Ho, int To, int N, int out_ld,
-                          int TH, int TW) {
+                          const TileShape& ts) {
   const uint64_t oesz = out_f32 ? 4 : 2;
   uint64_t d[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)To, (uint64_t)N};
   uint64_t st[4] = {(uint64_t)out_ld * oesz, (uint64_t)out_ld * oesz * Wo, (uint64_t)out_ld * oesz * Wo * Ho,
                     (uint64_t)out_ld * oesz * Wo * Ho * To};
-  uint32_t b[5] = {(uint32_t)(128 / oesz), (uint32_t)TW, (uint32_t)TH, 1, 1};
+  uint32_t b[5] = {(uint32_t)(128 / oesz), (uint32_t)ts.tw, (uint32_t)ts.th, (uint32_t)ts.tt, (uint32_t)ts.tb};
   uint32_t e[5] = {1, 1, 1, 1, 1};
   return encode_map(m, out_f32 != 0, 5, y, d, st, b, e);
 }
@@ -485,10 +529,12 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   ConvKernelParams q = p;
   Cfg::split(p.split_out ? 1 : p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1), &q.nstages, &q.ncbuf);
-  q.cgroup = (q.ncbuf >= 4 && !p.split_out) ? 4 : 1;
+  q.cgroup = (q.ncbuf >= 4 && !p.split_out) ? 4 : (q.ncbuf == 2 && !p.split_out ? 2 : 1);
+  if (const char* e = getenv("DT_CONV_DEBUG")) q.debug = atoi(e);
+  if (const char* e = getenv("DT_CONV_CGROUP")) { const int g = atoi(e); if (q.cgroup == 4 && (g == 1 || g == 2 || g == 4)) q.cgroup = g; }   // TUNING ONLY
   const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
-  conv_tc_kernel<BN, TF32><<<grid, 320, smem, stream>>>(tmA, tmB, tmC, q);
+  conv_tc_kernel<BN, TF32><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, q);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -531,16 +577,20 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && (d->res_mode == 0 || (res_ld * oesz) % 16 == 0),
                "dt_conv3d: out_ld/res_ld rows must be 16-byte multiples");
 
-  int TH, TW;
-  pick_tile(Ho, Wo, &TH, &TW);
+  // stacking frames inside one TMA box needs unit temporal stride (pointwise convs fold strides into the map)
+  const bool pointwise = d->kT == 1 && d->kH == 1 && d->kW == 1 && d->pT == 0 && d->pH == 0 && d->pW == 0;
+  const TileShape ts = pick_tile(Ho, Wo, To, d->N, pointwise ? 256 : 256 / d->sW, pointwise ? 256 : 256 / d->sH,
+                                 pointwise || d->sT == 1);
+  const int TH = ts.th, TW = ts.tw;
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->N; p.To = To; p.Ho = Ho; p.Wo = Wo; p.Cout = d->Cout;
   p.kT = d->kT; p.kH = d->kH; p.kW = d->kW; p.pT = d->pT; p.pH = d->pH; p.pW = d->pW;
   p.sT = d->sT; p.sH = d->sH; p.sW = d->sW;
   p.kchunks = cdiv(d->Cin, BK);
-  p.TH = TH; p.TW = TW; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW);
-  p.a_bytes = (uint32_t)TH * TW * 128u;
+  p.TH = TH; p.TW = TW; p.TT = ts.tt; p.TB = ts.tb;
+  p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_t = cdiv(To, ts.tt); p.tiles_b = cdiv(d->N, ts.tb);
+  p.a_bytes = (uint32_t)(TH * TW * ts.tt * ts.tb) * 128u;
   p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = d->res_mode; p.res_ld = res_ld;
   p.relu = d->relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32; p.round_tf32 = d->out_round_tf32;
   // 3xTF32 split operands / outputs
@@ -558,7 +608,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   int BN = d->Cout >= 256 ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32));
   if (d->Cout > 128 && d->Cout < 256) BN = 128;
   p.tiles_n = cdiv(d->Cout, BN);
-  const long long total = (long long)d->N * To * p.tiles_h * p.tiles_w * p.tiles_n;
+  const long long total = (long long)p.tiles_b * p.tiles_t * p.tiles_h * p.tiles_w * p.tiles_n;
   DT_CHECK_ARG(total < (1ll << 31), "dt_conv3d: too many tiles");
   p.total_tiles = (int)total;
 
@@ -567,19 +617,18 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   // padding) fold the stride into the global strides so no element-stride traversal is needed;
   // other strided convs use TMA element strides (box covers s*TW input columns, every s-th kept).
   CUtensorMap tmA, tmB;
-  const bool pointwise = d->kT == 1 && d->kH == 1 && d->kW == 1 && d->pT == 0 && d->pH == 0 && d->pW == 0;
   uint64_t dims[5], strides[4]; uint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   const uint64_t sC = (uint64_t)in_ld * esz, sW = sC * d->Wi, sH = sW * d->Hi, sT = sH * d->Ti;
   const uint64_t cdim = p.split_in ? (uint64_t)in_ld : (uint64_t)d->Cin;
   if (pointwise) {
     dims[0] = cdim; dims[1] = Wo; dims[2] = Ho; dims[3] = To; dims[4] = d->N;
     strides[0] = sC * d->sW; strides[1] = sW * d->sH; strides[2] = sH * d->sT; strides[3] = sT;
-    box[0] = BK; box[1] = TW; box[2] = TH; box[3] = 1; box[4] = 1;
+    box[0] = BK; box[1] = TW; box[2] = TH; box[3] = ts.tt; box[4] = ts.tb;
     p.sT = p.sH = p.sW = 1;
   } else {
     dims[0] = cdim; dims[1] = d->Wi; dims[2] = d->Hi; dims[3] = d->Ti; dims[4] = d->N;
     strides[0] = sC; strides[1] = sW; strides[2] = sH; strides[3] = sT;
-    box[0] = BK; box[1] = (uint32_t)TW * d->sW; box[2] = (uint32_t)TH * d->sH; box[3] = 1; box[4] = 1;
+    box[0] = BK; box[1] = (uint32_t)TW * d->sW; box[2] = (uint32_t)TH * d->sH; box[3] = ts.tt; box[4] = ts.tb;
     estr[1] = d->sW; estr[2] = d->sH;
     DT_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "dt_conv3d: strided tile too large for a TMA box");
   }
@@ -593,7 +642,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC;
-  if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, TH, TW)) return 1;
+  if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts)) return 1;
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -636,14 +685,15 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && out_ld >= Cout, "dt_conv1_7x7s2: bad out_ld %d", out_ld);
   const int Ho = Hp / 2, Wo = Wp / 2;
   const int BKe = 128 / esz;                       // elements per k-block
-  int TH, TW;
-  pick_tile(Ho, Wo, &TH, &TW);
+  const TileShape ts = pick_tile(Ho, Wo, 1, 1, 256, 128, false);      // spatial tiles only: rows are read with element stride 2
+  const int TH = ts.th, TW = ts.tw;
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
   p.N = F; p.To = 1; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.kT = 1; p.kH = 7; p.kW = 1; p.sT = 1; p.sH = 2; p.sW = 1; p.pT = 0; p.pH = 0; p.pW = 0;
   p.kchunks = 1;
-  p.TH = TH; p.TW = TW; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_n = 1;
+  p.TH = TH; p.TW = TW; p.TT = 1; p.TB = 1; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_t = 1; p.tiles_b = F;
+  p.tiles_n = 1;
   p.a_bytes = (uint32_t)TH * TW * 128u;
   p.scale = scale; p.bias = bias; p.relu = relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32;
   p.round_tf32 = out_round_tf32;
@@ -668,7 +718,7 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC;
-  if (encode_out_map(&tmC, y, out_f32, Cout, Wo, Ho, 1, F, out_ld, TH, TW)) return 1;
+  if (encode_out_map(&tmC, y, out_f32, Cout, Wo, Ho, 1, F, out_ld, ts)) return 1;
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

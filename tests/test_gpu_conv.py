@@ -50,6 +50,11 @@ CASES = [
     dict(N=1, T=3, H=64, W=96, Cin=8, Cout=64, k=(1, 7, 7), s=(1, 2, 2), p=(0, 3, 3), affine=True, relu=True),
     dict(N=2, T=3, H=30, W=44, Cin=64, Cout=128, k=(3, 3, 3), s=(1, 2, 2), p=(1, 1, 1), affine=True, relu=True),
     dict(N=1, T=1, H=33, W=47, Cin=64, Cout=64, k=(1, 3, 3), s=(1, 2, 2), p=(0, 1, 1)),
+    # small maps: the M tile stacks images / frames (ragged last stack included)
+    dict(N=20, T=1, H=14, W=14, Cin=64, Cout=96, k=(1, 3, 3), s=(1, 1, 1), p=(0, 1, 1), affine=True, res_mode=1, relu=True),
+    dict(N=2, T=3, H=25, W=42, Cin=64, Cout=64, k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1), affine=True, relu=True),
+    dict(N=5, T=3, H=7, W=7, Cin=64, Cout=128, k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1), bias=True),
+    dict(N=7, T=2, H=6, W=10, Cin=96, Cout=64, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0), res_mode=2),
 ]
 
 
@@ -120,6 +125,32 @@ def test_conv_bf16_output_and_channel_slices():
     got = out.cpu().float()
     assert torch.all(got[..., 64:] == 0)
     assert (got[..., :64] - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()     # bf16 output rounding (2^-8)
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 40, 56, 64, 256), (11, 1, 14, 14, 128, 200), (2, 3, 25, 42, 64, 256)])
+@pytest.mark.parametrize('res_mode', [1, 2])
+def test_conv_bf16_residual_epilogue(shape, res_mode):
+    """The hot-path epilogue: bf16 in / bf16 out, AffineChannel + residual (same shape, or nearest-2x
+    top-down add) + ReLU, including stacked M tiles and a ragged channel tail (Cout=200)."""
+    import torch
+    from detectandtrack_b200.ops import conv as cv
+    N, T, H, W, Cin, Cout = shape
+    if res_mode == 2 and (H % 2 or W % 2):
+        pytest.skip('upsample-add needs even output size')
+    g = torch.Generator().manual_seed(H * 131 + Cout + res_mode)
+    x = torch.randn((N, T, H, W, Cin), generator=g).bfloat16()
+    w = (torch.randn((Cout, Cin, 1, 1, 1), generator=g) * (1.0 / Cin) ** 0.5).bfloat16()
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    rs = (N, T, H, W, Cout) if res_mode == 1 else (N, T, H // 2, W // 2, Cout)
+    res = torch.randn(rs, generator=g).bfloat16()
+    wp = cv.pack_weight(w.float(), cv.BF16)
+    y = cv.conv3d(x.cuda(), wp, (1, 1, 1), (1, 1, 1), (0, 0, 0), scale.cuda(), bias.cuda(), res.cuda(), res_mode, True,
+                  out_f32=False, dtype=cv.BF16, cin=Cin)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x.float(), w.float(), (1, 1, 1), (0, 0, 0), scale, bias, res.float(), res_mode, True)
+    assert y.dtype == torch.bfloat16 and y.shape == ref.shape
+    assert (y.cpu().float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()   # bf16 output rounding (2^-8)
 
 
 def test_conv_rejects_bad_arguments():

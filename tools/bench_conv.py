@@ -18,9 +18,11 @@ LAYERS = [
     ('rpn_P2 256>256 1x3x3', 1, 200, 336, 256, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ('res2 64>64 1x3x3', 3, 200, 336, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
     ('res2 64>256 1x1x1', 3, 200, 336, 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ('res2 64>256 1x1x1 +res', 3, 200, 336, 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     ('res2 256>64 1x1x1', 3, 200, 336, 256, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     ('res3 128>128 3x3x3', 3, 100, 168, 128, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     ('res3 128>512 1x1x1', 3, 100, 168, 128, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ('res3 128>512 1x1x1 +res', 3, 100, 168, 128, 512, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     ('res4 256>256 3x3x3', 3, 50, 84, 256, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
     ('res4 1024>256 1x1x1', 3, 50, 84, 1024, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
     ('res5 512>512 3x3x3', 3, 25, 42, 512, 512, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
@@ -34,33 +36,37 @@ def main():
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--only', default='')
+    ap.add_argument('--n', type=int, default=1, help='clips per launch (body layers)')
     a = ap.parse_args()
     dtype = cv.BF16 if a.dtype == 'bf16' else cv.TF32
     tdt = torch.bfloat16 if dtype == cv.BF16 else torch.float32
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-    res = []
+    rows = []
     for (name, T, H, W, Cin, Cout, k, s, p) in LAYERS:
         if a.only and a.only not in name:
             continue
-        x = torch.randn((1, T, H, W, Cin), device='cuda').to(tdt)
+        nb = a.n if H > 14 and H * W > 1000 else 1
+        x = torch.randn((nb, T, H, W, Cin), device='cuda').to(tdt)
         w = cv.pack_weight(torch.randn((Cout, Cin) + k) * 0.02, dtype)
         sc = torch.ones(Cout, device='cuda'); bi = torch.zeros(Cout, device='cuda')
         y = cv.conv3d(x, w, k, s, p, sc, bi, relu=True, out_f32=(dtype == cv.TF32), dtype=dtype)
+        res = torch.randn_like(y) if name.endswith('+res') else None
+        rm = 1 if res is not None else 0
         torch.cuda.synchronize()
         ts = []
         for _ in range(a.iters):
             flush.zero_()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            cv.conv3d(x, w, k, s, p, sc, bi, relu=True, out_f32=(dtype == cv.TF32), dtype=dtype, out=y)
+            cv.conv3d(x, w, k, s, p, sc, bi, res, rm, relu=True, out_f32=(dtype == cv.TF32), dtype=dtype, out=y)
             e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
         flops = 2.0 * y.numel() * Cin * k[0] * k[1] * k[2]
-        res.append(dict(layer=name, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), gflop=round(flops / 1e9, 1)))
-        print(json.dumps(res[-1]), flush=True)
+        rows.append(dict(layer=name, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), gflop=round(flops / 1e9, 1)))
+        print(json.dumps(rows[-1]), flush=True)
     os.makedirs('gpurun_out', exist_ok=True)
-    json.dump(res, open('gpurun_out/bench_conv_%s.json' % a.dtype, 'w'), indent=1)
+    json.dump(rows, open('gpurun_out/bench_conv_%s.json' % a.dtype, 'w'), indent=1)
 
 
 if __name__ == '__main__':
