@@ -59,7 +59,7 @@ struct ConvKernelParams {
   int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
   int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
-  int debug;                   // TUNING ONLY
+  int nrbuf;                   // > 0: bf16 residual chunks arrive by TMA in a ring of this many staged chunks
   int cgroup;                  // output chunks staged per named-barrier pair / TMA commit group (divides ncbuf)
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
@@ -87,39 +87,47 @@ struct ConvCfg {
   static constexpr int MAX_STAGES = 8;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int C_BYTES = 128 * 128;            // one staged output chunk: 128 rows x 128 B
-  static constexpr int FIXED_BYTES = 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*scale, bias*/;
+  static constexpr int BAR_BYTES = 384;                // mbarriers + TMEM base pointer
+  static constexpr int FIXED_BYTES = BAR_BYTES + 2 * BN * 4 /*scale, bias*/;
   static constexpr int BUDGET = 227 * 1024;
   // K-heavy layers want a deep operand ring; K-light (HBM-bound) layers want output staging buffers so the
-  // epilogue never waits for a TMA store to drain.
-  static void split(int kiters, int* stages, int* ncbuf) {
+  // epilogue never waits for a TMA store to drain, and (with a residual) a ring of prefetched residual chunks.
+  static void split(int kiters, bool res_tma, int* stages, int* ncbuf, int* nrbuf) {
     int c = (kiters >= 12) ? ((BN >= 256) ? 1 : 2) : 4;
-    if (const char* e = getenv("DT_CONV_NCBUF")) { const int g = atoi(e); if (kiters > 1 && kiters < 12 && (g == 1 || g == 2 || g == 4)) c = g; }   // TUNING ONLY
-    int st = (BUDGET - FIXED_BYTES - c * C_BYTES) / STAGE_BYTES;
+    const int r = res_tma ? ((kiters >= 12) ? 2 : 4) : 0;
+    int st = (BUDGET - FIXED_BYTES - (c + r) * C_BYTES) / STAGE_BYTES;
     if (st > MAX_STAGES) st = MAX_STAGES;
-    *stages = st; *ncbuf = c;
+    *stages = st; *ncbuf = c; *nrbuf = r;
   }
-  static int smem_bytes(int stages, int ncbuf) { return stages * STAGE_BYTES + ncbuf * C_BYTES + FIXED_BYTES; }
+  static int smem_bytes(int stages, int ncbuf, int nrbuf) {
+    return stages * STAGE_BYTES + (ncbuf + nrbuf) * C_BYTES + FIXED_BYTES;
+  }
 };
 
 template <int BN, bool TF32>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const ConvKernelParams p) {
   using Cfg = ConvCfg<BN>;
   const int STAGES = p.nstages;
   constexpr int BK = TF32 ? 32 : 64;                 // elements per 128-byte k-block
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned operand ring (required by SWIZZLE_128B)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B operands need 1024-byte aligned tiles: the dynamic window is declared with that alignment
+  // (no static shared memory in this kernel) and checked once below instead of spending a kilobyte on slack
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* cbuf = smem + STAGES * Cfg::STAGE_BYTES;                  // [NCBUF][128 rows][128 B], 128B-swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + p.ncbuf * Cfg::C_BYTES);
+  uint8_t* rbuf = cbuf + p.ncbuf * Cfg::C_BYTES;                     // [NRBUF] residual chunks, same layout
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + p.nrbuf * Cfg::C_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + STAGES;             // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [BN]
-  float* s_bias = s_scale + BN;                                                           // [BN]
+  uint64_t* r_full = bars + 2 * STAGES + 4;    // [4]
+  uint64_t* r_empty = bars + 2 * STAGES + 8;   // [4]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
+  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [BN]
+  float* s_bias = s_scale + BN;                                                                      // [BN]
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,8 +136,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
+    if (p.nrbuf > 0) prefetch_tmap(&tmR);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
@@ -148,6 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // makes the compiler wrap every UTMALDG / UTCHMMA in an elect-broadcast "waterfall" loop, which costs
     // more than the MMAs of a narrow tile take to execute.
     int stage = 0; uint32_t phase = 0;
+    int rslot = 0; uint32_t rphase = 0;
     const uint32_t smem_u = smem_u32(smem);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
@@ -173,14 +184,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (elect_one()) {
                   const uint32_t a_dst = smem_u + stage * Cfg::STAGE_BYTES;
                   const uint32_t bar = smem_u32(&full[stage]);
-                  if (p.debug & 4) { mbar_arrive(&full[stage]); } else {
                   mbar_expect_tx_u(bar, p.a_bytes + Cfg::B_BYTES);
                   tma_load_5d_u(a_dst, &tmA, bar, ca, w_base + kw, h_base + kh, t_base + kt, n);
-                  tma_load_3d_u(a_dst + Cfg::A_BYTES, &tmB, bar, cb, nt * BN, tap); }
+                  tma_load_3d_u(a_dst + Cfg::A_BYTES, &tmB, bar, cb, nt * BN, tap);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
+      if (p.nrbuf > 0) {
+        // residual chunks of this tile (bf16, same box as the output chunks), consumed in order by the epilogue
+        const int nbase = nt * BN;
+        const int ncols = min(BN, p.Cout - nbase);
+        for (int cc = 0; cc < ncols; cc += 64) {
+          mbar_wait(&r_empty[rslot], rphase ^ 1);
+          if (elect_one()) {
+            const uint32_t bar = smem_u32(&r_full[rslot]);
+            mbar_expect_tx_u(bar, p.a_bytes);
+            tma_load_5d_u(smem_u32(rbuf) + rslot * Cfg::C_BYTES, &tmR, bar, nbase + cc, twi * p.TW, thi * p.TH,
+                          tti * p.TT, n);
+          }
+          __syncwarp();
+          if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp, one elected lane issues) =====================
@@ -243,6 +269,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int bstep = split_out ? 2 : 1;       // split output: buffers (2i, 2i+1) hold the hi / lo chunk
     const int inflight = split_out ? 1 : ncbuf / cgroup - 1;   // commit groups that may stay pending
     const uint32_t cbuf_u32 = smem_u32(cbuf);
+    const uint32_t rbuf_u32 = smem_u32(rbuf);
+    const bool res_tma = p.nrbuf > 0;
+    int rslot = 0; uint32_t rphase = 0;
     const uint32_t row_smem = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t q0 = (((uint32_t)(2 * part)) ^ swz) << 4, q1 = (((uint32_t)(2 * part + 1)) ^ swz) << 4;
@@ -329,12 +358,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // ---- bf16 output: this warp owns 16 columns = 32 bytes
           // residual rows first: the global loads overlap the TMEM wait and the scale/bias reads
           uint4 resq[2];
-          const bool res_on = res_mode != 0 && valid;
-          const bool res_vec = res_on && (cbase + 16 <= Cout);
+          const bool res_on = res_mode != 0 && valid && !res_tma;
+          bool res_vec = res_on && (cbase + 16 <= Cout);
           const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
           if (res_vec) {
             resq[0] = __ldg(reinterpret_cast<const uint4*>(rp));
             resq[1] = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+          }
+          if (res_tma) {
+            // the producer warp prefetched this chunk's residual rows (zero-filled outside the tensor) into
+            // the swizzled ring: read this thread's 32 bytes, then hand the slot back
+            mbar_wait(&r_full[rslot], rphase);
+            const uint32_t src = rbuf_u32 + (uint32_t)rslot * Cfg::C_BYTES + row_smem;
+            resq[0] = lds_u4(src + q0);
+            resq[1] = lds_u4(src + q1);
+            res_vec = true;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&r_empty[rslot]);
+            if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
           }
           tmem_ld_wait();
 #pragma unroll
@@ -380,7 +421,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t dst = buf + row_smem;
         buf_idx += bstep;
         if (buf_idx >= ncbuf) buf_idx = 0;
-        if (p.debug & 2) {} else
         if (out_f32) {
           if (split_out) {
             float lo[8];
@@ -412,7 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (gi == cgroup - 1 || !more) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           epi_bar_sync();
-          if (store_warp && elect_one() && !(p.debug & 1)) {
+          if (store_warp && elect_one()) {
             const int cw0 = twi * p.TW, ch0 = thi * p.TH, ct0 = tti * p.TT, cn0 = tbi * p.TB;
             if (split_out) {
               tma_store_5d(&tmC, buf, nbase + cc, cw0, ch0, ct0, cn0);
@@ -518,7 +558,7 @@ static int encode_out_map(CUtensorMap* m, void* y, int out_f32, int Cout, int Wo
 }
 
 template <int BN, bool TF32>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr = false;
@@ -528,13 +568,13 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr = true;
   }
   ConvKernelParams q = p;
-  Cfg::split(p.split_out ? 1 : p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1), &q.nstages, &q.ncbuf);
-  q.cgroup = (q.ncbuf >= 4 && !p.split_out) ? 4 : (q.ncbuf == 2 && !p.split_out ? 2 : 1);
-  if (const char* e = getenv("DT_CONV_DEBUG")) q.debug = atoi(e);
-  if (const char* e = getenv("DT_CONV_CGROUP")) { const int g = atoi(e); if (q.cgroup == 4 && (g == 1 || g == 2 || g == 4)) q.cgroup = g; }   // TUNING ONLY
-  const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf);
+  Cfg::split(p.split_out ? 1 : p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1), p.nrbuf > 0, &q.nstages, &q.ncbuf,
+             &q.nrbuf);
+  q.cgroup = p.split_out ? 1 : q.ncbuf;             // one named-barrier pair / commit group per ring of chunks
+  if (q.cgroup > 2 && BN < 256) q.cgroup = 2;       // ... but no longer than a tile (BN <= 128: two bf16 chunks)
+  const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf, q.nrbuf);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
-  conv_tc_kernel<BN, TF32><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, q);
+  conv_tc_kernel<BN, TF32><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, q);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -607,6 +647,12 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
 
   int BN = d->Cout >= 256 ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32));
   if (d->Cout > 128 && d->Cout < 256) BN = 128;
+  // bf16 same-shape residual: its chunks are prefetched by TMA into a shared-memory ring (coalesced 128-byte
+  // rows instead of one 32-byte global load per thread).  The ring needs room, so these layers use 128-wide
+  // column tiles (they are the K-light 1x1 expansions of the bottlenecks: HBM-bound, not MMA-bound).
+  const bool res_tma = d->res_mode == 1 && !out_f32 && !tf32 && ((uintptr_t)residual % 16) == 0;
+  if (res_tma && BN > 128) BN = 128;
+  p.nrbuf = res_tma ? 1 : 0;                         // ring depth is chosen with the smem split at launch
   p.tiles_n = cdiv(d->Cout, BN);
   const long long total = (long long)p.tiles_b * p.tiles_t * p.tiles_h * p.tiles_w * p.tiles_n;
   DT_CHECK_ARG(total < (1ll << 31), "dt_conv3d: too many tiles");
@@ -641,14 +687,19 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
     uint32_t we[3] = {1, 1, 1};
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
-  CUtensorMap tmC;
+  CUtensorMap tmC, tmR;
   if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts)) return 1;
+  if (res_tma) {
+    if (encode_out_map(&tmR, const_cast<void*>(residual), 0, d->Cout, Wo, Ho, To, d->N, res_ld, ts)) return 1;
+  } else {
+    tmR = tmC;
+  }
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
 #define DT_LAUNCH(BNv)                                                                      \
-  return tf32 ? launch_conv<BNv, true>(tmA, tmB, tmC, p, grid, stream) : launch_conv<BNv, false>(tmA, tmB, tmC, p, grid, stream)
+  return tf32 ? launch_conv<BNv, true>(tmA, tmB, tmC, tmR, p, grid, stream) : launch_conv<BNv, false>(tmA, tmB, tmC, tmR, p, grid, stream)
   switch (BN) {
     case 256: DT_LAUNCH(256);
     case 128: DT_LAUNCH(128);
@@ -723,5 +774,5 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  return tf32 ? launch_conv<64, true>(tmA, tmB, tmC, p, grid, stream) : launch_conv<64, false>(tmA, tmB, tmC, p, grid, stream);
+  return tf32 ? launch_conv<64, true>(tmA, tmB, tmC, tmC, p, grid, stream) : launch_conv<64, false>(tmA, tmB, tmC, tmC, p, grid, stream);
 }
