@@ -29,7 +29,7 @@ SIGNATURES = {
     'dt_distribute_fpn': [_p, _i, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p],
     'dt_box_decode': [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, C.POINTER(_f), C.c_double, _f, _p, _p, _p],
     'dt_limit_detections': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],
-    'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_conv1_7x7s2': [_p, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p],
     'dt_maxpool2d': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_roi_align': [C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _p, _i, _p, _i,
@@ -53,7 +53,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         'N', 'Ti', 'Hi', 'Wi', 'Cin', 'Cout', 'kT', 'kH', 'kW', 'sT', 'sH', 'sW', 'pT', 'pH', 'pW',
         'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode', 'x3', 'in_lo_off', 'out_lo_off',
-        'res_lo_off', 'out_round_tf32')]
+        'res_lo_off', 'out_round_tf32', 'out_time_major')]
 _RESTYPE = {'dt_last_error': C.c_char_p}
 
 

@@ -59,6 +59,7 @@ struct ConvKernelParams {
   int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
   int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
+  int row_planes;              // conv1: input rows de-interleaved by parity, filter row kh -> plane kh & 1, row + kh >> 1
   int nrbuf;                   // > 0: bf16 residual chunks arrive by TMA in a ring of this many staged chunks
   int cgroup;                  // output chunks staged per named-barrier pair / TMA commit group (divides ncbuf)
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
@@ -185,7 +186,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const uint32_t a_dst = smem_u + stage * Cfg::STAGE_BYTES;
                   const uint32_t bar = smem_u32(&full[stage]);
                   mbar_expect_tx_u(bar, p.a_bytes + Cfg::B_BYTES);
-                  tma_load_5d_u(a_dst, &tmA, bar, ca, w_base + kw, h_base + kh, t_base + kt, n);
+                  if (p.row_planes) tma_load_5d_u(a_dst, &tmA, bar, ca, w_base, h_base + (kh >> 1), kh & 1, n);
+                  else tma_load_5d_u(a_dst, &tmA, bar, ca, w_base + kw, h_base + kh, t_base + kt, n);
                   tma_load_3d_u(a_dst + Cfg::A_BYTES, &tmB, bar, cb, nt * BN, tap);
                 }
                 __syncwarp();
@@ -547,11 +549,12 @@ static TileShape pick_tile(int Ho, int Wo, int To, int N, int max_w, int max_h, 
 
 // Output map: dims (Cout, Wo, Ho, To, N) of the NDHWC result, box = one staged chunk (128 B of channels x one M tile).
 static int encode_out_map(CUtensorMap* m, void* y, int out_f32, int Cout, int Wo, int Ho, int To, int N, int out_ld,
-                          const TileShape& ts) {
+                          const TileShape& ts, bool time_major = false) {
   const uint64_t oesz = out_f32 ? 4 : 2;
   uint64_t d[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)To, (uint64_t)N};
-  uint64_t st[4] = {(uint64_t)out_ld * oesz, (uint64_t)out_ld * oesz * Wo, (uint64_t)out_ld * oesz * Wo * Ho,
-                    (uint64_t)out_ld * oesz * Wo * Ho * To};
+  const uint64_t frame = (uint64_t)out_ld * oesz * Wo * Ho;
+  uint64_t st[4] = {(uint64_t)out_ld * oesz, (uint64_t)out_ld * oesz * Wo, time_major ? frame * N : frame,
+                    time_major ? frame : frame * To};
   uint32_t b[5] = {(uint32_t)(128 / oesz), (uint32_t)ts.tw, (uint32_t)ts.th, (uint32_t)ts.tt, (uint32_t)ts.tb};
   uint32_t e[5] = {1, 1, 1, 1, 1};
   return encode_map(m, out_f32 != 0, 5, y, d, st, b, e);
@@ -688,7 +691,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC, tmR;
-  if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts)) return 1;
+  if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts, d->out_time_major != 0)) return 1;
   if (res_tma) {
     if (encode_out_map(&tmR, const_cast<void*>(residual), 0, d->Cout, Wo, Ho, To, d->N, res_ld, ts)) return 1;
   } else {
@@ -717,7 +720,9 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
 // dt_prep_clip), so the 7-pixel window of output column wo is ONE contiguous 112-byte run starting at
 // padded pixel 2*wo + 1.  The A tensor map is an overlapping strided view
 //   dim0 = 8 pixels x Cp (128 B, the 8th pixel meets zero weights), dim1 = wo (stride 2 pixels = 32 B),
-//   dim2 = padded rows (element stride 2), dim4 = frames
+//   dim2 = rows of one parity plane, dim3 = plane, dim4 = frames
+// (the blob's padded rows are de-interleaved by parity, so the stride-2 row walk of filter row kh is a
+// unit-stride box in plane kh & 1 starting at row ho + (kh >> 1); TMA element strides halve its throughput)
 // and the conv is 7 k-blocks (one per filter row) of K = 128 bytes: 3*7/ (8*8) = 33 % useful MACs instead
 // of 4.7 %.  w [7][Cout][8*Cp] (kw-major, channel-minor).  y [F, Hp/2, Wp/2, out_ld].
 extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
@@ -736,12 +741,13 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && out_ld >= Cout, "dt_conv1_7x7s2: bad out_ld %d", out_ld);
   const int Ho = Hp / 2, Wo = Wp / 2;
   const int BKe = 128 / esz;                       // elements per k-block
-  const TileShape ts = pick_tile(Ho, Wo, 1, 1, 256, 128, false);      // spatial tiles only: rows are read with element stride 2
+  const TileShape ts = pick_tile(Ho, Wo, 1, 1, 256, 128, false);      // spatial tiles only
   const int TH = ts.th, TW = ts.tw;
   ConvKernelParams p;
   memset(&p, 0, sizeof(p));
   p.N = F; p.To = 1; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
-  p.kT = 1; p.kH = 7; p.kW = 1; p.sT = 1; p.sH = 2; p.sW = 1; p.pT = 0; p.pH = 0; p.pW = 0;
+  p.kT = 1; p.kH = 7; p.kW = 1; p.sT = 1; p.sH = 1; p.sW = 1; p.pT = 0; p.pH = 0; p.pW = 0;
+  p.row_planes = 1;
   p.kchunks = 1;
   p.TH = TH; p.TW = TW; p.TT = 1; p.TB = 1; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_t = 1; p.tiles_b = F;
   p.tiles_n = 1;
@@ -751,14 +757,15 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   const long long total = (long long)F * p.tiles_h * p.tiles_w;
   DT_CHECK_ARG(total < (1ll << 31), "dt_conv1_7x7s2: too many tiles");
   p.total_tiles = (int)total;
-  const uint64_t pix = 16, row = (uint64_t)(Wp + 8) * pix, frame = row * (Hp + 6);
+  // padded rows are stored de-interleaved (dt_prep_clip row_planes): filter row kh of output row ho reads
+  // padded row 2*ho + kh = plane (kh & 1), plane row ho + (kh >> 1) -> unit-stride boxes, the plane is dim 3
+  const uint64_t pix = 16, row = (uint64_t)(Wp + 8) * pix, plane = row * ((Hp + 6) / 2), frame = 2 * plane;
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[5] = {(uint64_t)BKe, (uint64_t)Wo, (uint64_t)(Hp + 6), 1, (uint64_t)F};
-    uint64_t strides[4] = {2 * pix, row, frame, frame};
-    uint32_t box[5] = {(uint32_t)BKe, (uint32_t)TW, (uint32_t)(2 * TH), 1, 1};
-    uint32_t estr[5] = {1, 1, 2, 1, 1};
-    DT_CHECK_ARG(box[2] <= 256, "dt_conv1_7x7s2: tile too tall");
+    uint64_t dims[5] = {(uint64_t)BKe, (uint64_t)Wo, (uint64_t)((Hp + 6) / 2), 2, (uint64_t)F};
+    uint64_t strides[4] = {2 * pix, row, plane, frame};
+    uint32_t box[5] = {(uint32_t)BKe, (uint32_t)TW, (uint32_t)TH, 1, 1};
+    uint32_t estr[5] = {1, 1, 1, 1, 1};
     if (encode_map(&tmA, tf32, 5, (const char*)x_padded + pix, dims, strides, box, estr)) return 1;
   }
   {

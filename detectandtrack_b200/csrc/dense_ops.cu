@@ -78,8 +78,10 @@ __device__ __forceinline__ void store_vals(ET* p, int lo_off, float* v) {
 template <typename OT>
 __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F, int H, int W, float m0, float m1,
                                  float m2, double inv_scale, int Hr, int Wr, int Hp, int Wp, int Cp,
-                                 int by, int bx, int round_out, OT* __restrict__ out) {
-  // the output buffer is [F, Hp + 2*by, Wp + 2*bx, Cp]: `by` zero rows above/below, `bx` zero pixels left/right
+                                 int by, int bx, int round_out, int planes, OT* __restrict__ out) {
+  // the output buffer is [F, Hp + 2*by, Wp + 2*bx, Cp]: `by` zero rows above/below, `bx` zero pixels left/right;
+  // planes: the padded rows are de-interleaved, [F, 2 (row parity), Ht/2, Wt, Cp], so a stride-2 consumer
+  // (conv1) reads contiguous rows of one parity plane per filter row
   const int Ht = Hp + 2 * by, Wt = Wp + 2 * bx;
   const long long total = (long long)F * Ht * Wt;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -113,8 +115,21 @@ __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F
         }
       }
     }
-    OT* o = out + (size_t)idx * Cp;
-    for (int c = 0; c < Cp; ++c) o[c] = to_act<OT>(c < 3 ? (round_out ? round_to_tf32(v[c]) : v[c]) : 0.f);
+    size_t oidx = (size_t)idx;
+    if (planes) {
+      const int yt = y + by;
+      oidx = (((size_t)f * 2 + (yt & 1)) * (Ht >> 1) + (yt >> 1)) * Wt + (x + bx);
+    }
+    OT* o = out + oidx * Cp;
+    if (round_out) { v[0] = round_to_tf32(v[0]); v[1] = round_to_tf32(v[1]); v[2] = round_to_tf32(v[2]); }
+    if (Cp * sizeof(OT) == 16) {                      // one 16-byte store per pixel
+      float q[Vec<OT>::N];
+#pragma unroll
+      for (int c = 0; c < Vec<OT>::N; ++c) q[c] = c < 3 ? v[c] : 0.f;
+      Vec<OT>::store(o, q);
+    } else {
+      for (int c = 0; c < Cp; ++c) o[c] = to_act<OT>(c < 3 ? v[c] : 0.f);
+    }
   }
 }
 
@@ -250,6 +265,7 @@ __device__ __forceinline__ void cubic_coeffs(float x, float* c) {
 }
 
 #define KD_SW 256   // output columns per strip of the separable cubic resize
+#define KD_RB 256   // output rows per block of precomputed vertical weights
 
 __global__ void __launch_bounds__(256)
 keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, int T,
@@ -309,37 +325,68 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   const float wcorr = bw / (float)rw, hcorr = bh / (float)rh;
   const double sclx = 1.0 / ((double)rw / M), scly = 1.0 / ((double)rh / M);   // cv2: scale = 1 / (dsize / ssize)
   float* tmp = map + M * M;        // [M][KD_SW] horizontally resized strip
+  float4* cxs = reinterpret_cast<float4*>(tmp + M * KD_SW);   // [KD_SW] cubic weights of the strip's columns
+  int* sxs = reinterpret_cast<int*>(cxs + KD_SW);             // [KD_SW] their first source column
+  float4* cys = reinterpret_cast<float4*>(sxs + KD_SW);       // [KD_RB] cubic weights of a block of output rows
+  int* sys = reinterpret_cast<int*>(cys + KD_RB);             // [KD_RB] their first source row
   float best = -CUDART_INF_F; long long besti = 0x7fffffffffffffffll;
   float run_max = -CUDART_INF_F, run_sum = 0.f;
   for (int x0 = 0; x0 < rw; x0 += KD_SW) {
     const int sw = min(KD_SW, rw - x0);
-    for (int i = tid; i < M * sw; i += nth) {
-      const int y = i / sw, xl = i - y * sw;
+    // per-column weights once per strip (every source row reuses them)
+    for (int xl = tid; xl < sw; xl += nth) {
       float fx = (float)((x0 + xl + 0.5) * sclx - 0.5);
       const int sx = (int)floorf(fx);
       fx -= sx;
       float cx[4];
       cubic_coeffs(fx, cx);
-      float rowv = 0.f;
-#pragma unroll
-      for (int bq = 0; bq < 4; ++bq) rowv += map[y * M + min(max(sx - 1 + bq, 0), M - 1)] * cx[bq];
-      tmp[y * KD_SW + xl] = rowv;
+      cxs[xl] = make_float4(cx[0], cx[1], cx[2], cx[3]);
+      sxs[xl] = sx;
     }
     __syncthreads();
-    for (int xl = tid; xl < sw; xl += nth) {
-      for (int oy = 0; oy < rh; ++oy) {
-        float fy = (float)((oy + 0.5) * scly - 0.5);
+    for (int i = tid; i < M * sw; i += nth) {
+      const int y = i / sw, xl = i - y * sw;
+      const float4 c = cxs[xl];
+      const int sx = sxs[xl];
+      const float* mr = map + y * M;
+      float rowv = 0.f;
+      rowv += mr[min(max(sx - 1, 0), M - 1)] * c.x;
+      rowv += mr[min(max(sx, 0), M - 1)] * c.y;
+      rowv += mr[min(max(sx + 1, 0), M - 1)] * c.z;
+      rowv += mr[min(max(sx + 2, 0), M - 1)] * c.w;
+      tmp[y * KD_SW + xl] = rowv;
+    }
+    // vertical pass: the block's threads cover (column, row-phase) pairs so narrow boxes keep every lane
+    // busy; each thread keeps (max, first argmax, online sum of exp(v - max)) over the pixels it visits
+    const int nseg = max(1, nth / sw);
+    const int xl = tid % sw, seg = tid / sw;
+    for (int r0 = 0; r0 < rh; r0 += KD_RB) {
+      const int rb = min(KD_RB, rh - r0);
+      __syncthreads();                       // tmp complete / previous row block consumed
+      for (int r = tid; r < rb; r += nth) {
+        float fy = (float)((r0 + r + 0.5) * scly - 0.5);
         const int sy = (int)floorf(fy);
         fy -= sy;
         float cy[4];
         cubic_coeffs(fy, cy);
-        float v = 0.f;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) v += tmp[min(max(sy - 1 + a, 0), M - 1) * KD_SW + xl] * cy[a];
-        const long long lin = (long long)oy * rw + (x0 + xl);
-        if (v > best || (v == best && lin < besti)) { best = v; besti = lin; }
-        if (v > run_max) { run_sum = run_sum * expf(run_max - v) + 1.f; run_max = v; }
-        else run_sum += expf(v - run_max);
+        cys[r] = make_float4(cy[0], cy[1], cy[2], cy[3]);
+        sys[r] = sy;
+      }
+      __syncthreads();
+      if (seg < nseg) {
+        for (int r = seg; r < rb; r += nseg) {
+          const float4 c = cys[r];
+          const int sy = sys[r];
+          float v = 0.f;
+          v += tmp[min(max(sy - 1, 0), M - 1) * KD_SW + xl] * c.x;
+          v += tmp[min(max(sy, 0), M - 1) * KD_SW + xl] * c.y;
+          v += tmp[min(max(sy + 1, 0), M - 1) * KD_SW + xl] * c.z;
+          v += tmp[min(max(sy + 2, 0), M - 1) * KD_SW + xl] * c.w;
+          const long long lin = (long long)(r0 + r) * rw + (x0 + xl);
+          if (v > best || (v == best && lin < besti)) { best = v; besti = lin; }
+          if (v > run_max) { run_sum = run_sum * __expf(run_max - v) + 1.f; run_max = v; }
+          else run_sum += __expf(v - run_max);
+        }
       }
     }
     __syncthreads();
@@ -490,19 +537,20 @@ static int grid_for(long long total, int block) {
 
 extern "C" int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3 /*host*/,
                             double im_scale, int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x,
-                            int out_f32, void* out, void* stream) {
+                            int row_planes, int out_f32, void* out, void* stream) {
   DT_CHECK_ARG(F >= 0 && H >= 1 && W >= 1 && Hr >= 1 && Wr >= 1 && Hp >= Hr && Wp >= Wr && Cp >= 3 && im_scale > 0,
                "dt_prep_clip: bad shape F=%d H=%d W=%d Hr=%d Wr=%d Hp=%d Wp=%d Cp=%d", F, H, W, Hr, Wr, Hp, Wp, Cp);
   if (F == 0) return 0;
   DT_CHECK_ARG(frames && mean3 && out, "dt_prep_clip: null pointer");
   DT_CHECK_ARG(border_y >= 0 && border_x >= 0, "dt_prep_clip: negative border");
+  DT_CHECK_ARG(!row_planes || (Hp + 2 * border_y) % 2 == 0, "dt_prep_clip: row planes need an even padded height");
   const long long total = (long long)F * (Hp + 2 * border_y) * (Wp + 2 * border_x);
   if (out_f32)
     prep_clip_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, F, H, W, mean3[0], mean3[1], mean3[2],
-                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, out_f32 == 1, (float*)out);
+                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, out_f32 == 1, row_planes, (float*)out);
   else
     prep_clip_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, 0, (__nv_bfloat16*)out);
+        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, 0, row_planes, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -565,7 +613,7 @@ extern "C" int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, in
                "dt_keypoint_decode: bad shape S=%d K=%d T=%d D=%d ldl=%d ldb=%d", S, K, T, D, ldl, ldb);
   if (D == 0) return 0;
   DT_CHECK_ARG(lowres && boxes && xy_preds, "dt_keypoint_decode: null pointer");
-  const size_t smem = (size_t)(4 * S * S + 16 * S * S + 4 * S * KD_SW) * sizeof(float);
+  const size_t smem = (size_t)(4 * S * S + 16 * S * S + 4 * S * KD_SW) * sizeof(float) + (size_t)(KD_SW + KD_RB) * 20;
   static size_t attr = 0;
   if (smem > attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   dim3 grid(D, K, T);

@@ -45,9 +45,10 @@ class _Conv(object):
         self.scale = torch.from_numpy(np.ascontiguousarray(scale, dtype=np.float32)).cuda() if scale is not None else None
         self.bias = torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).cuda() if bias is not None else None
 
-    def __call__(self, x, residual=None, res_mode=0, relu=None, out_f32=None, cin=None, out=None):
+    def __call__(self, x, residual=None, res_mode=0, relu=None, out_f32=None, cin=None, out=None, time_major=False):
         return cv.conv3d(x, self.w, self.k, self.stride, self.pad, self.scale, self.bias, residual, res_mode,
-                         self.relu if relu is None else relu, out_f32=out_f32, dtype=self.dtype, cin=cin, out=out)
+                         self.relu if relu is None else relu, out_f32=out_f32, dtype=self.dtype, cin=cin, out=out,
+                         time_major=time_major)
 
 
 class DetectionEngine(object):
@@ -214,13 +215,13 @@ class DetectionEngine(object):
 
     # ------------------------------------------------------------------ backbone
     def body(self, x):
-        """x [B,T,Hp+6,Wp+8,cin_pad] (zero-bordered blob) -> stage outputs (finest first)."""
+        """x [B,T,2,(Hp+6)/2,Wp+8,cin_pad] (zero-bordered blob, rows split by parity) -> stage outputs (finest first)."""
         torch = self.torch
         B, T = x.shape[:2]
         if self.x3:      # exact fp32 conv1 on the raw (un-bordered) blob
             y = cv.conv1_7x7s2_f32(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, self.conv1_s, self.conv1_b)
         else:
-            hp, wp = x.shape[2] - 6, x.shape[3] - 8
+            hp, wp = 2 * x.shape[3] - 6, x.shape[4] - 8
             y = cv.conv1_7x7s2(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, (hp, wp), self.conv1_s, self.conv1_b,
                                relu=True, dtype=self.dtype)
         y = dense_ops.maxpool2d(y, 3, 2, 1, x3=self.x3)
@@ -249,12 +250,19 @@ class DetectionEngine(object):
                 conv = self.fpn_out[i]
                 y = cv.conv3d(xs, conv.w, conv.k, conv.stride, (0, 1, 1), conv.scale, conv.bias, dtype=conv.dtype)
             else:
-                y = self.fpn_out[i](x)
+                # frames-outermost output: the centre-frame link below is then a view, not a gather
+                y = self.fpn_out[i](x, time_major=(s.link == 'slice-center' and x.shape[1] > 1))
             outs.append(y)
         p5 = outs[0]
         B, T = p5.shape[:2]
-        p6 = dense_ops.maxpool2d(p5.view((B * T,) + tuple(p5.shape[2:])), 1, 2, 0, x3=self.x3)
-        outs.insert(0, p6.view((B, T) + tuple(p6.shape[1:])))
+        if p5.is_contiguous():
+            p6 = dense_ops.maxpool2d(p5.view((B * T,) + tuple(p5.shape[2:])), 1, 2, 0, x3=self.x3)
+            outs.insert(0, p6.view((B, T) + tuple(p6.shape[1:])))
+        else:                               # frames-outermost storage: pool the [T, B] stack, present [B, T]
+            p5t = p5.permute(1, 0, 2, 3, 4)
+            assert p5t.is_contiguous()
+            p6 = dense_ops.maxpool2d(p5t.view((T * B,) + tuple(p5.shape[2:])), 1, 2, 0, x3=self.x3)
+            outs.insert(0, p6.view((T, B) + tuple(p6.shape[1:])).permute(1, 0, 2, 3, 4))
         return outs[::-1]
 
     def link(self, feats):
@@ -426,8 +434,8 @@ class DetectionEngine(object):
                                     cpad=4, out_f32=2)
             return x.view(B, T, hp, wp, 4)
         x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
-                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4))
-        return x.view(B, T, hp + 6, wp + 8, self.cin_pad)
+                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4), row_planes=True)
+        return x.view(B, T, 2, (hp + 6) // 2, wp + 8, self.cin_pad)
 
     def forward_features(self, frames_u8):
         """frames [B, T, H, W, 3] uint8 cuda -> (feats2d finest first, im_info [B,3], scale)."""

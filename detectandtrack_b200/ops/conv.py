@@ -60,8 +60,10 @@ def round_tf32(t):
 
 def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias=None,
            residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None, round_tf32=None,
-           split_out=None):
-    """x [N,T,H,W,Cx] (first `cin` channels are the conv input); returns y [N,To,Ho,Wo,Cout]."""
+           split_out=None, time_major=False):
+    """x [N,T,H,W,Cx] (first `cin` channels are the conv input); returns y [N,To,Ho,Wo,Cout].
+    time_major: y is stored [To,N,Ho,Wo,Cout] and returned as the permuted [N,To,...] view, so y[:, t:t+1]
+    is contiguous (the centre-frame link needs no copy)."""
     torch = L.require_cuda()
     assert x.is_cuda and x.dim() == 5 and x.is_contiguous()
     assert x.dtype == _dt(dtype, torch), (x.dtype, dtype)
@@ -93,14 +95,17 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
         round_tf32 = False
     odt = torch.float32 if out_f32 else torch.bfloat16
     if out is None:
-        out = torch.empty((N, To, Ho, Wo, 2 * Cout if split_out else Cout), dtype=odt, device='cuda')
+        cw = 2 * Cout if split_out else Cout
+        out = torch.empty((To, N, Ho, Wo, cw) if time_major else (N, To, Ho, Wo, cw), dtype=odt, device='cuda')
+    else:
+        assert not time_major, 'time_major allocates its own output'
     assert out.dtype == odt and out.is_contiguous()
     d = L.ConvDesc(N=N, Ti=Ti, Hi=Hi, Wi=Wi, Cin=cin, Cout=Cout, kT=kT, kH=kH, kW=kW, sT=sT, sH=sH, sW=sW,
                    pT=pT, pH=pH, pW=pW, in_ld=Cx, w_ld=w_ld, out_ld=out.shape[-1],
                    res_ld=(residual.shape[-1] if residual is not None else 0), dtype=(TF32 if x3 else dtype),
                    out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode),
                    x3=(1 if x3 else 0) | (2 if split_out else 0), in_lo_off=0, out_lo_off=0, res_lo_off=0,
-                   out_round_tf32=int(bool(round_tf32)))
+                   out_round_tf32=int(bool(round_tf32)), out_time_major=int(bool(time_major)))
     if residual is not None:
         assert residual.dtype == odt and residual.is_contiguous()
     if scale is not None:
@@ -109,7 +114,7 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
         assert bias.dtype == torch.float32 and bias.numel() == Cout
     L.call('dt_conv3d', C.byref(d), L.ptr(x), L.ptr(w_packed), L.ptr(scale), L.ptr(bias), L.ptr(residual),
            L.ptr(out), L.stream_ptr())
-    return out
+    return out.permute(1, 0, 2, 3, 4) if time_major else out
 
 
 def pack_conv1_weight(w, dtype=BF16):
@@ -128,11 +133,11 @@ def pack_conv1_weight(w, dtype=BF16):
 
 
 def conv1_7x7s2(x_padded, w_packed, hw, scale=None, bias=None, relu=True, dtype=BF16, out_f32=None):
-    """x_padded [F, Hp+6, Wp+8, Cp] (dense_ops.prep_clip(border=(3, 4))) -> [F, Hp/2, Wp/2, Cout]."""
+    """x_padded [F, 2, (Hp+6)/2, Wp+8, Cp] (dense_ops.prep_clip(border=(3, 4), row_planes=True)) -> [F, Hp/2, Wp/2, Cout]."""
     torch = L.require_cuda()
-    F, Ht, Wt, Cp = x_padded.shape
+    F, two, Hh, Wt, Cp = x_padded.shape
     Hp, Wp = hw
-    assert Ht == Hp + 6 and Wt == Wp + 8 and x_padded.is_contiguous()
+    assert two == 2 and 2 * Hh == Hp + 6 and Wt == Wp + 8 and x_padded.is_contiguous()
     Cout = w_packed.shape[1]
     if out_f32 is None:
         out_f32 = dtype == TF32

@@ -4,19 +4,22 @@ import ctypes as C
 from .. import _lib as L
 
 
-def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=False, border=(0, 0)):
+def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=False, border=(0, 0), row_planes=False):
     """frames [F,H,W,3] uint8 cuda (BGR) -> [F,Hp+2by,Wp+2bx,cpad] (pixel - mean), resized, zero padded,
-    with `border` = (by, bx) physical zero rows / pixels on every side."""
+    with `border` = (by, bx) physical zero rows / pixels on every side.  row_planes: the padded rows are
+    de-interleaved by parity, [F, 2, (Hp+2by)/2, Wp+2bx, cpad] (the layout conv1_7x7s2 reads)."""
     torch = L.require_cuda()
     F, H, W, _ = frames_u8.shape
     Hr, Wr = out_hw
     Hp, Wp = pad_hw
     by, bx = border
+    Ht, Wt = Hp + 2 * by, Wp + 2 * bx
     # out_f32: False/0 bf16, True/1 fp32 rounded to tf32, 2 raw fp32
-    out = torch.empty((F, Hp + 2 * by, Wp + 2 * bx, cpad), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
+    shape = (F, 2, Ht // 2, Wt, cpad) if row_planes else (F, Ht, Wt, cpad)
+    out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
     m = (C.c_float * 3)(*[float(v) for v in pixel_means])
     L.call('dt_prep_clip', L.ptr(frames_u8.contiguous()), F, H, W, m, float(im_scale), Hr, Wr, Hp, Wp, cpad, by, bx,
-           int(out_f32), L.ptr(out), L.stream_ptr())
+           int(bool(row_planes)), int(out_f32), L.ptr(out), L.stream_ptr())
     return out
 
 

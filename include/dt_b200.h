@@ -141,6 +141,9 @@ typedef struct dt_conv_desc {
   int out_round_tf32; /* fp32 output rounded (nearest-even) to tf32: set when the consumer is another
                          DT_DTYPE_TF32 conv, because kind::tf32 truncates its operands (a one-sided
                          error that otherwise compounds to percents over ~50 layers) */
+  int out_time_major; /* 1: y is laid out [To, N, Ho, Wo, out_ld] instead of [N, To, Ho, Wo, out_ld], so one
+                         frame of the whole batch (the 'slice-center' link, model_builder.py:1024-1042) is a
+                         contiguous [N, Ho, Wo, out_ld] block and needs no gather */
 } dt_conv_desc;
 
 int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
@@ -148,7 +151,7 @@ int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, c
 
 /* conv1 of the ResNet bodies (lib/modeling/ResNet3D.py:258-261): 7x7 stride 2 pad 3 on the 3-channel
  * image + AffineChannel + ReLU, with the 7 taps of a filter row packed into one 128-byte k-block.
- * x_padded [F, Hp+6, Wp+8, Cp] from dt_prep_clip(border 3, 4), Cp*elemsize == 16;
+ * x_padded [F, 2, (Hp+6)/2, Wp+8, Cp] from dt_prep_clip(border 3, 4, row_planes 1), Cp*elemsize == 16;
  * w [7 (kh)][Cout <= 64][8*Cp] with w[kh][o][kw*Cp + c]; y [F, Hp/2, Wp/2, out_ld]. */
 int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
                    const float* scale, const float* bias, int relu, int dtype, int out_f32,
@@ -212,10 +215,12 @@ int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, in
  * out [F, Hp, Wp, Cp] (bf16 or fp32): (pixel - mean3) bilinearly resized by im_scale to Hr x Wr,
  * zero padded (Cp >= 3 channels, spatially to Hp x Wp) and framed by border_y zero rows / border_x
  * zero pixels on every side: out is [F, Hp + 2*border_y, Wp + 2*border_x, Cp] (dt_conv1_7x7s2 wants 3 / 4).
+ * row_planes != 0: the padded rows are de-interleaved by parity, out [F, 2, (Hp + 2*border_y)/2, Wt, Cp]
+ * with padded row r at [r & 1][r >> 1] (what dt_conv1_7x7s2 reads: its stride-2 row walk becomes contiguous).
  * out_f32: 0 bf16, 1 fp32 rounded to tf32 (kind::tf32 consumer), 2 raw fp32 (dt_conv1_7x7s2_f32). */
 int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3, double im_scale,
-                 int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x, int out_f32,
-                 void* out, void* stream);
+                 int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x, int row_planes,
+                 int out_f32, void* out, void* stream);
 
 /* Caffe2 MaxPool kernels [1,k,k] strides [1,s,s] pads [0,p,p] on NHWC (N = B*T frames).
  * x3 != 0: 3xTF32 storage, rows are [hi(C) | lo(C)] tf32 pairs at ld/2 (fp32 only). */

@@ -153,6 +153,22 @@ def test_conv_bf16_residual_epilogue(shape, res_mode):
     assert (y.cpu().float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()   # bf16 output rounding (2^-8)
 
 
+def test_conv_time_major_output():
+    """out_time_major: y stored [To, N, Ho, Wo, C]; the returned [N, To, ...] view equals the normal result and
+    a single-frame slice of it is contiguous (the centre-frame link becomes a view)."""
+    import torch
+    from detectandtrack_b200.ops import conv as cv
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((3, 3, 13, 21, 64), generator=g).bfloat16().cuda()
+    w = (torch.randn((64, 64, 3, 3, 3), generator=g) * 0.03).bfloat16()
+    wp = cv.pack_weight(w.float(), cv.BF16)
+    a = cv.conv3d(x, wp, (3, 3, 3), (1, 1, 1), (1, 1, 1), relu=True, out_f32=False, dtype=cv.BF16)
+    b = cv.conv3d(x, wp, (3, 3, 3), (1, 1, 1), (1, 1, 1), relu=True, out_f32=False, dtype=cv.BF16, time_major=True)
+    torch.cuda.synchronize()
+    assert b.shape == a.shape and not b.is_contiguous() and b[:, 1:2].is_contiguous()
+    assert torch.equal(a, b.contiguous())
+
+
 def test_conv_rejects_bad_arguments():
     import torch
     from detectandtrack_b200.ops import conv as cv
@@ -177,11 +193,13 @@ def test_conv1_packed_rows_vs_torch(mode):
     bi = torch.randn(64, generator=g) * 0.1
     dtype = cv.BF16 if mode == 'bf16' else cv.TF32
     cp = 8 if mode == 'bf16' else 4
-    x = dense_ops.prep_clip(frames.cuda(), means, 1.0, (H, W), (H, W), cpad=cp, out_f32=(mode == 'tf32'), border=(3, 4))
-    assert x.shape == (Fr, H + 6, W + 8, cp)
+    x = dense_ops.prep_clip(frames.cuda(), means, 1.0, (H, W), (H, W), cpad=cp, out_f32=(mode == 'tf32'), border=(3, 4),
+                            row_planes=True)
+    assert x.shape == (Fr, 2, (H + 6) // 2, W + 8, cp)
     wp = cv.pack_conv1_weight(w, dtype)
     y = cv.conv1_7x7s2(x, wp, (H, W), sc.cuda(), bi.cuda(), relu=True, dtype=dtype, out_f32=True).cpu()
-    xin = x[:, 3:3 + H, 4:4 + W, :3].float().cpu().permute(0, 3, 1, 2)          # what the kernel saw (rounded blob)
+    xfull = x.permute(0, 2, 1, 3, 4).reshape(Fr, H + 6, W + 8, cp)             # padded row r = [r & 1][r >> 1]
+    xin = xfull[:, 3:3 + H, 4:4 + W, :3].float().cpu().permute(0, 3, 1, 2)      # what the kernel saw (rounded blob)
     wr = w[:, :, 0].bfloat16().float() if mode == 'bf16' else w[:, :, 0]
     ref = F.conv2d(xin.double(), wr.double(), None, 2, 3) * sc.double().view(1, -1, 1, 1) + bi.double().view(1, -1, 1, 1)
     ref = ref.clamp_min(0).permute(0, 2, 3, 1).float()

@@ -26,6 +26,11 @@ def test_prep_clip_identity_scale_and_padding():
     ob = dense_ops.prep_clip(torch.from_numpy(fr).cuda(), means, 1.0, (H, W), (64, 96), cpad=8, out_f32=False, border=(3, 4)).float().cpu().numpy()
     assert ob.shape == (F, 70, 104, 8) and np.array_equal(ob[:, 3:67, 4:100], out_bf)
     assert np.all(ob[:, :3] == 0) and np.all(ob[:, 67:] == 0) and np.all(ob[:, :, :4] == 0) and np.all(ob[:, :, 100:] == 0)
+    # rows de-interleaved by parity (the layout conv1 reads): padded row r lives at [r & 1][r >> 1]
+    op = dense_ops.prep_clip(torch.from_numpy(fr).cuda(), means, 1.0, (H, W), (64, 96), cpad=8, out_f32=False, border=(3, 4),
+                             row_planes=True).float().cpu().numpy()
+    assert op.shape == (F, 2, 35, 104, 8)
+    assert np.array_equal(op[:, 0], ob[:, 0::2]) and np.array_equal(op[:, 1], ob[:, 1::2])
 
 
 @pytest.mark.parametrize('scale', [1.6, 0.53])

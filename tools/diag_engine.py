@@ -27,7 +27,7 @@ def rel(a, b):
 for mode in ('tf32', 'bf16'):
     eng = DetectionEngine(cfg, blobs, spec, dtype=mode)
     fr = torch.from_numpy(frames).cuda()
-    x = dense_ops.prep_clip(fr.view(3, 96, 128, 3), eng.pixel_means, 1.0, (96, 128), (96, 128), cpad=eng.cin_pad, out_f32=(mode == 'tf32'), border=(3, 4)).view(1, 3, 102, 136, eng.cin_pad)
+    x = dense_ops.prep_clip(fr.view(3, 96, 128, 3), eng.pixel_means, 1.0, (96, 128), (96, 128), cpad=eng.cin_pad, out_f32=(mode == 'tf32'), border=(3, 4), row_planes=True).view(1, 3, 2, 51, 136, eng.cin_pad)
     outs = eng.body(x)
     for i, o in enumerate(outs):
         r = stages[spec.stage_blobs[i]]
