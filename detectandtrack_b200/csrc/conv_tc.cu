@@ -17,12 +17,13 @@
 //           zero-filled by the TMA unit, so padding costs no instructions and no branches.
 //   W tile: 3-D TMA box (C=128B, BLOCK_N, 1) of the pre-packed [tap][Cout][Cin] weights.
 //   Both land in the 128B-swizzled K-major layout tcgen05.mma reads directly.
-// Roles (576 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0   : TMA producer (one elected lane)          smem ring: full[]/empty[] mbarriers
-//   warp 1   : TMEM allocator + MMA issuer (one lane)   tcgen05.mma -> TMEM, tcgen05.commit
-//   warps 2-17: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32, staged in
-//              128B-swizzled smem chunks and written with TMA stores.  Two TMEM accumulator stages
-//              overlap it with the next tile's MMAs.
+// Roles (640 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0, 19: TMA producers (activation / weight tiles; one elected lane each)   smem ring: full[]/empty[]
+//   warp 1    : TMEM allocator + MMA issuer (one lane)   tcgen05.mma -> TMEM, tcgen05.commit
+//   warp 2    : TMA store warp                           staged output chunks -> global, recycles staging slots
+//   warps 3-18: epilogue; TMEM -> registers (tcgen05.ld), scale/bias/residual/ReLU in fp32, staged in
+//               128B-swizzled smem chunks.  Two TMEM accumulator stages overlap it with the next tile's MMAs.
+// Everything is handed over through mbarriers; there is no block-wide barrier inside the tile loop.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/dt_b200.h"
@@ -31,6 +32,23 @@
 namespace dt {
 
 using namespace tc;
+
+// division by a run-time constant without the ~100-cycle integer-division sequence (valid for x < 2^31)
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = (uint32_t)d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    int l = 0;
+    while ((1u << l) < (uint32_t)d) ++l;
+    const int pw = 31 + l;
+    f.mul = (uint32_t)((((unsigned long long)1 << pw) + (unsigned long long)d - 1) / (unsigned long long)d);
+    f.shr = (uint32_t)(l - 1);
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return f.d == 1 ? x : (__umulhi(x, f.mul) >> f.shr); }
 
 struct ConvKernelParams {
   // output geometry
@@ -41,6 +59,7 @@ struct ConvKernelParams {
   // tiling
   int TH, TW, TT, TB;          // rows of one M tile = TB images x TT frames x TH x TW positions (<= 128)
   int tiles_h, tiles_w, tiles_t, tiles_b, tiles_n, total_tiles;
+  FastDiv fd_n, fd_w, fd_h, fd_t;    // tile index -> (column tile, w, h, t, image) tile coordinates
   uint32_t a_bytes;            // TB*TT*TH*TW*128
   // epilogue
   const float* scale;          // [Cout] or null (1)
@@ -59,9 +78,10 @@ struct ConvKernelParams {
   int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
   int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
+  int ks;                      // k-blocks per ring stage
+  int ktab;                    // entries of the k-block schedule (kiters + 1 padding, even)
   int row_planes;              // conv1: input rows de-interleaved by parity, filter row kh -> plane kh & 1, row + kh >> 1
   int nrbuf;                   // > 0: bf16 residual chunks arrive by TMA in a ring of this many staged chunks
-  int cgroup;                  // output chunks staged per named-barrier pair / TMA commit group (divides ncbuf)
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
 };
@@ -74,36 +94,60 @@ __device__ __forceinline__ float round_to_tf32(float v) {
 
 constexpr int EPI_WARPS = 16;                         // 4 TMEM lane groups x 4 column quarters
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int CONV_THREADS = 64 + EPI_THREADS;        // + TMA producer warp + MMA issuer warp
-
-__device__ __forceinline__ void epi_bar_sync() {      // named barrier 1: the epilogue warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-}
+constexpr int CONV_THREADS = 128 + EPI_THREADS;       // + two TMA producer warps, the MMA issuer and the TMA store warp
+constexpr int B_WARP = 3 + EPI_WARPS;                 // weight-tile producer (warps 3 .. 3+EPI_WARPS-1 are the epilogue)
 
 template <int BN>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;            // 128 rows x 128 B
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int KB_BYTES = A_BYTES + B_BYTES;   // one k-block of both operands
   static constexpr int MAX_STAGES = 8;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int C_BYTES = 128 * 128;            // one staged output chunk: 128 rows x 128 B
   static constexpr int BAR_BYTES = 384;                // mbarriers + TMEM base pointer
-  static constexpr int FIXED_BYTES = BAR_BYTES + 2 * BN * 4 /*scale, bias*/;
+  static constexpr int FIXED_BYTES = BAR_BYTES;
   static constexpr int BUDGET = 227 * 1024;
   // K-heavy layers want a deep operand ring; K-light (HBM-bound) layers want output staging buffers so the
   // epilogue never waits for a TMA store to drain, and (with a residual) a ring of prefetched residual chunks.
-  static void split(int kiters, bool res_tma, int* stages, int* ncbuf, int* nrbuf) {
-    int c = (kiters >= 12) ? ((BN >= 256) ? 1 : 2) : 4;
+  static int tab_bytes(int kiters) { return ((kiters + 2) * 24 + 127) / 128 * 128; }   // k-block schedule
+  static void split(int kiters, bool res_tma, bool split_out, bool out_f32, int* stages, int* ks, int* ncbuf, int* nrbuf) {
+    const int chunks = BN / (out_f32 ? 32 : 64);        // staged chunks per tile
+    int c = (kiters >= 12 && !split_out) ? ((BN >= 256) ? 1 : 2) : 4;   // split (hi, lo) output: two slots of two buffers
+    if (!split_out && c > 2 * chunks) c = chunks >= 1 ? 2 * chunks : 2;   // two tiles of staging are enough
     const int r = res_tma ? ((kiters >= 12) ? 2 : 4) : 0;
-    int st = (BUDGET - FIXED_BYTES - (c + r) * C_BYTES) / STAGE_BYTES;
+    // narrow tiles retire a k-block's MMAs faster than one producer / issuer round trip through the
+    // mbarriers: let a ring stage carry two k-blocks there (same bytes in flight, half the handshakes)
+    const int avail = BUDGET - FIXED_BYTES - tab_bytes(kiters) - (c + r) * C_BYTES;
+    const int k = (BN <= 128 && kiters >= 2 && avail / (2 * KB_BYTES) >= 3) ? 2 : 1;
+    int st = avail / (k * KB_BYTES);
     if (st > MAX_STAGES) st = MAX_STAGES;
-    *stages = st; *ncbuf = c; *nrbuf = r;
+    *stages = st; *ks = k; *ncbuf = c; *nrbuf = r;
   }
-  static int smem_bytes(int stages, int ncbuf, int nrbuf) {
-    return stages * STAGE_BYTES + (ncbuf + nrbuf) * C_BYTES + FIXED_BYTES;
+  static int smem_bytes(int kiters, int stages, int ks, int ncbuf, int nrbuf) {
+    return stages * ks * KB_BYTES + (ncbuf + nrbuf) * C_BYTES + FIXED_BYTES + tab_bytes(kiters);
   }
 };
+
+struct TileCoord { int nt, twi, thi, tti, tbi; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvKernelParams& p, int tile) {
+  TileCoord c;
+  uint32_t m = fdiv((uint32_t)tile, p.fd_n);  c.nt = tile - (int)m * p.tiles_n;
+  uint32_t q = fdiv(m, p.fd_w);               c.twi = (int)m - (int)q * p.tiles_w;  m = q;
+  q = fdiv(m, p.fd_h);                        c.thi = (int)m - (int)q * p.tiles_h;  m = q;
+  q = fdiv(m, p.fd_t);                        c.tti = (int)m - (int)q * p.tiles_t;
+  c.tbi = (int)q;
+  return c;
+}
+
+#ifdef DT_CONV_TRACE
+__device__ long long g_conv_trace[64 * 16];
+#define TRACE(ti, k) do { if (blockIdx.x == 0 && (ti) < 64) g_conv_trace[(ti) * 16 + (k)] = clock64(); } while (0)
+#define TRACE_ADD(ti, k, v) do { if (blockIdx.x == 0 && (ti) < 64) g_conv_trace[(ti) * 16 + (k)] += (v); } while (0)
+#else
+#define TRACE(ti, k) do {} while (0)
+#define TRACE_ADD(ti, k, v) do {} while (0)
+#endif
 
 template <int BN, bool TF32>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -116,19 +160,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // SWIZZLE_128B operands need 1024-byte aligned tiles: the dynamic window is declared with that alignment
   // (no static shared memory in this kernel) and checked once below instead of spending a kilobyte on slack
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* cbuf = smem + STAGES * Cfg::STAGE_BYTES;                  // [NCBUF][128 rows][128 B], 128B-swizzled
+  uint8_t* cbuf = smem + STAGES * p.ks * Cfg::KB_BYTES;              // [NCBUF][128 rows][128 B], 128B-swizzled
   uint8_t* rbuf = cbuf + p.ncbuf * Cfg::C_BYTES;                     // [NRBUF] residual chunks, same layout
   uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + p.nrbuf * Cfg::C_BYTES);
-  uint64_t* full = bars;                       // [STAGES]
-  uint64_t* empty = bars + STAGES;             // [STAGES]
-  uint64_t* tmem_full = bars + 2 * STAGES;     // [2]
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
-  uint64_t* r_full = bars + 2 * STAGES + 4;    // [4]
-  uint64_t* r_empty = bars + 2 * STAGES + 8;   // [4]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
-  float* s_scale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [BN]
-  float* s_bias = s_scale + BN;                                                                      // [BN]
+  uint64_t* full = bars;                       // [STAGES]  operands landed
+  uint64_t* empty = bars + STAGES;             // [STAGES]  operands consumed by the MMAs
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [2]       accumulator complete
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]       accumulator read out
+  uint64_t* r_full = tmem_full + 4;            // [4]       residual chunk landed
+  uint64_t* r_empty = tmem_full + 8;           // [4]       residual chunk consumed
+  uint64_t* c_full = tmem_full + 12;           // [4]       output chunk staged by all epilogue warps
+  uint64_t* c_free = tmem_full + 16;           // [4]       staging slot read out by its TMA store
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full + 20);
+  // k-block schedule of one tile: what the producers add to the tile's base coordinates for k-block j.
+  // Built once; walking taps / channel chunks with carry logic in the producer loop costs more cycles per
+  // k-block than a narrow tile's MMAs take.
+  int4* tabA = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // {c, dw, dh, dt}
+  int2* tabB = reinterpret_cast<int2*>(tabA + p.ktab);                                        // {c, tap}
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  {
+    const int nsub = p.split_in ? 3 : 1;
+    const int kit = p.kT * p.kH * p.kW * p.kchunks * nsub;
+    for (int j = threadIdx.x; j < p.ktab; j += blockDim.x) {
+      const int jj = min(j, kit - 1);                   // padding entries repeat the last k-block (never issued)
+      const int sub = jj % nsub;
+      int r = jj / nsub;
+      const int kc = r % p.kchunks; r /= p.kchunks;
+      const int tap = r;
+      const int kw = r % p.kW; r /= p.kW;
+      const int kh = r % p.kH;
+      const int kt = r / p.kH;
+      // sub 0: A_hi x B_hi, 1: A_lo x B_hi, 2: A_hi x B_lo
+      const int ca = kc * BK + (sub == 1 ? p.a_lo_off : 0);
+      const int cb = kc * BK + (sub == 2 ? p.b_lo_off : 0);
+      tabA[j] = p.row_planes ? make_int4(ca, 0, kh >> 1, kh & 1) : make_int4(ca, kw, kh, kt);
+      tabB[j] = make_int2(cb, tap);
+    }
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,9 +206,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     if (p.nrbuf > 0) prefetch_tmap(&tmR);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }    // full: A and B producers
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], EPI_WARPS); }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], EPI_WARPS);
+      mbar_init(&c_full[s], EPI_WARPS); mbar_init(&c_free[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_base_smem);
@@ -152,60 +223,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int taps = p.kT * p.kH * p.kW;
   const int kiters = taps * p.kchunks * (p.split_in ? 3 : 1);
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == B_WARP) {
+    // ===================== TMA producers =====================
+    // Two warps: warp 0 loads the activation tiles (and the residual ring), warp B_WARP the weight tiles; both
+    // arm the same full[] barrier with their own byte count.  One warp doing both spends ~500 cycles per
+    // k-block on scalar bookkeeping + TMA issue, more than a 128-column tile's MMAs take (256 cycles).
     // The whole warp runs the loop (warp-uniform control flow and addresses, so descriptors / coordinates
     // stay in uniform registers); one elected lane issues.  A divergent `if (lane == 0)` around the loop
-    // makes the compiler wrap every UTMALDG / UTCHMMA in an elect-broadcast "waterfall" loop, which costs
-    // more than the MMAs of a narrow tile take to execute.
+    // makes the compiler wrap every UTMALDG / UTCHMMA in an elect-broadcast "waterfall" loop.
+    const bool load_b = warp != 0;
     int stage = 0; uint32_t phase = 0;
     int rslot = 0; uint32_t rphase = 0;
-    const uint32_t smem_u = smem_u32(smem);
+    const uint32_t smem_u = smem_u32(smem) + (load_b ? (uint32_t)Cfg::A_BYTES : 0u);
+    const uint32_t full_u = smem_u32(full), empty_u = smem_u32(empty);
+    const int KS = p.ks;                                  // k-blocks per ring stage (one mbarrier round trip)
+    const uint32_t stage_bytes = (uint32_t)KS * Cfg::KB_BYTES;
+    const uint32_t kb_tx = load_b ? (uint32_t)Cfg::B_BYTES : p.a_bytes;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      int mt = tile / p.tiles_n;
-      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-      const int tti = mt % p.tiles_t;
-      const int n = (mt / p.tiles_t) * p.TB;
-      const int w_base = twi * p.TW * p.sW - p.pW;
-      const int h_base = thi * p.TH * p.sH - p.pH;
-      const int t_base = tti * p.TT * p.sT - p.pT;
-      const int nsub = p.split_in ? 3 : 1;
-      int tap = 0;
-      for (int kt = 0; kt < p.kT; ++kt)
-        for (int kh = 0; kh < p.kH; ++kh)
-          for (int kw = 0; kw < p.kW; ++kw, ++tap)
-            for (int kc = 0; kc < p.kchunks; ++kc)
-              for (int sub = 0; sub < nsub; ++sub) {
-                // sub 0: A_hi x B_hi, 1: A_lo x B_hi, 2: A_hi x B_lo
-                const int ca = kc * BK + (sub == 1 ? p.a_lo_off : 0);
-                const int cb = kc * BK + (sub == 2 ? p.b_lo_off : 0);
-                mbar_wait(&empty[stage], phase ^ 1);
-                if (elect_one()) {
-                  const uint32_t a_dst = smem_u + stage * Cfg::STAGE_BYTES;
-                  const uint32_t bar = smem_u32(&full[stage]);
-                  mbar_expect_tx_u(bar, p.a_bytes + Cfg::B_BYTES);
-                  if (p.row_planes) tma_load_5d_u(a_dst, &tmA, bar, ca, w_base, h_base + (kh >> 1), kh & 1, n);
-                  else tma_load_5d_u(a_dst, &tmA, bar, ca, w_base + kw, h_base + kh, t_base + kt, n);
-                  tma_load_3d_u(a_dst + Cfg::A_BYTES, &tmB, bar, cb, nt * BN, tap);
-                }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-              }
-      if (p.nrbuf > 0) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int n = tc.tbi * p.TB;
+      const int w_base = tc.twi * p.TW * p.sW - p.pW;
+      const int h_base = tc.thi * p.TH * p.sH - p.pH;
+      const int t_base = p.row_planes ? 0 : tc.tti * p.TT * p.sT - p.pT;
+      const int n_base = tc.nt * BN;
+#ifdef DT_CONV_TRACE
+      long long acc_wait = 0, acc_issue = 0;
+#endif
+      if (lane == 0 && !load_b) TRACE(tile / gridDim.x, 0);
+      for (int ki = 0; ki < kiters; ki += KS) {
+        const int nk = min(KS, kiters - ki);
+        // this stage's k-blocks from the schedule (uniform loads), then ONE elected issue block
+        int x0[2], x1[2], x2[2], x3[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (load_b) {
+            const int2 e = tabB[ki + q];
+            x0[q] = e.x; x1[q] = n_base; x2[q] = e.y; x3[q] = 0;
+          } else {
+            const int4 e = tabA[ki + q];
+            x0[q] = e.x; x1[q] = w_base + e.y; x2[q] = h_base + e.z; x3[q] = t_base + e.w;
+          }
+        }
+#ifdef DT_CONV_TRACE
+        const long long tw0 = clock64();
+#endif
+        mbar_wait_u(empty_u + stage * 8, phase ^ 1);
+#ifdef DT_CONV_TRACE
+        acc_wait += clock64() - tw0;
+        const long long tw2 = clock64();
+#endif
+        if (elect_one()) {
+          const uint32_t bar = full_u + stage * 8;
+          const uint32_t dst = smem_u + stage * stage_bytes;
+          mbar_expect_tx_u(bar, (uint32_t)nk * kb_tx);
+          if (load_b) {
+            tma_load_3d_u(dst, &tmB, bar, x0[0], x1[0], x2[0]);
+            if (nk > 1) tma_load_3d_u(dst + Cfg::KB_BYTES, &tmB, bar, x0[1], x1[1], x2[1]);
+          } else {
+            tma_load_5d_u(dst, &tmA, bar, x0[0], x1[0], x2[0], x3[0], n);
+            if (nk > 1) tma_load_5d_u(dst + Cfg::KB_BYTES, &tmA, bar, x0[1], x1[1], x2[1], x3[1], n);
+          }
+        }
+#ifdef DT_CONV_TRACE
+        acc_issue += clock64() - tw2;
+#endif
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (lane == 0 && !load_b) TRACE(tile / gridDim.x, 1);
+#ifdef DT_CONV_TRACE
+      if (lane == 0 && !load_b) { TRACE_ADD(tile / gridDim.x, 10, acc_wait); TRACE_ADD(tile / gridDim.x, 12, acc_issue); }
+#endif
+      if (p.nrbuf > 0 && !load_b) {
         // residual chunks of this tile (bf16, same box as the output chunks), consumed in order by the epilogue
-        const int nbase = nt * BN;
-        const int ncols = min(BN, p.Cout - nbase);
+        const int ncols = min(BN, p.Cout - n_base);
         for (int cc = 0; cc < ncols; cc += 64) {
           mbar_wait(&r_empty[rslot], rphase ^ 1);
           if (elect_one()) {
             const uint32_t bar = smem_u32(&r_full[rslot]);
             mbar_expect_tx_u(bar, p.a_bytes);
-            tma_load_5d_u(smem_u32(rbuf) + rslot * Cfg::C_BYTES, &tmR, bar, nbase + cc, twi * p.TW, thi * p.TH,
-                          tti * p.TT, n);
+            tma_load_5d_u(smem_u32(rbuf) + rslot * Cfg::C_BYTES, &tmR, bar, n_base + cc, tc.twi * p.TW, tc.thi * p.TH,
+                          tc.tti * p.TT, n);
           }
-          __syncwarp();
           if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
         }
       }
@@ -214,52 +312,107 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer (whole warp, one elected lane issues) =====================
     constexpr uint32_t idesc = make_idesc(128, BN, TF32 ? 2 : 1);
     const uint32_t smem_u = smem_u32(smem);
+    const uint32_t full_u = smem_u32(full);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int KS = p.ks;
+    const uint32_t stage_bytes = (uint32_t)KS * Cfg::KB_BYTES;
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_u + as * BN;
-      for (int ki = 0; ki < kiters; ++ki) {
-        mbar_wait(&full[stage], phase);
+      if (lane == 0) TRACE(tile / gridDim.x, 2);
+#ifdef DT_CONV_TRACE
+      long long acc_wf = 0;
+#endif
+      for (int ki = 0; ki < kiters; ki += KS) {
+        const int nk = min(KS, kiters - ki);
+#ifdef DT_CONV_TRACE
+        const long long tw1 = clock64();
+#endif
+        mbar_wait_u(full_u + stage * 8, phase);
+#ifdef DT_CONV_TRACE
+        acc_wf += clock64() - tw1;
+#endif
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u + stage * Cfg::STAGE_BYTES;
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + Cfg::A_BYTES);
+        const uint32_t a_addr = smem_u + stage * stage_bytes;
         if (elect_one()) {
+          for (int q = 0; q < nk; ++q) {
+            const uint64_t adesc = make_sw128_kmajor_desc(a_addr + q * Cfg::KB_BYTES);
+            const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + q * Cfg::KB_BYTES + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)          // 4 x 32 B = one 128-byte swizzle row of K
-            umma<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
-          if (ki == kiters - 1) umma_commit(&tmem_full[as]);   // accumulator ready for the epilogue
+            for (int k = 0; k < 4; ++k)          // 4 x 32 B = one 128-byte swizzle row of K
+              umma<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ki | q | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
+          if (ki + nk >= kiters) umma_commit(&tmem_full[as]);   // accumulator ready for the epilogue
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (lane == 0) TRACE(tile / gridDim.x, 3);
+#ifdef DT_CONV_TRACE
+      if (lane == 0) TRACE_ADD(tile / gridDim.x, 11, acc_wf);
+#endif
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+  } else if (warp == 2) {
+    // ===================== TMA store warp =====================
+    // Waits until all epilogue warps have staged a chunk (c_full), stores it (one elected lane, which also owns
+    // the bulk async-groups) and hands staging slots back (c_free) once their store has read them out.  Keeping
+    // this off the epilogue warps removes every block-wide barrier from the epilogue.
+    const bool split_out = p.split_out != 0;
+    const int CW = p.out_f32 ? 32 : 64;
+    const int nslots = split_out ? p.ncbuf / 2 : p.ncbuf;     // split output: a slot is a (hi, lo) buffer pair
+    const uint32_t slot_bytes = split_out ? 2u * Cfg::C_BYTES : (uint32_t)Cfg::C_BYTES;
+    const uint32_t cbuf_u32 = smem_u32(cbuf);
+    int slot = 0, prev_slot = 0; uint32_t sphase = 0;
+    int issued = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int nbase = tc.nt * BN;
+      const int ncols = min(BN, p.Cout - nbase);
+      const int cw0 = tc.twi * p.TW, ch0 = tc.thi * p.TH, ct0 = tc.tti * p.TT, cn0 = tc.tbi * p.TB;
+      for (int cc = 0; cc < ncols; cc += CW) {
+        mbar_wait(&c_full[slot], sphase);
+        if (elect_one()) {
+          const uint32_t buf = cbuf_u32 + (uint32_t)slot * slot_bytes;
+          tma_store_5d(&tmC, buf, nbase + cc, cw0, ch0, ct0, cn0);
+          if (split_out) tma_store_5d(&tmC, buf + Cfg::C_BYTES, nbase + cc + p.out_lo_off, cw0, ch0, ct0, cn0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // hand back the slot of the PREVIOUS chunk as soon as its store has read it out (at most this chunk's
+        // store stays pending), so the epilogue warps may run nslots - 1 chunks ahead of the slowest one
+        if (nslots == 1) {
+          if (elect_one()) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); mbar_arrive(&c_free[0]); }
+        } else if (issued > 0) {
+          if (elect_one()) { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); mbar_arrive(&c_free[prev_slot]); }
+        }
+        prev_slot = slot;
+        ++issued;
+        if (++slot == nslots) { slot = 0; sphase ^= 1; }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
-    // ===================== epilogue (warps 2..17) =====================
-    // TMEM -> registers -> fp32 epilogue -> 128B-swizzled smem chunk -> one TMA store per chunk.
-    // The loop is latency-bound per warp (dependent address / convert / store chains, named barriers), so
-    // it runs on SIXTEEN warps (four per scheduler): warp w reads TMEM lane group (w & 3) and owns column
-    // quarter ((w - 2) >> 2) of every staged 128-byte row (32 bytes: 16 bf16 or 8 fp32 outputs).
-    // The TMA store writes whole 128-byte lines and clips rows / channels outside the tensor, so ragged
-    // tiles need no predication on the store side.  All layer constants live in registers, ring positions
-    // are counters (no divisions), scale/bias come from shared memory with explicit ld.shared.v4, ReLU rides
-    // on the bf16 pack (cvt.rn.relu), and the TMEM load of chunk c+1 is issued as soon as chunk c's
-    // accumulators have been consumed.
+    // ===================== epilogue (warps 3..18) =====================
+    // TMEM -> registers -> fp32 epilogue -> 128B-swizzled smem chunk -> TMA store (store warp).
+    // Sixteen warps (four per scheduler): warp w reads TMEM lane group (w & 3) and owns column quarter
+    // ((w - 3) >> 2) of every staged 128-byte row (32 bytes: 16 bf16 or 8 fp32 outputs).  No block-wide
+    // barriers: staging slots are handed over through mbarriers (c_full / c_free), scale / bias are uniform
+    // 16-byte loads through L1, ReLU rides on the bf16 pack (cvt.rn.relu), the TMEM load of chunk c+1 is issued
+    // as soon as chunk c's accumulators have been consumed, and the accumulator is released to the MMA warp
+    // right after its last column has been read.  The TMA store writes whole 128-byte lines and clips rows /
+    // channels outside the tensor, so ragged tiles need no predication on the store side.
     const int lg = warp & 3;                   // TMEM lane group this warp may access
-    const int part = (warp - 2) >> 2;          // which 32-byte quarter of the staged row this warp fills
+    const int part = (warp - 3) >> 2;          // which 32-byte quarter of the staged row this warp fills
     const int row = lg * 32 + lane;            // accumulator row == TMEM lane == staging row
     int rr = row;
     const int tw = rr % p.TW; rr /= p.TW;
     const int th = rr % p.TH; rr /= p.TH;
     const int tl = rr % p.TT;
     const int nl = rr / p.TT;                  // >= TB for the unused tail rows of a short tile
-    const bool store_warp = (warp == 2);       // one elected lane of warp 2 issues / tracks the TMA stores
-    const int ep_tid = threadIdx.x - 64;       // 0..511
     const bool out_f32 = p.out_f32 != 0;
     const bool split_out = p.split_out != 0;
     const bool relu = p.relu != 0;
@@ -267,51 +420,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int Cout = p.Cout;
     const int CW = out_f32 ? 32 : 64;          // output columns per 128-byte staged row
     const int colw = out_f32 ? 8 : 16;         // columns this warp owns per chunk
-    const int ncbuf = p.ncbuf, cgroup = p.cgroup;
-    const int bstep = split_out ? 2 : 1;       // split output: buffers (2i, 2i+1) hold the hi / lo chunk
-    const int inflight = split_out ? 1 : ncbuf / cgroup - 1;   // commit groups that may stay pending
+    const int nslots = split_out ? p.ncbuf / 2 : p.ncbuf;
+    const uint32_t slot_bytes = split_out ? 2u * Cfg::C_BYTES : (uint32_t)Cfg::C_BYTES;
     const uint32_t cbuf_u32 = smem_u32(cbuf);
     const uint32_t rbuf_u32 = smem_u32(rbuf);
     const bool res_tma = p.nrbuf > 0;
+    const bool res_ldg = res_mode != 0 && !res_tma;
     int rslot = 0; uint32_t rphase = 0;
     const uint32_t row_smem = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t q0 = (((uint32_t)(2 * part)) ^ swz) << 4, q1 = (((uint32_t)(2 * part + 1)) ^ swz) << 4;
-    const uint32_t sc_u32 = smem_u32(s_scale) + (uint32_t)(colw * part) * 4u;
-    const uint32_t bi_u32 = sc_u32 + BN * 4u;
+    const float* __restrict__ g_scale = p.scale;
+    const float* __restrict__ g_bias = p.bias;
     int as = 0; uint32_t aphase = 0;
-    int buf_idx = 0, gi = 0, grp_buf = 0, grp_cc = 0;
-    int cur_nt = -1;
+    int slot = 0; uint32_t sphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      int mt = tile / p.tiles_n;
-      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-      const int tti = mt % p.tiles_t;
-      const int tbi = mt / p.tiles_t;
-      const int ho = thi * p.TH + th, wo = twi * p.TW + tw;
-      const int t = tti * p.TT + tl, n = tbi * p.TB + nl;
-      const bool valid = (nl < p.TB) && (ho < p.Ho) && (wo < p.Wo) && (t < p.To) && (n < p.N);
-      const size_t pos = ((size_t)(n * p.To + t) * p.Ho + ho) * p.Wo + wo;
-      size_t rpos = pos;
-      if (res_mode == 2)
-        rpos = ((size_t)(n * p.To + t) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
-      const int nbase = nt * BN;
-      const int ncols = min(BN, Cout - nbase);     // live output columns of this tile
-
-      // scale / bias of this column tile -> smem (readers of the previous values are past their last
-      // named barrier); skipped while consecutive tiles share the column tile
-      if (nt != cur_nt) {
-        cur_nt = nt;
-        for (int j = ep_tid; j < BN; j += EPI_THREADS) {
-          const int c = nbase + j;
-          s_scale[j] = (p.scale && c < Cout) ? __ldg(p.scale + c) : 1.f;
-          s_bias[j] = (p.bias && c < Cout) ? __ldg(p.bias + c) : 0.f;
-        }
-        epi_bar_sync();
+      const TileCoord tc = decode_tile(p, tile);
+      bool valid = true;
+      size_t rpos = 0;
+      if (res_ldg) {                           // per-thread residual row (fp32 / upsample-add paths only)
+        const int ho = tc.thi * p.TH + th, wo = tc.twi * p.TW + tw;
+        const int t = tc.tti * p.TT + tl, n = tc.tbi * p.TB + nl;
+        valid = (nl < p.TB) && (ho < p.Ho) && (wo < p.Wo) && (t < p.To) && (n < p.N);
+        rpos = (res_mode == 2) ? ((size_t)(n * p.To + t) * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)
+                               : ((size_t)(n * p.To + t) * p.Ho + ho) * p.Wo + wo;
       }
+      const int nbase = tc.nt * BN;
+      const int ncols = min(BN, Cout - nbase);     // live output columns of this tile
+      if (threadIdx.x == 96) TRACE(tile / gridDim.x, 4);
 
       mbar_wait(&tmem_full[as], aphase);
+      if (threadIdx.x == 96) TRACE(tile / gridDim.x, 5);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)(colw * part);
       uint32_t r[16];
@@ -321,19 +460,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c0 = cc + colw * part;           // first column (inside the tile) this warp handles
         const int cbase = nbase + c0;
         const bool more = cc + CW < ncols;
+        // AffineChannel scale / bias of this warp's columns: uniform 16-byte loads (L1 hits after first touch)
+        float sc[16], bi[16];
+        if (cbase + colw <= Cout) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < (colw >> 2)) {
+              const float4 s4 = g_scale ? __ldg(reinterpret_cast<const float4*>(g_scale + cbase) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 b4 = g_bias ? __ldg(reinterpret_cast<const float4*>(g_bias + cbase) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+              sc[4 * q] = s4.x; sc[4 * q + 1] = s4.y; sc[4 * q + 2] = s4.z; sc[4 * q + 3] = s4.w;
+              bi[4 * q] = b4.x; bi[4 * q + 1] = b4.y; bi[4 * q + 2] = b4.z; bi[4 * q + 3] = b4.w;
+            }
+          }
+        } else {                                   // ragged channel tail
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool in = j < colw && cbase + j < Cout;
+            sc[j] = (in && g_scale) ? __ldg(g_scale + cbase + j) : 1.f;
+            bi[j] = (in && g_bias) ? __ldg(g_bias + cbase + j) : 0.f;
+          }
+        }
         float v[16];
         if (out_f32) {
           // ---- fp32 output: this warp owns 8 columns = 32 bytes
           tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 s4 = lds_f4(sc_u32 + (uint32_t)(cc + 4 * q) * 4u), b4 = lds_f4(bi_u32 + (uint32_t)(cc + 4 * q) * 4u);
-            v[4 * q] = fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x);
-            v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y);
-            v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z);
-            v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w);
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
+          if (more) {
+            tmem_ld_32x32b_x8_lo(taddr + cc + CW, r);
+          } else {                                 // accumulator fully read: release it to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          if (more) tmem_ld_32x32b_x8_lo(taddr + cc + CW, r);
           if (res_mode != 0 && valid) {
             const float* rp = reinterpret_cast<const float*>(p.residual) + rpos * p.res_ld + cbase;
             if (cbase + 8 <= Cout) {
@@ -358,9 +517,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else {
           // ---- bf16 output: this warp owns 16 columns = 32 bytes
-          // residual rows first: the global loads overlap the TMEM wait and the scale/bias reads
+          // residual rows first: the global loads overlap the TMEM wait
           uint4 resq[2];
-          const bool res_on = res_mode != 0 && valid && !res_tma;
+          const bool res_on = res_ldg && valid;
           bool res_vec = res_on && (cbase + 16 <= Cout);
           const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
           if (res_vec) {
@@ -381,14 +540,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 s4 = lds_f4(sc_u32 + (uint32_t)(cc + 4 * q) * 4u), b4 = lds_f4(bi_u32 + (uint32_t)(cc + 4 * q) * 4u);
-            v[4 * q] = fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x);
-            v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y);
-            v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z);
-            v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w);
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
+          if (more) {
+            tmem_ld_32x32b_x16(taddr + cc + CW, r);
+          } else {                                 // accumulator fully read: release it to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          if (more) tmem_ld_32x32b_x16(taddr + cc + CW, r);
           if (res_vec) {
 #pragma unroll
             for (int g4 = 0; g4 < 2; ++g4) {
@@ -406,29 +565,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
 
-        // staging buffers: the TMA stores that used this group's buffers last must have read them out
-        if (gi == 0) {
-          grp_buf = buf_idx; grp_cc = cc;
-          if (store_warp) {
-            if (elect_one()) {
-              if (inflight <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-              else if (inflight == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-              else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-            }
-            __syncwarp();
-          }
-          epi_bar_sync();
-        }
-        const uint32_t buf = cbuf_u32 + (uint32_t)buf_idx * Cfg::C_BYTES;
-        const uint32_t dst = buf + row_smem;
-        buf_idx += bstep;
-        if (buf_idx >= ncbuf) buf_idx = 0;
+        // staging slot: the TMA store that used it last must have read it out (c_free)
+        mbar_wait(&c_free[slot], sphase ^ 1);
+        if (threadIdx.x == 96) TRACE(tile / gridDim.x, 6);
+        const uint32_t dst = cbuf_u32 + (uint32_t)slot * slot_bytes + row_smem;
         if (out_f32) {
           if (split_out) {
             float lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float hi = round_to_tf32(v[j]); lo[j] = round_to_tf32(v[j] - hi); v[j] = hi; }
-            const uint32_t dst_lo = dst + Cfg::C_BYTES;               // the lo chunk uses the next staging buffer
+            const uint32_t dst_lo = dst + Cfg::C_BYTES;               // the lo chunk uses the slot's second buffer
             sts_f4(dst_lo + q0, lo[0], lo[1], lo[2], lo[3]);
             sts_f4(dst_lo + q1, lo[4], lo[5], lo[6], lo[7]);
           } else if (p.round_tf32) {
@@ -449,36 +595,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           sts_b4(dst + q0, h[0], h[1], h[2], h[3]);
           sts_b4(dst + q1, h[4], h[5], h[6], h[7]);
         }
-        // group complete (or last chunk of the tile): generic-proxy smem writes -> visible to the async
-        // proxy, one barrier, then one thread stores every chunk of the group and commits them together
-        if (gi == cgroup - 1 || !more) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_bar_sync();
-          if (store_warp && elect_one()) {
-            const int cw0 = twi * p.TW, ch0 = thi * p.TH, ct0 = tti * p.TT, cn0 = tbi * p.TB;
-            if (split_out) {
-              tma_store_5d(&tmC, buf, nbase + cc, cw0, ch0, ct0, cn0);
-              tma_store_5d(&tmC, buf + Cfg::C_BYTES, nbase + cc + p.out_lo_off, cw0, ch0, ct0, cn0);
-            } else {
-              for (int g = 0; g <= gi; ++g)
-                tma_store_5d(&tmC, cbuf_u32 + (uint32_t)(grp_buf + g) * Cfg::C_BYTES, nbase + grp_cc + g * CW, cw0, ch0, ct0, cn0);
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          // keep groups aligned in the buffer ring when a tile ends with a short group
-          buf_idx = grp_buf + cgroup * bstep;
-          if (buf_idx >= ncbuf) buf_idx = 0;
-          gi = 0;
-        } else {
-          ++gi;
-        }
+        // generic-proxy smem writes -> visible to the async proxy, then this warp's arrival on the slot
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_full[slot]);
+        if (threadIdx.x == 96) TRACE(tile / gridDim.x, 7);
+        if (++slot == nslots) { slot = 0; sphase ^= 1; }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (threadIdx.x == 96) TRACE(tile / gridDim.x, 9);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (store_warp && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tcgen05_fence_before();
@@ -571,11 +697,11 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr = true;
   }
   ConvKernelParams q = p;
-  Cfg::split(p.split_out ? 1 : p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1), p.nrbuf > 0, &q.nstages, &q.ncbuf,
-             &q.nrbuf);
-  q.cgroup = p.split_out ? 1 : q.ncbuf;             // one named-barrier pair / commit group per ring of chunks
-  if (q.cgroup > 2 && BN < 256) q.cgroup = 2;       // ... but no longer than a tile (BN <= 128: two bf16 chunks)
-  const int smem = Cfg::smem_bytes(q.nstages, q.ncbuf, q.nrbuf);
+  const int kiters = p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1);
+  DT_CHECK_ARG(kiters <= 2048, "conv: %d k-blocks per tile exceed the schedule table", kiters);
+  Cfg::split(kiters, p.nrbuf > 0, p.split_out != 0, p.out_f32 != 0, &q.nstages, &q.ks, &q.ncbuf, &q.nrbuf);
+  q.ktab = (kiters + 2) & ~1;
+  const int smem = Cfg::smem_bytes(kiters, q.nstages, q.ks, q.ncbuf, q.nrbuf);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
   conv_tc_kernel<BN, TF32><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, q);
   DT_CHECK_LAUNCH();
@@ -583,6 +709,11 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }
 
 }  // namespace dt
+
+#ifdef DT_CONV_TRACE
+extern "C" int dt_conv_trace_write(const long long* in) { return cudaMemcpyToSymbol(dt::g_conv_trace, in, sizeof(long long) * 64 * 16) != cudaSuccess; }
+extern "C" int dt_conv_trace_read(long long* out) { return cudaMemcpyFromSymbol(out, dt::g_conv_trace, sizeof(long long) * 64 * 16) != cudaSuccess; }
+#endif
 
 using namespace dt;
 
@@ -657,6 +788,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   if (res_tma && BN > 128) BN = 128;
   p.nrbuf = res_tma ? 1 : 0;                         // ring depth is chosen with the smem split at launch
   p.tiles_n = cdiv(d->Cout, BN);
+  p.fd_n = make_fastdiv(p.tiles_n); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h); p.fd_t = make_fastdiv(p.tiles_t);
   const long long total = (long long)p.tiles_b * p.tiles_t * p.tiles_h * p.tiles_w * p.tiles_n;
   DT_CHECK_ARG(total < (1ll << 31), "dt_conv3d: too many tiles");
   p.total_tiles = (int)total;
@@ -754,6 +886,7 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   p.a_bytes = (uint32_t)TH * TW * 128u;
   p.scale = scale; p.bias = bias; p.relu = relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32;
   p.round_tf32 = out_round_tf32;
+  p.fd_n = make_fastdiv(1); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h); p.fd_t = make_fastdiv(1);
   const long long total = (long long)F * p.tiles_h * p.tiles_w;
   DT_CHECK_ARG(total < (1ll << 31), "dt_conv1_7x7s2: too many tiles");
   p.total_tiles = (int)total;
