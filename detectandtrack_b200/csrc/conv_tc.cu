@@ -82,6 +82,8 @@ struct ConvKernelParams {
   int ktab;                    // entries of the k-block schedule (kiters + 1 padding, even)
   int row_planes;              // conv1: input rows de-interleaved by parity, filter row kh -> plane kh & 1, row + kh >> 1
   int nrbuf;                   // > 0: bf16 residual chunks arrive by TMA in a ring of this many staged chunks
+  int res_up;                  // with nrbuf > 0: the residual is the (Ho/2, Wo/2) map of the FPN top-down add;
+                               // its (TH/2 x TW/2) box is loaded and every row is read by its four children
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
 };
@@ -300,9 +302,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&r_empty[rslot], rphase ^ 1);
           if (elect_one()) {
             const uint32_t bar = smem_u32(&r_full[rslot]);
-            mbar_expect_tx_u(bar, p.a_bytes);
-            tma_load_5d_u(smem_u32(rbuf) + rslot * Cfg::C_BYTES, &tmR, bar, n_base + cc, tc.twi * p.TW, tc.thi * p.TH,
-                          tc.tti * p.TT, n);
+            mbar_expect_tx_u(bar, p.res_up ? p.a_bytes >> 2 : p.a_bytes);
+            tma_load_5d_u(smem_u32(rbuf) + rslot * Cfg::C_BYTES, &tmR, bar, n_base + cc, (tc.twi * p.TW) >> p.res_up,
+                          (tc.thi * p.TH) >> p.res_up, tc.tti * p.TT, n);
           }
           if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
         }
@@ -426,6 +428,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t rbuf_u32 = smem_u32(rbuf);
     const bool res_tma = p.nrbuf > 0;
     const bool res_ldg = res_mode != 0 && !res_tma;
+    // residual row of this thread inside a ring slot: its own row, or (top-down add) the row of its parent
+    // position in the (TH/2 x TW/2) box of the coarser map
+    const int rrow = p.res_up ? ((nl * p.TT + tl) * (p.TH >> 1) + (th >> 1)) * (p.TW >> 1) + (tw >> 1) : row;
+    const uint32_t rrow_smem = (uint32_t)rrow * 128u;
+    const uint32_t rswz = (uint32_t)(rrow & 7);
+    const uint32_t rq0 = (((uint32_t)(2 * part)) ^ rswz) << 4, rq1 = (((uint32_t)(2 * part + 1)) ^ rswz) << 4;
     int rslot = 0; uint32_t rphase = 0;
     const uint32_t row_smem = (uint32_t)row * 128u;
     const uint32_t swz = (uint32_t)(row & 7);
@@ -530,9 +538,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the producer warp prefetched this chunk's residual rows (zero-filled outside the tensor) into
             // the swizzled ring: read this thread's 32 bytes, then hand the slot back
             mbar_wait(&r_full[rslot], rphase);
-            const uint32_t src = rbuf_u32 + (uint32_t)rslot * Cfg::C_BYTES + row_smem;
-            resq[0] = lds_u4(src + q0);
-            resq[1] = lds_u4(src + q1);
+            const uint32_t src = rbuf_u32 + (uint32_t)rslot * Cfg::C_BYTES + rrow_smem;
+            resq[0] = lds_u4(src + rq0);
+            resq[1] = lds_u4(src + rq1);
             res_vec = true;
             __syncwarp();
             if (lane == 0) mbar_arrive(&r_empty[rslot]);
@@ -784,9 +792,14 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   // bf16 same-shape residual: its chunks are prefetched by TMA into a shared-memory ring (coalesced 128-byte
   // rows instead of one 32-byte global load per thread).  The ring needs room, so these layers use 128-wide
   // column tiles (they are the K-light 1x1 expansions of the bottlenecks: HBM-bound, not MMA-bound).
-  const bool res_tma = d->res_mode == 1 && !out_f32 && !tf32 && ((uintptr_t)residual % 16) == 0;
+  // The FPN top-down add (res_mode 2) goes the same way when the tile is even-sized (tile origins are then even
+  // too): the (TH/2 x TW/2) box of the coarser map is loaded and each row serves its four children.
+  const bool res_even = (TH % 2 == 0) && (TW % 2 == 0);
+  const bool res_tma = (d->res_mode == 1 || (d->res_mode == 2 && res_even)) && !out_f32 && !tf32 &&
+                       ((uintptr_t)residual % 16) == 0;
   if (res_tma && BN > 128) BN = 128;
   p.nrbuf = res_tma ? 1 : 0;                         // ring depth is chosen with the smem split at launch
+  p.res_up = (res_tma && d->res_mode == 2) ? 1 : 0;
   p.tiles_n = cdiv(d->Cout, BN);
   p.fd_n = make_fastdiv(p.tiles_n); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h); p.fd_t = make_fastdiv(p.tiles_t);
   const long long total = (long long)p.tiles_b * p.tiles_t * p.tiles_h * p.tiles_w * p.tiles_n;
@@ -824,7 +837,10 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   }
   CUtensorMap tmC, tmR;
   if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts, d->out_time_major != 0)) return 1;
-  if (res_tma) {
+  if (res_tma && p.res_up) {
+    const TileShape half = {ts.th / 2, ts.tw / 2, ts.tt, ts.tb};
+    if (encode_out_map(&tmR, const_cast<void*>(residual), 0, d->Cout, Wo / 2, Ho / 2, To, d->N, res_ld, half)) return 1;
+  } else if (res_tma) {
     if (encode_out_map(&tmR, const_cast<void*>(residual), 0, d->Cout, Wo, Ho, To, d->N, res_ld, ts)) return 1;
   } else {
     tmR = tmC;

@@ -356,10 +356,12 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
       rowv += mr[min(max(sx + 2, 0), M - 1)] * c.w;
       tmp[y * KD_SW + xl] = rowv;
     }
-    // vertical pass: the block's threads cover (column, row-phase) pairs so narrow boxes keep every lane
-    // busy; each thread keeps (max, first argmax, online sum of exp(v - max)) over the pixels it visits
-    const int nseg = max(1, nth / sw);
-    const int xl = tid % sw, seg = tid / sw;
+    // vertical pass: a thread owns FOUR adjacent columns and a row phase, so the per-row weights are fetched
+    // once per four pixels, the source rows come in as 16-byte vectors and narrow boxes keep every lane busy;
+    // each thread keeps (max, first argmax, online sum of exp(v - max)) over the pixels it visits
+    const int ncol4 = (sw + 3) >> 2;
+    const int nseg = max(1, nth / ncol4);
+    const int xl = (tid % ncol4) << 2, seg = tid / ncol4;
     for (int r0 = 0; r0 < rh; r0 += KD_RB) {
       const int rb = min(KD_RB, rh - r0);
       __syncthreads();                       // tmp complete / previous row block consumed
@@ -377,15 +379,28 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
         for (int r = seg; r < rb; r += nseg) {
           const float4 c = cys[r];
           const int sy = sys[r];
-          float v = 0.f;
-          v += tmp[min(max(sy - 1, 0), M - 1) * KD_SW + xl] * c.x;
-          v += tmp[min(max(sy, 0), M - 1) * KD_SW + xl] * c.y;
-          v += tmp[min(max(sy + 1, 0), M - 1) * KD_SW + xl] * c.z;
-          v += tmp[min(max(sy + 2, 0), M - 1) * KD_SW + xl] * c.w;
+          const float4 t0 = *reinterpret_cast<const float4*>(tmp + min(max(sy - 1, 0), M - 1) * KD_SW + xl);
+          const float4 t1 = *reinterpret_cast<const float4*>(tmp + min(max(sy, 0), M - 1) * KD_SW + xl);
+          const float4 t2 = *reinterpret_cast<const float4*>(tmp + min(max(sy + 1, 0), M - 1) * KD_SW + xl);
+          const float4 t3 = *reinterpret_cast<const float4*>(tmp + min(max(sy + 2, 0), M - 1) * KD_SW + xl);
+          float v[4];
+          {
+            const float a0[4] = {t0.x, t0.y, t0.z, t0.w}, a1[4] = {t1.x, t1.y, t1.z, t1.w};
+            const float a2[4] = {t2.x, t2.y, t2.z, t2.w}, a3[4] = {t3.x, t3.y, t3.z, t3.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float vv = 0.f;
+              vv += a0[j] * c.x; vv += a1[j] * c.y; vv += a2[j] * c.z; vv += a3[j] * c.w;
+              v[j] = (xl + j < sw) ? vv : -CUDART_INF_F;          // columns past the strip never win / add 0
+            }
+          }
           const long long lin = (long long)(r0 + r) * rw + (x0 + xl);
-          if (v > best || (v == best && lin < besti)) { best = v; besti = lin; }
-          if (v > run_max) { run_sum = run_sum * __expf(run_max - v) + 1.f; run_max = v; }
-          else run_sum += __expf(v - run_max);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)                              // ascending index: '>' keeps the first maximum
+            if (v[j] > best || (v[j] == best && lin + j < besti)) { best = v[j]; besti = lin + j; }
+          const float m4 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+          if (m4 > run_max) { run_sum *= __expf(run_max - m4); run_max = m4; }
+          run_sum += (__expf(v[0] - run_max) + __expf(v[1] - run_max)) + (__expf(v[2] - run_max) + __expf(v[3] - run_max));
         }
       }
     }

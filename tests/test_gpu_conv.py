@@ -127,7 +127,8 @@ def test_conv_bf16_output_and_channel_slices():
     assert (got[..., :64] - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()     # bf16 output rounding (2^-8)
 
 
-@pytest.mark.parametrize('shape', [(1, 3, 40, 56, 64, 256), (11, 1, 14, 14, 128, 200), (2, 3, 25, 42, 64, 256)])
+@pytest.mark.parametrize('shape', [(1, 3, 40, 56, 64, 256), (11, 1, 14, 14, 128, 200), (2, 3, 25, 42, 64, 256), (2, 1, 16, 32, 64, 256),
+                                   (3, 2, 24, 48, 128, 192)])
 @pytest.mark.parametrize('res_mode', [1, 2])
 def test_conv_bf16_residual_epilogue(shape, res_mode):
     """The hot-path epilogue: bf16 in / bf16 out, AffineChannel + residual (same shape, or nearest-2x
