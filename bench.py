@@ -385,7 +385,7 @@ def run_ours(args):
                     e2e=dict(value=e2e, unit='clips/s', h2d_bytes_per_step=int(host.numel()), d2h_bytes_per_step=d2h),
                     gpu_launches=launches, clocks=clocks,
                     roofline=dict(bound='tensor', kernel='conv_tc_kernel (all conv/FC launches of the step)', achieved=achieved,
-                                  peak=pk['tflops'], unit='TFLOP/s', frac=achieved / pk['tflops'], traffic=None,
+                                  peak=pk['tflops'], unit='TFLOP/s', frac=achieved / pk['tflops'], traffic=conv_traffic(B),
                                   peak_source=pk['src']))
         if args.layers:
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
@@ -395,6 +395,17 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def conv_traffic(clips_per_step):
+    """DRAM bytes moved by the conv_tc launches of one step, from the committed ncu capture of this same bench
+    command (profiles/conv_dram_r01.json, tools/ncu_conv_traffic.py); scaled if the step size differs."""
+    path = os.path.join(ROOT, 'profiles', 'conv_dram_r01.json')
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    return dict(dram_bytes_per_step=d['dram_bytes'] * clips_per_step / float(d['clips_per_step']), launches=d['launches'],
+                source='profiles/conv_dram_r01.json (ncu dram__bytes_read+write, %d clips/step)' % d['clips_per_step'])
 
 
 def cpu_baseline(cfg, blobs, spec, args):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DT_B200_ABI_VERSION 1
+#define DT_B200_ABI_VERSION 2
 #define DT_MAX_T 8              /* frames per tube supported by the box kernels */
 #define DT_NMS_MAX_BOXES 8192   /* per problem */
 #define DT_LSA_MAX_DIM 224      /* max(prev, cur) detections per frame pair */
