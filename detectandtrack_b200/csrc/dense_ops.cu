@@ -329,32 +329,33 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   int* sxs = reinterpret_cast<int*>(cxs + KD_SW);             // [KD_SW] their first source column
   float4* cys = reinterpret_cast<float4*>(sxs + KD_SW);       // [KD_RB] cubic weights of a block of output rows
   int* sys = reinterpret_cast<int*>(cys + KD_RB);             // [KD_RB] their first source row
-  float best = -CUDART_INF_F; long long besti = 0x7fffffffffffffffll;
+  float best = -CUDART_INF_F; int besti = 0x7fffffff;          // rw * rh < 2^31: boxes are clipped to the image
   float run_max = -CUDART_INF_F, run_sum = 0.f;
   for (int x0 = 0; x0 < rw; x0 += KD_SW) {
     const int sw = min(KD_SW, rw - x0);
-    // per-column weights once per strip (every source row reuses them)
-    for (int xl = tid; xl < sw; xl += nth) {
-      float fx = (float)((x0 + xl + 0.5) * sclx - 0.5);
-      const int sx = (int)floorf(fx);
-      fx -= sx;
-      float cx[4];
-      cubic_coeffs(fx, cx);
-      cxs[xl] = make_float4(cx[0], cx[1], cx[2], cx[3]);
-      sxs[xl] = sx;
-    }
-    __syncthreads();
-    for (int i = tid; i < M * sw; i += nth) {
-      const int y = i / sw, xl = i - y * sw;
-      const float4 c = cxs[xl];
-      const int sx = sxs[xl];
-      const float* mr = map + y * M;
-      float rowv = 0.f;
-      rowv += mr[min(max(sx - 1, 0), M - 1)] * c.x;
-      rowv += mr[min(max(sx, 0), M - 1)] * c.y;
-      rowv += mr[min(max(sx + 1, 0), M - 1)] * c.z;
-      rowv += mr[min(max(sx + 2, 0), M - 1)] * c.w;
-      tmp[y * KD_SW + xl] = rowv;
+    // horizontal pass: a thread owns one output column of the strip (weights and clamped source columns in
+    // registers) and a phase of the M source rows
+    {
+      const int nsegh = max(1, nth / sw);
+      const int xh = tid % sw, segh = tid / sw;
+      if (segh < nsegh) {
+        float fx = (float)((x0 + xh + 0.5) * sclx - 0.5);
+        const int sx = (int)floorf(fx);
+        fx -= sx;
+        float cx[4];
+        cubic_coeffs(fx, cx);
+        const int i0 = min(max(sx - 1, 0), M - 1), i1 = min(max(sx, 0), M - 1);
+        const int i2 = min(max(sx + 1, 0), M - 1), i3 = min(max(sx + 2, 0), M - 1);
+        for (int y = segh; y < M; y += nsegh) {
+          const float* mr = map + y * M;
+          float rowv = 0.f;
+          rowv += mr[i0] * cx[0];
+          rowv += mr[i1] * cx[1];
+          rowv += mr[i2] * cx[2];
+          rowv += mr[i3] * cx[3];
+          tmp[y * KD_SW + xh] = rowv;
+        }
+      }
     }
     // vertical pass: a thread owns FOUR adjacent columns and a row phase, so the per-row weights are fetched
     // once per four pixels, the source rows come in as 16-byte vectors and narrow boxes keep every lane busy;
@@ -394,7 +395,7 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
               v[j] = (xl + j < sw) ? vv : -CUDART_INF_F;          // columns past the strip never win / add 0
             }
           }
-          const long long lin = (long long)(r0 + r) * rw + (x0 + xl);
+          const int lin = (r0 + r) * rw + (x0 + xl);
 #pragma unroll
           for (int j = 0; j < 4; ++j)                              // ascending index: '>' keeps the first maximum
             if (v[j] > best || (v[j] == best && lin + j < besti)) { best = v[j]; besti = lin + j; }
@@ -408,7 +409,7 @@ keypoint_decode_kernel(const float* __restrict__ lowres, int ldl, int S, int K, 
   }
   // block reduction: (max value, lowest linear index) and the softmax denominator at the global max
   __shared__ long long s_redl[32];
-  float bm = best; long long bi = besti;
+  float bm = best; long long bi = besti;     // (idle threads carry -inf / INT_MAX)
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, bm, o);
     const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "../../include/dt_b200.h"
 #include <cuda_bf16.h>
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 namespace dt {
@@ -102,7 +103,7 @@ __device__ __forceinline__ float load_act(const void* p, size_t i, int f32) {
 }
 
 // ------------------------------------------------------------------- RPN top-k + decode
-// One CTA per (image, level): all FPN levels of a clip batch run in ONE launch.
+// One 8-CTA cluster per (image, level): all FPN levels of a clip batch run in ONE launch.
 // logits [B, H*W, ld_s] (first A channels), deltas [B, H*W, ld_d] (first 4*A*T).
 // Flat anchor index i = (h*W + w)*A + a  (generate_proposals.py:58-70 ordering).
 struct RpnLevel {
@@ -114,12 +115,21 @@ struct RpnLevel {
 };
 struct RpnLevels { RpnLevel lv[8]; };
 
+// A thread-block CLUSTER of RPN_CS CTAs works on one (image, level): the big levels are pure streaming (P2:
+// 604 800 anchors, ~25 MB through several passes) and one SM moves ~0.1 TB/s, so a single CTA per image-level
+// took 0.55 ms while 80 % of the GPU idled.  Every CTA owns a fixed strided slice of the anchors in all passes
+// (so it only ever re-reads keys it wrote itself); histograms, counts and the selected candidates are exchanged
+// through distributed shared memory; rank 0 sorts and decodes the K survivors.
+constexpr int RPN_CS = 8;
+
 __global__ void __launch_bounds__(1024, 1)
 rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* __restrict__ im_info /*[B,3]*/,
                      int pre_topn, float min_size, float clipv_f, double clipv_d, long long out_bstride,
                      int counts_stride, int kcap /*pow2 >= K*/, int time_major) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ unsigned long long skeys[];          // [kcap] selected (key<<32 | ~idx)
-  __shared__ int hist[4096];
+  __shared__ __align__(16) int hist[4096];
   __shared__ int s_warp[32];
   __shared__ int s_run, s_bin, s_need, s_cnt;
   __shared__ uint32_t s_lo, s_hi;
@@ -129,9 +139,11 @@ rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* 
   const double* __restrict__ anchors = lv.anchors;
   const int ld_s = lv.ld_s, ld_d = lv.ld_d, H = lv.H, W = lv.W;
   const double feat_stride = lv.feat_stride;
-  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS, tid = threadIdx.x, nth = blockDim.x;
   const int n = H * W * A;
   const int K = (pre_topn <= 0 || pre_topn > n) ? n : pre_topn;
+  const int i0 = rank * nth + tid, istep = CS * nth;    // this thread's slice of the anchors, every pass
   uint32_t* __restrict__ keys = lv.keys + (size_t)b * n;
   // time_major (3-D RPN head, model_builder.py:509-563): logits / deltas are [B, T, H*W, ld] with A / 4A
   // channels per frame; the tube score is the mean over frames of the per-frame logits (TimePool 'avg',
@@ -145,21 +157,26 @@ rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* 
     for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, load_act(logits, sbase + ((size_t)t * HW + pos) * ld_s + a, act_f32));
     return sigmoidf_ref(__fdiv_rn(acc, (float)T));
   };
-  // ---- pass 0: scores -> sortable keys (stored once), global min / max --------------------------
+  // ---- pass 0: scores -> sortable keys (stored once), min / max over the cluster -----------------
   if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; }
   __syncthreads();
   uint32_t tlo = 0xffffffffu, thi = 0u;
-  for (int i = tid; i < n; i += nth) {
+  for (int i = i0; i < n; i += istep) {
     const uint32_t key = sort_key_f32(score_at(i));
     keys[i] = key;
     tlo = min(tlo, key); thi = max(thi, key);
   }
   for (int o = 16; o > 0; o >>= 1) { tlo = min(tlo, __shfl_xor_sync(0xffffffffu, tlo, o)); thi = max(thi, __shfl_xor_sync(0xffffffffu, thi, o)); }
   if ((tid & 31) == 0) { atomicMin(&s_lo, tlo); atomicMax(&s_hi, thi); }
-  __syncthreads();
+  __threadfence();                       // the tie fallback below lets rank 0 read every slice's keys
+  cluster.sync();
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int r = 0; r < CS; ++r) {
+    lo = min(lo, *cluster.map_shared_rank(&s_lo, r));
+    hi = max(hi, *cluster.map_shared_rank(&s_hi, r));
+  }
   // ---- exact K-th largest key: iterative range refinement with 4096 adaptive-width bins ----------
   // invariant: `need` of the elements with key in [lo, hi] belong to the top K (all keys > hi already do)
-  uint32_t lo = s_lo, hi = s_hi;
   int need = K;
   while (lo < hi) {
     const unsigned long long range = (unsigned long long)hi - lo + 1ull;
@@ -167,7 +184,7 @@ rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* 
     while ((range >> shift) > 4096ull) ++shift;
     for (int x = tid; x < 4096; x += nth) hist[x] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += nth) {
+    for (int i = i0; i < n; i += istep) {
       const uint32_t key = keys[i];
       if (key >= lo && key <= hi) {
         // warp-aggregated histogram update: RPN scores cluster, so many lanes hit the same bin
@@ -177,9 +194,24 @@ rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* 
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      int cum = 0, bin = 4095;
-      for (; bin >= 0; --bin) { if (cum + hist[bin] >= need) break; cum += hist[bin]; }
+    cluster.sync();                      // every CTA's histogram is complete
+    // cluster-wide histogram of this thread's four bins (every CTA computes the same totals), then the bin
+    // holding the need-th largest element by a block-wide suffix scan (thread t owns bins 4t .. 4t+3)
+    int h[4] = {0, 0, 0, 0};
+    for (int r = 0; r < CS; ++r) {
+      const int4 q = *reinterpret_cast<const int4*>(cluster.map_shared_rank(&hist[0], r) + 4 * tid);
+      h[0] += q.x; h[1] += q.y; h[2] += q.z; h[3] += q.w;
+    }
+    const int local = h[0] + h[1] + h[2] + h[3];
+    int suf = local;                     // inclusive suffix sum over lanes >= this one
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, suf, o); if ((tid & 31) + o < 32) suf += v; }
+    if ((tid & 31) == 0) s_warp[tid >> 5] = suf;
+    __syncthreads();
+    int above = suf - local;             // elements in bins above this thread's four
+    for (int w = (tid >> 5) + 1; w < (nth >> 5); ++w) above += s_warp[w];
+    if (above < need && above + local >= need) {          // exactly one thread
+      int cum = above, bin = 4 * tid + 3;
+      for (int j = 3; j >= 0; --j, --bin) { if (cum + h[j] >= need) break; cum += h[j]; }
       s_bin = bin; s_need = need - cum;
     }
     __syncthreads();
@@ -188,17 +220,17 @@ rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* 
     hi = (nhi64 > hi) ? hi : (uint32_t)nhi64;
     lo = nlo;
     need = s_need;
-    __syncthreads();
+    cluster.sync();                      // peers are done reading this CTA's histogram / s_bin is consumed
   }
   const uint32_t kth = lo;              // keys > kth are all selected; `need` keys == kth, lowest index first
-  // ---- gather the K selected.  Order is fixed by the sort below, so keys > kth are appended unordered;
-  // keys == kth must be the `need` LOWEST indices: unordered too when every equal key is taken (the usual
-  // case: a unique K-th score), otherwise an ordered compaction.
+  // ---- gather the selected candidates of this slice into this CTA's list.  Order is fixed by the sort below,
+  // so keys > kth are appended unordered; keys == kth must be the `need` LOWEST indices: unordered too when
+  // every equal key is taken (the usual case: a unique K-th score), otherwise rank 0 compacts them in order.
   if (tid == 0) { s_run = 0; s_cnt = 0; }
   for (int x = tid; x < kcap; x += nth) skeys[x] = 0ull;
   __syncthreads();
   int my_eq = 0;
-  for (int i = tid; i < n; i += nth) {
+  for (int i = i0; i < n; i += istep) {
     const uint32_t key = keys[i];
     if (key > kth) {
       const int slot = atomicAdd(&s_run, 1);
@@ -207,15 +239,35 @@ rpn_proposals_kernel(const RpnLevels L, int act_f32, int A, int T, const float* 
   }
   if (my_eq) atomicAdd(&s_cnt, my_eq);
   __syncthreads();
-  const int total_eq = s_cnt;
-  if (total_eq == need) {
-    for (int i = tid; i < n; i += nth)
+  cluster.sync();
+  int total_eq = 0;
+  for (int r = 0; r < CS; ++r) total_eq += *cluster.map_shared_rank(&s_cnt, r);
+  const bool take_all_eq = (total_eq == need);
+  if (take_all_eq) {
+    for (int i = i0; i < n; i += istep)
       if (keys[i] == kth) {
         const int slot = atomicAdd(&s_run, 1);
         skeys[slot] = ((unsigned long long)kth << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
       }
     __syncthreads();
-  } else {
+  }
+  cluster.sync();                        // every list is final
+  if (rank == 0) {
+    // concatenate the peers' lists behind this CTA's own
+    int off = s_run;
+    for (int r = 1; r < CS; ++r) {
+      const int cnt = *cluster.map_shared_rank(&s_run, r);
+      const unsigned long long* src = cluster.map_shared_rank(&skeys[0], r);
+      for (int x = tid; x < cnt; x += nth) skeys[off + x] = src[x];
+      off += cnt;
+    }
+    __syncthreads();
+    if (tid == 0) s_run = off;
+    __syncthreads();
+  }
+  cluster.sync();                        // peers may exit: nobody reads their shared memory any more
+  if (rank != 0) return;
+  if (!take_all_eq) {
     int eq_base = 0;                     // == kth elements seen so far (uniform)
     for (int start = 0; start < n && eq_base < need; start += nth) {
       const int i = start + tid;
@@ -553,10 +605,19 @@ extern "C" int dt_rpn_proposals_multi(const dt_rpn_level* levels, int nlevels, i
     DT_CHECK_CUDA(cudaFuncSetAttribute(rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     attr = true;
   }
-  dim3 grid(B, nlevels);
-  rpn_proposals_kernel<<<grid, 1024, (size_t)kcap * sizeof(unsigned long long), (cudaStream_t)stream>>>(
-      L, act_f32, A, T, im_info, pre_nms_topn, min_size, (float)bbox_xform_clip, bbox_xform_clip, out_batch_stride,
-      counts_stride, kcap, time_major);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(B * RPN_CS), (unsigned)nlevels, 1);
+  cfg.blockDim = dim3(1024, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)kcap * sizeof(unsigned long long);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RPN_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rpn_proposals_kernel, L, act_f32, A, T, im_info, pre_nms_topn, min_size,
+                                   (float)bbox_xform_clip, bbox_xform_clip, out_batch_stride, counts_stride, kcap,
+                                   time_major));
   DT_CHECK_LAUNCH();
   return 0;
 }
