@@ -37,6 +37,7 @@ SIGNATURES = {
     'dt_keypoint_decode': [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p],
     'dt_conv1_7x7s2_f32': [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    'dt_time_mean': [_p, _i, _i, C.c_longlong, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_fold_tube_heads': [_p, _i, _i, _i, _i, _p, _p, _p],
 }
 
@@ -53,7 +54,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         'N', 'Ti', 'Hi', 'Wi', 'Cin', 'Cout', 'kT', 'kH', 'kW', 'sT', 'sH', 'sW', 'pT', 'pH', 'pW',
         'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode', 'x3', 'in_lo_off', 'out_lo_off',
-        'res_lo_off', 'out_round_tf32', 'out_time_major')]
+        'res_lo_off', 'out_round_tf32', 'out_time_major', 'out_t_first', 'out_t_count')]
 _RESTYPE = {'dt_last_error': C.c_char_p}
 
 

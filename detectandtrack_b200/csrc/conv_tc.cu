@@ -80,6 +80,7 @@ struct ConvKernelParams {
   int nstages, ncbuf;          // smem split chosen per layer: operand ring depth / output staging buffers
   int ks;                      // k-blocks per ring stage
   int ktab;                    // entries of the k-block schedule (kiters + 1 padding, even)
+  int t_first;                 // first output frame computed (frames before it are skipped)
   int row_planes;              // conv1: input rows de-interleaved by parity, filter row kh -> plane kh & 1, row + kh >> 1
   int nrbuf;                   // > 0: bf16 residual chunks arrive by TMA in a ring of this many staged chunks
   int res_up;                  // with nrbuf > 0: the residual is the (Ho/2, Wo/2) map of the FPN top-down add;
@@ -246,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n = tc.tbi * p.TB;
       const int w_base = tc.twi * p.TW * p.sW - p.pW;
       const int h_base = tc.thi * p.TH * p.sH - p.pH;
-      const int t_base = p.row_planes ? 0 : tc.tti * p.TT * p.sT - p.pT;
+      const int t_base = p.row_planes ? 0 : (tc.tti * p.TT + p.t_first) * p.sT - p.pT;
       const int n_base = tc.nt * BN;
 #ifdef DT_CONV_TRACE
       long long acc_wait = 0, acc_issue = 0;
@@ -737,7 +738,11 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
                "dt_conv3d: bad input shape N=%d T=%d H=%d W=%d Cin=%d Cout=%d", d->N, d->Ti, d->Hi, d->Wi, d->Cin, d->Cout);
   DT_CHECK_ARG(d->kT >= 1 && d->kH >= 1 && d->kW >= 1 && d->sT >= 1 && d->sH >= 1 && d->sW >= 1 && d->pT >= 0 &&
                    d->pH >= 0 && d->pW >= 0, "dt_conv3d: bad filter geometry");
-  const int To = (d->Ti + 2 * d->pT - d->kT) / d->sT + 1;
+  const int To_full = (d->Ti + 2 * d->pT - d->kT) / d->sT + 1;
+  DT_CHECK_ARG(d->out_t_first >= 0 && d->out_t_count >= 0 && d->out_t_first + d->out_t_count <= (To_full > 0 ? To_full : 0),
+               "dt_conv3d: output frame range [%d, +%d) outside the %d output frames", d->out_t_first, d->out_t_count, To_full);
+  DT_CHECK_ARG(d->out_t_count == 0 || d->res_mode == 0, "dt_conv3d: an output frame range cannot be combined with a residual");
+  const int To = d->out_t_count > 0 ? d->out_t_count : To_full;
   const int Ho = (d->Hi + 2 * d->pH - d->kH) / d->sH + 1;
   const int Wo = (d->Wi + 2 * d->pW - d->kW) / d->sW + 1;
   DT_CHECK_ARG(To >= 1 && Ho >= 1 && Wo >= 1, "dt_conv3d: empty output (%d,%d,%d)", To, Ho, Wo);
@@ -798,6 +803,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   const bool res_tma = (d->res_mode == 1 || (d->res_mode == 2 && res_even)) && !out_f32 && !tf32 &&
                        ((uintptr_t)residual % 16) == 0;
   if (res_tma && BN > 128) BN = 128;
+  p.t_first = d->out_t_count > 0 ? d->out_t_first : 0;
   p.nrbuf = res_tma ? 1 : 0;                         // ring depth is chosen with the smem split at launch
   p.res_up = (res_tma && d->res_mode == 2) ? 1 : 0;
   p.tiles_n = cdiv(d->Cout, BN);
@@ -815,7 +821,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   const uint64_t sC = (uint64_t)in_ld * esz, sW = sC * d->Wi, sH = sW * d->Hi, sT = sH * d->Ti;
   const uint64_t cdim = p.split_in ? (uint64_t)in_ld : (uint64_t)d->Cin;
   if (pointwise) {
-    dims[0] = cdim; dims[1] = Wo; dims[2] = Ho; dims[3] = To; dims[4] = d->N;
+    dims[0] = cdim; dims[1] = Wo; dims[2] = Ho; dims[3] = To_full; dims[4] = d->N;
     strides[0] = sC * d->sW; strides[1] = sW * d->sH; strides[2] = sH * d->sT; strides[3] = sT;
     box[0] = BK; box[1] = TW; box[2] = TH; box[3] = ts.tt; box[4] = ts.tb;
     p.sT = p.sH = p.sW = 1;

@@ -478,6 +478,33 @@ __global__ void spatial_mean_kernel(const ET* __restrict__ x, int N, int H, int 
   }
 }
 
+// TimePool 'avg' body/head link (lib/modeling/model_builder.py:1024-1042, detector.py:559-576):
+// x [B, T, P, ldx] -> y [B, P, ldy], mean over the T frames (sequential fp32 sum, then / T).
+template <typename ET>
+__global__ void time_mean_kernel(const ET* __restrict__ x, int B, int T, long long P, int C, int ldx, ET* __restrict__ y,
+                                 int ldy, int round_out, int lo_in, int lo_out) {
+  constexpr int V = Vec<ET>::N;
+  const int cv = C / V;
+  const long long total = (long long)B * P * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V;
+    const long long r = idx / cv;
+    const long long pos = r % P;
+    const long long b = r / P;
+    float acc[V];
+    load_vals<ET>(x + ((size_t)(b * T) * P + pos) * ldx + c, lo_in, acc);
+    for (int t = 1; t < T; ++t) {
+      float v[V];
+      load_vals<ET>(x + ((size_t)(b * T + t) * P + pos) * ldx + c, lo_in, v);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) { acc[e] /= (float)T; if (round_out && !lo_out) acc[e] = round_to_tf32(acc[e]); }
+    store_vals<ET>(y + ((size_t)b * P + pos) * ldy + c, lo_out, acc);
+  }
+}
+
 // add_fast_rcnn_outputs, 3-D head (lib/modeling/model_builder.py:427-473): per-frame outputs
 // in [R*T, ld] = [cls logits (C) | bbox (4C, channel c*4+k)] -> cls [R, C] = mean over T,
 // bbox [R, C*T*4] with channel c*4T + t*4 + k.
@@ -650,6 +677,23 @@ extern "C" int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ld
     spatial_mean_kernel<float><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, (float*)y, ldy, round_tf32, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   else
     spatial_mean_kernel<__nv_bfloat16><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, (__nv_bfloat16*)y, ldy, 0, 0, 0);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_time_mean(const void* x, int B, int T, long long P, int C, int ldx, int f32, int round_tf32, int x3,
+                            void* y, int ldy, void* stream) {
+  const int V = f32 ? 4 : 8;
+  DT_CHECK_ARG(B >= 0 && T >= 1 && P >= 1 && C >= 1 && C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C,
+               "dt_time_mean: bad shape (C/ld must be multiples of %d)", V);
+  DT_CHECK_ARG(!x3 || (f32 && ldx >= 2 * C && ldy >= 2 * C), "dt_time_mean: x3 storage needs fp32 rows of 2*C");
+  if (B == 0) return 0;
+  DT_CHECK_ARG(x && y, "dt_time_mean: null pointer");
+  const long long total = (long long)B * P * (C / V);
+  if (f32)
+    time_mean_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, B, T, P, C, ldx, (float*)y, ldy, round_tf32, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
+  else
+    time_mean_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, T, P, C, ldx, (__nv_bfloat16*)y, ldy, 0, 0, 0);
   DT_CHECK_LAUNCH();
   return 0;
 }

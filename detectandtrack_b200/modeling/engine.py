@@ -45,10 +45,11 @@ class _Conv(object):
         self.scale = torch.from_numpy(np.ascontiguousarray(scale, dtype=np.float32)).cuda() if scale is not None else None
         self.bias = torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float32)).cuda() if bias is not None else None
 
-    def __call__(self, x, residual=None, res_mode=0, relu=None, out_f32=None, cin=None, out=None, time_major=False):
+    def __call__(self, x, residual=None, res_mode=0, relu=None, out_f32=None, cin=None, out=None, time_major=False,
+                 out_frames=None):
         return cv.conv3d(x, self.w, self.k, self.stride, self.pad, self.scale, self.bias, residual, res_mode,
                          self.relu if relu is None else relu, out_f32=out_f32, dtype=self.dtype, cin=cin, out=out,
-                         time_major=time_major)
+                         time_major=time_major, out_frames=out_frames)
 
 
 class DetectionEngine(object):
@@ -63,7 +64,7 @@ class DetectionEngine(object):
             raise NotImplementedError('3-D FPN heads are unimplemented in the reference too (FPN3D.py:228)')
         if not s.fpn and not s.head3d:
             raise NotImplementedError('engine: single-level bodies are wired for 3-D heads (BODY_HEAD_LINK \'\') only')
-        if s.link not in ('slice-center', 'none2d', ''):
+        if s.link not in ('slice-center', 'avg', 'none2d', ''):
             raise NotImplementedError('engine: BODY_HEAD_LINK %r' % s.link)
         # 'bf16': fast path; 'tf32': fp32 storage, tf32 MMAs (1e-3 per layer); 'tf32x3': fp32-accurate
         # parity mode (activations / weights as [hi | lo] tf32 pairs, 3 MMAs per k-block)
@@ -242,13 +243,10 @@ class DetectionEngine(object):
             inner.append(self.fpn_inner[i](coarse_first[i], residual=inner[i - 1], res_mode=2))
         outs = []
         for i, x in enumerate(inner):
-            if self.skip_dead_frames and s.link == 'slice-center' and x.shape[1] > 1 and s.tk_body == 3:
+            if self.skip_dead_frames and s.link == 'slice-center' and x.shape[1] > 1:
+                # only the frame the link slices is consumed: compute just that output frame
                 c = int(self.cfg.VIDEO.NUM_FRAMES_MID / 2)
-                xs = x[:, c - 1:c + 2]
-                if x.shape[0] > 1:
-                    xs = xs.contiguous()
-                conv = self.fpn_out[i]
-                y = cv.conv3d(xs, conv.w, conv.k, conv.stride, (0, 1, 1), conv.scale, conv.bias, dtype=conv.dtype)
+                y = self.fpn_out[i](x, out_frames=(c, 1))
             else:
                 # frames-outermost output: the centre-frame link below is then a view, not a gather
                 y = self.fpn_out[i](x, time_major=(s.link == 'slice-center' and x.shape[1] > 1))
@@ -266,7 +264,7 @@ class DetectionEngine(object):
         return outs[::-1]
 
     def link(self, feats):
-        """model_builder.time_pool_blobs (:1024-1042): centre-frame slice -> [B, 1, h, w, C]."""
+        """model_builder.time_pool_blobs (:1024-1042): centre-frame slice or mean over T -> [B, 1, h, w, C]."""
         s = self.spec
         if s.head3d:
             return feats
@@ -274,6 +272,9 @@ class DetectionEngine(object):
         for f in feats:
             if f.shape[1] == 1:
                 out.append(f)
+                continue
+            if s.link == 'avg':             # TimePool 'avg': mean over the frames
+                out.append(dense_ops.time_mean(f, round_tf32=(self.dtype == cv.TF32), x3=self.x3))
                 continue
             c = int(self.cfg.VIDEO.NUM_FRAMES_MID / 2)
             v = f[:, c:c + 1]

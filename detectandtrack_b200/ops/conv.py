@@ -60,10 +60,11 @@ def round_tf32(t):
 
 def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias=None,
            residual=None, res_mode=0, relu=False, out_f32=None, dtype=BF16, cin=None, out=None, round_tf32=None,
-           split_out=None, time_major=False):
+           split_out=None, time_major=False, out_frames=None):
     """x [N,T,H,W,Cx] (first `cin` channels are the conv input); returns y [N,To,Ho,Wo,Cout].
     time_major: y is stored [To,N,Ho,Wo,Cout] and returned as the permuted [N,To,...] view, so y[:, t:t+1]
-    is contiguous (the centre-frame link needs no copy)."""
+    is contiguous (the centre-frame link needs no copy).
+    out_frames=(first, count): compute only those output frames (y has `count` frames)."""
     torch = L.require_cuda()
     assert x.is_cuda and x.dim() == 5 and x.is_contiguous()
     assert x.dtype == _dt(dtype, torch), (x.dtype, dtype)
@@ -87,6 +88,10 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     To = (Ti + 2 * pT - kT) // sT + 1
     Ho = (Hi + 2 * pH - kH) // sH + 1
     Wo = (Wi + 2 * pW - kW) // sW + 1
+    t_first, t_count = (0, 0) if out_frames is None else (int(out_frames[0]), int(out_frames[1]))
+    if t_count:
+        assert 0 <= t_first and t_first + t_count <= To and residual is None
+        To = t_count
     if out_f32 is None:
         out_f32 = dtype == TF32
     if round_tf32 is None:
@@ -105,7 +110,8 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
                    res_ld=(residual.shape[-1] if residual is not None else 0), dtype=(TF32 if x3 else dtype),
                    out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode),
                    x3=(1 if x3 else 0) | (2 if split_out else 0), in_lo_off=0, out_lo_off=0, res_lo_off=0,
-                   out_round_tf32=int(bool(round_tf32)), out_time_major=int(bool(time_major)))
+                   out_round_tf32=int(bool(round_tf32)), out_time_major=int(bool(time_major)), out_t_first=t_first,
+                   out_t_count=t_count)
     if residual is not None:
         assert residual.dtype == odt and residual.is_contiguous()
     if scale is not None:

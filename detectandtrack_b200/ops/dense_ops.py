@@ -86,6 +86,18 @@ def spatial_mean(x, round_tf32=False, x3=False):
     return y
 
 
+def time_mean(x, round_tf32=False, x3=False):
+    """x [B, T, H, W, ld] -> [B, 1, H, W, ld]: mean over the frames (the 'avg' body/head link)."""
+    torch = L.require_cuda()
+    B, T, H, W, ld = x.shape
+    assert x.is_contiguous()
+    Cc = ld // 2 if x3 else ld
+    y = torch.empty((B, 1, H, W, ld), dtype=x.dtype, device='cuda')
+    L.call('dt_time_mean', L.ptr(x), B, T, H * W, Cc, ld, int(x.dtype == torch.float32), int(bool(round_tf32)), int(bool(x3)),
+           L.ptr(y), ld, L.stream_ptr())
+    return y
+
+
 def fold_tube_heads(o, R, T, C):
     """o [R*T, ld] fp32 = per-frame [cls | bbox] -> (cls [R, C], bbox [R, C*T*4])."""
     torch = L.require_cuda()

@@ -144,6 +144,9 @@ typedef struct dt_conv_desc {
   int out_time_major; /* 1: y is laid out [To, N, Ho, Wo, out_ld] instead of [N, To, Ho, Wo, out_ld], so one
                          frame of the whole batch (the 'slice-center' link, model_builder.py:1024-1042) is a
                          contiguous [N, Ho, Wo, out_ld] block and needs no gather */
+  int out_t_first, out_t_count; /* compute only output frames [out_t_first, out_t_first + out_t_count) of the
+                         conv (0, 0 = all): y then has out_t_count frames.  Lets a caller skip frames nothing
+                         consumes (the post-hoc FPN convs under the 'slice-center' link) */
 } dt_conv_desc;
 
 int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
@@ -260,6 +263,12 @@ int dt_conv1_7x7s2_f32(const float* blob, int F, int Hp, int Wp, int Cp, const f
  * (lib/modeling/model_builder.py:427-473). */
 int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ldx, int f32, int round_tf32, int x3,
                     void* y, int ldy, void* stream);
+
+/* TimePool 'avg' body/head link (lib/modeling/model_builder.py:1024-1042, lib/modeling/detector.py:559-576):
+ * x [B, T, P, ldx] -> y [B, P, ldy], mean over the T frames (fp32 sum in frame order, then / T); P = H*W.
+ * f32 / round_tf32 / x3 as in dt_spatial_mean. */
+int dt_time_mean(const void* x, int B, int T, long long P, int C, int ldx, int f32, int round_tf32, int x3,
+                 void* y, int ldy, void* stream);
 int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, float* cls, float* bbox, void* stream);
 
 #ifdef __cplusplus

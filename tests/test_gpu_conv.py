@@ -170,6 +170,23 @@ def test_conv_time_major_output():
     assert torch.equal(a, b.contiguous())
 
 
+@pytest.mark.parametrize('first,count', [(0, 1), (1, 1), (2, 1), (1, 2)])
+def test_conv_output_frame_range(first, count):
+    """out_t_first / out_t_count: only the requested output frames are computed, bit-identical to the same
+    frames of the full conv (temporal zero padding at the clip borders included)."""
+    import torch
+    from detectandtrack_b200.ops import conv as cv
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn((2, 3, 13, 21, 64), generator=g).bfloat16().cuda()
+    w = (torch.randn((64, 64, 3, 3, 3), generator=g) * 0.03).bfloat16()
+    wp = cv.pack_weight(w.float(), cv.BF16)
+    full = cv.conv3d(x, wp, (3, 3, 3), (1, 1, 1), (1, 1, 1), relu=True, out_f32=False, dtype=cv.BF16)
+    part = cv.conv3d(x, wp, (3, 3, 3), (1, 1, 1), (1, 1, 1), relu=True, out_f32=False, dtype=cv.BF16, out_frames=(first, count))
+    torch.cuda.synchronize()
+    assert part.shape == (2, count, 13, 21, 64)
+    assert torch.equal(part, full[:, first:first + count])
+
+
 def test_conv_rejects_bad_arguments():
     import torch
     from detectandtrack_b200.ops import conv as cv

@@ -125,3 +125,28 @@ def test_keypoint_decode_vs_cv2_oracle():
     np.testing.assert_allclose(got[:, 3], ref[:, 3], rtol=2e-3, atol=1e-6)      # prob
     # positions: identical unless two resized samples tie within float noise (none expected here)
     np.testing.assert_allclose(got[:, :2], ref[:, :2], rtol=0, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['bf16', 'f32', 'x3'])
+def test_time_mean(mode):
+    """dt_time_mean (the 'avg' body/head link): mean over T of [B, T, H, W, C]."""
+    import torch
+    from detectandtrack_b200.ops import dense_ops, conv as cv
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, 3, 5, 7, 64), generator=g)
+    if mode == 'bf16':
+        xd = x.bfloat16().cuda()
+        y = dense_ops.time_mean(xd).float().cpu()
+        ref = x.bfloat16().float().mean(dim=1, keepdim=True)
+        tol = 1e-2
+    elif mode == 'f32':
+        y = dense_ops.time_mean(x.cuda()).cpu()
+        ref = x.mean(dim=1, keepdim=True)
+        tol = 1e-6
+    else:
+        y = cv.join_tf32(dense_ops.time_mean(cv.split_tf32(x.cuda()), x3=True)).cpu()
+        ref = x.mean(dim=1, keepdim=True)
+        tol = 1e-6
+    assert y.shape == (2, 1, 5, 7, 64)
+    assert (y - ref).abs().max().item() <= tol * ref.abs().max().item()

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 from oracle import net as onet
 
 
-def _cfg():
+def _cfg(link='slice-center'):
     from detectandtrack_b200.core.config import cfg, reset_cfg, assert_and_infer_cfg
     reset_cfg()
     cfg.MODEL.TYPE = 'keypoint_rcnn'
@@ -39,7 +39,7 @@ def _cfg():
     cfg.VIDEO.NUM_FRAMES = 3; cfg.VIDEO.TIME_INTERVAL = 1
     cfg.VIDEO.TIME_KERNEL_DIM.BODY = 3; cfg.VIDEO.TIME_KERNEL_DIM.HEAD_RPN = 3
     cfg.VIDEO.TIME_KERNEL_DIM.HEAD_KPS = 3; cfg.VIDEO.TIME_KERNEL_DIM.HEAD_DET = 3
-    cfg.VIDEO.BODY_HEAD_LINK = 'slice-center'; cfg.VIDEO.NUM_FRAMES_MID = 1
+    cfg.VIDEO.BODY_HEAD_LINK = link; cfg.VIDEO.NUM_FRAMES_MID = 1
     cfg.TEST.SCALES = (96,); cfg.TEST.MAX_SIZE = 160
     cfg.TEST.NMS = 0.5; cfg.TEST.RPN_PRE_NMS_TOP_N = 1000; cfg.TEST.RPN_POST_NMS_TOP_N = 200
     assert_and_infer_cfg()
@@ -94,6 +94,41 @@ def test_backbone_fpn_rpn_features(setup, mode, tol):
         e1 = (got_lg - lg[0]).abs().max().item() / max(lg.abs().max().item(), 1e-6)
         e2 = (got_dl - dl[0]).abs().max().item() / max(dl.abs().max().item(), 1e-6)
         assert e1 <= hm and e2 <= hm, ('rpn level', l, e1, e2)
+
+
+def test_avg_body_head_link(setup):
+    """BODY_HEAD_LINK 'avg' (TimePool mean over the frames, model_builder.py:1024-1042) vs the oracle graph."""
+    import torch
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    try:
+        cfg = _cfg('avg')
+        spec = P.GraphSpec(cfg)
+        assert spec.link == 'avg'
+        eng = DetectionEngine(cfg, setup['blobs'], spec, dtype='tf32x3')
+        feats, _, _ = eng.forward_features(torch.from_numpy(setup['frames']).cuda())
+        ref = [onet.time_pool(p, 'avg', 1) for p in setup['pyr']][::-1]          # finest first
+        for l, (f, r) in enumerate(zip(feats, ref)):
+            got = eng.plain(f)[:, 0].permute(0, 3, 1, 2).float().cpu()
+            err = (got - r).abs().max().item() / r.abs().max().item()
+            assert got.shape == r.shape and err <= 5e-4, ('avg link level', l, err)
+    finally:
+        _cfg()                                                                  # restore the shared global cfg
+
+
+def test_dead_frame_elimination_is_exact(setup):
+    """Computing only the consumed centre frame of the post-hoc FPN convs (engine.skip_dead_frames) gives
+    bit-identical features: same taps, same accumulation order, two clips so the frames-outermost storage
+    of the default path is exercised too."""
+    import torch
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    eng = DetectionEngine(setup['cfg'], setup['blobs'], setup['spec'], dtype='bf16')
+    fr = torch.from_numpy(np.concatenate([setup['frames'], setup['frames'][:, ::-1].copy()], 0)).cuda()
+    full, _, _ = eng.forward_features(fr)
+    eng.skip_dead_frames = True
+    dce, _, _ = eng.forward_features(fr)
+    for a, b in zip(full, dce):
+        assert a.shape == b.shape and torch.equal(a.contiguous(), b.contiguous())
 
 
 @pytest.mark.parametrize('mode', ['tf32x3', 'tf32'])
