@@ -328,13 +328,42 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * args.steps
     # ---- timed: end to end (pinned host -> device -> host) --------------------------------------
-    for _ in range(2):
-        res = step_e2e()
+    # Every step copies its own frames from pinned host memory and reads its results back, all inside the timed
+    # region.  With a captured graph the upload of step i+1 runs on a copy stream into a second staging buffer
+    # while step i computes (what a serving loop does); the step then starts with a device-side hand-over.
+    if args.graph:
+        copy_stream = torch.cuda.Stream()
+        staging = [torch.empty_like(static_in) for _ in range(2)]
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+
+        def issue_h2d(i):
+            with torch.cuda.stream(copy_stream):
+                staging[i % 2].copy_(host, non_blocking=True)
+                h2d_done[i % 2].record(copy_stream)
+
+        def e2e_loop(n):
+            issue_h2d(0)
+            r = None
+            for i in range(n):
+                if i + 1 < n:
+                    issue_h2d(i + 1)                       # overlaps this step's compute
+                torch.cuda.current_stream().wait_event(h2d_done[i % 2])
+                flush.zero_()
+                static_in.copy_(staging[i % 2], non_blocking=True)
+                out = run()
+                r = (out['dets'].cpu(), out['det_counts'].cpu(), out['xy'].cpu())   # D2H of the step's results
+            return r
+    else:
+        def e2e_loop(n):
+            r = None
+            for _ in range(n):
+                r = step_e2e()
+            return r
+    res = e2e_loop(2)
     barrier()
     f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        res = step_e2e()
+    res = e2e_loop(args.steps)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)

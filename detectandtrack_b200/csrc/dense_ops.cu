@@ -165,6 +165,53 @@ __global__ void maxpool_kernel(const ET* __restrict__ x, int N, int H, int W, in
   }
 }
 
+// pool1 (3x3, stride 2, pad 1): a thread walks a vertical strip of PR output rows for one (wo, channel vector)
+// and keeps the horizontal max of the shared input row (2*ho + 1 is the last row of window ho and the first of
+// window ho + 1), so an output costs 6 vector loads instead of 9.
+#define POOL_PR 8
+template <typename ET>
+__global__ void maxpool3x3s2_kernel(const ET* __restrict__ x, int N, int H, int W, int C, int ldx, int Ho, int Wo,
+                                    ET* __restrict__ y, int ldy, int lo_in, int lo_out) {
+  constexpr int V = Vec<ET>::N;
+  const int cv = C / V;
+  const int strips = (Ho + POOL_PR - 1) / POOL_PR;
+  const long long total = (long long)N * strips * Wo * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * V;
+    long long r = idx / cv;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int st = (int)(r % strips);
+    const int n = (int)(r / strips);
+    const int w0 = 2 * wo - 1;
+    auto hmax = [&](int hi, float* m) {           // max over the three columns of input row hi (-inf outside)
+#pragma unroll
+      for (int e = 0; e < V; ++e) m[e] = -CUDART_INF_F;
+      if (hi < 0 || hi >= H) return;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = w0 + kw;
+        if (wi < 0 || wi >= W) continue;
+        float v[V];
+        load_vals<ET>(x + (((size_t)n * H + hi) * W + wi) * ldx + c, lo_in, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    };
+    const int ho0 = st * POOL_PR, ho1 = min(ho0 + POOL_PR, Ho);
+    float prev[V];
+    hmax(2 * ho0 - 1, prev);
+    for (int ho = ho0; ho < ho1; ++ho) {
+      float a[V], b[V];
+      hmax(2 * ho, a);
+      hmax(2 * ho + 1, b);
+      float m[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) { m[e] = fmaxf(fmaxf(prev[e], a[e]), b[e]); prev[e] = b[e]; }
+      store_vals<ET>(y + (((size_t)n * Ho + ho) * Wo + wo) * ldy + c, lo_out, m);
+    }
+  }
+}
+
 // ------------------------------------------------------------------- RoIAlign (multi-level, tubes)
 struct RoiLevels {
   const void* feat[8];
@@ -607,6 +654,17 @@ extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, 
   if (N == 0) return 0;
   DT_CHECK_ARG(x && y, "dt_maxpool2d: null pointer");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;      // Caffe2 legacy (floor) pooling
+  if (k == 3 && s == 2 && p == 1) {                                           // pool1: rolling-row kernel
+    const long long tot = (long long)N * ((Ho + POOL_PR - 1) / POOL_PR) * Wo * (C / V);
+    if (f32)
+      maxpool3x3s2_kernel<float><<<grid_for(tot, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, Ho, Wo, (float*)y, ldy,
+                                                                                        x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
+    else
+      maxpool3x3s2_kernel<__nv_bfloat16><<<grid_for(tot, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, Ho, Wo,
+                                                                                                (__nv_bfloat16*)y, ldy, 0, 0);
+    DT_CHECK_LAUNCH();
+    return 0;
+  }
   const long long total = (long long)N * Ho * Wo * (C / V);
   if (f32)
     maxpool_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (float*)y, ldy,
