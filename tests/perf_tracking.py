@@ -2,7 +2,7 @@
 V videos x 30 frames x 100 detections (synthetic, oracle.tracking.synth_video), linked by
 core.tracking_engine (fused (1 - IoU) cost + Hungarian assignment for every frame pair + id scan on the GPU),
 next to the CPU restatement of the reference loop (bbox_overlaps -> scipy linear_sum_assignment, 1 core).
-Checks that both give identical track ids.   python tools/bench_tracking.py [--videos 64]"""
+Checks that both give identical track ids.   python tests/perf_tracking.py [--videos 64]"""
 import argparse
 import json
 import os
