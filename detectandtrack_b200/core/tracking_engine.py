@@ -4,7 +4,8 @@ reference's ``core.tracking_engine`` (lib/core/tracking_engine.py).
 Kept surface: ``_compute_matches``, ``_compute_tracks_video``,
 ``compute_matches_tracks``, ``_prune_bad_detections``, ``_center_detections``,
 ``run_posetrack_tracking`` with the reference's argument meaning and the
-``detections.pkl`` / ``detections_withTracks.pkl`` schema.
+``detections.pkl`` / ``detections_withTracks.pkl`` schema; the PoseTrack JSON
+writer that follows it lives in ``core/mpii_eval_engine.py``.
 
 What changed underneath: instead of one python loop per frame pair
 (bbox_overlaps -> scipy LSA -> id list), all frames of all videos are packed
@@ -231,10 +232,10 @@ def compute_matches_tracks(json_data, dets, lstm_model=None):
     return dets
 
 
-def run_posetrack_tracking(test_output_dir, json_data):
-    """:758-795 up to and including detections_withTracks.pkl.  The PoseTrack
-    evaluation that follows in the reference (run_mpii_eval, :792-795) needs the
-    dataset and the vendored poseval; it is out of the hot-path scope."""
+def run_posetrack_tracking(test_output_dir, json_data, write_json=True):
+    """:758-795.  Writes detections_withTracks.pkl and then, like the reference's run_mpii_eval call
+    (:792-795), the per-video PoseTrack JSON files (core/mpii_eval_engine.py).  The evaluation itself
+    (vendored poseval + annotations) stays outside the package."""
     det_file = cfg.TRACKING.DETECTIONS_FILE if len(cfg.TRACKING.DETECTIONS_FILE) else \
         osp.join(test_output_dir, 'detections.pkl')
     out_det_file = osp.join(test_output_dir, 'detections_withTracks.pkl')
@@ -251,4 +252,7 @@ def run_posetrack_tracking(test_output_dir, json_data):
     dets = _prune_bad_detections(dets, json_data, conf)
     dets_withTracks = compute_matches_tracks(json_data, dets, None)
     _write_det_file(dets_withTracks, out_det_file)
+    if write_json:
+        from . import mpii_eval_engine
+        mpii_eval_engine.run_mpii_eval(test_output_dir, json_data)
     return dets_withTracks
