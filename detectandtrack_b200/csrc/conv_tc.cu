@@ -68,8 +68,6 @@ struct ConvKernelParams {
   int res_mode;                // 0 none, 1 same shape, 2 nearest-2x upsample of (Ho/2, Wo/2)
   int res_ld;
   int relu;
-  void* out;
-  int out_ld;                  // elements between consecutive positions
   int out_f32;                 // 1: fp32 output, 0: bf16
   // 3xTF32 ("fp32-accurate") mode: activations / weights are stored as [hi | lo] tf32 pairs along the
   // channel axis; D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the lo*lo term is below fp32 resolution).
@@ -779,7 +777,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_t = cdiv(To, ts.tt); p.tiles_b = cdiv(d->N, ts.tb);
   p.a_bytes = (uint32_t)(TH * TW * ts.tt * ts.tb) * 128u;
   p.scale = scale; p.bias = bias; p.residual = residual; p.res_mode = d->res_mode; p.res_ld = res_ld;
-  p.relu = d->relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32; p.round_tf32 = d->out_round_tf32;
+  p.relu = d->relu; p.out_f32 = out_f32; p.round_tf32 = d->out_round_tf32;
   // 3xTF32 split operands / outputs
   p.split_in = (d->x3 & 1) ? 1 : 0;
   p.split_out = (d->x3 & 2) ? 1 : 0;
@@ -906,7 +904,7 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   p.TH = TH; p.TW = TW; p.TT = 1; p.TB = 1; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_t = 1; p.tiles_b = F;
   p.tiles_n = 1;
   p.a_bytes = (uint32_t)TH * TW * 128u;
-  p.scale = scale; p.bias = bias; p.relu = relu; p.out = y; p.out_ld = out_ld; p.out_f32 = out_f32;
+  p.scale = scale; p.bias = bias; p.relu = relu; p.out_f32 = out_f32;
   p.round_tf32 = out_round_tf32;
   p.fd_n = make_fastdiv(1); p.fd_w = make_fastdiv(p.tiles_w); p.fd_h = make_fastdiv(p.tiles_h); p.fd_t = make_fastdiv(1);
   const long long total = (long long)F * p.tiles_h * p.tiles_w;

@@ -55,9 +55,9 @@ def main():
         L.lib().dt_conv_trace_read.argtypes = [C.c_void_p]
         assert L.lib().dt_conv_trace_read(buf) == 0
         t0 = buf[0]
-        print(name, 'columns: P.begin P.end M.begin M.end E.tile E.acc_ready E.stage_free E.staged E.synced E.done  (cycles since first stamp)')
+        print(name, 'columns: P.begin P.end M.begin M.end E.tile E.acc_ready E.slot_free E.staged E.done  (cycles since first stamp; epilogue = warp 3)')
         for i in range(24):
-            print(i, ' '.join('%7d' % (buf[i * 16 + j] - t0) for j in range(10)) + '  | wait_empty %6d wait_full %6d tma_issue %6d (A only %6d)' % (buf[i * 16 + 10], buf[i * 16 + 11], buf[i * 16 + 12], buf[i * 16 + 13]))
+            print(i, ' '.join('%7d' % (buf[i * 16 + j] - t0) for j in (0, 1, 2, 3, 4, 5, 6, 7, 9)) + '  | wait_empty %6d wait_full %6d tma_issue %6d' % (buf[i * 16 + 10], buf[i * 16 + 11], buf[i * 16 + 12]))
         break
 
 
