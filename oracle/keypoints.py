@@ -84,3 +84,31 @@ def deconv_k4s2p1(x, w, b):
     """Caffe2 ConvTranspose kernel 4 stride 2 pad 1; w is (Cin, Cout, 4, 4) like Caffe2/torch."""
     import torch.nn.functional as Fn
     return Fn.conv_transpose2d(x, w, b, stride=2, padding=1)
+
+
+# ------------------------------------------------------------------ pose-PCK tracking cost
+# lib/utils/keypoints.py:266-291 and lib/core/tracking_engine.py:113-129 ('pose-pck' entry of
+# TRACKING.DISTANCE_METRICS, weight 0 in every shipped yaml).  Restated for the device kernel of the next round;
+# pinned by tests/golden/pose_pck.npz (generated from the reference's own functions).
+def compute_head_size(kps, kpt_names):
+    """:266-274.  |head_top - head_bottom| + 1 in the dtype of kps (float32 poses stay float32)."""
+    ht = kps[:2, kpt_names.index('head_top')]
+    hb = kps[:2, kpt_names.index('head_bottom')]
+    return np.linalg.norm(ht - hb) + 1
+
+
+def pck_distance(kps_a, kps_b, kpt_names, dist_thresh=0.5):
+    """:277-291.  1 - (fraction of joints closer than dist_thresh head sizes); kps_a supplies the head size."""
+    head = compute_head_size(kps_a, kpt_names)
+    normed = np.linalg.norm(kps_a[:2] - kps_b[:2], axis=0) / head
+    match = normed < dist_thresh
+    return 1.0 - np.sum(match) / match.size
+
+
+def pairwise_kpt_distance(a, b, kpt_names):
+    """tracking_engine.py:113-129: res[i, j] = pck_distance(a[i], b[j]) as float64 [len(a), len(b)]."""
+    res = np.zeros((len(a), len(b)))
+    for i in range(len(a)):
+        for j in range(len(b)):
+            res[i, j] = pck_distance(a[i], b[j], kpt_names)
+    return res

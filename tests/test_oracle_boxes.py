@@ -151,3 +151,20 @@ def test_collect_distribute_golden(golden, name):
 def test_roi_to_batch_format_golden(golden):
     g = golden('r2b')
     assert np.array_equal(op.roi_to_batch_format(g['r2b_in']), g['r2b_out'])
+
+
+def test_pose_pck_distance_vs_reference_golden():
+    """oracle.keypoints.pck_distance / pairwise_kpt_distance against the reference's own functions
+    (tests/golden/gen_golden_pose_pck.py): the 'pose-pck' tracking cost, SURVEY §8(f) rank 4."""
+    import os
+    from oracle import keypoints as okp
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'pose_pck.npz'))
+    names = [str(x) for x in g['names']]
+    for tag in ('small', 'frame', 'far'):
+        a = [x for x in g[tag + '_a']]
+        b = [x for x in g[tag + '_b']]
+        d = okp.pairwise_kpt_distance(a, b, names)
+        assert d.dtype == np.float64 and np.array_equal(d, g[tag + '_dist'])
+        heads = np.array([okp.compute_head_size(x, names) for x in a], dtype=np.float64)
+        assert np.array_equal(heads, g[tag + '_head'])
+    assert g['small_dist'].min() == 0.0 and g['far_dist'].max() > 0.8          # the fixtures span both regimes
