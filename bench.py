@@ -437,7 +437,8 @@ def run_ours(args):
                     e2e=dict(value=e2e, unit='clips/s', h2d_bytes_per_step=int(host.numel()), d2h_bytes_per_step=d2h),
                     gpu_launches=launches, clocks=clocks,
                     roofline=dict(bound='tensor', kernel='conv_tc_kernel (all conv/FC launches of the step)', achieved=achieved,
-                                  peak=pk['tflops'], unit='TFLOP/s', frac=achieved / pk['tflops'], traffic=conv_traffic(B),
+                                  peak=pk['tflops'], unit='TFLOP/s', frac=achieved / pk['tflops'], traffic=conv_traffic(B)[0],
+                                  traffic_source=conv_traffic(B)[1],
                                   peak_source=pk['src']))
         if dce_extra is not None:
             line['config']['with_dead_frame_elimination'] = dce_extra
@@ -452,14 +453,16 @@ def run_ours(args):
 
 
 def conv_traffic(clips_per_step):
-    """DRAM bytes moved by the conv_tc launches of one step, from the committed ncu capture of this same bench
-    command (profiles/conv_dram_r01.json, tools/ncu_conv_traffic.py); scaled if the step size differs."""
+    """DRAM bytes moved by the conv_tc launches of ONE step (the unit `roofline.achieved` is computed over), from the
+    committed ncu capture of this same bench command (profiles/conv_dram_r01.json, tools/ncu_conv_traffic.py);
+    scaled if the step size differs.  Returns (bytes or None, provenance string)."""
     path = os.path.join(ROOT, 'profiles', 'conv_dram_r01.json')
     if not os.path.exists(path):
-        return None
+        return None, 'no ncu capture committed'
     d = json.load(open(path))
-    return dict(dram_bytes_per_step=d['dram_bytes'] * clips_per_step / float(d['clips_per_step']), launches=d['launches'],
-                source='profiles/conv_dram_r01.json (ncu dram__bytes_read+write, %d clips/step)' % d['clips_per_step'])
+    return (d['dram_bytes'] * clips_per_step / float(d['clips_per_step']),
+            'dram__bytes_read.sum + dram__bytes_write.sum over the %d conv_tc launches of one step, ncu, %d clips/step '
+            '(profiles/conv_dram_r01.json)' % (d['launches'], d['clips_per_step']))
 
 
 def cpu_baseline(cfg, blobs, spec, args):
