@@ -80,3 +80,28 @@ def test_write_posetrack_json_groups_by_video(tmp_path):
     b = json.load(open(paths['images/vidB']))['annolist']
     assert b[0]['image'] == 'images/vidB/00001.jpg' and b[0]['imagenum'] == [1] and len(b[0]['annorect']) == 3
     assert len(b[0]['annorect'][0]['annopoints'][0]['point']) == 15
+
+
+def test_run_mpii_eval_reads_pickle_and_calls_evaluator(tmp_path):
+    import pickle
+    from detectandtrack_b200.core.config import reset_cfg
+    from detectandtrack_b200.core import mpii_eval_engine as me
+    reset_cfg()
+    assert me.run_mpii_eval(str(tmp_path), []) is None                      # no detections_withTracks.pkl yet
+    rng = np.random.default_rng(1)
+    roidb = [{'image': 'images/v/%05d.jpg' % i, 'frame_id': i + 1} for i in range(2)]
+    boxes = [np.hstack([rng.uniform(0, 300, (2, 4)), [[0.9], [0.2]]]).astype(np.float32), np.zeros((0, 5), np.float32)]
+    keyps = [[rng.uniform(0, 300, (4, 17)).astype(np.float32) for _ in range(2)], []]
+    dets = {'all_boxes': [[], boxes], 'all_keyps': [[], keyps], 'all_tracks': [[], [[5, 6], []]]}
+    with open(tmp_path / 'detections_withTracks.pkl', 'wb') as f:
+        pickle.dump(dets, f)
+    seen = {}
+
+    def evaluator(annot_dir, out_dir, eval_tracking):
+        seen['args'] = (annot_dir, out_dir, eval_tracking)
+        return 'scores'
+    paths, res = me.run_mpii_eval(str(tmp_path), roidb, evaluator=evaluator)
+    assert res == 'scores' and seen['args'][2] is True and seen['args'][1].endswith('detections_withTracks.pkl_json/')
+    ann = json.load(open(paths['images/v']))['annolist']
+    assert len(ann) == 2 and len(ann[0]['annorect']) == 1 and ann[0]['annorect'][0]['track_id'] == [5]   # 0.2 < drop threshold
+    assert ann[1]['annorect'][0]['score'] == [0]                                                         # dummy for the empty frame
