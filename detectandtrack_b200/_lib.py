@@ -22,6 +22,7 @@ SIGNATURES = {
     'dt_match_frames': [_p, _i, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p],
     'dt_assign_track_ids': [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p],
     'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
+    'dt_conv_plan': [C.c_void_p, _i, C.c_void_p],
     'dt_conv3d': [_p, _p, _p, _p, _p, _p, _p, _p],
     'dt_rpn_workspace_bytes': [_i, _i, C.POINTER(_i), C.POINTER(_i), _i, C.POINTER(_sz)],
     'dt_rpn_proposals_multi': [_p, _i, _i, _i, _i, _i, _p, _i, _f, C.c_double, C.c_longlong, _i, _i, _p, _sz, _p],
@@ -55,6 +56,14 @@ class ConvDesc(C.Structure):
         'N', 'Ti', 'Hi', 'Wi', 'Cin', 'Cout', 'kT', 'kH', 'kW', 'sT', 'sH', 'sW', 'pT', 'pH', 'pW',
         'in_ld', 'w_ld', 'out_ld', 'res_ld', 'dtype', 'out_f32', 'relu', 'res_mode', 'x3', 'in_lo_off', 'out_lo_off',
         'res_lo_off', 'out_round_tf32', 'out_time_major', 'out_t_first', 'out_t_count')]
+
+
+class ConvPlan(C.Structure):
+    """dt_conv_plan_t (include/dt_b200.h)."""
+    _fields_ = [(n, C.c_int) for n in ('BN', 'TH', 'TW', 'TT', 'TB', 'tiles', 'kiters', 'stages', 'ks', 'ncbuf', 'nrbuf',
+                                        'smem_bytes')] + [('useful_rows', C.c_double)]
+
+
 _RESTYPE = {'dt_last_error': C.c_char_p}
 
 

@@ -865,6 +865,53 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
 }
 
 
+// Planning query: MIRRORS the choices of dt_conv3d above (tile picker, column tile, residual ring, smem split) without
+// touching the device, so that the host logic is testable without a GPU (tests/test_conv_plan.py).
+template <int BN>
+static void plan_split(int kiters, bool res_tma, bool split_out, bool out_f32, dt_conv_plan_t* o) {
+  using Cfg = ConvCfg<BN>;
+  Cfg::split(kiters, res_tma, split_out, out_f32, &o->stages, &o->ks, &o->ncbuf, &o->nrbuf);
+  o->smem_bytes = Cfg::smem_bytes(kiters, o->stages, o->ks, o->ncbuf, o->nrbuf);
+}
+
+extern "C" int dt_conv_plan(const dt_conv_desc* d, int residual_aligned, dt_conv_plan_t* o) {
+  DT_CHECK_ARG(d != nullptr && o != nullptr, "dt_conv_plan: null pointer");
+  DT_CHECK_ARG(d->dtype == DT_DTYPE_BF16 || d->dtype == DT_DTYPE_TF32, "dt_conv_plan: dtype %d not in {BF16, TF32}", d->dtype);
+  DT_CHECK_ARG(d->N >= 1 && d->Ti >= 1 && d->Hi >= 1 && d->Wi >= 1 && d->Cin >= 1 && d->Cout >= 1 && d->kT >= 1 && d->kH >= 1 &&
+                   d->kW >= 1 && d->sT >= 1 && d->sH >= 1 && d->sW >= 1 && d->pT >= 0 && d->pH >= 0 && d->pW >= 0,
+               "dt_conv_plan: bad shape");
+  const bool tf32 = d->dtype == DT_DTYPE_TF32;
+  const int BK = tf32 ? 32 : 64;
+  const int To_full = (d->Ti + 2 * d->pT - d->kT) / d->sT + 1;
+  const int To = d->out_t_count > 0 ? d->out_t_count : To_full;
+  const int Ho = (d->Hi + 2 * d->pH - d->kH) / d->sH + 1;
+  const int Wo = (d->Wi + 2 * d->pW - d->kW) / d->sW + 1;
+  DT_CHECK_ARG(To >= 1 && Ho >= 1 && Wo >= 1, "dt_conv_plan: empty output (%d,%d,%d)", To, Ho, Wo);
+  const bool pointwise = d->kT == 1 && d->kH == 1 && d->kW == 1 && d->pT == 0 && d->pH == 0 && d->pW == 0;
+  const TileShape ts = pick_tile(Ho, Wo, To, d->N, pointwise ? 256 : 256 / d->sW, pointwise ? 256 : 256 / d->sH,
+                                 pointwise || d->sT == 1);
+  int BN = d->Cout >= 256 ? 256 : (d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32));
+  if (d->Cout > 128 && d->Cout < 256) BN = 128;
+  const bool res_even = (ts.th % 2 == 0) && (ts.tw % 2 == 0);
+  const bool res_tma = (d->res_mode == 1 || (d->res_mode == 2 && res_even)) && !d->out_f32 && !tf32 && residual_aligned;
+  if (res_tma && BN > 128) BN = 128;
+  const bool split_in = (d->x3 & 1) != 0, split_out = (d->x3 & 2) != 0;
+  memset(o, 0, sizeof(*o));
+  o->BN = BN; o->TH = ts.th; o->TW = ts.tw; o->TT = ts.tt; o->TB = ts.tb;
+  o->kiters = d->kT * d->kH * d->kW * cdiv(d->Cin, BK) * (split_in ? 3 : 1);
+  const long long mt = (long long)cdiv(Wo, ts.tw) * cdiv(Ho, ts.th) * cdiv(To, ts.tt) * cdiv(d->N, ts.tb);
+  o->tiles = (int)(mt * cdiv(d->Cout, BN));
+  o->useful_rows = (double)Ho * Wo * To * d->N / ((double)mt * 128.0);
+  switch (BN) {
+    case 256: plan_split<256>(o->kiters, res_tma, split_out, d->out_f32 != 0, o); break;
+    case 128: plan_split<128>(o->kiters, res_tma, split_out, d->out_f32 != 0, o); break;
+    case 64: plan_split<64>(o->kiters, res_tma, split_out, d->out_f32 != 0, o); break;
+    default: plan_split<32>(o->kiters, res_tma, split_out, d->out_f32 != 0, o); break;
+  }
+  return 0;
+}
+
+
 // conv1 of the ResNet bodies: 7x7 stride 2 pad 3 on a 3-channel image (lib/modeling/ResNet3D.py:258-261,
 // ResNet.py).  With Cin = 3 a per-tap k-block would waste 61/64 of every MMA, so the taps of one filter
 // ROW are packed into K instead: the image blob is channel-padded to Cp (8 bf16 / 4 fp32 = 16 bytes per

@@ -152,6 +152,18 @@ typedef struct dt_conv_desc {
 int dt_conv3d(const dt_conv_desc* desc /*host*/, const void* x, const void* w, const float* scale,
               const float* bias, const void* residual, void* y, void* stream);
 
+/* Host-only planning query (no device work, usable without a GPU): the tiling dt_conv3d would pick for `desc` —
+ * column tile BN, M tile (TB images x TT frames x TH x TW positions <= 128 rows), tiles per launch, operand ring
+ * (stages x ks k-blocks), output staging / residual ring chunks, dynamic shared memory, k-blocks per tile and the
+ * fraction of MMA rows that are real output positions.  residual_aligned: the residual pointer would be 16-byte
+ * aligned (enables the TMA residual ring for bf16 residual modes). */
+typedef struct dt_conv_plan_t {
+  int BN, TH, TW, TT, TB;
+  int tiles, kiters, stages, ks, ncbuf, nrbuf, smem_bytes;
+  double useful_rows;
+} dt_conv_plan_t;
+int dt_conv_plan(const dt_conv_desc* desc /*host*/, int residual_aligned, dt_conv_plan_t* plan /*host out*/);
+
 /* conv1 of the ResNet bodies (lib/modeling/ResNet3D.py:258-261): 7x7 stride 2 pad 3 on the 3-channel
  * image + AffineChannel + ReLU, with the 7 taps of a filter row packed into one 128-byte k-block.
  * x_padded [F, 2, (Hp+6)/2, Wp+8, Cp] from dt_prep_clip(border 3, 4, row_planes 1), Cp*elemsize == 16;
