@@ -102,3 +102,20 @@ def test_plan_rejects_bad_arguments():
     o = L.ConvPlan()
     assert L.lib().dt_conv_plan(C.byref(d), 1, C.byref(o)) != 0
     assert b'bad shape' in L.lib().dt_last_error()
+
+
+def test_workspace_queries_are_host_only_and_consistent():
+    """dt_nms_workspace_bytes / dt_rpn_workspace_bytes need no device: sizes grow with the problem and cover the
+    documented contents (one u32 key per anchor per image for the RPN top-k)."""
+    lib = L.lib()
+    a, b = C.c_size_t(0), C.c_size_t(0)
+    assert lib.dt_nms_workspace_bytes(1, 1000, C.byref(a)) == 0 and lib.dt_nms_workspace_bytes(8, 8192, C.byref(b)) == 0
+    assert 0 < a.value < b.value
+    assert lib.dt_nms_workspace_bytes(-1, 10, C.byref(a)) != 0 and b'bad args' in lib.dt_last_error()
+    assert b.value >= 8 * 8192 * (4 + 128 * 8 + 1)                              # order + 64-bit mask rows + flags
+    Hs = (C.c_int * 5)(200, 100, 50, 25, 13)
+    Ws = (C.c_int * 5)(336, 168, 84, 42, 21)
+    n = C.c_size_t(0)
+    assert lib.dt_rpn_workspace_bytes(8, 5, Hs, Ws, 3, C.byref(n)) == 0
+    anchors = sum(h * w for h, w in zip(Hs, Ws)) * 3
+    assert 8 * anchors * 4 <= n.value <= 8 * anchors * 4 + 5 * 256
