@@ -208,7 +208,8 @@ class ConvMeter(object):
             e0.record()
             y = orig(x, w_packed, ksize, *a, **kw)
             e1.record()
-            cin = kw.get('cin') or min(x.shape[-1], w_packed.shape[-1])
+            split = kw.get('dtype') in cv.SPLIT_MODES           # [hi | lo] rows: half of the row is the channel count
+            cin = kw.get('cin') or (min(x.shape[-1], w_packed.shape[-1]) // (2 if split else 1))
             cout = w_packed.shape[1]
             meter.flops += 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * y.shape[3] * cout * cin * ksize[0] * ksize[1] * ksize[2]
             meter.ev.append((e0, e1))
@@ -485,7 +486,7 @@ if __name__ == '__main__':
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'tf32', 'tf32x3'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'tf32', 'tf32x3', 'bf16x3'])
     ap.add_argument('--clips', type=int, default=8, help='clips per GPU per step')
     ap.add_argument('--height', type=int, default=800)
     ap.add_argument('--width', type=int, default=1333)

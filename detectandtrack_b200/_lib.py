@@ -15,6 +15,8 @@ _sz = C.c_size_t
 # name -> argtypes (every function returns int unless listed in _RESTYPE)
 SIGNATURES = {
     'dt_abi_version': [],
+    'dt_memset': [_p, _i, _sz, _p],
+    'dt_scale_rois': [_p, _i, _i, _i, _p, _i, C.c_double, _p, _p],
     'dt_bbox_overlaps': [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p],
     'dt_nms_workspace_bytes': [_i, _i, C.POINTER(_sz)],
     'dt_nms_batched': [_p, _i, _i, _i, _i, _p, _f, _i, _i, _i, _p, _p, _p, _sz, _p],
@@ -31,12 +33,12 @@ SIGNATURES = {
     'dt_box_decode': [_p, _p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, C.POINTER(_f), C.c_double, _f, _p, _p, _p],
     'dt_limit_detections': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     'dt_prep_clip': [_p, _i, _i, _i, C.POINTER(_f), C.c_double, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
-    'dt_conv1_7x7s2': [_p, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p],
+    'dt_conv1_7x7s2': [_p, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_maxpool2d': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_roi_align': [C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _i, _i, _p, _i, _p, _i,
                      _i, _p, _i, _i, _i, _i, _p, _p],
     'dt_keypoint_decode': [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p],
-    'dt_conv1_7x7s2_f32': [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    'dt_conv1_7x7s2_f32': [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p],
     'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_time_mean': [_p, _i, _i, C.c_longlong, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_fold_tube_heads': [_p, _i, _i, _i, _i, _p, _p, _p],
@@ -110,6 +112,14 @@ def ptr(t):
         return None
     assert t.is_contiguous(), 'tensor must be contiguous'
     return C.c_void_p(t.data_ptr())
+
+
+def zeros(shape, dtype):
+    """torch.empty + dt_memset on the current stream: zero-initialised device tensor without a library kernel."""
+    import torch
+    t = torch.empty(shape, dtype=dtype, device='cuda')
+    call('dt_memset', C.c_void_p(t.data_ptr()), 0, t.numel() * t.element_size(), stream_ptr())
+    return t
 
 
 def stream_ptr():

@@ -331,12 +331,8 @@ extern "C" int dt_nms_batched(const float* dets, int batch, int nmax, int ld, in
 
   const int npow2 = next_pow2(nmax);
   const size_t sort_smem = (size_t)npow2 * sizeof(unsigned long long);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DT_CHECK_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(next_pow2(DT_NMS_MAX_BOXES) * sizeof(unsigned long long))));
-    attr_set = true;
-  }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(nms_sort_kernel, (int)(next_pow2(DT_NMS_MAX_BOXES) * sizeof(unsigned long long)), &grant));
   nms_sort_kernel<<<batch, npow2 >= 1024 ? 1024 : (npow2 < 64 ? 64 : npow2), sort_smem, stream>>>(
       dets, nmax, ld, T, counts, npow2, order);
   DT_CHECK_LAUNCH();

@@ -15,3 +15,12 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* dt_last_error(void) { return dt::last_error_buf(); }
 extern "C" int dt_abi_version(void) { return DT_B200_ABI_VERSION; }
+
+// Asynchronous fill of a caller-owned device buffer on the caller's stream (a memset node when the stream is being
+// captured into a CUDA graph): the hot path zeroes its count / output buffers with this instead of library kernels.
+extern "C" int dt_memset(void* ptr, int value, size_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  DT_CHECK_ARG(ptr != nullptr, "dt_memset: null pointer");
+  DT_CHECK_CUDA(cudaMemsetAsync(ptr, value, bytes, (cudaStream_t)stream));
+  return 0;
+}

@@ -31,6 +31,22 @@ void set_error(const char* fmt, ...);
 
 #define DT_CHECK_LAUNCH() DT_CHECK_CUDA(cudaGetLastError())
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember, per launch site and device, the
+// largest size already granted (a process may use the library on several GPUs and from several threads).
+struct DynSmemGrant {
+  int granted[64];                     // bytes set so far on device i (0 = never); races only repeat the call
+};
+template <typename K>
+static inline cudaError_t grant_dyn_smem(K kernel, int bytes, DynSmemGrant* g) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && __atomic_load_n(&g->granted[dev], __ATOMIC_ACQUIRE) >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) __atomic_store_n(&g->granted[dev], bytes, __ATOMIC_RELEASE);
+  return e;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

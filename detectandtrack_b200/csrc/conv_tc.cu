@@ -72,6 +72,8 @@ struct ConvKernelParams {
   // 3xTF32 ("fp32-accurate") mode: activations / weights are stored as [hi | lo] tf32 pairs along the
   // channel axis; D = A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the lo*lo term is below fp32 resolution).
   int split_in;                // 1: three k-blocks per (tap, channel chunk) with the offsets below
+  int nsub;                    // k-blocks per (tap, channel chunk): 1 plain, 3 split operands (hi*hi, lo*hi, hi*lo),
+                               // 2 split conv1 (the blob pixel carries [hi3 | lo3]: one block against [W_hi | W_hi], one against [W_lo | 0])
   int a_lo_off, b_lo_off;      // element offsets of the lo halves in the x rows / packed weight rows
   int split_out;               // 1: write hi at channel c and lo at out_lo_off + c (fp32)
   int out_lo_off, res_lo_off;  // lo-half offsets of the output / residual rows
@@ -116,17 +118,18 @@ struct ConvCfg {
     const int chunks = BN / (out_f32 ? 32 : 64);        // staged chunks per tile
     int c = (kiters >= 12 && !split_out) ? ((BN >= 256) ? 1 : 2) : 4;   // split (hi, lo) output: two slots of two buffers
     if (!split_out && c > 2 * chunks) c = chunks >= 1 ? 2 * chunks : 2;   // two tiles of staging are enough
-    const int r = res_tma ? ((kiters >= 12) ? 2 : 4) : 0;
+    const int r = res_tma ? ((kiters >= 12 || split_out) ? 2 : 4) : 0;      // split output: a residual slot is a chunk pair
+    const int rb = split_out ? 2 * r : r;
     // narrow tiles retire a k-block's MMAs faster than one producer / issuer round trip through the
     // mbarriers: let a ring stage carry two k-blocks there (same bytes in flight, half the handshakes)
-    const int avail = BUDGET - FIXED_BYTES - tab_bytes(kiters) - (c + r) * C_BYTES;
+    const int avail = BUDGET - FIXED_BYTES - tab_bytes(kiters) - (c + rb) * C_BYTES;
     const int k = (BN <= 128 && kiters >= 2 && avail / (2 * KB_BYTES) >= 3) ? 2 : 1;
     int st = avail / (k * KB_BYTES);
     if (st > MAX_STAGES) st = MAX_STAGES;
     *stages = st; *ks = k; *ncbuf = c; *nrbuf = r;
   }
-  static int smem_bytes(int kiters, int stages, int ks, int ncbuf, int nrbuf) {
-    return stages * ks * KB_BYTES + (ncbuf + nrbuf) * C_BYTES + FIXED_BYTES + tab_bytes(kiters);
+  static int smem_bytes(int kiters, int stages, int ks, int ncbuf, int nrbuf, bool split_out) {
+    return stages * ks * KB_BYTES + (ncbuf + (split_out ? 2 : 1) * nrbuf) * C_BYTES + FIXED_BYTES + tab_bytes(kiters);
   }
 };
 
@@ -150,7 +153,9 @@ __device__ long long g_conv_trace[64 * 16];
 #define TRACE_ADD(ti, k, v) do {} while (0)
 #endif
 
-template <int BN, bool TF32>
+// SPLIT: the output (and the residual) rows are [hi | lo] pairs (the x3 modes' intermediate activations); a template
+// parameter so that the plain kernels do not carry the pair logic's registers (the epilogue sits at the 96-register cap).
+template <int BN, bool TF32, bool SPLIT>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -163,7 +168,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* cbuf = smem + STAGES * p.ks * Cfg::KB_BYTES;              // [NCBUF][128 rows][128 B], 128B-swizzled
   uint8_t* rbuf = cbuf + p.ncbuf * Cfg::C_BYTES;                     // [NRBUF] residual chunks, same layout
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + p.nrbuf * Cfg::C_BYTES);
+  constexpr uint32_t rslot_bytes = SPLIT ? 2u * Cfg::C_BYTES : (uint32_t)Cfg::C_BYTES;   // split: (hi, lo) chunk pair
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + p.nrbuf * rslot_bytes);
   uint64_t* full = bars;                       // [STAGES]  operands landed
   uint64_t* empty = bars + STAGES;             // [STAGES]  operands consumed by the MMAs
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]       accumulator complete
@@ -180,7 +186,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   int2* tabB = reinterpret_cast<int2*>(tabA + p.ktab);                                        // {c, tap}
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   {
-    const int nsub = p.split_in ? 3 : 1;
+    const int nsub = p.nsub;
     const int kit = p.kT * p.kH * p.kW * p.kchunks * nsub;
     for (int j = threadIdx.x; j < p.ktab; j += blockDim.x) {
       const int jj = min(j, kit - 1);                   // padding entries repeat the last k-block (never issued)
@@ -194,8 +200,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // sub 0: A_hi x B_hi, 1: A_lo x B_hi, 2: A_hi x B_lo
       const int ca = kc * BK + (sub == 1 ? p.a_lo_off : 0);
       const int cb = kc * BK + (sub == 2 ? p.b_lo_off : 0);
-      tabA[j] = p.row_planes ? make_int4(ca, 0, kh >> 1, kh & 1) : make_int4(ca, kw, kh, kt);
-      tabB[j] = make_int2(cb, tap);
+      if (p.row_planes) {          // conv1: one box per filter row; split mode: weight blocks 2*kh (hi) and 2*kh + 1 (lo)
+        tabA[j] = make_int4(0, 0, kh >> 1, kh & 1);
+        tabB[j] = make_int2(0, tap * nsub + sub);
+      } else {
+        tabA[j] = make_int4(ca, kw, kh, kt);
+        tabB[j] = make_int2(cb, tap);
+      }
     }
   }
 
@@ -222,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_base_smem;
 
   const int taps = p.kT * p.kH * p.kW;
-  const int kiters = taps * p.kchunks * (p.split_in ? 3 : 1);
+  const int kiters = taps * p.kchunks * p.nsub;
 
   if (warp == 0 || warp == B_WARP) {
     // ===================== TMA producers =====================
@@ -301,9 +312,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&r_empty[rslot], rphase ^ 1);
           if (elect_one()) {
             const uint32_t bar = smem_u32(&r_full[rslot]);
-            mbar_expect_tx_u(bar, p.res_up ? p.a_bytes >> 2 : p.a_bytes);
-            tma_load_5d_u(smem_u32(rbuf) + rslot * Cfg::C_BYTES, &tmR, bar, n_base + cc, (tc.twi * p.TW) >> p.res_up,
+            const uint32_t rbytes = p.res_up ? p.a_bytes >> 2 : p.a_bytes;
+            mbar_expect_tx_u(bar, SPLIT ? 2u * rbytes : rbytes);
+            tma_load_5d_u(smem_u32(rbuf) + rslot * rslot_bytes, &tmR, bar, n_base + cc, (tc.twi * p.TW) >> p.res_up,
                           (tc.thi * p.TH) >> p.res_up, tc.tti * p.TT, n);
+            if (SPLIT)
+              tma_load_5d_u(smem_u32(rbuf) + rslot * rslot_bytes + Cfg::C_BYTES, &tmR, bar, n_base + cc + p.res_lo_off,
+                            (tc.twi * p.TW) >> p.res_up, (tc.thi * p.TH) >> p.res_up, tc.tti * p.TT, n);
           }
           if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
         }
@@ -362,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // Waits until all epilogue warps have staged a chunk (c_full), stores it (one elected lane, which also owns
     // the bulk async-groups) and hands staging slots back (c_free) once their store has read them out.  Keeping
     // this off the epilogue warps removes every block-wide barrier from the epilogue.
-    const bool split_out = p.split_out != 0;
+    constexpr bool split_out = SPLIT;
     const int CW = p.out_f32 ? 32 : 64;
     const int nslots = split_out ? p.ncbuf / 2 : p.ncbuf;     // split output: a slot is a (hi, lo) buffer pair
     const uint32_t slot_bytes = split_out ? 2u * Cfg::C_BYTES : (uint32_t)Cfg::C_BYTES;
@@ -415,7 +430,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tl = rr % p.TT;
     const int nl = rr / p.TT;                  // >= TB for the unused tail rows of a short tile
     const bool out_f32 = p.out_f32 != 0;
-    const bool split_out = p.split_out != 0;
+    constexpr bool split_out = SPLIT;
     const bool relu = p.relu != 0;
     const int res_mode = p.res_mode;
     const int Cout = p.Cout;
@@ -527,24 +542,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // residual rows first: the global loads overlap the TMEM wait
           uint4 resq[2];
           const bool res_on = res_ldg && valid;
-          bool res_vec = res_on && (cbase + 16 <= Cout);
+          const bool res_vec = res_on && (cbase + 16 <= Cout);
           const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + rpos * p.res_ld + cbase;
           if (res_vec) {
             resq[0] = __ldg(reinterpret_cast<const uint4*>(rp));
             resq[1] = __ldg(reinterpret_cast<const uint4*>(rp + 8));
           }
-          if (res_tma) {
-            // the producer warp prefetched this chunk's residual rows (zero-filled outside the tensor) into
-            // the swizzled ring: read this thread's 32 bytes, then hand the slot back
-            mbar_wait(&r_full[rslot], rphase);
-            const uint32_t src = rbuf_u32 + (uint32_t)rslot * Cfg::C_BYTES + rrow_smem;
-            resq[0] = lds_u4(src + rq0);
-            resq[1] = lds_u4(src + rq1);
-            res_vec = true;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&r_empty[rslot]);
-            if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
-          }
+          // the producer warp prefetched this chunk's residual rows (zero-filled outside the tensor) into the swizzled ring
+          if (res_tma) mbar_wait(&r_full[rslot], rphase);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r[j]), sc[j], bi[j]);
@@ -555,20 +560,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
-          if (res_vec) {
+          auto add16 = [&](const uint4& a, const uint4& b) {          // 16 bf16 residual values onto v
+            const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int g4 = 0; g4 < 2; ++g4) {
-              const uint32_t w4[4] = {resq[g4].x, resq[g4].y, resq[g4].z, resq[g4].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * g4 + 2 * e] += __uint_as_float(w4[e] << 16);
-                v[8 * g4 + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
-              }
+            for (int e = 0; e < 8; ++e) {
+              v[2 * e] += __uint_as_float(w8[e] << 16);
+              v[2 * e + 1] += __uint_as_float(w8[e] & 0xffff0000u);
             }
+          };
+          if (res_tma) {
+            // read this thread's 32 bytes (hi, then the lo chunk in the slot's second buffer), then hand the slot back
+            const uint32_t src = rbuf_u32 + (uint32_t)rslot * rslot_bytes + rrow_smem;
+            add16(lds_u4(src + rq0), lds_u4(src + rq1));
+            if (SPLIT) add16(lds_u4(src + Cfg::C_BYTES + rq0), lds_u4(src + Cfg::C_BYTES + rq1));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&r_empty[rslot]);
+            if (++rslot == p.nrbuf) { rslot = 0; rphase ^= 1; }
+          } else if (res_vec) {
+            add16(resq[0], resq[1]);
+            if (SPLIT)                                                // residual = hi + lo (bf16 pairs)
+              add16(__ldg(reinterpret_cast<const uint4*>(rp + p.res_lo_off)), __ldg(reinterpret_cast<const uint4*>(rp + p.res_lo_off + 8)));
           } else if (res_on) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (cbase + j < Cout) v[j] += __bfloat162float(rp[j]);
+              if (cbase + j < Cout) v[j] += __bfloat162float(rp[j]) + (SPLIT ? __bfloat162float(rp[p.res_lo_off + j]) : 0.f);
           }
         }
 
@@ -592,7 +607,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           sts_f4(dst + q1, v[4], v[5], v[6], v[7]);
         } else {
           uint32_t h[8];
-          if (relu) {
+          if (split_out) {
+            // bf16 pair storage: hi = bf16(v), lo = bf16(v - hi) (v - hi is exact in fp32); hi + lo carries 16
+            // mantissa bits, which three bf16 MMAs per k-block turn into an fp32-accurate product
+            uint32_t l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = v[2 * j], b = v[2 * j + 1];
+              if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              h[j] = pack_bf16x2(a, b);
+              l[j] = pack_bf16x2(a - __uint_as_float(h[j] << 16), b - __uint_as_float(h[j] & 0xffff0000u));
+            }
+            const uint32_t dst_lo = dst + Cfg::C_BYTES;
+            sts_b4(dst_lo + q0, l[0], l[1], l[2], l[3]);
+            sts_b4(dst_lo + q1, l[4], l[5], l[6], l[7]);
+          } else if (relu) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) h[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
           } else {
@@ -693,26 +722,29 @@ static int encode_out_map(CUtensorMap* m, void* y, int out_f32, int Cout, int Wo
   return encode_map(m, out_f32 != 0, 5, y, d, st, b, e);
 }
 
-template <int BN, bool TF32>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+template <int BN, bool TF32, bool SPLIT>
+static int launch_conv1(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        const ConvKernelParams& p, int grid, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
-  static bool attr = false;
-  if (!attr) {
-    DT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::BUDGET));
-    attr = true;
-  }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(conv_tc_kernel<BN, TF32, SPLIT>, Cfg::BUDGET, &grant));
   ConvKernelParams q = p;
-  const int kiters = p.kT * p.kH * p.kW * p.kchunks * (p.split_in ? 3 : 1);
+  const int kiters = p.kT * p.kH * p.kW * p.kchunks * p.nsub;
   DT_CHECK_ARG(kiters <= 2048, "conv: %d k-blocks per tile exceed the schedule table", kiters);
   Cfg::split(kiters, p.nrbuf > 0, p.split_out != 0, p.out_f32 != 0, &q.nstages, &q.ks, &q.ncbuf, &q.nrbuf);
   q.ktab = (kiters + 2) & ~1;
-  const int smem = Cfg::smem_bytes(kiters, q.nstages, q.ks, q.ncbuf, q.nrbuf);
+  const int smem = Cfg::smem_bytes(kiters, q.nstages, q.ks, q.ncbuf, q.nrbuf, p.split_out != 0);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
-  conv_tc_kernel<BN, TF32><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, q);
+  conv_tc_kernel<BN, TF32, SPLIT><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, q);
   DT_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, bool TF32>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                       const ConvKernelParams& p, int grid, cudaStream_t stream) {
+  return p.split_out ? launch_conv1<BN, TF32, true>(tmA, tmB, tmC, tmR, p, grid, stream)
+                     : launch_conv1<BN, TF32, false>(tmA, tmB, tmC, tmR, p, grid, stream);
 }
 
 }  // namespace dt
@@ -781,8 +813,10 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   // 3xTF32 split operands / outputs
   p.split_in = (d->x3 & 1) ? 1 : 0;
   p.split_out = (d->x3 & 2) ? 1 : 0;
-  DT_CHECK_ARG(!p.split_in || (tf32 && d->Cin % BK == 0), "dt_conv3d: x3 inputs need DT_DTYPE_TF32 and Cin %% %d == 0 (Cin=%d)", BK, d->Cin);
-  DT_CHECK_ARG(!p.split_out || (out_f32 && d->Cout % 32 == 0), "dt_conv3d: x3 outputs need fp32 and Cout %% 32 == 0 (Cout=%d)", d->Cout);
+  p.nsub = p.split_in ? 3 : 1;
+  DT_CHECK_ARG(!p.split_in || d->Cin % BK == 0, "dt_conv3d: x3 inputs need Cin %% %d == 0 (Cin=%d)", BK, d->Cin);
+  DT_CHECK_ARG(!p.split_out || ((tf32 ? out_f32 : !out_f32) && d->Cout % (out_f32 ? 32 : 64) == 0),
+               "dt_conv3d: x3 outputs are fp32 pairs (TF32) / bf16 pairs (BF16) with Cout %% %d == 0 (Cout=%d)", out_f32 ? 32 : 64, d->Cout);
   p.a_lo_off = d->in_lo_off > 0 ? d->in_lo_off : in_ld / 2;
   p.b_lo_off = w_ld / 2;
   p.out_lo_off = d->out_lo_off > 0 ? d->out_lo_off : out_ld / 2;
@@ -843,9 +877,9 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts, d->out_time_major != 0)) return 1;
   if (res_tma && p.res_up) {
     const TileShape half = {ts.th / 2, ts.tw / 2, ts.tt, ts.tb};
-    if (encode_out_map(&tmR, const_cast<void*>(residual), 0, d->Cout, Wo / 2, Ho / 2, To, d->N, res_ld, half)) return 1;
+    if (encode_out_map(&tmR, const_cast<void*>(residual), 0, p.split_out ? res_ld : d->Cout, Wo / 2, Ho / 2, To, d->N, res_ld, half)) return 1;
   } else if (res_tma) {
-    if (encode_out_map(&tmR, const_cast<void*>(residual), 0, d->Cout, Wo, Ho, To, d->N, res_ld, ts)) return 1;
+    if (encode_out_map(&tmR, const_cast<void*>(residual), 0, p.split_out ? res_ld : d->Cout, Wo, Ho, To, d->N, res_ld, ts)) return 1;
   } else {
     tmR = tmC;
   }
@@ -871,7 +905,7 @@ template <int BN>
 static void plan_split(int kiters, bool res_tma, bool split_out, bool out_f32, dt_conv_plan_t* o) {
   using Cfg = ConvCfg<BN>;
   Cfg::split(kiters, res_tma, split_out, out_f32, &o->stages, &o->ks, &o->ncbuf, &o->nrbuf);
-  o->smem_bytes = Cfg::smem_bytes(kiters, o->stages, o->ks, o->ncbuf, o->nrbuf);
+  o->smem_bytes = Cfg::smem_bytes(kiters, o->stages, o->ks, o->ncbuf, o->nrbuf, split_out);
 }
 
 extern "C" int dt_conv_plan(const dt_conv_desc* d, int residual_aligned, dt_conv_plan_t* o) {
@@ -926,7 +960,7 @@ extern "C" int dt_conv_plan(const dt_conv_desc* d, int residual_aligned, dt_conv
 // of 4.7 %.  w [7][Cout][8*Cp] (kw-major, channel-minor).  y [F, Hp/2, Wp/2, out_ld].
 extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
                               const float* scale, const float* bias, int relu, int dtype, int out_f32,
-                              int out_round_tf32, void* y, int out_ld, void* stream_) {
+                              int out_round_tf32, int x3, void* y, int out_ld, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DT_CHECK_ARG(dtype == DT_DTYPE_BF16 || dtype == DT_DTYPE_TF32, "dt_conv1_7x7s2: bad dtype %d", dtype);
   const bool tf32 = dtype == DT_DTYPE_TF32;
@@ -935,9 +969,12 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   DT_CHECK_ARG(F >= 1 && Hp >= 2 && Wp >= 2 && Hp % 2 == 0 && Wp % 2 == 0 && Cout >= 1 && Cout <= 64,
                "dt_conv1_7x7s2: bad shape F=%d Hp=%d Wp=%d Cout=%d", F, Hp, Wp, Cout);
   DT_CHECK_ARG(x_padded && w && y, "dt_conv1_7x7s2: null pointer");
+  // x3 (bf16 only): the blob pixel is [hi(3) | lo(3) | 0 0] (dt_prep_clip out mode 3), w holds 14 blocks
+  // [2*kh]: [W_hi | W_hi] per pixel, [2*kh + 1]: [W_lo | 0], and y rows are [hi(Cout) | lo(Cout)] bf16 pairs
+  DT_CHECK_ARG(!x3 || (!tf32 && !out_f32 && Cout == 64), "dt_conv1_7x7s2: x3 needs DT_DTYPE_BF16, bf16 pair output and Cout == 64");
   const int oesz = out_f32 ? 4 : 2;
-  if (out_ld <= 0) out_ld = Cout;
-  DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && out_ld >= Cout, "dt_conv1_7x7s2: bad out_ld %d", out_ld);
+  if (out_ld <= 0) out_ld = x3 ? 2 * Cout : Cout;
+  DT_CHECK_ARG((out_ld * oesz) % 16 == 0 && out_ld >= (x3 ? 2 * Cout : Cout), "dt_conv1_7x7s2: bad out_ld %d", out_ld);
   const int Ho = Hp / 2, Wo = Wp / 2;
   const int BKe = 128 / esz;                       // elements per k-block
   const TileShape ts = pick_tile(Ho, Wo, 1, 1, 256, 128, false);      // spatial tiles only
@@ -948,6 +985,9 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   p.kT = 1; p.kH = 7; p.kW = 1; p.sT = 1; p.sH = 1; p.sW = 1; p.pT = 0; p.pH = 0; p.pW = 0;
   p.row_planes = 1;
   p.kchunks = 1;
+  p.nsub = x3 ? 2 : 1;
+  p.split_out = x3 ? 1 : 0;
+  p.out_lo_off = out_ld / 2;
   p.TH = TH; p.TW = TW; p.TT = 1; p.TB = 1; p.tiles_h = cdiv(Ho, TH); p.tiles_w = cdiv(Wo, TW); p.tiles_t = 1; p.tiles_b = F;
   p.tiles_n = 1;
   p.a_bytes = (uint32_t)TH * TW * 128u;
@@ -969,14 +1009,14 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
     if (encode_map(&tmA, tf32, 5, (const char*)x_padded + pix, dims, strides, box, estr)) return 1;
   }
   {
-    uint64_t wd[3] = {(uint64_t)BKe, (uint64_t)Cout, 7};
+    uint64_t wd[3] = {(uint64_t)BKe, (uint64_t)Cout, (uint64_t)(x3 ? 14 : 7)};
     uint64_t ws[2] = {128, (uint64_t)128 * Cout};
     uint32_t wb[3] = {(uint32_t)BKe, 64, 1};
     uint32_t we[3] = {1, 1, 1};
     if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC;
-  if (encode_out_map(&tmC, y, out_f32, Cout, Wo, Ho, 1, F, out_ld, ts)) return 1;
+  if (encode_out_map(&tmC, y, out_f32, x3 ? out_ld : Cout, Wo, Ho, 1, F, out_ld, ts)) return 1;
   int dev = 0, sms = 148;
   DT_CHECK_CUDA(cudaGetDevice(&dev));
   DT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

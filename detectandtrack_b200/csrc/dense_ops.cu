@@ -48,8 +48,12 @@ template <> struct Vec<__nv_bfloat16> {
   }
 };
 
-// 3xTF32 storage: a value is kept as hi + lo with hi = tf32(v), lo = tf32(v - hi), the two halves `lo_off`
-// elements apart in the channel row (fp32 tensors only; lo_off == 0 means plain storage).
+// Split ("x3") storage: a value is kept as hi + lo, the two halves `lo_off` elements apart in the channel row
+// (lo_off == 0 means plain storage).  fp32 tensors: hi = tf32(v), lo = tf32(v - hi) (3xTF32 mode);
+// bf16 tensors: hi = bf16(v), lo = bf16(v - hi) (bf16x3 mode, 16 mantissa bits).
+template <typename ET> __device__ __forceinline__ float split_hi(float v);
+template <> __device__ __forceinline__ float split_hi<float>(float v) { return round_to_tf32(v); }
+template <> __device__ __forceinline__ float split_hi<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 template <typename ET>
 __device__ __forceinline__ void load_vals(const ET* p, int lo_off, float* v) {
   Vec<ET>::load(p, v);
@@ -65,7 +69,7 @@ __device__ __forceinline__ void store_vals(ET* p, int lo_off, float* v) {
   if (lo_off) {
     float l[Vec<ET>::N];
 #pragma unroll
-    for (int e = 0; e < Vec<ET>::N; ++e) { const float h = round_to_tf32(v[e]); l[e] = round_to_tf32(v[e] - h); v[e] = h; }
+    for (int e = 0; e < Vec<ET>::N; ++e) { const float h = split_hi<ET>(v[e]); l[e] = split_hi<ET>(v[e] - h); v[e] = h; }
     Vec<ET>::store(p + lo_off, l);
   }
   Vec<ET>::store(p, v);
@@ -78,7 +82,7 @@ __device__ __forceinline__ void store_vals(ET* p, int lo_off, float* v) {
 template <typename OT>
 __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F, int H, int W, float m0, float m1,
                                  float m2, double inv_scale, int Hr, int Wr, int Hp, int Wp, int Cp,
-                                 int by, int bx, int round_out, int planes, OT* __restrict__ out) {
+                                 int by, int bx, int round_out, int planes, int split_px, OT* __restrict__ out) {
   // the output buffer is [F, Hp + 2*by, Wp + 2*bx, Cp]: `by` zero rows above/below, `bx` zero pixels left/right;
   // planes: the padded rows are de-interleaved, [F, 2 (row parity), Ht/2, Wt, Cp], so a stride-2 consumer
   // (conv1) reads contiguous rows of one parity plane per filter row
@@ -126,6 +130,12 @@ __global__ void prep_clip_kernel(const unsigned char* __restrict__ frames, int F
       float q[Vec<OT>::N];
 #pragma unroll
       for (int c = 0; c < Vec<OT>::N; ++c) q[c] = c < 3 ? v[c] : 0.f;
+      if constexpr (Vec<OT>::N >= 8) {
+        if (split_px) {                               // bf16x3 conv1 blob: [hi3 | lo3 | 0 0]
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { const float h = split_hi<OT>(v[c]); q[c] = h; q[3 + c] = v[c] - h; }
+        }
+      }
       Vec<OT>::store(o, q);
     } else {
       for (int c = 0; c < Cp; ++c) o[c] = to_act<OT>(c < 3 ? v[c] : 0.f);
@@ -574,9 +584,10 @@ __global__ void fold_tube_heads_kernel(const float* __restrict__ in, int ld, int
 // 7x7 stride 2 pad 3 conv + AffineChannel + ReLU in plain fp32 FMAs (lib/modeling/ResNet3D.py:258-263);
 // output stored as [hi | lo] tf32 pairs for the 3xTF32 consumers.  blob [F, Hp, Wp, Cp] raw fp32.
 // One CTA = 32 output pixels x 64 channels; thread = (pixel, 8 channels); weights [147][64] in smem.
+template <typename OT>
 __global__ void __launch_bounds__(256)
 conv1_f32_kernel(const float* __restrict__ blob, int F, int Hp, int Wp, int Cp, const float* __restrict__ w /*[7][7][3][64]*/,
-                 const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ y /*[F,Ho,Wo,128]*/) {
+                 const float* __restrict__ scale, const float* __restrict__ bias, OT* __restrict__ y /*[F,Ho,Wo,128]*/) {
   __shared__ float sw[147 * 64];
   for (int i = threadIdx.x; i < 147 * 64; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -605,13 +616,14 @@ conv1_f32_kernel(const float* __restrict__ blob, int F, int Hp, int Wp, int Cp, 
       }
     }
   }
-  float* o = y + (size_t)pix * 128 + cg;
+  OT* o = y + (size_t)pix * 128 + cg;
+  constexpr int V = Vec<OT>::N;
 #pragma unroll
-  for (int e = 0; e < 8; e += 4) {
-    float v[4];
+  for (int e = 0; e < 8; e += V) {
+    float v[V];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = fmaxf(fmaf(acc[e + q], scale[cg + e + q], bias[cg + e + q]), 0.f);
-    store_vals<float>(o + e, 64, v);
+    for (int q = 0; q < V; ++q) v[q] = fmaxf(fmaf(acc[e + q], scale[cg + e + q], bias[cg + e + q]), 0.f);
+    store_vals<OT>(o + e, 64, v);
   }
 }
 
@@ -635,12 +647,16 @@ extern "C" int dt_prep_clip(const unsigned char* frames, int F, int H, int W, co
   DT_CHECK_ARG(border_y >= 0 && border_x >= 0, "dt_prep_clip: negative border");
   DT_CHECK_ARG(!row_planes || (Hp + 2 * border_y) % 2 == 0, "dt_prep_clip: row planes need an even padded height");
   const long long total = (long long)F * (Hp + 2 * border_y) * (Wp + 2 * border_x);
-  if (out_f32)
+  DT_CHECK_ARG(out_f32 >= 0 && out_f32 <= 3 && (out_f32 != 3 || Cp == 8), "dt_prep_clip: bad output mode %d (mode 3 needs Cp == 8)", out_f32);
+  if (out_f32 == 3)
+    prep_clip_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, 0, row_planes, 1, (__nv_bfloat16*)out);
+  else if (out_f32)
     prep_clip_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, F, H, W, mean3[0], mean3[1], mean3[2],
-                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, out_f32 == 1, row_planes, (float*)out);
+                                                                                 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, out_f32 == 1, row_planes, 0, (float*)out);
   else
     prep_clip_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, 0, row_planes, (__nv_bfloat16*)out);
+        frames, F, H, W, mean3[0], mean3[1], mean3[2], 1.0 / im_scale, Hr, Wr, Hp, Wp, Cp, border_y, border_x, 0, row_planes, 0, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -650,7 +666,7 @@ extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, 
   const int V = f32 ? 4 : 8;
   DT_CHECK_ARG(N >= 0 && H >= 1 && W >= 1 && C >= 1 && k >= 1 && s >= 1 && p >= 0 && p < k, "dt_maxpool2d: bad shape");
   DT_CHECK_ARG(C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C, "dt_maxpool2d: C/ld must be multiples of %d", V);
-  DT_CHECK_ARG(!x3 || (f32 && ldx >= 2 * C && ldy >= 2 * C), "dt_maxpool2d: x3 storage needs fp32 rows of 2*C");
+  DT_CHECK_ARG(!x3 || (ldx >= 2 * C && ldy >= 2 * C), "dt_maxpool2d: x3 storage needs rows of 2*C");
   if (N == 0) return 0;
   DT_CHECK_ARG(x && y, "dt_maxpool2d: null pointer");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;      // Caffe2 legacy (floor) pooling
@@ -661,7 +677,7 @@ extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, 
                                                                                         x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
     else
       maxpool3x3s2_kernel<__nv_bfloat16><<<grid_for(tot, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, Ho, Wo,
-                                                                                                (__nv_bfloat16*)y, ldy, 0, 0);
+                                                                                                (__nv_bfloat16*)y, ldy, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
     DT_CHECK_LAUNCH();
     return 0;
   }
@@ -670,7 +686,8 @@ extern "C" int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, 
     maxpool_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (float*)y, ldy,
                                                                                    x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   else
-    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (__nv_bfloat16*)y, ldy, 0, 0);
+    maxpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, k, s, p, Ho, Wo, (__nv_bfloat16*)y, ldy,
+                                                                                           x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -689,21 +706,19 @@ extern "C" int dt_roi_align(const void* const* feats /*host array [nlevels] of d
   for (int l = 0; l < nlevels; ++l) { lv.feat[l] = feats[l]; lv.H[l] = Hs[l]; lv.W[l] = Ws[l]; lv.scale[l] = scales[l]; }
   dim3 grid(R * T, P);
   const int threads = 256;
+  // x3_mode 0: plain; 1: [hi | lo] per position (rows of 2C); 2: planar [R][hi block | lo block] (for the FC head)
+  DT_CHECK_ARG(x3_mode == 0 || ldf >= 2 * C, "dt_roi_align: x3 storage needs feature rows of 2*C");
+  const long long blk = (long long)T * P * P * C;
+  const int lo_in = x3_mode ? ldf / 2 : 0;
+  const long long o_row = x3_mode ? 2 * blk : blk;
+  const int o_pos = (x3_mode == 1) ? 2 * C : C;
+  const int o_lo = (x3_mode == 1) ? C : (x3_mode == 2 ? (int)blk : 0);
   if (f32)
-  {
-    // x3_mode 0: plain; 1: [hi | lo] per position (rows of 2C); 2: planar [R][hi block | lo block] (for the FC head)
-    DT_CHECK_ARG(x3_mode == 0 || (f32 && ldf >= 2 * C), "dt_roi_align: x3 storage needs fp32 feature rows of 2*C");
-    const long long blk = (long long)T * P * P * C;
-    const int lo_in = x3_mode ? ldf / 2 : 0;
-    const long long o_row = x3_mode ? 2 * blk : blk;
-    const int o_pos = (x3_mode == 1) ? 2 * C : C;
-    const int o_lo = (x3_mode == 1) ? C : (x3_mode == 2 ? (int)blk : 0);
     roi_align_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio,
                                                                         round_tf32, lo_in, o_row, o_pos, o_lo, (float*)out);
-  }
   else
     roi_align_kernel<__nv_bfloat16><<<grid, threads, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, ldf, P, sampling_ratio, 0,
-                                                                                0, (long long)T * P * P * C, C, 0, (__nv_bfloat16*)out);
+                                                                                lo_in, o_row, o_pos, o_lo, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -715,8 +730,8 @@ extern "C" int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, in
   if (D == 0) return 0;
   DT_CHECK_ARG(lowres && boxes && xy_preds, "dt_keypoint_decode: null pointer");
   const size_t smem = (size_t)(4 * S * S + 16 * S * S + 4 * S * KD_SW) * sizeof(float) + (size_t)(KD_SW + KD_RB) * 20;
-  static size_t attr = 0;
-  if (smem > attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(keypoint_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(keypoint_decode_kernel, (int)smem, &grant));
   dim3 grid(D, K, T);
   keypoint_decode_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(lowres, ldl, S, K, T, boxes, ldb, n_dev, D, min_size, heatmaps, xy_preds);
   DT_CHECK_LAUNCH();
@@ -734,7 +749,7 @@ extern "C" int dt_spatial_mean(const void* x, int N, int H, int W, int C, int ld
   if (f32)
     spatial_mean_kernel<float><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const float*)x, N, H, W, C, ldx, (float*)y, ldy, round_tf32, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   else
-    spatial_mean_kernel<__nv_bfloat16><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, (__nv_bfloat16*)y, ldy, 0, 0, 0);
+    spatial_mean_kernel<__nv_bfloat16><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, ldx, (__nv_bfloat16*)y, ldy, 0, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -744,14 +759,14 @@ extern "C" int dt_time_mean(const void* x, int B, int T, long long P, int C, int
   const int V = f32 ? 4 : 8;
   DT_CHECK_ARG(B >= 0 && T >= 1 && P >= 1 && C >= 1 && C % V == 0 && ldx % V == 0 && ldy % V == 0 && ldx >= C && ldy >= C,
                "dt_time_mean: bad shape (C/ld must be multiples of %d)", V);
-  DT_CHECK_ARG(!x3 || (f32 && ldx >= 2 * C && ldy >= 2 * C), "dt_time_mean: x3 storage needs fp32 rows of 2*C");
+  DT_CHECK_ARG(!x3 || (ldx >= 2 * C && ldy >= 2 * C), "dt_time_mean: x3 storage needs rows of 2*C");
   if (B == 0) return 0;
   DT_CHECK_ARG(x && y, "dt_time_mean: null pointer");
   const long long total = (long long)B * P * (C / V);
   if (f32)
     time_mean_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, B, T, P, C, ldx, (float*)y, ldy, round_tf32, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   else
-    time_mean_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, T, P, C, ldx, (__nv_bfloat16*)y, ldy, 0, 0, 0);
+    time_mean_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, B, T, P, C, ldx, (__nv_bfloat16*)y, ldy, 0, x3 ? ldx / 2 : 0, x3 ? ldy / 2 : 0);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -766,11 +781,14 @@ extern "C" int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, 
 }
 
 extern "C" int dt_conv1_7x7s2_f32(const float* blob, int F, int Hp, int Wp, int Cp, const float* w, const float* scale,
-                                  const float* bias, float* y, void* stream) {
+                                  const float* bias, int out_bf16, void* y, void* stream) {
   DT_CHECK_ARG(F >= 1 && Hp >= 2 && Wp >= 2 && Hp % 2 == 0 && Wp % 2 == 0 && Cp >= 3, "dt_conv1_7x7s2_f32: bad shape");
   DT_CHECK_ARG(blob && w && scale && bias && y, "dt_conv1_7x7s2_f32: null pointer");
   const long long total = (long long)F * (Hp / 2) * (Wp / 2);
-  conv1_f32_kernel<<<(unsigned)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(blob, F, Hp, Wp, Cp, w, scale, bias, y);
+  if (out_bf16)
+    conv1_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(blob, F, Hp, Wp, Cp, w, scale, bias, (__nv_bfloat16*)y);
+  else
+    conv1_f32_kernel<float><<<(unsigned)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(blob, F, Hp, Wp, Cp, w, scale, bias, (float*)y);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -329,11 +329,8 @@ static int lsa_launch(int mode, int algo, const float* src, int batch, int dmax,
                       int* matches, int* status, cudaStream_t stream) {
   const size_t smem = lsa_smem_bytes(dmax);
   DT_CHECK_ARG(smem <= 227 * 1024, "dt_lsa: dmax=%d needs %zu B of shared memory (> 227 KB)", dmax, smem);
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    DT_CHECK_CUDA(cudaFuncSetAttribute(lsa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(lsa_kernel, (int)smem, &grant));
   lsa_kernel<<<batch, 32, smem, stream>>>(mode, algo, src, dmax, ld, T, nrows, ncols, is_start, weight, matches, status);
   DT_CHECK_LAUNCH();
   return 0;

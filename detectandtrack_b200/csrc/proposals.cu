@@ -600,11 +600,8 @@ extern "C" int dt_rpn_proposals_multi(const dt_rpn_level* levels, int nlevels, i
   DT_CHECK_ARG(used <= workspace_bytes, "dt_rpn_proposals_multi: workspace %zu < %zu bytes", workspace_bytes, used);
   const int kcap = next_pow2i(kmax);
   DT_CHECK_ARG(kcap <= 16384, "dt_rpn_proposals_multi: pre-NMS top-N %d exceeds 16384", kmax);
-  static bool attr = false;
-  if (!attr) {
-    DT_CHECK_CUDA(cudaFuncSetAttribute(rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    attr = true;
-  }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(rpn_proposals_kernel, 16384 * 8, &grant));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(B * RPN_CS), (unsigned)nlevels, 1);
@@ -629,8 +626,8 @@ extern "C" int dt_collect_rpn(const float* props, const int* keep, const int* nk
   DT_CHECK_ARG(props && keep && nkeep && rois && roi_scores && roi_counts, "dt_collect_rpn: null pointer");
   const int cap = next_pow2i(L * K);
   DT_CHECK_ARG(cap <= 16384, "dt_collect_rpn: L*K=%d exceeds 16384", L * K);
-  static bool attr = false;
-  if (!attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8)); attr = true; }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(collect_kernel, 16384 * 8, &grant));
   collect_kernel<<<B, 1024, (size_t)cap * 8, (cudaStream_t)stream>>>(props, keep, nkeep, L, K, T, post_nms_topn, rois,
                                                                      roi_scores, roi_counts, R, cap);
   DT_CHECK_LAUNCH();
@@ -674,10 +671,35 @@ extern "C" int dt_limit_detections(const float* dets, const int* keep, const int
   DT_CHECK_ARG(dets && keep && nkeep && out && out_counts, "dt_limit_detections: null pointer");
   const int sortcap = next_pow2i((num_classes - 1) * R);
   DT_CHECK_ARG(sortcap <= 16384, "dt_limit_detections: (C-1)*R=%d exceeds 16384", (num_classes - 1) * R);
-  static bool attr = false;
-  if (!attr) { DT_CHECK_CUDA(cudaFuncSetAttribute(limit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8)); attr = true; }
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(limit_kernel, 16384 * 8, &grant));
   limit_kernel<<<B, 1024, (size_t)sortcap * 8, (cudaStream_t)stream>>>(dets, keep, nkeep, num_classes - 1, R, T, max_per_im,
                                                                        out, out_counts, cap, sortcap);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+
+// lib/core/test.py:76-113 _get_rois_blob / _project_im_rois for the keypoint head: rois[i] = (image index,
+// boxes[i] * im_scale), the product taken in fp64 and stored as fp32 exactly as numpy does.  boxes [n, ldb] (first ncols
+// columns), image index = bidx[i] if given, else i / per_image.
+namespace dt {
+__global__ void scale_rois_kernel(const float* __restrict__ boxes, int ldb, int n, int ncols, const float* __restrict__ bidx,
+                                  int per_image, double im_scale, float* __restrict__ rois) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (ncols + 1)) return;
+  const int r = i / (ncols + 1), c = i - r * (ncols + 1);
+  rois[i] = c == 0 ? (bidx ? bidx[r] : (float)(r / per_image)) : (float)((double)boxes[(size_t)r * ldb + c - 1] * im_scale);
+}
+}  // namespace dt
+
+extern "C" int dt_scale_rois(const float* boxes, int ldb, int n, int ncols, const float* bidx, int per_image, double im_scale,
+                             float* rois, void* stream) {
+  DT_CHECK_ARG(n >= 0 && ncols >= 1 && ldb >= ncols && (bidx || per_image >= 1), "dt_scale_rois: bad shape n=%d ncols=%d ldb=%d", n, ncols, ldb);
+  if (n == 0) return 0;
+  DT_CHECK_ARG(boxes && rois, "dt_scale_rois: null pointer");
+  const int total = n * (ncols + 1);
+  dt::scale_rois_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boxes, ldb, n, ncols, bidx, per_image, im_scale, rois);
   DT_CHECK_LAUNCH();
   return 0;
 }

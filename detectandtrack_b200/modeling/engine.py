@@ -66,12 +66,15 @@ class DetectionEngine(object):
             raise NotImplementedError('engine: single-level bodies are wired for 3-D heads (BODY_HEAD_LINK \'\') only')
         if s.link not in ('slice-center', 'avg', 'none2d', ''):
             raise NotImplementedError('engine: BODY_HEAD_LINK %r' % s.link)
-        # 'bf16': fast path; 'tf32': fp32 storage, tf32 MMAs (1e-3 per layer); 'tf32x3': fp32-accurate
-        # parity mode (activations / weights as [hi | lo] tf32 pairs, 3 MMAs per k-block)
-        self.dtype = {'bf16': cv.BF16, 'tf32': cv.TF32, 'tf32x3': cv.TF32X3}[dtype]
-        self.x3 = self.dtype == cv.TF32X3
-        self.act_dtype = torch.bfloat16 if dtype == 'bf16' else torch.float32
-        self.cin_pad = 8 if dtype == 'bf16' else 4
+        # 'bf16x3': the parity mode (default of the drop-in surface): activations / weights as [hi | lo] bf16 pairs,
+        # 3 bf16 MMAs per k-block -> 16 mantissa bits, <= 1e-3 end to end (tests) at the full kind::f16 MMA rate;
+        # 'tf32x3': the same scheme on tf32 pairs (fp32 storage, ~21 bits, half MMA rate, twice the bytes);
+        # 'tf32': fp32 storage, one tf32 MMA (1e-3 per layer, ~1.5e-3 end to end); 'bf16': fast, ~1e-2 end to end
+        self.dtype_name = dtype
+        self.dtype = cv.MODE_NAMES[dtype]
+        self.x3 = self.dtype in cv.SPLIT_MODES
+        self.act_dtype = torch.bfloat16 if dtype in ('bf16', 'bf16x3') else torch.float32
+        self.cin_pad = 8 if dtype in ('bf16', 'bf16x3') else 4
         self.skip_dead_frames = False       # compute only the consumed (centre) frame of the post-hoc FPN convs
         self._geom = {}
         self._build(blobs)
@@ -108,7 +111,9 @@ class DetectionEngine(object):
         s, cfg, torch = self.spec, self.cfg, self.torch
         # conv1: 7x7/2 on the 3-channel blob with the filter row packed into K (dt_conv1_7x7s2)
         w1 = torch.from_numpy(np.ascontiguousarray(blobs['conv1_w']))
-        self.conv1_w = cv.pack_conv1_weight_f32(w1) if self.x3 else cv.pack_conv1_weight(w1, self.dtype)
+        # conv1: tf32x3 runs it as exact fp32 FMAs; bf16x3 on the tensor cores over a split-pixel blob
+        self.conv1_exact = self.dtype == cv.TF32X3
+        self.conv1_w = cv.pack_conv1_weight_f32(w1) if self.conv1_exact else cv.pack_conv1_weight(w1, self.dtype)
         self.conv1_s = torch.from_numpy(np.ascontiguousarray(blobs['res_conv1_bn_s'], dtype=np.float32)).cuda()
         self.conv1_b = torch.from_numpy(np.ascontiguousarray(blobs['res_conv1_bn_b'], dtype=np.float32)).cuda()
         self.stages = []
@@ -219,7 +224,7 @@ class DetectionEngine(object):
         """x [B,T,2,(Hp+6)/2,Wp+8,cin_pad] (zero-bordered blob, rows split by parity) -> stage outputs (finest first)."""
         torch = self.torch
         B, T = x.shape[:2]
-        if self.x3:      # exact fp32 conv1 on the raw (un-bordered) blob
+        if self.conv1_exact:      # exact fp32 conv1 on the raw (un-bordered) blob
             y = cv.conv1_7x7s2_f32(x.view((B * T,) + tuple(x.shape[2:])), self.conv1_w, self.conv1_s, self.conv1_b)
         else:
             hp, wp = 2 * x.shape[3] - 6, x.shape[4] - 8
@@ -289,8 +294,8 @@ class DetectionEngine(object):
         Lv = len(feats2d)
         K = cfg.TEST.RPN_PRE_NMS_TOP_N
         A = s.num_anchors
-        props = torch.zeros((B, Lv, K, 5), dtype=torch.float32, device='cuda')
-        counts = torch.zeros((B, Lv), dtype=torch.int32, device='cuda')
+        props = L.zeros((B, Lv, K, 5), torch.float32)
+        counts = L.zeros((B, Lv), torch.int32)
         levels = []
         for l, f in enumerate(feats2d):
             h = self.rpn_conv(f)
@@ -333,14 +338,15 @@ class DetectionEngine(object):
                                           box_ops.ORDER_INDEX)
         return rpn_ops.limit_detections(dets, keep, nkeep, cfg.TEST.DETECTIONS_PER_IM, cap=min(R, self.det_cap))
 
-    def keypoint_head(self, feats, boxes, batch_idx, im_scale, want_heatmaps=False):
-        """boxes [D, 4*Th] image space (fp32 cuda), batch_idx [D] -> xy_preds [D, 4, Th*K].
+    def keypoint_head(self, feats, boxes, batch_idx, im_scale, want_heatmaps=False, per_image=1):
+        """boxes [D, >= 4*Th] image space (fp32 cuda, any row stride), batch_idx [D] fp32 (or None: image index =
+        row // per_image) -> xy_preds [D, 4, Th*K].
         2-D heads: feats = per-level centre-frame maps; tube heads: feats = [conv feature 5-D]."""
         torch, cfg, s = self.torch, self.cfg, self.spec
         D = boxes.shape[0]
         Th = s.T_head
         # _get_rois_blob (test.py:76-113): float64 product, stored fp32, image index in col 0
-        rois = torch.cat([batch_idx.double()[:, None], boxes.double() * float(im_scale)], 1).float().contiguous()
+        rois = dense_ops.scale_rois(boxes, 4 * Th, im_scale, batch_idx, per_image)
         res, samp = cfg.KRCNN.ROI_XFORM_RESOLUTION, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO
         if s.head3d:
             x = self._roi_feats_tube(feats[0], rois, res, samp)               # [D, Th, S, S, C]
@@ -375,8 +381,8 @@ class DetectionEngine(object):
         self.rpn_out(h, out_f32=True, out=o)
         n = H * W * A
         Kc = n if (K <= 0 or K > n) else K
-        props = torch.zeros((B, 1, Kc, 4 * T + 1), dtype=torch.float32, device='cuda')
-        counts = torch.zeros((B, 1), dtype=torch.int32, device='cuda')
+        props = L.zeros((B, 1, Kc, 4 * T + 1), torch.float32)
+        counts = L.zeros((B, 1), torch.int32)
         rpn_ops.rpn_proposals(o[..., :A], o[..., A:5 * A], self.anchors[0], self.feat_stride, im_info, K,
                               float(cfg.TEST.RPN_MIN_SIZE), T, out=props[:, 0], counts=counts[:, 0], time_major=True)
         keep, nkeep = box_ops.nms_batched(props.view(B, Kc, 4 * T + 1), counts.view(-1), cfg.TEST.RPN_NMS_THRESH,
@@ -424,18 +430,19 @@ class DetectionEngine(object):
 
     def plain(self, t):
         """Activation tensor as plain values (joins the [hi | lo] pairs of the 3xTF32 mode)."""
-        return cv.join_tf32(t) if self.x3 else t
+        return cv.join_split(t) if self.x3 else t
 
     def _blob(self, frames_u8, scale, hr, wr, hp, wp):
         """uint8 frames -> network input: zero-bordered bf16 / tf32 blob for the packed-row conv1, or the raw
         fp32 blob for the exact conv1 of the 3xTF32 mode."""
         B, T, H, W, _ = frames_u8.shape
-        if self.x3:
+        if self.conv1_exact:
             x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
                                     cpad=4, out_f32=2)
             return x.view(B, T, hp, wp, 4)
+        mode = 3 if self.dtype == cv.BF16X3 else int(self.dtype == cv.TF32)
         x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
-                                cpad=self.cin_pad, out_f32=(self.dtype == cv.TF32), border=(3, 4), row_planes=True)
+                                cpad=self.cin_pad, out_f32=mode, border=(3, 4), row_planes=True)
         return x.view(B, T, 2, (hp + 6) // 2, wp + 8, self.cin_pad)
 
     def forward_features(self, frames_u8):
@@ -455,11 +462,9 @@ class DetectionEngine(object):
         if g is None:
             torch = self.torch
             scale, (hr, wr), (hp, wp) = self.blob_geometry(H, W)
-            cap = self.det_cap
             g = dict(scale=scale, hr=hr, wr=wr, hp=hp, wp=wp,
                      im_info=torch.tensor([[hp, wp, scale]] * B, dtype=torch.float32, device='cuda'),
-                     im_hw=torch.tensor([[H, W]] * B, dtype=torch.float32, device='cuda'),
-                     bidx=torch.arange(B, dtype=torch.float32, device='cuda').repeat_interleave(cap))
+                     im_hw=torch.tensor([[H, W]] * B, dtype=torch.float32, device='cuda'))
             self._geom[key] = g
         return g
 
@@ -488,8 +493,11 @@ class DetectionEngine(object):
         out = dict(dets=dets, det_counts=det_counts, xy=None, heat=None)
         if self.kps_convs:
             cap = dets.shape[2]
-            boxes = dets[:, 0, :, :4 * s.T_head].reshape(B * cap, 4 * s.T_head)
-            out['xy'], out['heat'] = self.keypoint_head(feats, boxes, g['bidx'], g['scale'], want_heatmaps)
+            if dets.shape[1] == 1:          # one foreground class: the detections ARE the keypoint boxes (a view)
+                boxes = dets.view(B * cap, dets.shape[3])
+            else:
+                boxes = dets[:, 0].reshape(B * cap, dets.shape[3])
+            out['xy'], out['heat'] = self.keypoint_head(feats, boxes, None, g['scale'], want_heatmaps, per_image=cap)
         return out
 
     def gather(self, out):

@@ -52,7 +52,7 @@ def nms_batched(dets, counts=None, thresh=0.5, cmp_mode=None, out_order=None, ma
     if out_order is None:
         out_order = ORDER_INDEX if cmp_mode == NMS_2D_GE else ORDER_SCORE
     keep = torch.empty((B, max(nmax, 1)), dtype=torch.int32, device='cuda')
-    num = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    num = L.zeros((B,), torch.int32)
     if counts is not None:
         counts = counts.to(device='cuda', dtype=torch.int32).contiguous()
     need = C.c_size_t(0)

@@ -7,10 +7,19 @@ from .. import _lib as L
 
 BF16, TF32 = 0, 1
 TF32X3 = 2      # host-level mode: DT_DTYPE_TF32 kernels on [hi | lo] tf32 pairs (3 MMAs per k-block, ~fp32 accuracy)
+BF16X3 = 3      # host-level mode: DT_DTYPE_BF16 kernels on [hi | lo] bf16 pairs (3 MMAs per k-block at the full
+                # kind::f16 rate, 16 mantissa bits: the headline parity mode)
+SPLIT_MODES = (TF32X3, BF16X3)
+MODE_NAMES = {'bf16': BF16, 'tf32': TF32, 'tf32x3': TF32X3, 'bf16x3': BF16X3}
 
 
 def _dt(dtype, torch):
-    return torch.bfloat16 if dtype == BF16 else torch.float32
+    return torch.bfloat16 if dtype in (BF16, BF16X3) else torch.float32
+
+
+def kernel_dtype(dtype):
+    """Host-level mode -> DT_DTYPE_* of the kernels."""
+    return BF16 if dtype in (BF16, BF16X3) else TF32
 
 
 def pack_weight(w, dtype=BF16):
@@ -23,15 +32,36 @@ def pack_weight(w, dtype=BF16):
     elif w.dim() == 4:
         w = w[:, :, None, :, :]
     Cout, Cin, kT, kH, kW = w.shape
-    mult = 8 if dtype == BF16 else 4
+    mult = 8 if dtype in (BF16, BF16X3) else 4
     Cp = (Cin + mult - 1) // mult * mult
-    out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=_dt(dtype, torch), device='cuda')
+    out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=torch.bfloat16 if dtype == BF16 else torch.float32, device='cuda')
     out[:, :, :Cin] = w.to('cuda').permute(2, 3, 4, 0, 1).reshape(kT * kH * kW, Cout, Cin).to(out.dtype)
     if dtype == TF32:
         out = round_tf32(out)
     elif dtype == TF32X3:
         out = split_tf32(out)                         # [taps, Cout, 2*Cp] = [hi | lo]
+    elif dtype == BF16X3:
+        out = split_bf16(out)                         # [taps, Cout, 2*Cp] bf16 = [hi | lo]
     return out
+
+
+def split_bf16(t):
+    """fp32 [..., C] -> bf16 [..., 2C] = [hi | lo], hi = bf16(t), lo = bf16(t - hi) (bf16x3 storage)."""
+    torch = L.require_cuda()
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def split_for(dtype, t):
+    """fp32 tensor -> the split storage of `dtype` (TF32X3: fp32 tf32 pairs, BF16X3: bf16 pairs)."""
+    return split_bf16(t.float()) if dtype == BF16X3 else split_tf32(t.float())
+
+
+def join_split(t):
+    """[..., 2C] split rows (either storage type) -> fp32 values hi + lo."""
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
 
 
 def split_tf32(t):
@@ -72,14 +102,14 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     taps, Cout, w_ld = w_packed.shape
     kT, kH, kW = ksize
     assert taps == kT * kH * kW
-    x3 = dtype == TF32X3
+    x3 = dtype in SPLIT_MODES
     if x3:
         cin = cin if cin is not None else min(Cx // 2, w_ld // 2)
         if split_out is None:
             split_out = out is None                  # intermediate activations stay split; given buffers are final
         if out_f32 is None:
-            out_f32 = True
-        assert out_f32, '3xTF32 outputs are fp32'
+            out_f32 = (dtype == TF32X3) or not split_out
+        assert out_f32 == (dtype == TF32X3) or not split_out, 'split outputs are fp32 pairs (tf32x3) / bf16 pairs (bf16x3)'
     else:
         split_out = False
     cin = cin if cin is not None else min(Cx, w_ld)
@@ -107,7 +137,7 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
     assert out.dtype == odt and out.is_contiguous()
     d = L.ConvDesc(N=N, Ti=Ti, Hi=Hi, Wi=Wi, Cin=cin, Cout=Cout, kT=kT, kH=kH, kW=kW, sT=sT, sH=sH, sW=sW,
                    pT=pT, pH=pH, pW=pW, in_ld=Cx, w_ld=w_ld, out_ld=out.shape[-1],
-                   res_ld=(residual.shape[-1] if residual is not None else 0), dtype=(TF32 if x3 else dtype),
+                   res_ld=(residual.shape[-1] if residual is not None else 0), dtype=kernel_dtype(dtype),
                    out_f32=int(out_f32), relu=int(relu), res_mode=int(res_mode),
                    x3=(1 if x3 else 0) | (2 if split_out else 0), in_lo_off=0, out_lo_off=0, res_lo_off=0,
                    out_round_tf32=int(bool(round_tf32)), out_time_major=int(bool(time_major)), out_t_first=t_first,
@@ -132,8 +162,20 @@ def pack_conv1_weight(w, dtype=BF16):
     Cout, Cin, kh, kw = w.shape
     assert (kh, kw) == (7, 7) and Cin <= 3 + 1
     Cp = 4 if dtype == TF32 else 8
+    wk = w.to('cuda').float().permute(2, 0, 3, 1)                                  # (kh, Cout, kw, c)
+    if dtype == BF16X3:
+        # split-pixel blob [hi3 | lo3 | 0 0]: block 2*kh = [W_hi | W_hi] (x_hi*W_hi + x_lo*W_hi in one MMA),
+        # block 2*kh + 1 = [W_lo | 0] (x_hi*W_lo)
+        assert Cin == 3
+        hi = wk.to(torch.bfloat16)
+        lo = (wk - hi.float()).to(torch.bfloat16)
+        out = torch.zeros((7, 2, Cout, 8, 8), dtype=torch.bfloat16, device='cuda')
+        out[:, 0, :, :7, 0:3] = hi
+        out[:, 0, :, :7, 3:6] = hi
+        out[:, 1, :, :7, 0:3] = lo
+        return out.reshape(14, Cout, 64)
     out = torch.zeros((7, Cout, 8, Cp), dtype=_dt(dtype, torch), device='cuda')
-    out[:, :, :7, :Cin] = w.to('cuda').permute(2, 0, 3, 1).to(out.dtype)          # (kh, Cout, kw, c)
+    out[:, :, :7, :Cin] = wk.to(out.dtype)
     out = out.reshape(7, Cout, 8 * Cp)
     return round_tf32(out) if dtype == TF32 else out
 
@@ -145,21 +187,25 @@ def conv1_7x7s2(x_padded, w_packed, hw, scale=None, bias=None, relu=True, dtype=
     Hp, Wp = hw
     assert two == 2 and 2 * Hh == Hp + 6 and Wt == Wp + 8 and x_padded.is_contiguous()
     Cout = w_packed.shape[1]
+    x3 = dtype == BF16X3                       # split-pixel blob, 14 weight blocks, [hi | lo] bf16 pair output
     if out_f32 is None:
         out_f32 = dtype == TF32
-    y = torch.empty((F, Hp // 2, Wp // 2, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
+    assert not (x3 and out_f32)
+    ld = 2 * Cout if x3 else Cout
+    y = torch.empty((F, Hp // 2, Wp // 2, ld), dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
     L.call('dt_conv1_7x7s2', L.ptr(x_padded), F, Hp, Wp, Cp, L.ptr(w_packed), Cout, L.ptr(scale), L.ptr(bias), int(relu),
-           dtype, int(out_f32), int(bool(out_f32) and dtype == TF32), L.ptr(y), Cout, L.stream_ptr())
+           kernel_dtype(dtype), int(out_f32), int(bool(out_f32) and dtype == TF32), int(x3), L.ptr(y), ld, L.stream_ptr())
     return y
 
 
-def conv1_7x7s2_f32(blob, w, scale, bias):
-    """3xTF32 mode conv1: exact fp32 (dt_conv1_7x7s2_f32).  blob [F, Hp, Wp, Cp] raw fp32;
-    w (64, 3, [1,] 7, 7) -> [F, Hp/2, Wp/2, 128] as [hi | lo]."""
+def conv1_7x7s2_f32(blob, w, scale, bias, out_bf16=False):
+    """Split-storage modes' conv1: exact fp32 (dt_conv1_7x7s2_f32).  blob [F, Hp, Wp, Cp] raw fp32;
+    w (64, 3, [1,] 7, 7) -> [F, Hp/2, Wp/2, 128] as [hi | lo] (tf32 pairs in fp32, or bf16 pairs)."""
     torch = L.require_cuda()
     F, Hp, Wp, Cp = blob.shape
-    y = torch.empty((F, Hp // 2, Wp // 2, 128), dtype=torch.float32, device='cuda')
-    L.call('dt_conv1_7x7s2_f32', L.ptr(blob), F, Hp, Wp, Cp, L.ptr(w), L.ptr(scale), L.ptr(bias), L.ptr(y), L.stream_ptr())
+    y = torch.empty((F, Hp // 2, Wp // 2, 128), dtype=torch.bfloat16 if out_bf16 else torch.float32, device='cuda')
+    L.call('dt_conv1_7x7s2_f32', L.ptr(blob), F, Hp, Wp, Cp, L.ptr(w), L.ptr(scale), L.ptr(bias), int(bool(out_bf16)),
+           L.ptr(y), L.stream_ptr())
     return y
 
 

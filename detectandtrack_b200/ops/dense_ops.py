@@ -14,9 +14,9 @@ def prep_clip(frames_u8, pixel_means, im_scale, out_hw, pad_hw, cpad=8, out_f32=
     Hp, Wp = pad_hw
     by, bx = border
     Ht, Wt = Hp + 2 * by, Wp + 2 * bx
-    # out_f32: False/0 bf16, True/1 fp32 rounded to tf32, 2 raw fp32
+    # out_f32: False/0 bf16, True/1 fp32 rounded to tf32, 2 raw fp32, 3 bf16 split pixel [hi3 | lo3 | 0 0] (cpad 8)
     shape = (F, 2, Ht // 2, Wt, cpad) if row_planes else (F, Ht, Wt, cpad)
-    out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device='cuda')
+    out = torch.empty(shape, dtype=torch.float32 if out_f32 in (True, 1, 2) else torch.bfloat16, device='cuda')
     m = (C.c_float * 3)(*[float(v) for v in pixel_means])
     L.call('dt_prep_clip', L.ptr(frames_u8.contiguous()), F, H, W, m, float(im_scale), Hr, Wr, Hp, Wp, cpad, by, bx,
            int(bool(row_planes)), int(out_f32), L.ptr(out), L.stream_ptr())
@@ -66,13 +66,25 @@ def keypoint_decode(lowres, boxes, K=17, T=1, n_dev=None, min_size=0, want_heatm
     torch = L.require_cuda()
     DT_, S, _, ldl = lowres.shape
     D = DT_ // T
-    xy = torch.zeros((D, 4, T * K), dtype=torch.float32, device='cuda')
-    heat = torch.zeros((D, T * K, 4 * S, 4 * S), dtype=torch.float32, device='cuda') if want_heatmaps else None
-    boxes = boxes.contiguous()
+    xy = L.zeros((D, 4, T * K), torch.float32)
+    heat = L.zeros((D, T * K, 4 * S, 4 * S), torch.float32) if want_heatmaps else None
+    assert boxes.stride(1) == 1 and boxes.dtype == torch.float32
     assert lowres.dtype == torch.float32 and lowres.is_contiguous()
-    L.call('dt_keypoint_decode', L.ptr(lowres), ldl, S, K, T, L.ptr(boxes), boxes.shape[1], L.ptr(n_dev), D, int(min_size),
+    L.call('dt_keypoint_decode', L.ptr(lowres), ldl, S, K, T, C.c_void_p(boxes.data_ptr()), boxes.stride(0), L.ptr(n_dev), D, int(min_size),
            L.ptr(heat), L.ptr(xy), L.stream_ptr())
     return xy, heat
+
+
+def scale_rois(boxes, ncols, im_scale, batch_idx=None, per_image=1):
+    """boxes [n, >=ncols] fp32 (row stride free) -> rois [n, ncols+1] = (image index, boxes * im_scale in fp64 -> fp32)
+    (lib/core/test.py:76-113); image index = batch_idx[i] or i // per_image."""
+    torch = L.require_cuda()
+    n = boxes.shape[0]
+    assert boxes.dtype == torch.float32 and boxes.stride(1) == 1 and boxes.shape[1] >= ncols
+    rois = torch.empty((n, ncols + 1), dtype=torch.float32, device='cuda')
+    L.call('dt_scale_rois', C.c_void_p(boxes.data_ptr()), boxes.stride(0), n, ncols, L.ptr(batch_idx), int(per_image),
+           float(im_scale), L.ptr(rois), L.stream_ptr())
+    return rois
 
 
 def spatial_mean(x, round_tf32=False, x3=False):

@@ -69,9 +69,9 @@ def rpn_proposals(logits, deltas, anchors, feat_stride, im_info, pre_nms_topn, m
     n = H * W * A
     K = n if (pre_nms_topn <= 0 or pre_nms_topn > n) else pre_nms_topn
     if out is None:
-        out = torch.zeros((B, K, 4 * T + 1), dtype=torch.float32, device='cuda')
+        out = L.zeros((B, K, 4 * T + 1), torch.float32)
     if counts is None:
-        counts = torch.zeros((B,), dtype=torch.int32, device='cuda')
+        counts = L.zeros((B,), torch.int32)
     assert out.shape[-2] >= K
     rpn_proposals_levels([dict(logits=logits, deltas=deltas, anchors=anchors, feat_stride=feat_stride, out=out, counts=counts)],
                          im_info, pre_nms_topn, A, min_size, T, clip, time_major)
@@ -84,9 +84,9 @@ def collect(props, keep, nkeep, post_nms_topn, R=None):
     B, Lv, K, ld = props.shape
     T = (ld - 1) // 4
     R = R or (post_nms_topn if post_nms_topn > 0 else Lv * K)
-    rois = torch.zeros((B, R, ld), dtype=torch.float32, device='cuda')
-    scores = torch.zeros((B, R), dtype=torch.float32, device='cuda')
-    counts = torch.zeros((B,), dtype=torch.int32, device='cuda')
+    rois = L.zeros((B, R, ld), torch.float32)
+    scores = L.zeros((B, R), torch.float32)
+    counts = L.zeros((B,), torch.int32)
     L.call('dt_collect_rpn', L.ptr(props.contiguous()), L.ptr(keep.contiguous()), L.ptr(nkeep.contiguous()), B, Lv, K, T,
            int(post_nms_topn), L.ptr(rois), L.ptr(scores), L.ptr(counts), R, L.stream_ptr())
     return rois, scores, counts
@@ -97,9 +97,9 @@ def distribute(rois, n_dev=None, col0=1, T=1, k_min=2, k_max=5, s0=224.0, lvl0=4
     torch = L.require_cuda()
     rois = rois.contiguous()
     n, ld = rois.shape
-    levels = torch.zeros((max(n, 1),), dtype=torch.int32, device='cuda')
-    restore = torch.zeros((max(n, 1),), dtype=torch.int32, device='cuda') if want_restore else None
-    lc = torch.zeros((k_max - k_min + 1,), dtype=torch.int32, device='cuda')
+    levels = L.zeros((max(n, 1),), torch.int32)
+    restore = L.zeros((max(n, 1),), torch.int32) if want_restore else None
+    lc = L.zeros((k_max - k_min + 1,), torch.int32)
     L.call('dt_distribute_fpn', L.ptr(rois), n, L.ptr(n_dev), ld, col0, T, k_min, k_max, float(s0), float(lvl0),
            L.ptr(levels), L.ptr(restore), L.ptr(lc), L.stream_ptr())
     return levels[:n], (restore[:n] if want_restore else None), lc
@@ -111,8 +111,8 @@ def box_decode(rois, roi_counts, cls_logits, bbox_deltas, num_classes, im_info, 
     Returns dets [B, C-1, R, 4T+1], det_counts [B*(C-1)]."""
     torch = L.require_cuda()
     B, R, _ = rois.shape
-    dets = torch.zeros((B, num_classes - 1, R, 4 * T + 1), dtype=torch.float32, device='cuda')
-    cnt = torch.zeros((B * (num_classes - 1),), dtype=torch.int32, device='cuda')
+    dets = L.zeros((B, num_classes - 1, R, 4 * T + 1), torch.float32)
+    cnt = L.zeros((B * (num_classes - 1),), torch.int32)
     w4 = (C.c_float * 4)(*[float(w) for w in weights])
     assert cls_logits.dtype == torch.float32 and bbox_deltas.dtype == torch.float32
     assert cls_logits.stride(1) == 1 and bbox_deltas.stride(1) == 1
@@ -128,8 +128,8 @@ def limit_detections(dets, keep, nkeep, max_per_im, cap=None):
     B, C1, R, ld = dets.shape
     T = (ld - 1) // 4
     cap = cap or R
-    out = torch.zeros((B, C1, cap, ld), dtype=torch.float32, device='cuda')
-    cnt = torch.zeros((B * C1,), dtype=torch.int32, device='cuda')
+    out = L.zeros((B, C1, cap, ld), torch.float32)
+    cnt = L.zeros((B * C1,), torch.int32)
     L.call('dt_limit_detections', L.ptr(dets), L.ptr(keep.contiguous()), L.ptr(nkeep), B, C1 + 1, R, T, int(max_per_im),
            L.ptr(out), L.ptr(cnt), cap, L.stream_ptr())
     return out, cnt

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DT_B200_ABI_VERSION 2
+#define DT_B200_ABI_VERSION 3
 #define DT_MAX_T 8              /* frames per tube supported by the box kernels */
 #define DT_NMS_MAX_BOXES 8192   /* per problem */
 #define DT_LSA_MAX_DIM 224      /* max(prev, cur) detections per frame pair */
@@ -48,6 +48,10 @@ extern "C" {
 
 const char* dt_last_error(void);
 int dt_abi_version(void);
+
+/* cudaMemsetAsync on the caller's stream (a memset node under CUDA-graph capture): how the hot path zeroes its
+ * fixed-capacity count / output buffers without library kernels. */
+int dt_memset(void* ptr, int value, size_t bytes, void* stream);
 
 /* ---- boxes.cu ----------------------------------------------------------- */
 
@@ -134,9 +138,13 @@ typedef struct dt_conv_desc {
   int out_f32;    /* 1: y/residual fp32, 0: bf16 */
   int relu;
   int res_mode;
-  int x3;             /* 3xTF32 mode (DT_DTYPE_TF32 only), bit 0: x and w rows are [hi | lo] tf32 pairs
-                         (lo half at in_lo_off / w_ld/2) and D = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo;
-                         bit 1: y (and the residual) rows are written / read as [hi | lo] pairs */
+  int x3;             /* split ("x3") storage, the fp32-accurate modes.  bit 0: x and w rows are [hi | lo] pairs
+                         (lo half at in_lo_off / w_ld/2) and D = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (three MMAs per
+                         k-block); bit 1: y (and the residual) rows are written / read as [hi | lo] pairs.
+                         DT_DTYPE_TF32 ("tf32x3"): fp32 storage, hi = tf32(v), lo = tf32(v - hi), y fp32.
+                         DT_DTYPE_BF16 ("bf16x3"): bf16 storage, hi = bf16(v), lo = bf16(v - hi) — 16 mantissa
+                         bits at the full kind::f16 MMA rate and half the bytes of tf32x3; y pairs are bf16
+                         (out_f32 = 0), plain fp32 outputs (out_f32 = 1, bit 1 clear) are allowed */
   int in_lo_off, out_lo_off, res_lo_off;  /* element offsets of the lo halves (0 => ld / 2) */
   int out_round_tf32; /* fp32 output rounded (nearest-even) to tf32: set when the consumer is another
                          DT_DTYPE_TF32 conv, because kind::tf32 truncates its operands (a one-sided
@@ -167,10 +175,13 @@ int dt_conv_plan(const dt_conv_desc* desc /*host*/, int residual_aligned, dt_con
 /* conv1 of the ResNet bodies (lib/modeling/ResNet3D.py:258-261): 7x7 stride 2 pad 3 on the 3-channel
  * image + AffineChannel + ReLU, with the 7 taps of a filter row packed into one 128-byte k-block.
  * x_padded [F, 2, (Hp+6)/2, Wp+8, Cp] from dt_prep_clip(border 3, 4, row_planes 1), Cp*elemsize == 16;
- * w [7 (kh)][Cout <= 64][8*Cp] with w[kh][o][kw*Cp + c]; y [F, Hp/2, Wp/2, out_ld]. */
+ * w [7 (kh)][Cout <= 64][8*Cp] with w[kh][o][kw*Cp + c]; y [F, Hp/2, Wp/2, out_ld].
+ * x3 != 0 (bf16x3 mode, DT_DTYPE_BF16): the blob pixel is [hi(3) | lo(3) | 0 0] (dt_prep_clip out mode 3), w holds
+ * 14 blocks — [2*kh][o][kw*8 + s] = W_hi[c] for s = c and s = 3 + c, [2*kh+1][o][kw*8 + c] = W_lo[c] — so two MMAs
+ * per filter row give x_hi*W_hi + x_lo*W_hi + x_hi*W_lo; y rows are [hi(Cout) | lo(Cout)] bf16 pairs. */
 int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
                    const float* scale, const float* bias, int relu, int dtype, int out_f32,
-                   int out_round_tf32, void* y, int out_ld, void* stream);
+                   int out_round_tf32, int x3, void* y, int out_ld, void* stream);
 
 /* ---- proposals.cu -------------------------------------------------------- */
 
@@ -218,6 +229,12 @@ int dt_box_decode(const float* rois, const int* roi_counts, int B, int R, int T,
                   const float* im_hw, const float* weights4, double bbox_xform_clip, float score_thresh,
                   float* dets, int* det_counts, void* stream);
 
+/* lib/core/test.py:76-113 (_get_rois_blob / _project_im_rois) for the keypoint head: rois [n, ncols+1] =
+ * (image index, boxes[i, :ncols] * im_scale) with the product in fp64, stored fp32 (what numpy computes).
+ * boxes [n, ldb]; image index = bidx[i] (fp32, may be NULL) else i / per_image. */
+int dt_scale_rois(const float* boxes, int ldb, int n, int ncols, const float* bidx, int per_image, double im_scale,
+                  float* rois, void* stream);
+
 /* lib/core/test.py:768-800: gather dets[keep] per class and apply the DETECTIONS_PER_IM score
  * threshold over all classes.  out [B, C-1, cap, 4T+1]; out_counts [B*(C-1)] is the reference's count and
  * may exceed cap when scores tie at the threshold (rows beyond cap are not written). */
@@ -232,13 +249,14 @@ int dt_limit_detections(const float* dets, const int* keep, const int* nkeep, in
  * zero pixels on every side: out is [F, Hp + 2*border_y, Wp + 2*border_x, Cp] (dt_conv1_7x7s2 wants 3 / 4).
  * row_planes != 0: the padded rows are de-interleaved by parity, out [F, 2, (Hp + 2*border_y)/2, Wt, Cp]
  * with padded row r at [r & 1][r >> 1] (what dt_conv1_7x7s2 reads: its stride-2 row walk becomes contiguous).
- * out_f32: 0 bf16, 1 fp32 rounded to tf32 (kind::tf32 consumer), 2 raw fp32 (dt_conv1_7x7s2_f32). */
+ * out_f32: 0 bf16, 1 fp32 rounded to tf32 (kind::tf32 consumer), 2 raw fp32 (dt_conv1_7x7s2_f32),
+ * 3 bf16 split pixel (Cp == 8): channels [hi(b,g,r) | lo(b,g,r) | 0 0], hi = bf16(v), lo = bf16(v - hi). */
 int dt_prep_clip(const unsigned char* frames, int F, int H, int W, const float* mean3, double im_scale,
                  int Hr, int Wr, int Hp, int Wp, int Cp, int border_y, int border_x, int row_planes,
                  int out_f32, void* out, void* stream);
 
 /* Caffe2 MaxPool kernels [1,k,k] strides [1,s,s] pads [0,p,p] on NHWC (N = B*T frames).
- * x3 != 0: 3xTF32 storage, rows are [hi(C) | lo(C)] tf32 pairs at ld/2 (fp32 only). */
+ * x3 != 0: split storage, rows are [hi(C) | lo(C)] pairs at ld/2 (tf32 pairs in fp32 tensors, bf16 pairs in bf16). */
 int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int s, int p, int f32, int x3,
                  void* y, int ldy, void* stream);
 
@@ -248,7 +266,7 @@ int dt_maxpool2d(const void* x, int N, int H, int W, int C, int ldx, int k, int 
  * rois [R, ldr] (col 0 image index, then 4*T), levels [R] (NULL if nlevels == 1);
  * out [R, T, P, P, C]; rows >= *n_dev are zero-filled.  round_tf32: round fp32 outputs to tf32
  * (when they feed a DT_DTYPE_TF32 GEMM; prep_clip does the same for its fp32 output).
- * x3_mode (3xTF32 storage, features are [hi | lo] rows): 1 = out [R,T,P,P,2C] per-position pairs,
+ * x3_mode (split storage, features are [hi | lo] rows, fp32 or bf16): 1 = out [R,T,P,P,2C] per-position pairs,
  * 2 = out [R, 2, T*P*P*C] planar hi / lo blocks (input of the FC head). */
 int dt_roi_align(const void* const* feats, const int* Hs, const int* Ws, const float* scales, int nlevels,
                  int k_min, int C, int ldf, int f32, const float* rois, int ldr, const int* n_dev, int R,
@@ -263,10 +281,11 @@ int dt_keypoint_decode(const float* lowres, int ldl, int S, int K, int T, const 
                        const int* n_dev, int D, int min_size, float* heatmaps, float* xy_preds,
                        void* stream);
 
-/* 3xTF32 mode conv1: exact fp32 7x7/2 conv + AffineChannel + ReLU on the raw fp32 blob [F, Hp, Wp, Cp];
- * w [7][7][3][64] fp32; y [F, Hp/2, Wp/2, 128] = [hi(64) | lo(64)] tf32 pairs. */
+/* split-storage modes' conv1: exact fp32 7x7/2 conv + AffineChannel + ReLU on the raw fp32 blob [F, Hp, Wp, Cp];
+ * w [7][7][3][64] fp32; y [F, Hp/2, Wp/2, 128] = [hi(64) | lo(64)]: fp32 tf32 pairs (out_bf16 = 0) or bf16
+ * pairs (out_bf16 = 1). */
 int dt_conv1_7x7s2_f32(const float* blob, int F, int Hp, int Wp, int Cp, const float* w, const float* scale,
-                       const float* bias, float* y, void* stream);
+                       const float* bias, int out_bf16, void* y, void* stream);
 
 /* 3-D box head glue.  dt_spatial_mean: ReduceBackMean over W then H
  * (lib/modeling/ResNet3D.py:321-322), x [N, H, W, ldx] -> y [N, ldy] (first C channels).

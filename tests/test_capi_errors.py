@@ -35,14 +35,16 @@ def _cases():
         ('dt_box_decode', (None, None, 1, 0, 1, None, 2, None, 8, 2, None, None, f4, 4.135, 0.05, None, None, None), b'dt_box_decode'),
         ('dt_limit_detections', (None, None, None, 1, 1, 10, 1, 100, None, None, 104, None), b'dt_limit_detections'),
         ('dt_prep_clip', (None, 1, 0, 10, f3, 1.0, 10, 10, 10, 10, 8, 0, 0, 0, 0, None, None), b'dt_prep_clip'),
-        ('dt_conv1_7x7s2', (None, 1, 7, 8, 8, None, 64, None, None, 1, 0, 0, 0, None, 64, None), b'dt_conv1_7x7s2'),
+        ('dt_conv1_7x7s2', (None, 1, 7, 8, 8, None, 64, None, None, 1, 0, 0, 0, 0, None, 64, None), b'dt_conv1_7x7s2'),
         ('dt_maxpool2d', (None, 1, 8, 8, 12, 12, 3, 2, 1, 0, 0, None, 12, None), b'multiples of 8'),
         ('dt_roi_align', (ptrs, one, one, onef, 0, 2, 256, 256, 0, None, 5, None, 10, 1, None, 7, 2, 0, 0, None, None), b'dt_roi_align'),
         ('dt_keypoint_decode', (None, 68, 99, 17, 1, None, 4, None, 10, 0, None, None, None), b'S=99'),
-        ('dt_conv1_7x7s2_f32', (None, 1, 7, 8, 4, None, None, None, None, None), b'dt_conv1_7x7s2_f32'),
+        ('dt_conv1_7x7s2_f32', (None, 1, 7, 8, 4, None, None, None, 0, None, None), b'dt_conv1_7x7s2_f32'),
         ('dt_spatial_mean', (None, 1, 7, 7, 10, 10, 1, 0, 0, None, 10, None), b'multiples of 4'),
         ('dt_time_mean', (None, 1, 3, 49, 10, 10, 1, 0, 0, None, 10, None), b'multiples of 4'),
         ('dt_fold_tube_heads', (None, 4, 10, 99, 2, None, None, None), b'dt_fold_tube_heads'),
+        ('dt_memset', (None, 0, 16, None), b'dt_memset'),
+        ('dt_scale_rois', (None, 2, 10, 4, None, 1, 1.0, None, None), b'dt_scale_rois'),
     ]
 
 

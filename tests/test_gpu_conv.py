@@ -8,6 +8,8 @@ Tolerances (north star: 1e-3 relative fp32):
              accumulation order differs: |err| <= 2e-4 * max|y| (fp32 output).
   tf32 mode: fp32 inputs, tf32 multiplies: |err| <= 1e-3 * max|y|.
   tf32x3   : [hi | lo] tf32 pairs, 3 MMAs per k-block (fp32-accurate parity mode): |err| <= 1e-4 * max|y|.
+  bf16x3   : [hi | lo] bf16 pairs, 3 bf16 MMAs per k-block (the headline parity mode; operands carry 16 mantissa
+             bits, 2^-17 relative): |err| <= 1e-4 * max|y| for both the bf16-pair output and the plain fp32 output.
 """
 import numpy as np
 import pytest
@@ -58,7 +60,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('mode', ['bf16', 'tf32', 'tf32x3'])
+@pytest.mark.parametrize('mode', ['bf16', 'tf32', 'tf32x3', 'bf16x3', 'bf16x3-f32out'])
 @pytest.mark.parametrize('case', range(len(CASES)))
 def test_conv_parity(case, mode):
     import torch
@@ -80,8 +82,15 @@ def test_conv_parity(case, mode):
         res = torch.randn((N, To, Ho, Wo, Cout), generator=g)
     elif rm == 2:
         res = torch.randn((N, To, Ho // 2, Wo // 2, Cout), generator=g)
-    dtype = {'bf16': cv.BF16, 'tf32': cv.TF32, 'tf32x3': cv.TF32X3}[mode]
-    if mode == 'tf32x3':
+    f32out = mode.endswith('-f32out')
+    mode = mode.split('-')[0]
+    dtype = cv.MODE_NAMES[mode]
+    if mode == 'bf16x3':
+        if Cin % 64 or (Cout % 64 and not f32out):
+            pytest.skip('bf16-pair storage needs channel counts that are multiples of 64 (true for every layer that uses it)')
+        xd = cv.split_bf16(x.cuda())
+        tol = 1e-4          # operands exact to 2^-17, lo*lo dropped (2^-18), bf16-pair output 2^-17
+    elif mode == 'tf32x3':
         if Cin % 32 or Cout % 32:
             pytest.skip('3xTF32 storage needs channel counts that are multiples of 32 (true for every layer that uses it)')
         xd = cv.split_tf32(x.cuda())
@@ -95,13 +104,17 @@ def test_conv_parity(case, mode):
         tol = 1e-3
     wp = cv.pack_weight(w, dtype)
     resd = res.cuda().contiguous() if res is not None else None
-    if mode == 'tf32x3' and resd is not None:
-        resd = cv.split_tf32(resd)
+    if mode in ('tf32x3', 'bf16x3') and resd is not None:
+        if f32out:
+            pytest.skip('plain fp32 outputs of the split modes are the final head outputs: no residual')
+        resd = cv.split_for(dtype, resd)
+    out = torch.empty((N, To, Ho, Wo, Cout), dtype=torch.float32, device='cuda') if f32out else None
     y = cv.conv3d(xd.contiguous(), wp, k, s, p,
                   scale.cuda() if scale is not None else None, bias.cuda() if bias is not None else None,
-                  resd, rm, bool(c.get('relu')), out_f32=True, dtype=dtype, cin=Cin, round_tf32=False)
-    if mode == 'tf32x3':
-        y = cv.join_tf32(y)
+                  resd, rm, bool(c.get('relu')), out_f32=(None if mode == 'bf16x3' else True), dtype=dtype, cin=Cin,
+                  round_tf32=False, out=out)
+    if mode in ('tf32x3', 'bf16x3') and not f32out:
+        y = cv.join_split(y)
     torch.cuda.synchronize()
     ref = _ref_conv(x, w, s, p, scale, bias, res, rm, bool(c.get('relu')))
     err = (y.cpu() - ref).abs().max().item()
@@ -196,7 +209,7 @@ def test_conv_rejects_bad_arguments():
         cv.conv3d(x, wp, (1, 1, 1), cin=12)
 
 
-@pytest.mark.parametrize('mode', ['bf16', 'tf32'])
+@pytest.mark.parametrize('mode', ['bf16', 'tf32', 'bf16x3'])
 def test_conv1_packed_rows_vs_torch(mode):
     """dt_conv1_7x7s2 (filter row packed into K over a zero-bordered blob) == conv 7x7 s2 p3 + affine + relu."""
     import torch
@@ -209,12 +222,20 @@ def test_conv1_packed_rows_vs_torch(mode):
     w = torch.randn((64, 3, 1, 7, 7), generator=g) * 0.01
     sc = torch.rand(64, generator=g) + 0.5
     bi = torch.randn(64, generator=g) * 0.1
-    dtype = cv.BF16 if mode == 'bf16' else cv.TF32
-    cp = 8 if mode == 'bf16' else 4
-    x = dense_ops.prep_clip(frames.cuda(), means, 1.0, (H, W), (H, W), cpad=cp, out_f32=(mode == 'tf32'), border=(3, 4),
-                            row_planes=True)
+    dtype = cv.MODE_NAMES[mode]
+    cp = 4 if mode == 'tf32' else 8
+    x = dense_ops.prep_clip(frames.cuda(), means, 1.0, (H, W), (H, W), cpad=cp, out_f32={'bf16': 0, 'tf32': 1, 'bf16x3': 3}[mode],
+                            border=(3, 4), row_planes=True)
     assert x.shape == (Fr, 2, (H + 6) // 2, W + 8, cp)
     wp = cv.pack_conv1_weight(w, dtype)
+    if mode == 'bf16x3':
+        # split-pixel blob [hi3 | lo3 | 0 0], 14 weight blocks, bf16-pair output: fp32-accurate (<= 1e-4) vs the exact conv
+        y = cv.join_split(cv.conv1_7x7s2(x, wp, (H, W), sc.cuda(), bi.cuda(), relu=True, dtype=dtype)).cpu()
+        xin = (frames.float() - torch.tensor(means).view(1, 1, 1, 3)).permute(0, 3, 1, 2)
+        ref = F.conv2d(xin.double(), w[:, :, 0].double(), None, 2, 3) * sc.double().view(1, -1, 1, 1) + bi.double().view(1, -1, 1, 1)
+        ref = ref.clamp_min(0).permute(0, 2, 3, 1).float()
+        assert y.shape == ref.shape and (y - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+        return
     y = cv.conv1_7x7s2(x, wp, (H, W), sc.cuda(), bi.cuda(), relu=True, dtype=dtype, out_f32=True).cpu()
     xfull = x.permute(0, 2, 1, 3, 4).reshape(Fr, H + 6, W + 8, cp)             # padded row r = [r & 1][r >> 1]
     xin = xfull[:, 3:3 + H, 4:4 + W, :3].float().cpu().permute(0, 3, 1, 2)      # what the kernel saw (rounded blob)

@@ -128,7 +128,7 @@ def test_keypoint_decode_vs_cv2_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('mode', ['bf16', 'f32', 'x3'])
+@pytest.mark.parametrize('mode', ['bf16', 'f32', 'x3', 'bf16x3'])
 def test_time_mean(mode):
     """dt_time_mean (the 'avg' body/head link): mean over T of [B, T, H, W, C]."""
     import torch
@@ -144,6 +144,10 @@ def test_time_mean(mode):
         y = dense_ops.time_mean(x.cuda()).cpu()
         ref = x.mean(dim=1, keepdim=True)
         tol = 1e-6
+    elif mode == 'bf16x3':
+        y = cv.join_split(dense_ops.time_mean(cv.split_bf16(x.cuda()), x3=True)).cpu()
+        ref = x.mean(dim=1, keepdim=True)
+        tol = 3e-5          # bf16 pairs: 2^-17 on the way in, 2^-17 on the way out
     else:
         y = cv.join_tf32(dense_ops.time_mean(cv.split_tf32(x.cuda()), x3=True)).cpu()
         ref = x.mean(dim=1, keepdim=True)

@@ -65,7 +65,7 @@ def setup():
     return dict(cfg=cfg, blobs=blobs, spec=spec, frames=frames, stages=stages, pyr=pyr, feats2d=feats2d, rpn=rpn)
 
 
-@pytest.mark.parametrize('mode,tol', [('tf32x3', 5e-4), ('tf32', 2.5e-3), ('bf16', 3e-2)])
+@pytest.mark.parametrize('mode,tol', [('bf16x3', 5e-4), ('tf32x3', 5e-4), ('tf32', 2.5e-3), ('bf16', 3e-2)])
 def test_backbone_fpn_rpn_features(setup, mode, tol):
     import torch
     from detectandtrack_b200.modeling.engine import DetectionEngine
@@ -81,16 +81,18 @@ def test_backbone_fpn_rpn_features(setup, mode, tol):
     # RPN heads given the ORACLE's features (teacher forcing)
     A = setup['spec'].num_anchors
     for l, r in enumerate(ref):
-        x = r.permute(0, 2, 3, 1)[:, None].contiguous().to(eng.act_dtype).cuda()
+        x = r.permute(0, 2, 3, 1)[:, None].contiguous().cuda()
         if eng.x3:
             from detectandtrack_b200.ops import conv as cv
-            x = cv.split_tf32(x)
+            x = cv.split_for(eng.dtype, x)
+        else:
+            x = x.to(eng.act_dtype)
         h = eng.rpn_conv(x)
         o = torch.empty((1, 1, h.shape[2], h.shape[3], eng.rpn_out_ld), dtype=torch.float32, device='cuda')
         eng.rpn_out(h, out_f32=True, out=o)
         lg, dl = setup['rpn'][l]
         got_lg = o[0, 0, :, :, :A].permute(2, 0, 1).cpu(); got_dl = o[0, 0, :, :, A:5 * A].permute(2, 0, 1).cpu()
-        hm = {'tf32x3': 5e-4, 'tf32': 1.5e-3, 'bf16': 2e-2}[mode]      # two stacked layers
+        hm = {'bf16x3': 5e-4, 'tf32x3': 5e-4, 'tf32': 1.5e-3, 'bf16': 2e-2}[mode]      # two stacked layers
         e1 = (got_lg - lg[0]).abs().max().item() / max(lg.abs().max().item(), 1e-6)
         e2 = (got_dl - dl[0]).abs().max().item() / max(dl.abs().max().item(), 1e-6)
         assert e1 <= hm and e2 <= hm, ('rpn level', l, e1, e2)
@@ -105,7 +107,7 @@ def test_avg_body_head_link(setup):
         cfg = _cfg('avg')
         spec = P.GraphSpec(cfg)
         assert spec.link == 'avg'
-        eng = DetectionEngine(cfg, setup['blobs'], spec, dtype='tf32x3')
+        eng = DetectionEngine(cfg, setup['blobs'], spec, dtype='bf16x3')
         feats, _, _ = eng.forward_features(torch.from_numpy(setup['frames']).cuda())
         ref = [onet.time_pool(p, 'avg', 1) for p in setup['pyr']][::-1]          # finest first
         for l, (f, r) in enumerate(zip(feats, ref)):
@@ -131,7 +133,7 @@ def test_dead_frame_elimination_is_exact(setup):
         assert a.shape == b.shape and torch.equal(a.contiguous(), b.contiguous())
 
 
-@pytest.mark.parametrize('mode', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('mode', ['bf16x3', 'tf32x3', 'tf32'])
 def test_heads_given_oracle_rois(setup, mode):
     """box head and keypoint head on the oracle's features with shared rois."""
     import torch
@@ -139,11 +141,11 @@ def test_heads_given_oracle_rois(setup, mode):
     from detectandtrack_b200.ops import rpn_ops, dense_ops, conv as cv
     cfg, blobs, spec = setup['cfg'], setup['blobs'], setup['spec']
     eng = DetectionEngine(cfg, blobs, spec, dtype=mode)
-    x3 = mode == 'tf32x3'
+    x3 = mode in ('tf32x3', 'bf16x3')
     ref_feats = setup['feats2d'][::-1]
     feats_dev = [r.permute(0, 2, 3, 1)[:, None].contiguous().cuda() for r in ref_feats]
     if x3:
-        feats_dev = [cv.split_tf32(f) for f in feats_dev]
+        feats_dev = [cv.split_for(eng.dtype, f) for f in feats_dev]
     rng = np.random.RandomState(5)
     R = 64
     x1 = rng.uniform(0, 90, R); y1 = rng.uniform(0, 60, R)
@@ -158,7 +160,7 @@ def test_heads_given_oracle_rois(setup, mode):
     rois_d = torch.from_numpy(rois).cuda()
     x = eng._roi_feats(feats_dev, rois_d, 7, 2)
     got_rf = eng.plain(x)[:, 0].permute(0, 3, 1, 2).cpu()
-    assert (got_rf - rf).abs().max().item() <= (1e-5 if x3 else 6e-4) * rf.abs().max().item() + 1e-5     # tf32 mode: rounded output (2^-11)
+    assert (got_rf - rf).abs().max().item() <= ({'tf32x3': 1e-5, 'bf16x3': 3e-5}.get(mode, 6e-4)) * rf.abs().max().item() + 1e-5     # tf32 mode: rounded output (2^-11); bf16 pairs 2^-16
     if x3:
         x = eng._roi_feats(feats_dev, rois_d, 7, 2, planar=True)
     x = eng.fc7(eng.fc6(x.view(1, 1, 1, R, -1)))

@@ -1,6 +1,7 @@
 """GPU parity of the shipped 3-D config (configs/video/3d/03_R-18-3D_PTFromCOCO.yaml semantics: R18
 conv4 3-D body, 3-D RPN with tube anchors, res5 RoI head, 3-D keypoint head) against the torch-fp32
-oracle graph, stage by stage with teacher forcing.  tf32 mode; bars as in test_gpu_engine.py."""
+oracle graph, stage by stage with teacher forcing.  Modes: bf16x3 (the parity mode) and tf32x3 must meet the north
+star's 1e-3 (asserted at 5e-4 .. 1e-3); tf32 keeps its single-MMA bars (2e-3 .. 2.5e-3, see test_gpu_engine.py)."""
 import numpy as np
 import pytest
 
@@ -53,24 +54,35 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
-def test_body_and_rpn_3d(setup):
+MODES = [('bf16x3', 5e-4, 5e-4, 1e-3), ('tf32x3', 5e-4, 5e-4, 1e-3), ('tf32', 2e-3, 1.5e-3, 2.5e-3)]
+
+
+def _dev_feat(eng, feat):
+    """oracle NCTHW feature -> the engine's NDHWC storage (split pairs in the x3 modes)."""
+    from detectandtrack_b200.ops import conv as cv
+    x = feat.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    return cv.split_for(eng.dtype, x) if eng.x3 else x.to(eng.act_dtype)
+
+
+@pytest.mark.parametrize('mode,tol_feat,tol_rpn,tol_head', MODES)
+def test_body_and_rpn_3d(setup, mode, tol_feat, tol_rpn, tol_head):
     import torch
     from detectandtrack_b200.modeling.engine import DetectionEngine
-    eng = DetectionEngine(setup['cfg'], setup['blobs'], setup['spec'], dtype='tf32')
+    eng = DetectionEngine(setup['cfg'], setup['blobs'], setup['spec'], dtype=mode)
     feats, im_info, scale = eng.forward_features(torch.from_numpy(setup['frames']).cuda())
-    got = feats[0].permute(0, 4, 1, 2, 3).float().cpu()
-    assert got.shape == setup['feat'].shape and _rel(got, setup['feat']) <= 2e-3
+    got = eng.plain(feats[0]).permute(0, 4, 1, 2, 3).float().cpu()
+    assert got.shape == setup['feat'].shape and _rel(got, setup['feat']) <= tol_feat
     # RPN head on the oracle's feature (teacher forcing): per-frame outputs -> time pooled / folded
-    x = setup['feat'].permute(0, 2, 3, 4, 1).contiguous().cuda()
+    x = _dev_feat(eng, setup['feat'])
     h = eng.rpn_conv(x)
     B, T, H, W, _ = h.shape
     o = torch.empty((B, T, H, W, eng.rpn_out_ld), dtype=torch.float32, device='cuda')
     eng.rpn_out(h, out_f32=True, out=o)
     A = setup['spec'].num_anchors
     lg = o[..., :A].mean(dim=1).permute(0, 3, 1, 2).cpu()
-    assert _rel(lg, setup['lg']) <= 1.5e-3
+    assert _rel(lg, setup['lg']) <= tol_rpn
     dl = o[..., A:5 * A].view(B, T, H, W, A, 4).permute(0, 4, 1, 5, 2, 3).reshape(B, A * T * 4, H, W).cpu()
-    assert _rel(dl, setup['dl']) <= 1.5e-3
+    assert _rel(dl, setup['dl']) <= tol_rpn
     # device proposals from the oracle's raw head outputs == oracle proposals (tube decode is fp64: bit-exact)
     from detectandtrack_b200.ops import rpn_ops, box_ops
     o2 = torch.zeros_like(o)
@@ -87,13 +99,14 @@ def test_body_and_rpn_3d(setup):
     assert np.array_equal(props[0, :n, :-1].cpu().numpy(), pre_b)
 
 
-def test_tube_heads_given_oracle_rois(setup):
+@pytest.mark.parametrize('mode,tol_feat,tol_rpn,tol_head', MODES)
+def test_tube_heads_given_oracle_rois(setup, mode, tol_feat, tol_rpn, tol_head):
     import torch
     from detectandtrack_b200.modeling.engine import DetectionEngine
     cfg, blobs, spec = setup['cfg'], setup['blobs'], setup['spec']
-    eng = DetectionEngine(cfg, blobs, spec, dtype='tf32')
+    eng = DetectionEngine(cfg, blobs, spec, dtype=mode)
     feat = setup['feat']
-    x = feat.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    x = _dev_feat(eng, feat)
     rng = np.random.RandomState(9)
     R, T = 48, 3
     x1 = rng.uniform(0, 100, R); y1 = rng.uniform(0, 80, R)
@@ -106,21 +119,21 @@ def test_tube_heads_given_oracle_rois(setup):
         heat_ref = onet.keypoint_head_3d(blobs, kf)
     rois_d = torch.from_numpy(rois).cuda()
     xr = eng._roi_feats_tube(x, rois_d, 7, 2)
-    assert _rel(xr.permute(0, 4, 1, 2, 3).cpu(), rf) <= 6e-4
+    assert _rel(eng.plain(xr).permute(0, 4, 1, 2, 3).cpu(), rf) <= (3e-5 if eng.x3 else 6e-4)
     from detectandtrack_b200.ops import dense_ops
     y = xr
     for blk in eng.res5:
         y = eng._run_block(blk, y)
     n, _, hh, ww, ch = y.shape
-    y = dense_ops.spatial_mean(y.view(n * T, hh, ww, ch), round_tf32=True)
+    y = dense_ops.spatial_mean(y.view(n * T, hh, ww, ch), round_tf32=(mode == 'tf32'), x3=eng.x3)
     o = torch.empty((1, 1, 1, n * T, eng.cls_bbox_ld), dtype=torch.float32, device='cuda')
     eng.cls_bbox(y.view(1, 1, 1, n * T, ch), out_f32=True, out=o)
     cls, bbox = dense_ops.fold_tube_heads(o.view(n * T, eng.cls_bbox_ld), n, T, 2)
-    assert _rel(cls.cpu(), cls_ref) <= 2e-3 and _rel(bbox.cpu(), bb_ref) <= 2e-3
+    assert _rel(cls.cpu(), cls_ref) <= min(tol_head, 2e-3) and _rel(bbox.cpu(), bb_ref) <= min(tol_head, 2e-3)
     boxes = rois_d[:8, 1:].contiguous()
     xy, heat = eng.keypoint_head([x], boxes, torch.zeros(8, device='cuda'), 1.0, want_heatmaps=True)
     assert heat.shape == heat_ref.shape == (8, 51, 56, 56)
-    assert _rel(heat.cpu(), heat_ref) <= 2.5e-3
+    assert _rel(heat.cpu(), heat_ref) <= tol_head
     assert xy.shape == (8, 4, 51) and torch.isfinite(xy).all()
 
 
