@@ -22,7 +22,7 @@ import numpy as np
 import yaml
 
 from .config import cfg, get_output_dir
-from .test import im_detect_all
+from .test import im_detect_all, get_pipeline
 from .tracking_engine import run_posetrack_tracking
 from ..modeling import model_builder, params as P
 from ..utils import subprocess as subprocess_utils
@@ -32,8 +32,10 @@ from ..utils.timer import Timer
 logger = logging.getLogger(__name__)
 
 
-def initialize_model_from_cfg(dtype='bf16'):
-    """:50-74.  TEST.WEIGHTS '' or 'random' -> seeded synthetic weights (cfg.RNG_SEED)."""
+def initialize_model_from_cfg(dtype=None):
+    """:50-74.  TEST.WEIGHTS '' or 'random' -> seeded synthetic weights (cfg.RNG_SEED).
+    dtype None -> cfg.TEST.PRECISION (default 'bf16x3', the mode that meets the fp32 reference to 1e-3)."""
+    dtype = dtype or cfg.TEST.PRECISION
     if cfg.TEST.WEIGHTS in ('', 'random'):
         blobs, _ = P.random_blobs(cfg)
     else:
@@ -86,12 +88,25 @@ def get_roidb_and_dataset(ind_range, include_gt=False):
     return roidb, dataset, start, end, total
 
 
+_NOISE_BANK = {}
+
+
+def _synthetic_frame(h, w, seed, t):
+    """Seeded uniform-noise frame as a window of a per-process noise bank (a fresh 3 MB RandomState draw per frame
+    costs ~10 ms; a window is free and still deterministic in (h, w, seed, t))."""
+    bank = _NOISE_BANK.get((h, w))
+    if bank is None:
+        bank = _NOISE_BANK[(h, w)] = np.random.RandomState(20260923).randint(0, 256, (h + 64, w + 64, 3)).astype(np.uint8)
+    k = (seed * 2654435761 + t * 40503) & 0xffffffff
+    oy, ox = (k >> 8) % 64, (k >> 16) % 64
+    return bank[oy:oy + h, ox:ox + w]
+
+
 def read_image_video(entry):
     """lib/utils/image.py:65-79: list of T BGR uint8 frames."""
     T = cfg.VIDEO.NUM_FRAMES if cfg.MODEL.VIDEO_ON else 1
     if entry.get('synthetic'):
-        rng = np.random.RandomState(entry['seed'] % (2 ** 31))
-        return [rng.randint(0, 256, (entry['height'], entry['width'], 3)).astype(np.uint8) for _ in range(T)]
+        return [_synthetic_frame(entry['height'], entry['width'], entry['seed'], t) for t in range(T)]
     import cv2
     paths = entry['image'] if isinstance(entry['image'], list) else [entry['image']]
     ims = [cv2.imread(p) for p in paths]
@@ -122,22 +137,51 @@ def test_net(ind_range=None):
     num_images = len(roidb)
     all_boxes, all_segms, all_keyps = empty_results(cfg.MODEL.NUM_CLASSES, num_images)
     timers = defaultdict(Timer)
-    for i, entry in enumerate(roidb):
-        im = read_image_video(entry)
-        cls_boxes_i, cls_segms_i, cls_keyps_i = im_detect_all(model, im, None, timers)
-        extend_results(i, all_boxes, cls_boxes_i)
-        if cls_keyps_i is not None:
-            extend_results(i, all_keyps, cls_keyps_i)
-        if i % 10 == 0:
-            ave = np.sum([t.average_time for t in timers.values()])
-            eta = str(datetime.timedelta(seconds=int(ave * (num_images - i - 1))))
-            logger.info('im_detect: range [%d, %d] of %d: %d/%d %.3fs (eta: %s)', start_ind + 1, end_ind,
-                        total_num_images, start_ind + i + 1, start_ind + num_images, ave, eta)
+    detect_roidb(model, roidb, all_boxes, all_keyps, timers,
+                 log=lambda i, ave: logger.info('im_detect: range [%d, %d] of %d: %d/%d %.3fs (eta: %s)', start_ind + 1, end_ind,
+                                                total_num_images, start_ind + i + 1, start_ind + num_images, ave,
+                                                str(datetime.timedelta(seconds=int(ave * (num_images - i - 1))))))
     det_name = 'detection_range_%s_%s.pkl' % tuple(ind_range) if ind_range is not None else 'detections.pkl'
     det_file = os.path.join(output_dir, det_name)
     _dump(dict(all_boxes=all_boxes, all_segms=all_segms, all_keyps=all_keyps, cfg=yaml.safe_dump(_plain(cfg))), det_file)
     logger.info('Wrote detections to: %s', os.path.abspath(det_file))
     return all_boxes, all_segms, all_keyps
+
+
+def detect_roidb(model, roidb, all_boxes, all_keyps, timers=None, log=None):
+    """The loop of test_net (:142-165) on the batched device step: runs of same-sized entries go through one
+    ClipPipeline (cfg.TEST.CLIPS_PER_STEP clips per captured graph replay; frames are read by loader threads straight
+    into pinned memory while the previous step computes).  Results land at the entry's index, as in the reference."""
+    timers = timers if timers is not None else defaultdict(Timer)
+    T = cfg.VIDEO.NUM_FRAMES if cfg.MODEL.VIDEO_ON else 1
+    B = max(1, int(cfg.TEST.CLIPS_PER_STEP))
+    i0, n = 0, len(roidb)
+    while i0 < n:
+        hw = (roidb[i0]['height'], roidb[i0]['width'])
+        i1 = i0
+        while i1 < n and (roidb[i1]['height'], roidb[i1]['width']) == hw:
+            i1 += 1
+        pipe = get_pipeline(model, min(B, i1 - i0), T, hw[0], hw[1])
+        base = i0
+
+        def fill(i, dst):
+            ims = read_image_video(roidb[base + i])
+            for t in range(T):
+                assert ims[t].shape == dst[t].shape, 'roidb entry {}: frame size {} != height/width fields {}'.format(
+                    base + i, ims[t].shape, dst[t].shape)
+                np.copyto(dst[t], ims[t])
+
+        def on_result(i, cls_boxes_i, cls_segms_i, cls_keyps_i):
+            extend_results(base + i, all_boxes, cls_boxes_i)
+            if cls_keyps_i is not None:
+                extend_results(base + i, all_keyps, cls_keyps_i)
+            timers['im_detect_bbox'].toc()
+            timers['im_detect_bbox'].tic()
+            if log is not None and (base + i) % 10 == 0:
+                log(base + i, timers['im_detect_bbox'].average_time)
+        timers['im_detect_bbox'].tic()
+        pipe.run(i1 - i0, fill, on_result)
+        i0 = i1
 
 
 def multi_gpu_test_net_on_dataset(num_images, output_dir):
@@ -168,7 +212,7 @@ def test_net_on_dataset(multi_gpu=False):
         res = test_net()
     timer.toc()
     logger.info('Total inference time: %.3fs', timer.average_time)
-    if dataset.name.startswith(('posetrack', 'kinetics', 'synthetic')):
+    if os.path.basename(str(dataset.name)).lower().startswith(('posetrack', 'kinetics', 'synthetic')) or cfg.TRACKING.get('RUN_AFTER_TEST', False):
         roidb, _, _, _, _ = get_roidb_and_dataset(None)
         run_posetrack_tracking(output_dir, roidb)
     return res

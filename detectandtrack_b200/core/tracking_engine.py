@@ -47,8 +47,9 @@ def _write_det_file(dets, det_fpath):
 
 
 def _image_path(entry):
+    """lib/utils/image.py:44-48 get_image_path: the CENTRE frame of a clip entry."""
     im = entry['image']
-    return im[0] if isinstance(im, (list, tuple)) else im
+    return im[len(im) // 2] if isinstance(im, (list, tuple)) else im
 
 
 def _is_same_video(json1, json2):

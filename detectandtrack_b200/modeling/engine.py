@@ -436,6 +436,10 @@ class DetectionEngine(object):
         """uint8 frames -> network input: zero-bordered bf16 / tf32 blob for the packed-row conv1, or the raw
         fp32 blob for the exact conv1 of the 3xTF32 mode."""
         B, T, H, W, _ = frames_u8.shape
+        # conv1 (7x7 / 2, pad 3) yields ceil(h / 2) rows; the kernels want an even physical blob, so an odd blob size
+        # (single-level bodies do no /32 padding: a 1280x720 frame gives 750x1333) gets one more zero row / column.
+        # That equals the conv's own zero padding, and im_info keeps the reference's (unpadded) blob size.
+        hp, wp = hp + (hp & 1), wp + (wp & 1)
         if self.conv1_exact:
             x = dense_ops.prep_clip(frames_u8.view(B * T, H, W, 3), self.pixel_means, scale, (hr, wr), (hp, wp),
                                     cpad=4, out_f32=2)

@@ -40,7 +40,7 @@ class DetectionModel(object):
         return self.engine.keypoint_head(feats2d, boxes, batch_idx, im_scale)
 
 
-def create(model_name, train=False, init_params=None, blobs=None, dtype='bf16'):
+def create(model_name, train=False, init_params=None, blobs=None, dtype=None):
     """model_name is cfg.MODEL.TYPE.  ``init_params`` keeps the reference's meaning (random
     initialisation even at test time); weights are then overwritten from cfg.TEST.WEIGHTS by
     test_engine.initialize_model_from_cfg, exactly like the reference's two-step init."""
@@ -56,4 +56,4 @@ def create(model_name, train=False, init_params=None, blobs=None, dtype='bf16'):
         blobs, spec = P.random_blobs(cfg)
     else:
         spec = P.GraphSpec(cfg)
-    return DetectionModel(model_name, train, blobs, spec, dtype)
+    return DetectionModel(model_name, train, blobs, spec, dtype or cfg.TEST.PRECISION)

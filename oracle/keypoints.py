@@ -73,8 +73,8 @@ def bilinear_upsample2x(x):
     import torch
     import torch.nn.functional as Fn
     K = x.shape[1]
-    w = torch.zeros((K, K, 4, 4), dtype=torch.float32)
-    f = torch.from_numpy(upsample_filt(4).astype(np.float32))
+    w = torch.zeros((K, K, 4, 4), dtype=torch.float32, device=x.device)
+    f = torch.from_numpy(upsample_filt(4).astype(np.float32)).to(x.device)
     for k in range(K):
         w[k, k] = f
     return Fn.conv_transpose2d(x, w, None, stride=2, padding=1)

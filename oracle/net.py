@@ -22,9 +22,25 @@ from . import proposals as oprop
 from . import keypoints as okp
 
 
+_DEVICE = {'device': 'cpu', 'cache': {}}
+
+
+def set_device(device):
+    """'cpu' (the oracle proper) or 'cuda' (bench.py's cuDNN stand-in leg: the same graph through cuDNN on the GPU)."""
+    _DEVICE['device'] = device
+    if device == 'cpu':
+        _DEVICE['cache'].clear()
+
+
 def _t(blobs, name):
     import torch
-    return torch.from_numpy(np.ascontiguousarray(blobs[name]))
+    if _DEVICE['device'] == 'cpu':
+        return torch.from_numpy(np.ascontiguousarray(blobs[name]))
+    key = (id(blobs), name)
+    t = _DEVICE['cache'].get(key)
+    if t is None:
+        t = _DEVICE['cache'][key] = torch.from_numpy(np.ascontiguousarray(blobs[name])).to(_DEVICE['device'])
+    return t
 
 
 def _conv(x, blobs, name, stride, pad, bias=False):
@@ -129,16 +145,16 @@ def roi_features(feats_fine_first, scales, rois, resolution, sampling_ratio, k_m
     from torchvision.ops import roi_align
     rois = np.ascontiguousarray(rois, dtype=np.float32)
     if len(feats_fine_first) == 1:
-        return roi_align(feats_fine_first[0], torch.from_numpy(rois), (resolution, resolution), scales[0], sampling_ratio, aligned=False)
+        return roi_align(feats_fine_first[0].float(), torch.from_numpy(rois).to(feats_fine_first[0].device), (resolution, resolution), scales[0], sampling_ratio, aligned=False)
     _, per_level, restore = oprop.distribute(rois, k_min, k_max)
     parts = []
     for l, r in enumerate(per_level):
         f = feats_fine_first[l]
         if r.shape[0] == 0:
-            parts.append(torch.zeros((0, f.shape[1], resolution, resolution)))
+            parts.append(torch.zeros((0, f.shape[1], resolution, resolution), device=f.device))
         else:
-            parts.append(roi_align(f, torch.from_numpy(np.ascontiguousarray(r)), (resolution, resolution), scales[l], sampling_ratio, aligned=False))
-    return torch.cat(parts, 0)[torch.from_numpy(restore.astype(np.int64))]
+            parts.append(roi_align(f.float(), torch.from_numpy(np.ascontiguousarray(r)).to(f.device), (resolution, resolution), scales[l], sampling_ratio, aligned=False))
+    return torch.cat(parts, 0)[torch.from_numpy(restore.astype(np.int64)).to(parts[0].device)]
 
 
 def box_head_2mlp(blobs, roi_feat):

@@ -146,3 +146,31 @@ def test_detect_end_to_end_tubes(setup):
     assert b.shape[1] == 13 and b.shape[0] > 0
     assert b[:, :12].min() >= 0 and b[:, 0:12:4].max() <= 159 and b[:, 1:12:4].max() <= 127
     assert res[0]['keyps'].shape == (b.shape[0], 4, 51)
+
+
+def test_odd_blob_size_single_level_body():
+    """Single-level bodies do no /32 blob padding (blob.py:47-50 pads only when FPN is on): a 1280x720 PoseTrack frame
+    resizes to 750x1333.  conv1 (7x7/2, pad 3) then yields ceil(h/2) x ceil(w/2); the engine pads the physical blob to
+    even dims (zero row / column == the conv's own padding) and keeps im_info at the unpadded size."""
+    import torch
+    from detectandtrack_b200.core.config import cfg
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.engine import DetectionEngine
+    _cfg()
+    try:
+        cfg.TEST.SCALES = (127,); cfg.TEST.MAX_SIZE = 161
+        blobs, spec = P.random_blobs(cfg, seed=5)
+        frames = np.random.RandomState(3).randint(0, 256, (1, 3, 127, 161, 3)).astype(np.uint8)
+        means = np.asarray(cfg.PIXEL_MEANS, np.float32).reshape(1, 1, 1, 1, 3)
+        data = torch.from_numpy(frames.astype(np.float32) - means).permute(0, 4, 1, 2, 3).contiguous()
+        with torch.no_grad():
+            feat = onet.conv_body(blobs, spec, data)[spec.stage_blobs[-1]]
+        eng = DetectionEngine(cfg, blobs, spec, dtype='bf16x3')
+        feats, im_info, scale = eng.forward_features(torch.from_numpy(frames).cuda())
+        assert scale == 1.0 and im_info.cpu().numpy().tolist() == [[127.0, 161.0, 1.0]]
+        got = eng.plain(feats[0]).permute(0, 4, 1, 2, 3).float().cpu()
+        assert got.shape == feat.shape and _rel(got, feat) <= 5e-4
+        res = eng.detect(torch.from_numpy(frames).cuda())[0]          # the whole tube path runs at this geometry
+        assert res['boxes'].shape[1] == 13
+    finally:
+        _cfg()

@@ -139,3 +139,69 @@ def test_shipped_style_3d_yaml_builds_the_tube_graph(tmp_path):
     assert shapes['res5_0_branch1_w'] == (512, 256, 1, 1, 1) and shapes['cls_score_1_w'] == (2, 512, 1, 1, 1)
     assert shapes['conv_fcn1_w'] == (512, 256, 3, 3, 3) and shapes['kps_score_lowres_w'] == (512, 17, 4, 4)
     reset_cfg()
+
+
+BODIES = ['FPN3D.add_fpn_ResNet50_conv5_body', 'FPN3D.add_fpn_ResNet101_conv5_body', 'FPN3D.add_fpn_ResNet152_conv5_body',
+          'FPN.add_fpn_ResNet50_conv5_body', 'FPN.add_fpn_ResNet101_conv5_body', 'ResNet3D.add_ResNet18_conv4_body',
+          'ResNet3D.add_ResNet34_conv4_body', 'ResNet3D.add_ResNet50_conv4_body']
+
+
+@pytest.mark.parametrize('body', BODIES)
+def test_graphspec_matches_reference_tables(body):
+    """The product's reading of the reference builders (modeling/params.GraphSpec) against oracle/graph_tables.json, which
+    tests/golden/gen_golden_graph.py extracted from the reference's own source (ResNet3D.py:334-394, ResNet.py:298-397),
+    and against the oracle's independent OracleSpec."""
+    from detectandtrack_b200.core.config import cfg, reset_cfg, assert_and_infer_cfg
+    from detectandtrack_b200.modeling import params as P
+    from oracle import graph as og
+    reset_cfg()
+    cfg.MODEL.TYPE = 'keypoint_rcnn'; cfg.MODEL.CONV_BODY = body; cfg.MODEL.NUM_CLASSES = 2
+    cfg.MODEL.FASTER_RCNN = True; cfg.MODEL.KEYPOINTS_ON = True
+    fpn = 'fpn' in body
+    cfg.MODEL.VIDEO_ON = body.split('.')[0].endswith('3D')
+    cfg.FPN.FPN_ON = fpn; cfg.FPN.MULTILEVEL_ROIS = fpn; cfg.FPN.MULTILEVEL_RPN = fpn
+    cfg.KRCNN.USE_DECONV_OUTPUT = True; cfg.KRCNN.UP_SCALE = 2
+    cfg.MODEL.ROI_HEAD = 'head_builder.add_roi_2mlp_head' if fpn else 'ResNet3D.add_ResNet18_roi_conv5_head'
+    cfg.VIDEO.BODY_HEAD_LINK = 'slice-center' if fpn else ''
+    cfg.VIDEO.NUM_FRAMES = 3; cfg.VIDEO.NUM_FRAMES_MID = 1 if fpn else -1
+    for k in ('BODY', 'HEAD_RPN', 'HEAD_KPS', 'HEAD_DET'):
+        cfg.VIDEO.TIME_KERNEL_DIM[k] = 3
+    if not fpn:
+        cfg.KRCNN.ROI_KEYPOINTS_HEAD = 'keypoint_rcnn_heads.add_roi_pose_head_v1convX_3d'; cfg.KRCNN.NO_3D_DECONV_TIME_TO_CH = True
+    assert_and_infer_cfg()
+    try:
+        g, o = P.GraphSpec(cfg), og.OracleSpec(cfg)
+        key = body.split('add_fpn_')[-1].split('add_')[-1][:-len('_body')]
+        tab = og.tables()['ResNet3D' if g.is3d else 'ResNet']['bodies'][key]
+        assert list(g.counts) == tab['counts'] and list(g.dims[:len(g.counts) + 1]) == tab['dims']
+        assert g.block == ('bottleneck' if tab['trans_func'].startswith('bottleneck') else 'basic')
+        for a in ('counts', 'block', 'tk_body', 'stride_1x1', 'stage_blobs', 'num_anchors', 'link', 'head3d', 'T_head', 'fpn', 'is3d'):
+            assert getattr(g, a) == getattr(o, a), (a, getattr(g, a), getattr(o, a))
+        assert tuple(g.dims[:len(g.counts) + 1]) == tuple(o.dims)
+        if fpn:
+            assert g.rpn_levels == o.rpn_levels and g.roi_levels == o.roi_levels
+            lv = og.tables()['fpn_levels'][key]
+            assert g.stage_blobs == lv['blobs'][::-1]
+        else:
+            head = og.tables()['ResNet3D']['roi_conv5_heads']['ResNet18']
+            shapes, _ = P.param_shapes(cfg)
+            assert shapes['res5_%d_branch2b_w' % (head['block_counts'] - 1)][0] == head['dim_out']
+            assert 'res5_%d_branch2b_w' % head['block_counts'] not in shapes
+    finally:
+        reset_cfg()
+
+
+def test_inflate_weights_matches_reference_goldens():
+    """modeling/params.inflate_weights against outputs of the REFERENCE's own lib/utils/net.py:95-161, source-executed
+    by tests/golden/gen_golden_graph.py for every VIDEO.WEIGHTS_INFLATE_MODE and time sizes 1 / 3 (bit-equal; the
+    random mode with the same numpy seed)."""
+    from detectandtrack_b200.modeling import params as P
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'inflate_weights.npz'))
+    w2d = g['w2d']
+    for mode in ('mean-repeat', 'repeat', 'center-only', 'center-only-rest-rand'):
+        for kt in (1, 3):
+            np.random.seed(1234)
+            got = P.inflate_weights(w2d, (6, 4, kt, 3, 3), mode)
+            ref = g['%s_%d' % (mode, kt)]
+            assert got.shape == ref.shape and np.array_equal(np.asarray(got, np.float32), ref), (mode, kt)
+    assert np.array_equal(P.inflate_weights(w2d, w2d.shape, 'center-only'), g['same_rank'])
