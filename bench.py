@@ -377,7 +377,7 @@ def measure_mode(mode, cfg, blobs, args, ctx, full):
             json.dump(meter.layers(args.steps), open(os.path.join(ROOT, 'gpurun_out', 'conv_layers.json'), 'w'), indent=0)
         res['clocks'] = sampler.stop() if sampler is not None else None
         # ---- extra (not the headline): the same step with dead-frame elimination ----------------------
-        if not args.dce and world == 1 and eng.spec.fpn and eng.spec.link == 'slice-center' and T > 1:
+        if not args.dce and not args.no_extras and world == 1 and eng.spec.fpn and eng.spec.link == 'slice-center' and T > 1:
             eng.skip_dead_frames = True
             for _ in range(2):
                 eng.detect_static(dev)

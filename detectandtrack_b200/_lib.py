@@ -42,7 +42,15 @@ SIGNATURES = {
     'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_time_mean': [_p, _i, _i, C.c_longlong, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_fold_tube_heads': [_p, _i, _i, _i, _i, _p, _p, _p],
+    'dt_to_planes': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_wgrad': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_bwd_pointwise': [_p, _p, _p, _p, C.c_longlong, _i, _p, _p],
+    'dt_upsample_add_bwd': [_p, _p, _i, _i, _i, _i, _p, _p],
+    'dt_scatter_stride2': [_p, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_sgd_update': [_p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p],
 }
+# host-only helpers (not error-code functions)
+HOST_FUNCS = {'dt_planes_ld': ([_i, _i, _i, _i], C.c_int)}
 
 
 
@@ -84,6 +92,10 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPE.get(name, C.c_int)
+        for name, (args, res) in HOST_FUNCS.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = res
         _lib = l
     return _lib
 

@@ -28,6 +28,7 @@
 #include "tc_common.cuh"
 #include "../../include/dt_b200.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace dt {
 
@@ -231,6 +232,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch, the k-block
+  // schedule) touched only kernel parameters and shared memory, so it may overlap the tail of the previous kernel of
+  // the stream; no global data is read or written before this wait.  The trigger lets the NEXT kernel's prologue do
+  // the same under this one's tail (its CTAs become resident as this kernel's CTAs retire: 1 CTA / SM by shared memory).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int taps = p.kT * p.kH * p.kW;
   const int kiters = taps * p.kchunks * p.nsub;
@@ -648,39 +655,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-// ------------------------------------------------------------------ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
-static int encode_map(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
-                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, const uint32_t* estr) {
-  PFN_encodeTiled enc = get_encode();
-  DT_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
-  cuuint64_t d[5], s[4]; cuuint32_t b[5], e[5];
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
-  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
-                   const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  DT_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu ..., box %u %u %u)",
-               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
-               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
-  return 0;
-}
-
+// ------------------------------------------------------------------ host side (encode_map: tc_common.cuh)
 // M tile = TB images x TT frames x TH x TW output positions (<= 128 rows).  Small feature maps (14x14 RoI
 // heads, 25x42 res5) would waste a quarter of every 128-row MMA with purely spatial tiles; stacking frames /
 // images fills the rows.  Among the shapes within 4 % of the best useful-row fraction a purely spatial tile
@@ -735,8 +710,17 @@ static int launch_conv1(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   q.ktab = (kiters + 2) & ~1;
   const int smem = Cfg::smem_bytes(kiters, q.nstages, q.ks, q.ncbuf, q.nrbuf, p.split_out != 0);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
-  conv_tc_kernel<BN, TF32, SPLIT><<<grid, CONV_THREADS, smem, stream>>>(tmA, tmB, tmC, tmR, q);
-  DT_CHECK_LAUNCH();
+  // launched with programmatic stream serialization (the kernel waits on griddepcontrol before its first global
+  // access); DT_PDL=0 in the environment falls back to plain stream order for A/B measurements
+  static const bool pdl = [] { const char* e = getenv("DT_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(CONV_THREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+  DT_CHECK_CUDA(cudaLaunchKernelEx(&lc, conv_tc_kernel<BN, TF32, SPLIT>, tmA, tmB, tmC, tmR, q));
   return 0;
 }
 

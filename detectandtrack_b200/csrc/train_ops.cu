@@ -1,0 +1,451 @@
+// Training-step kernels of the data-parallel path (BASELINE.json configs[4]; the reference builds these with
+// model.AddGradientOperators + add_parameter_update_ops, lib/modeling/model_builder.py:908-985):
+//
+//   dt_wgrad            Conv / ConvNd filter gradient on the tcgen05 tensor cores:
+//                         dW[tap][co][ci] = sum over positions of gz[pos, co] * x[pos @ tap, ci]
+//                       a GEMM whose K axis is the position axis.  Both operands are read from CHANNEL-MAJOR PLANES
+//                       ([N, T, C, plane], plane = the zero-bordered (H+2p) x (W+2p) map flattened), so a position run is
+//                       contiguous (a K-major operand for tcgen05, staged by TMA with the 128B swizzle) and a filter tap is
+//                       a constant offset along the flattened plane (the physical zero border supplies the padding, TMA's
+//                       out-of-bounds zero fill the plane ends and the temporal padding).  Split-K over positions across
+//                       CTAs, fp32 partial sums reduced into dW with vector red.global.
+//   dt_to_planes        NDHWC activation / gradient -> those planes (tiled transpose through shared memory, optional
+//                       spatial subsampling for the strided 1x1 convs).
+//   dt_bwd_pointwise    the elementwise part of a block's backward: gz = (g1 + g2) * [y > 0] * scale[c]
+//                       (Relu / Sum / AffineChannelNd gradients, lib/ops/affine_channel_nd_op.cu:73-92: dX = dY * scale;
+//                       the affine parameters themselves are frozen in Detectron-style fine-tuning)
+//   dt_upsample_add_bwd FPN top-down join backward (lib/modeling/FPN3D.py:186-222): the coarser level receives the 2x2 sum
+//   dt_scatter_stride2  dgrad of a stride-2 pointwise conv: values land on the even positions of a zeroed map
+//   dt_sgd_update       MomentumSGDUpdate with weight decay (model_builder.py:954-985) on fp32 master weights kept in the
+//                       packed [tap][Cout][Cin] order, re-emitting the bf16 forward weights and the (flipped, transposed)
+//                       bf16 dgrad weights in the same pass
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/dt_b200.h"
+#include <cuda_bf16.h>
+
+namespace dt {
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradParams {
+  int Cout, Cin, taps;
+  int kT, kH, kW, pT, pH, pW;
+  int Wp;                 // row length of the padded plane (W + 2*pW)
+  int T, N;               // frames, images
+  int kchunks;            // 64-position chunks per plane
+  int tiles_m, tiles_n, ksplit;
+  float* dW;              // [taps][Cout][Cin] fp32, accumulated into (caller zeroes)
+};
+
+constexpr int WG_THREADS = 192;       // warp 0 TMA producer, warp 1 TMEM + MMA issuer, warps 2-5 epilogue
+constexpr int WG_STAGES = 4;
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, ST_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * ST_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* acc_full = empty + WG_STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    prefetch_tmap(&tmG); prefetch_tmap(&tmX);
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_base_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  // work item: (tap, m tile, n tile, k split)
+  int w = blockIdx.x;
+  const int ks = w % p.ksplit; w /= p.ksplit;
+  const int nt = w % p.tiles_n; w /= p.tiles_n;
+  const int mt = w % p.tiles_m;
+  const int tap = w / p.tiles_m;
+  const int kw = tap % p.kW, kh = (tap / p.kW) % p.kH, kt = tap / (p.kW * p.kH);
+  const int shift = (kh - p.pH) * p.Wp + (kw - p.pW);          // tap offset along the flattened padded plane
+  const int dt_ = kt - p.pT;
+  // k-blocks = (image, frame, chunk) triples; frames whose tap-shifted source frame is outside the clip contribute zero
+  // (temporal zero padding) and are skipped by producer and issuer alike
+  const long long total = (long long)p.N * p.T * p.kchunks;
+  const long long k0 = total * ks / p.ksplit, k1 = total * (ks + 1) / p.ksplit;
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    long long r = k0 / p.kchunks;
+    int chunk = (int)(k0 - r * p.kchunks);
+    int t = (int)(r % p.T), n = (int)(r / p.T);
+    for (long long kb = k0; kb < k1; ++kb) {
+      const int ts = t + dt_;
+      if (ts >= 0 && ts < p.T) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(smem) + stage * ST_BYTES;
+          const uint32_t bar = smem_u32(&full[stage]);
+          mbar_expect_tx_u(bar, (uint32_t)ST_BYTES);
+          // A: gz planes, box (64 positions, 128 channels); B: x planes at the tap-shifted position / frame
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(bar), "r"(chunk * 64), "r"(mt * 128), "r"(t), "r"(n) : "memory");
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar), "r"(chunk * 64 + shift), "r"(nt * BN), "r"(ts), "r"(n) : "memory");
+        }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++chunk == p.kchunks) { chunk = 0; if (++t == p.T) { t = 0; ++n; } }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(128, BN, 1);
+    int stage = 0; uint32_t phase = 0;
+    long long r = k0 / p.kchunks;
+    int chunk = (int)(k0 - r * p.kchunks);
+    int t = (int)(r % p.T);
+    uint32_t first = 1;
+    for (long long kb = k0; kb < k1; ++kb) {
+      const int ts = t + dt_;
+      if (ts >= 0 && ts < p.T) {
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem) + stage * ST_BYTES;
+        if (elect_one()) {
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma<false>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+          umma_commit(&empty[stage]);
+        }
+        first = 0;
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++chunk == p.kchunks) { chunk = 0; if (++t == p.T) t = 0; }
+    }
+    if (elect_one()) umma_commit(acc_full);          // fires when every MMA above has retired (immediately if none)
+  } else {
+    // epilogue warps 2..5: TMEM lane group (warp & 3), 32 rows each.  While the MMAs run these warps are idle, so they
+    // replay the k-block walk to learn whether this CTA accumulated anything at all (a range made only of temporally
+    // padded frames leaves the accumulator unwritten).
+    bool nothing = true;
+    {
+      long long r = k0 / p.kchunks;
+      int chunk = (int)(k0 - r * p.kchunks);
+      int t = (int)(r % p.T);
+      for (long long kb = k0; kb < k1 && nothing; ) {
+        const int ts = t + dt_;
+        if (ts >= 0 && ts < p.T) nothing = false;
+        const long long step = p.kchunks - chunk;           // jump to the next frame
+        kb += step; chunk = 0; if (++t == p.T) t = 0;
+      }
+    }
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    const int lg = warp & 3;
+    const int row = mt * 128 + lg * 32 + lane;
+    if (!nothing) {
+      float* out = p.dW + ((size_t)tap * p.Cout + row) * p.Cin + nt * BN;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row < p.Cout) {
+          const int col = nt * BN + c0;
+          if (col + 16 <= p.Cin && (p.Cin & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                           "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3])) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.Cin) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmG, const CUtensorMap& tmX, const WgradParams& p, cudaStream_t stream) {
+  constexpr int smem = WG_STAGES * (128 * 128 + BN * 128) + 256;
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(wgrad_kernel<BN>, smem, &grant));
+  const long long grid = (long long)p.taps * p.tiles_m * p.tiles_n * p.ksplit;
+  DT_CHECK_ARG(grid < (1ll << 31), "dt_wgrad: grid too large");
+  wgrad_kernel<BN><<<(unsigned)grid, WG_THREADS, smem, stream>>>(tmG, tmX, p);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ planes
+// x [N*T frames, H, W, ldx] (first C channels) -> planes [N*T, C, Pld]: plane position ((h / sh) + pH) * Wp + (w / sw) + pW
+// for h % sh == 0, w % sw == 0; border and row tail zero.  Tile: 64 plane positions x 64 channels through shared memory.
+__global__ void __launch_bounds__(256)
+to_planes_kernel(const __nv_bfloat16* __restrict__ x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW,
+                 int Ho, int Wo, int Pld, __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int Wp = Wo + 2 * pW;
+  const int plane = (Ho + 2 * pH) * Wp;
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, f = blockIdx.z;
+  // load: thread -> (position, 16-byte channel group)
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const int pp = i >> 3, cg = (i & 7) * 8;
+    const int pos = p0 + pp;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (pos < plane && c0 + cg < C) {
+      const int hp = pos / Wp, wp = pos - hp * Wp;
+      const int ho = hp - pH, wo = wp - pW;
+      if (ho >= 0 && ho < Ho && wo >= 0 && wo < Wo)
+        v = *reinterpret_cast<const uint4*>(x + (((size_t)f * H + (size_t)ho * sh) * W + (size_t)wo * sw) * ldx + c0 + cg);
+    }
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[pp][cg + j] = e[j];
+  }
+  __syncthreads();
+  // store: thread -> (channel, 8 consecutive positions)
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const int cc = i >> 3, pg = (i & 7) * 8;
+    if (c0 + cc >= C || p0 + pg >= Pld) continue;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tile[pg + j][cc];
+    *reinterpret_cast<uint4*>(out + ((size_t)f * C + c0 + cc) * Pld + p0 + pg) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pointwise backward
+__global__ void bwd_pointwise_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
+                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, long long rows,
+                                     int C, __nv_bfloat16* __restrict__ out) {
+  const int cv = C / 8;
+  const long long total = rows * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * 8;
+    const size_t off = (size_t)(idx / cv) * C + c;
+    const uint4 a = *reinterpret_cast<const uint4*>(g1 + off);
+    const __nv_bfloat16* ae = reinterpret_cast<const __nv_bfloat16*>(&a);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(ae[j]);
+    if (g2) {
+      const uint4 b = *reinterpret_cast<const uint4*>(g2 + off);
+      const __nv_bfloat16* be = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(be[j]);
+    }
+    if (y) {
+      const uint4 m = *reinterpret_cast<const uint4*>(y + off);
+      const __nv_bfloat16* me = reinterpret_cast<const __nv_bfloat16*>(&m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(me[j]) > 0.f ? v[j] : 0.f;
+    }
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= scale[c + j];
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// coarse_out[f, h, w, c] = coarse_in[f, h, w, c] (optional) + sum of the 2x2 children of fine[f, 2h.., 2w.., c]
+__global__ void upsample_add_bwd_kernel(const __nv_bfloat16* __restrict__ fine, const __nv_bfloat16* __restrict__ coarse_in,
+                                        int F, int Hc, int Wc, int C, __nv_bfloat16* __restrict__ out) {
+  const int cv = C / 8;
+  const long long total = (long long)F * Hc * Wc * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * 8;
+    long long r = idx / cv;
+    const int w = (int)(r % Wc); r /= Wc;
+    const int h = (int)(r % Hc);
+    const int f = (int)(r / Hc);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const uint4 a = *reinterpret_cast<const uint4*>(fine + (((size_t)f * 2 * Hc + 2 * h + dy) * (2 * Wc) + 2 * w + dx) * C + c);
+        const __nv_bfloat16* ae = reinterpret_cast<const __nv_bfloat16*>(&a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(ae[j]);
+      }
+    const size_t off = (((size_t)f * Hc + h) * Wc + w) * C + c;
+    if (coarse_in) {
+      const uint4 a = *reinterpret_cast<const uint4*>(coarse_in + off);
+      const __nv_bfloat16* ae = reinterpret_cast<const __nv_bfloat16*>(&a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(ae[j]);
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// out [F, 2*Hs, 2*Ws (cropped to H, W), C]: out[f, 2h, 2w] = src[f, h, w], zero elsewhere
+__global__ void scatter_stride2_kernel(const __nv_bfloat16* __restrict__ src, int F, int Hs, int Ws, int H, int W, int C,
+                                       __nv_bfloat16* __restrict__ out) {
+  const int cv = C / 8;
+  const long long total = (long long)F * H * W * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * 8;
+    long long r = idx / cv;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int f = (int)(r / H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(h & 1) && !(w & 1) && (h >> 1) < Hs && (w >> 1) < Ws)
+      v = *reinterpret_cast<const uint4*>(src + (((size_t)f * Hs + (h >> 1)) * Ws + (w >> 1)) * C + c);
+    *reinterpret_cast<uint4*>(out + (((size_t)f * H + h) * W + w) * C + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SGD
+// Caffe2 MomentumSGDUpdate (non-Nesterov): g' = lr * (grad_scale * g + wd * w) + momentum * m;  m = g';  w -= g'
+// w / g / m [taps][Cout][Cin] fp32.  Re-emits wf [taps][Cout][Cin] bf16 (forward operand) and wd_ [taps][Cin][Cout] bf16
+// with the taps FLIPPED (dgrad of a stride-1 "same" conv is the conv of the gradient with the flipped, transposed filter).
+__global__ void sgd_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, long long n,
+                                  int taps, int Cout, int Cin, float lr, float momentum, float wd, float grad_scale,
+                                  __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wdg) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float wi = w[i];
+    const float adj = lr * (grad_scale * g[i] + wd * wi) + momentum * m[i];
+    m[i] = adj;
+    const float nw = wi - adj;
+    w[i] = nw;
+    if (wf) wf[i] = __float2bfloat16_rn(nw);
+    if (wdg) {
+      const int ci = (int)(i % Cin);
+      const long long r = i / Cin;
+      const int co = (int)(r % Cout);
+      const int tap = (int)(r / Cout);
+      wdg[((size_t)(taps - 1 - tap) * Cin + ci) * Cout + co] = __float2bfloat16_rn(nw);
+    }
+  }
+}
+
+}  // namespace dt
+
+using namespace dt;
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int dt_planes_ld(int Ho, int Wo, int pH, int pW) { return ((Ho + 2 * pH) * (Wo + 2 * pW) + 7) / 8 * 8; }
+
+extern "C" int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, void* out,
+                            void* stream) {
+  DT_CHECK_ARG(F >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && ldx >= C && ldx % 8 == 0 && sh >= 1 && sw >= 1 && pH >= 0 && pW >= 0,
+               "dt_to_planes: bad shape F=%d H=%d W=%d C=%d ldx=%d", F, H, W, C, ldx);
+  if (F == 0) return 0;
+  DT_CHECK_ARG(x && out, "dt_to_planes: null pointer");
+  const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
+  const int Pld = dt_planes_ld(Ho, Wo, pH, pW);
+  dim3 grid((Pld + 63) / 64, (C + 63) / 64, F);
+  to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, F, H, W, C, ldx, sh, sw, pH, pW, Ho, Wo, Pld,
+                                                           (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int T, int Ho, int Wo, int Cout, int Cin, int kT, int kH,
+                        int kW, float* dW, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DT_CHECK_ARG(N >= 1 && T >= 1 && Ho >= 1 && Wo >= 1 && Cout >= 1 && Cin >= 8 && Cin % 8 == 0 && kT >= 1 && kH >= 1 && kW >= 1 &&
+                   (kT & 1) && (kH & 1) && (kW & 1),
+               "dt_wgrad: bad shape N=%d T=%d %dx%d Cout=%d Cin=%d k=%dx%dx%d (odd 'same' kernels, Cin %% 8 == 0)", N, T, Ho, Wo, Cout, Cin, kT, kH, kW);
+  DT_CHECK_ARG(gz_planes && x_planes && dW, "dt_wgrad: null pointer");
+  const int pT = kT / 2, pH = kH / 2, pW = kW / 2;
+  const int Wp = Wo + 2 * pW, plane = (Ho + 2 * pH) * Wp;
+  const int Pld = dt_planes_ld(Ho, Wo, pH, pW);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.Cout = Cout; p.Cin = Cin; p.taps = kT * kH * kW; p.kT = kT; p.kH = kH; p.kW = kW; p.pT = pT; p.pH = pH; p.pW = pW;
+  p.Wp = Wp; p.T = T; p.N = N; p.kchunks = cdiv(plane, 64); p.dW = dW;
+  const int BN = Cin >= 256 ? 256 : (Cin > 64 ? 128 : 64);
+  p.tiles_m = cdiv(Cout, 128); p.tiles_n = cdiv(Cin, BN);
+  const long long units = (long long)p.taps * p.tiles_m * p.tiles_n;
+  const long long kblocks = (long long)N * T * p.kchunks;
+  long long ksplit = (148 * 3 + units - 1) / units;               // ~3 waves of CTAs
+  if (ksplit > kblocks / 4) ksplit = kblocks / 4;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = (int)ksplit;
+  CUtensorMap tmG, tmX;
+  {
+    uint64_t d[4] = {(uint64_t)plane, (uint64_t)Cout, (uint64_t)T, (uint64_t)N};
+    uint64_t s[3] = {(uint64_t)Pld * 2, (uint64_t)Pld * 2 * Cout, (uint64_t)Pld * 2 * Cout * T};
+    uint32_t b[4] = {64, 128, 1, 1}, e[4] = {1, 1, 1, 1};
+    if (encode_map(&tmG, false, 4, gz_planes, d, s, b, e)) return 1;
+  }
+  {
+    uint64_t d[4] = {(uint64_t)plane, (uint64_t)Cin, (uint64_t)T, (uint64_t)N};
+    uint64_t s[3] = {(uint64_t)Pld * 2, (uint64_t)Pld * 2 * Cin, (uint64_t)Pld * 2 * Cin * T};
+    uint32_t b[4] = {64, (uint32_t)BN, 1, 1}, e[4] = {1, 1, 1, 1};
+    if (encode_map(&tmX, false, 4, x_planes, d, s, b, e)) return 1;
+  }
+  switch (BN) {
+    case 256: return launch_wgrad<256>(tmG, tmX, p, stream);
+    case 128: return launch_wgrad<128>(tmG, tmX, p, stream);
+    default: return launch_wgrad<64>(tmG, tmX, p, stream);
+  }
+}
+
+extern "C" int dt_bwd_pointwise(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
+                                void* stream) {
+  DT_CHECK_ARG(rows >= 0 && C >= 8 && C % 8 == 0, "dt_bwd_pointwise: bad shape rows=%lld C=%d (C %% 8 == 0)", rows, C);
+  if (rows == 0) return 0;
+  DT_CHECK_ARG(g1 && out, "dt_bwd_pointwise: null pointer");
+  bwd_pointwise_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale, rows, C, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_upsample_add_bwd(const void* fine, const void* coarse_in, int F, int Hc, int Wc, int C, void* out, void* stream) {
+  DT_CHECK_ARG(F >= 0 && Hc >= 1 && Wc >= 1 && C >= 8 && C % 8 == 0, "dt_upsample_add_bwd: bad shape");
+  if (F == 0) return 0;
+  DT_CHECK_ARG(fine && out, "dt_upsample_add_bwd: null pointer");
+  upsample_add_bwd_kernel<<<grid_for((long long)F * Hc * Wc * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)fine, (const __nv_bfloat16*)coarse_in, F, Hc, Wc, C, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_scatter_stride2(const void* src, int F, int Hs, int Ws, int H, int W, int C, void* out, void* stream) {
+  DT_CHECK_ARG(F >= 0 && Hs >= 1 && Ws >= 1 && H >= 1 && W >= 1 && (H + 1) / 2 == Hs && (W + 1) / 2 == Ws && C >= 8 && C % 8 == 0,
+               "dt_scatter_stride2: bad shape %dx%d -> %dx%d C=%d", Hs, Ws, H, W, C);
+  if (F == 0) return 0;
+  DT_CHECK_ARG(src && out, "dt_scatter_stride2: null pointer");
+  scatter_stride2_kernel<<<grid_for((long long)F * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, F, Hs, Ws, H, W, C, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_sgd_update(float* w, const float* g, float* m, int taps, int Cout, int Cin, float lr, float momentum, float wd,
+                             float grad_scale, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream) {
+  DT_CHECK_ARG(taps >= 1 && Cout >= 1 && Cin >= 1, "dt_sgd_update: bad shape");
+  DT_CHECK_ARG(w && g && m, "dt_sgd_update: null pointer");
+  const long long n = (long long)taps * Cout * Cin;
+  sgd_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, n, taps, Cout, Cin, lr, momentum, wd, grad_scale,
+                                                                        (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
+  DT_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,86 @@
+"""Device-tensor API over csrc/train_ops.cu (training step kernels: filter gradient on the tensor cores over
+channel-major planes, elementwise backward joins, SGD update).  See include/dt_b200.h."""
+import ctypes as C
+
+from .. import _lib as L
+from . import conv as cv
+
+
+def planes_ld(Ho, Wo, pH, pW):
+    return int(L.lib().dt_planes_ld(int(Ho), int(Wo), int(pH), int(pW)))
+
+
+def to_planes(x, pad=(0, 0), stride=(1, 1), channels=None):
+    """x [N, T, H, W, ld] bf16 -> planes [N, T, C, Pld] (zero border pad, spatial subsampling stride)."""
+    torch = L.require_cuda()
+    N, T, H, W, ld = x.shape
+    Cc = channels or ld
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    Ho, Wo = (H + stride[0] - 1) // stride[0], (W + stride[1] - 1) // stride[1]
+    out = torch.empty((N, T, Cc, planes_ld(Ho, Wo, pad[0], pad[1])), dtype=torch.bfloat16, device='cuda')
+    L.call('dt_to_planes', L.ptr(x), N * T, H, W, Cc, ld, stride[0], stride[1], pad[0], pad[1], L.ptr(out), L.stream_ptr())
+    return out
+
+
+def wgrad(gz_planes, x_planes, out_hw, ksize, dW=None):
+    """gz_planes [N,T,Cout,Pld], x_planes [N,T,Cin,Pld] (same geometry, pad = k // 2) -> dW [taps, Cout, Cin] fp32
+    (accumulated into `dW` if given, else a zeroed buffer)."""
+    torch = L.require_cuda()
+    N, T, Cout, Pld = gz_planes.shape
+    Cin = x_planes.shape[2]
+    kT, kH, kW = ksize
+    assert x_planes.shape[0] == N and x_planes.shape[1] == T and x_planes.shape[3] == Pld
+    assert Pld == planes_ld(out_hw[0], out_hw[1], kH // 2, kW // 2)
+    if dW is None:
+        dW = L.zeros((kT * kH * kW, Cout, Cin), torch.float32)
+    assert dW.dtype == torch.float32 and tuple(dW.shape) == (kT * kH * kW, Cout, Cin) and dW.is_contiguous()
+    L.call('dt_wgrad', L.ptr(gz_planes), L.ptr(x_planes), N, T, out_hw[0], out_hw[1], Cout, Cin, kT, kH, kW, L.ptr(dW), L.stream_ptr())
+    return dW
+
+
+def bwd_pointwise(g1, g2=None, y=None, scale=None):
+    """(g1 + g2) * [y > 0] * scale[c] over NDHWC bf16 tensors of one shape."""
+    torch = L.require_cuda()
+    Cc = g1.shape[-1]
+    out = torch.empty_like(g1)
+    for t in (g1, g2, y):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == g1.shape)
+    L.call('dt_bwd_pointwise', L.ptr(g1), L.ptr(g2), L.ptr(y), L.ptr(scale), g1.numel() // Cc, Cc, L.ptr(out), L.stream_ptr())
+    return out
+
+
+def upsample_add_bwd(fine, coarse_in=None):
+    """fine [N,T,2Hc,2Wc,C] -> [N,T,Hc,Wc,C] = coarse_in + 2x2 sums (backward of the FPN nearest-2x top-down add)."""
+    torch = L.require_cuda()
+    N, T, H2, W2, Cc = fine.shape
+    out = torch.empty((N, T, H2 // 2, W2 // 2, Cc), dtype=torch.bfloat16, device='cuda')
+    L.call('dt_upsample_add_bwd', L.ptr(fine), L.ptr(coarse_in), N * T, H2 // 2, W2 // 2, Cc, L.ptr(out), L.stream_ptr())
+    return out
+
+
+def scatter_stride2(src, hw):
+    """src [N,T,ceil(H/2),ceil(W/2),C] -> [N,T,H,W,C] with src on the even positions (dgrad of a stride-2 1x1 conv)."""
+    torch = L.require_cuda()
+    N, T, Hs, Ws, Cc = src.shape
+    out = torch.empty((N, T, hw[0], hw[1], Cc), dtype=torch.bfloat16, device='cuda')
+    L.call('dt_scatter_stride2', L.ptr(src), N * T, Hs, Ws, hw[0], hw[1], Cc, L.ptr(out), L.stream_ptr())
+    return out
+
+
+def sgd_update(w, g, m, lr, momentum=0.9, wd=1e-4, grad_scale=1.0, w_fwd=None, w_dgrad=None):
+    """MomentumSGDUpdate on packed fp32 master weights [taps, Cout, Cin]; refreshes the bf16 forward / dgrad filters."""
+    taps, Cout, Cin = w.shape
+    L.call('dt_sgd_update', L.ptr(w), L.ptr(g), L.ptr(m), taps, Cout, Cin, float(lr), float(momentum), float(wd), float(grad_scale),
+           L.ptr(w_fwd), L.ptr(w_dgrad), L.stream_ptr())
+
+
+def pack_dgrad_weight(w):
+    """Filter (Cout, Cin, kT, kH, kW) -> the dgrad filter in dt_conv3d's packed order [taps (flipped), Cin, Cout] bf16:
+    dX = conv(dY, flip(W)^T) for a stride-1 'same' conv."""
+    torch = L.require_cuda()
+    if w.dim() == 2:
+        w = w[:, :, None, None, None]
+    elif w.dim() == 4:
+        w = w[:, :, None]
+    wt = w.to('cuda').float().flip(2, 3, 4).permute(1, 0, 2, 3, 4).contiguous()      # (Cin, Cout, kT, kH, kW), flipped
+    return cv.pack_weight(wt, cv.BF16)

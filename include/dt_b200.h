@@ -302,6 +302,45 @@ int dt_time_mean(const void* x, int B, int T, long long P, int C, int ldx, int f
                  void* y, int ldy, void* stream);
 int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, float* cls, float* bbox, void* stream);
 
+/* ---- train_ops.cu (training step, BASELINE.json configs[4]) --------------------------------------------------
+ * The reference builds its backward graph with model.AddGradientOperators and updates with MomentumSGDUpdate after an
+ * NCCL / muji all-reduce of the per-GPU gradients (lib/modeling/model_builder.py:908-985).  Here:
+ *   dgrad   of a stride-1 'same' conv = dt_conv3d of the gradient with the flipped, transposed filter (w_dgrad below);
+ *           stride-2 pointwise convs: dt_conv3d on the coarse map + dt_scatter_stride2
+ *   wgrad   dt_wgrad on channel-major planes (dt_to_planes) of the gradient and of the saved input
+ *   the elementwise joins (Relu / Sum / AffineChannelNd gradient, lib/ops/affine_channel_nd_op.cu:73-92) dt_bwd_pointwise,
+ *   the FPN top-down join dt_upsample_add_bwd, the update dt_sgd_update.  All tensors bf16 unless noted. */
+
+/* row length (in positions, multiple of 8) of one channel-major plane of an Ho x Wo map with a zero border pH / pW */
+int dt_planes_ld(int Ho, int Wo, int pH, int pW);
+
+/* x [F = N*T frames, H, W, ldx] (first C channels) -> planes [F, C, dt_planes_ld(Ho, Wo, pH, pW)], Ho = ceil(H / sh),
+ * Wo = ceil(W / sw): plane position (ho + pH) * (Wo + 2 pW) + wo + pW holds x[f, ho*sh, wo*sw, c]; border and tail zero. */
+int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, void* out, void* stream);
+
+/* Filter gradient of a stride-1 'same' conv (odd kT/kH/kW, pads k/2): dW [kT*kH*kW][Cout][Cin] fp32 +=
+ * sum_{n,t,h,w} gz[n,t,h,w,co] * x[n, t+kt-pT, h+kh-pH, w+kw-pW, ci].  gz_planes [N*T, Cout, Pld], x_planes
+ * [N*T, Cin, Pld] from dt_to_planes with pH = kH/2, pW = kW/2 (strided 1x1 convs: x subsampled by dt_to_planes).
+ * dW is ACCUMULATED into (split-K partial sums, red.global): the caller zeroes it (dt_memset). */
+int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int T, int Ho, int Wo, int Cout, int Cin, int kT, int kH, int kW,
+             float* dW, void* stream);
+
+/* out = (g1 + g2?) * [y > 0]? * scale[c]? over [rows, C] (any of g2 / y / scale may be NULL) */
+int dt_bwd_pointwise(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
+                     void* stream);
+
+/* out[f,h,w,c] = coarse_in?[f,h,w,c] + sum of the 2x2 children fine[f, 2h+dy, 2w+dx, c]; fine is [F, 2Hc, 2Wc, C] */
+int dt_upsample_add_bwd(const void* fine, const void* coarse_in, int F, int Hc, int Wc, int C, void* out, void* stream);
+
+/* out [F, H, W, C] = zeros except out[f, 2h, 2w] = src[f, h, w]; src [F, ceil(H/2), ceil(W/2), C] */
+int dt_scatter_stride2(const void* src, int F, int Hs, int Ws, int H, int W, int C, void* out, void* stream);
+
+/* Caffe2 MomentumSGDUpdate + weight decay (model_builder.py:954-985): g' = lr * (grad_scale * g + wd * w) + momentum * m;
+ * m = g'; w -= g'.  w / g / m fp32 [taps][Cout][Cin] (the packed order of dt_conv3d's filter).  w_fwd_bf16 (may be NULL)
+ * receives the new filter as bf16 in the same order, w_dgrad_bf16 (may be NULL) the dgrad filter [taps (flipped)][Cin][Cout]. */
+int dt_sgd_update(float* w, const float* g, float* m, int taps, int Cout, int Cin, float lr, float momentum, float wd,
+                  float grad_scale, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,7 @@ def _cfg(link='slice-center'):
     cfg.VIDEO.BODY_HEAD_LINK = link; cfg.VIDEO.NUM_FRAMES_MID = 1
     cfg.TEST.SCALES = (96,); cfg.TEST.MAX_SIZE = 160
     cfg.TEST.NMS = 0.5; cfg.TEST.RPN_PRE_NMS_TOP_N = 1000; cfg.TEST.RPN_POST_NMS_TOP_N = 200
+    cfg.TEST.COMPETITION_MODE = False
     assert_and_infer_cfg()
     return cfg
 

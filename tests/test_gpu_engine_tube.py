@@ -30,6 +30,7 @@ def _cfg():
     cfg.VIDEO.BODY_HEAD_LINK = ''
     cfg.TEST.SCALES = (128,); cfg.TEST.MAX_SIZE = 192
     cfg.TEST.NMS = 0.5; cfg.TEST.RPN_PRE_NMS_TOP_N = 1000; cfg.TEST.RPN_POST_NMS_TOP_N = 200
+    cfg.TEST.COMPETITION_MODE = False
     assert_and_infer_cfg()
     return cfg
 

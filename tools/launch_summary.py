@@ -22,8 +22,8 @@ def main():
     if len(sys.argv) > 2:
         rows = rows[-int(sys.argv[2]):]
     else:
-        last = max(i for i, (k, _) in enumerate(rows) if 'prep_clip' in k)
-        rows = rows[last:]
+        marks = [i for i, (k, _) in enumerate(rows) if 'prep_clip' in k]
+        rows = rows[marks[-1]:] if marks else rows
     agg = OrderedDict()
     for k, us in rows:
         k = k.split('(')[0][:70]
