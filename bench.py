@@ -505,6 +505,66 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """`--train`: training step of the RPN model trunk (modeling/trainer.py: res3..res5 + FPN3D + RPN heads and losses, bf16,
+    TRAIN.IMS_PER_BATCH = 2 clips per GPU) with the bucketed NCCL gradient all-reduce overlapped with the backward pass and
+    the fused SGD update.  It is the trainable conv trunk of BASELINE.json configs[4], NOT the whole keypoint R-CNN step (the
+    RoI heads' backward and the lib/roi_data target generators are not implemented): reported under its own metric name."""
+    import torch
+    import torch.distributed as dist
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.trainer import RpnTrainer
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    cfg = bench_cfg(args.height, args.width, 'r50fpn3d')
+    blobs, spec = P.random_blobs(cfg)
+    B, T, H, W = cfg.TRAIN.IMS_PER_BATCH, 3, args.height, args.width
+    tr = RpnTrainer(cfg, blobs, spec, world=world, buckets=args.buckets)
+    frames = torch.from_numpy(synth_frames(B, T, H, W, 100 + rank)).cuda()
+    targets = tr.synthetic_targets(B, H, W, seed=rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        loss = tr.step(frames, targets)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.step(frames, targets)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    if rank == 0:
+        nparam = int(tr.flat_g.numel())
+        line = dict(metric='training clips/sec, RPN-model trunk (res3..res5 + FPN3D + RPN heads/losses), T=3, %dx%d' % (H, W),
+                    value=world * B * args.steps / (ms / 1000.0), unit='clips/s', n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='bf16', data='synthetic',
+                    config=dict(workload='BASELINE.json configs[4] trunk: R50-FPN-3D, %d clips/GPU, bf16 forward/backward, fp32 master weights; '
+                                         'RoI heads / target generators NOT included (partial training step)' % B,
+                                trainable_params=nparam, allreduce_bytes_per_step=4 * nparam if world > 1 else 0,
+                                allreduce='NCCL SUM, %d buckets issued as their wgrads are enqueued (overlaps the backward pass)' % len(tr.bucket_ends),
+                                loss=[float(x) for x in loss.cpu().tolist()], eager_launches=True),
+                    clocks=sampler.stop())
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def conv_traffic(clips_per_step, mode):
     """DRAM bytes moved by the conv_tc launches of ONE step (the unit `roofline.achieved` is computed over), from the
     committed ncu capture of this same bench command (profiles/conv_dram_<round>_<mode>.json, tools/ncu_conv_traffic.py);
@@ -627,8 +687,12 @@ if __name__ == '__main__':
     ap.add_argument('--no-extras', action='store_true', help='skip the extra modes, the cuDNN stand-in and the tracking leg')
     ap.add_argument('--layers', action='store_true', help='dump per-conv timings to gpurun_out/conv_layers.json')
     ap.add_argument('--graph', type=int, default=1, help='(kept for old command lines; the step is always a captured graph)')
+    ap.add_argument('--train', action='store_true', help='training step of the RPN-model trunk with NCCL gradient all-reduce (see run_train)')
+    ap.add_argument('--buckets', type=int, default=4, help='--train: gradient all-reduce buckets')
     a = ap.parse_args()
-    if a.impl == 'reference':
+    if a.train:
+        run_train(a)
+    elif a.impl == 'reference':
         if a.steps == 10 and a.warmup == 3:
             a.steps, a.warmup = 2, 1
         run_reference(a)

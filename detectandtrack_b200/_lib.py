@@ -48,6 +48,8 @@ SIGNATURES = {
     'dt_upsample_add_bwd': [_p, _p, _i, _i, _i, _i, _p, _p],
     'dt_scatter_stride2': [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_sgd_update': [_p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p],
+    'dt_bias_grad': [_p, C.c_longlong, _i, _i, _p, _p],
+    'dt_rpn_loss_grad': [_p, _i, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _p, _i, _p, _p],
 }
 # host-only helpers (not error-code functions)
 HOST_FUNCS = {'dt_planes_ld': ([_i, _i, _i, _i], C.c_int)}

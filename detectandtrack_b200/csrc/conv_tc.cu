@@ -710,9 +710,11 @@ static int launch_conv1(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   q.ktab = (kiters + 2) & ~1;
   const int smem = Cfg::smem_bytes(kiters, q.nstages, q.ks, q.ncbuf, q.nrbuf, p.split_out != 0);
   DT_CHECK_ARG(q.nstages >= 2 && smem <= Cfg::BUDGET, "conv: smem split failed (%d stages, %d B)", q.nstages, smem);
-  // launched with programmatic stream serialization (the kernel waits on griddepcontrol before its first global
-  // access); DT_PDL=0 in the environment falls back to plain stream order for A/B measurements
-  static const bool pdl = [] { const char* e = getenv("DT_PDL"); return !(e && e[0] == '0'); }();
+  // DT_PDL=1 in the environment launches with programmatic stream serialization (the kernel waits on griddepcontrol
+  // before its first global access).  Measured on B200 (profiles/r02_pdl_ab.md): no gain inside the captured step
+  // (126.0 vs 126.3 clips/s bf16x3, 329.6 vs 330.4 bf16) — the replayed graph has no launch gaps left to hide — so plain
+  // stream order stays the default.
+  static const bool pdl = [] { const char* e = getenv("DT_PDL"); return e && e[0] == '1'; }();
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(CONV_THREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = stream;

@@ -338,6 +338,55 @@ __global__ void sgd_update_kernel(float* __restrict__ w, const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bias gradient, RPN losses
+// db[c] += sum over rows of g[row, c]   (Conv bias gradient; biases of the FPN / RPN convs are trainable)
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C, int ld, float* __restrict__ db) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per * blockIdx.x, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += __bfloat162float(g[(size_t)r * ld + c]);
+  if (r1 > r0) atomicAdd(db + c, acc);
+}
+
+// FPN RPN losses and their gradients at one level (lib/modeling/FPN.py:282-321 with the Detectron ops
+// SigmoidCrossEntropyLoss(normalize=0, scale=s_cls) and SmoothL1Loss(beta, scale=s_box), the latter divided by the batch size):
+//   out rows [rows, ld_o] fp32 = [A logits | 4A deltas (a*4 + k)];  labels [rows, A] int32 (-1 = ignore);
+//   targets / inside / outside weights [rows, 4A] fp32.  grad rows [rows, ld_g] bf16 in the same channel order (padding 0).
+//   loss[0] += cls loss, loss[1] += bbox loss.
+__global__ void rpn_loss_grad_kernel(const float* __restrict__ out, int ld_o, const int* __restrict__ labels,
+                                     const float* __restrict__ targets, const float* __restrict__ iw, const float* __restrict__ ow,
+                                     long long rows, int A, float s_cls, float s_box, float beta, __nv_bfloat16* __restrict__ grad,
+                                     int ld_g, float* __restrict__ loss) {
+  float lc = 0.f, lb = 0.f;
+  const long long total = rows * ld_g;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % ld_g);
+    const long long r = idx / ld_g;
+    float gv = 0.f;
+    if (ch < A) {
+      const int t = labels[r * A + ch];
+      if (t >= 0) {
+        const float x = out[r * ld_o + ch];
+        // -x*(t - [x>=0]) + log(1 + exp(x - 2x[x>=0]))   (the op's stable form)
+        lc += s_cls * (-x * ((float)t - (x >= 0.f ? 1.f : 0.f)) + log1pf(expf(x - 2.f * x * (x >= 0.f ? 1.f : 0.f))));
+        gv = s_cls * (1.f / (1.f + expf(-x)) - (float)t);
+      }
+    } else if (ch < 5 * A) {
+      const int j = ch - A;
+      const float w_in = iw[r * 4 * A + j], w_out = ow[r * 4 * A + j];
+      const float d = w_in * (out[r * ld_o + ch] - targets[r * 4 * A + j]);
+      const float ad = fabsf(d);
+      lb += s_box * w_out * (ad < beta ? 0.5f * d * d / beta : ad - 0.5f * beta);
+      gv = s_box * w_out * w_in * (ad < beta ? d / beta : (d > 0.f ? 1.f : -1.f));
+    }
+    grad[idx] = __float2bfloat16_rn(gv);
+  }
+  for (int o = 16; o > 0; o >>= 1) { lc += __shfl_xor_sync(0xffffffffu, lc, o); lb += __shfl_xor_sync(0xffffffffu, lb, o); }
+  if ((threadIdx.x & 31) == 0 && loss) { if (lc != 0.f) atomicAdd(loss, lc); if (lb != 0.f) atomicAdd(loss + 1, lb); }
+}
+
 }  // namespace dt
 
 using namespace dt;
@@ -446,6 +495,29 @@ extern "C" int dt_sgd_update(float* w, const float* g, float* m, int taps, int C
   const long long n = (long long)taps * Cout * Cin;
   sgd_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, n, taps, Cout, Cin, lr, momentum, wd, grad_scale,
                                                                         (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_bias_grad(const void* g, long long rows, int C, int ld, float* db, void* stream) {
+  DT_CHECK_ARG(rows >= 0 && C >= 1 && ld >= C, "dt_bias_grad: bad shape rows=%lld C=%d ld=%d", rows, C, ld);
+  if (rows == 0) return 0;
+  DT_CHECK_ARG(g && db, "dt_bias_grad: null pointer");
+  long long gx = rows / 256; if (gx < 1) gx = 1; if (gx > 592) gx = 592;
+  dim3 grid((unsigned)gx, (C + 127) / 128);
+  bias_grad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, rows, C, ld, db);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_rpn_loss_grad(const float* out, int ld_o, const int* labels, const float* targets, const float* inside_w,
+                                const float* outside_w, long long rows, int A, float scale_cls, float scale_box, float beta,
+                                void* grad, int ld_g, float* loss, void* stream) {
+  DT_CHECK_ARG(rows >= 0 && A >= 1 && ld_o >= 5 * A && ld_g >= 5 * A && beta > 0.f, "dt_rpn_loss_grad: bad shape rows=%lld A=%d ld_o=%d ld_g=%d", rows, A, ld_o, ld_g);
+  if (rows == 0) return 0;
+  DT_CHECK_ARG(out && labels && targets && inside_w && outside_w && grad, "dt_rpn_loss_grad: null pointer");
+  rpn_loss_grad_kernel<<<grid_for(rows * ld_g, 256), 256, 0, (cudaStream_t)stream>>>(out, ld_o, labels, targets, inside_w, outside_w, rows, A,
+                                                                                  scale_cls, scale_box, beta, (__nv_bfloat16*)grad, ld_g, loss);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -341,6 +341,18 @@ int dt_scatter_stride2(const void* src, int F, int Hs, int Ws, int H, int W, int
 int dt_sgd_update(float* w, const float* g, float* m, int taps, int Cout, int Cin, float lr, float momentum, float wd,
                   float grad_scale, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);
 
+/* db [C] fp32 += column sums of g [rows, ld] bf16 (first C columns): the conv-bias gradient (caller zeroes db) */
+int dt_bias_grad(const void* g, long long rows, int C, int ld, float* db, void* stream);
+
+/* FPN RPN losses of one level and their gradient (lib/modeling/FPN.py:282-321; Detectron SigmoidCrossEntropyLoss with
+ * normalize=0 and SmoothL1Loss with beta): out [rows, ld_o] fp32 = [A logits | 4A deltas (a*4+k)], labels [rows, A] int32
+ * (-1 ignored), targets / inside_w / outside_w [rows, 4A] fp32; scale_cls = 1 / NUM_GPUS / RPN_BATCH_SIZE_PER_IM /
+ * IMS_PER_BATCH, scale_box = 1 / NUM_GPUS / time_dim / batch.  grad [rows, ld_g] bf16 (same channel order, padding 0);
+ * loss (may be NULL) [2] fp32 += (cls, bbox). */
+int dt_rpn_loss_grad(const float* out, int ld_o, const int* labels, const float* targets, const float* inside_w,
+                     const float* outside_w, long long rows, int A, float scale_cls, float scale_box, float beta, void* grad,
+                     int ld_g, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

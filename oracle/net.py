@@ -34,6 +34,8 @@ def set_device(device):
 
 def _t(blobs, name):
     import torch
+    if torch.is_tensor(blobs[name]):          # a dict of (possibly requires_grad) tensors: the autograd oracle of the training tests
+        return blobs[name]
     if _DEVICE['device'] == 'cpu':
         return torch.from_numpy(np.ascontiguousarray(blobs[name]))
     key = (id(blobs), name)

@@ -27,7 +27,7 @@ def test_library_loads_and_exports_all_header_symbols():
 
 def test_ctypes_table_matches_header():
     names = set(_header_functions())
-    table = set(_lib.SIGNATURES) | {'dt_last_error'}
+    table = set(_lib.SIGNATURES) | set(_lib.HOST_FUNCS) | {'dt_last_error'}
     assert names == table, (names - table, table - names)
 
 
