@@ -5,10 +5,13 @@
 //                         dW[tap][co][ci] = sum over positions of gz[pos, co] * x[pos @ tap, ci]
 //                       a GEMM whose K axis is the position axis.  Both operands are read from CHANNEL-MAJOR PLANES
 //                       ([N, T, C, plane], plane = the zero-bordered (H+2p) x (W+2p) map flattened), so a position run is
-//                       contiguous (a K-major operand for tcgen05, staged by TMA with the 128B swizzle) and a filter tap is
-//                       a constant offset along the flattened plane (the physical zero border supplies the padding, TMA's
-//                       out-of-bounds zero fill the plane ends and the temporal padding).  Split-K over positions across
-//                       CTAs, fp32 partial sums reduced into dW with vector red.global.
+//                       contiguous (a K-major operand for tcgen05, staged by TMA with the 128B swizzle) and a filter ROW
+//                       offset (kh) is a constant offset along the flattened plane (rows are padded to a multiple of 8
+//                       positions, so the offset keeps TMA's 16-byte alignment of the innermost coordinate; the physical
+//                       zero border supplies the padding, TMA's out-of-bounds zero fill the plane ends and the temporal
+//                       padding).  A +-1 COLUMN offset (kw) would break that alignment, so the input planes are stored kW
+//                       times, copy kw pre-shifted by kw - pW positions (dt_to_planes wshift).  Split-K over positions
+//                       across CTAs, fp32 partial sums reduced into dW with vector red.global.
 //   dt_to_planes        NDHWC activation / gradient -> those planes (tiled transpose through shared memory, optional
 //                       spatial subsampling for the strided 1x1 convs).
 //   dt_bwd_pointwise    the elementwise part of a block's backward: gz = (g1 + g2) * [y > 0] * scale[c]
@@ -32,7 +35,7 @@ using namespace tc;
 struct WgradParams {
   int Cout, Cin, taps;
   int kT, kH, kW, pT, pH, pW;
-  int Wp;                 // row length of the padded plane (W + 2*pW)
+  int Wp;                 // row length of the padded plane (W + 2*pW rounded up to 8)
   int T, N;               // frames, images
   int kchunks;            // 64-position chunks per plane
   int tiles_m, tiles_n, ksplit;
@@ -72,7 +75,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   const int mt = w % p.tiles_m;
   const int tap = w / p.tiles_m;
   const int kw = tap % p.kW, kh = (tap / p.kW) % p.kH, kt = tap / (p.kW * p.kH);
-  const int shift = (kh - p.pH) * p.Wp + (kw - p.pW);          // tap offset along the flattened padded plane
+  const int shift = (kh - p.pH) * p.Wp;          // filter-row offset along the flattened padded plane (multiple of 8: 16-byte
+                                                 // aligned TMA coordinate); the column offset selects the pre-shifted copy kw
   const int dt_ = kt - p.pT;
   // k-blocks = (image, frame, chunk) triples; frames whose tap-shifted source frame is outside the clip contribute zero
   // (temporal zero padding) and are skipped by producer and issuer alike
@@ -95,8 +99,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
           // A: gz planes, box (64 positions, 128 channels); B: x planes at the tap-shifted position / frame
           asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(bar), "r"(chunk * 64), "r"(mt * 128), "r"(t), "r"(n) : "memory");
-          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                       ::"r"(dst + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar), "r"(chunk * 64 + shift), "r"(nt * BN), "r"(ts), "r"(n) : "memory");
+          asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                       ::"r"(dst + A_BYTES), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar), "r"(chunk * 64 + shift), "r"(nt * BN), "r"(ts), "r"(n), "r"(kw) : "memory");
         }
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
@@ -192,9 +196,9 @@ static int launch_wgrad(const CUtensorMap& tmG, const CUtensorMap& tmX, const Wg
 // for h % sh == 0, w % sw == 0; border and row tail zero.  Tile: 64 plane positions x 64 channels through shared memory.
 __global__ void __launch_bounds__(256)
 to_planes_kernel(const __nv_bfloat16* __restrict__ x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW,
-                 int Ho, int Wo, int Pld, __nv_bfloat16* __restrict__ out) {
+                 int wshift, int Ho, int Wo, int Pld, __nv_bfloat16* __restrict__ out) {
   __shared__ __nv_bfloat16 tile[64][66];
-  const int Wp = Wo + 2 * pW;
+  const int Wp = (Wo + 2 * pW + 7) / 8 * 8;
   const int plane = (Ho + 2 * pH) * Wp;
   const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, f = blockIdx.z;
   // load: thread -> (position, 16-byte channel group)
@@ -204,7 +208,7 @@ to_planes_kernel(const __nv_bfloat16* __restrict__ x, int F, int H, int W, int C
     uint4 v = make_uint4(0, 0, 0, 0);
     if (pos < plane && c0 + cg < C) {
       const int hp = pos / Wp, wp = pos - hp * Wp;
-      const int ho = hp - pH, wo = wp - pW;
+      const int ho = hp - pH, wo = wp - pW + wshift;         // copy `wshift`: column c holds the pixel of column c + wshift
       if (ho >= 0 && ho < Ho && wo >= 0 && wo < Wo)
         v = *reinterpret_cast<const uint4*>(x + (((size_t)f * H + (size_t)ho * sh) * W + (size_t)wo * sw) * ldx + c0 + cg);
     }
@@ -397,18 +401,19 @@ static int grid_for(long long total, int block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-extern "C" int dt_planes_ld(int Ho, int Wo, int pH, int pW) { return ((Ho + 2 * pH) * (Wo + 2 * pW) + 7) / 8 * 8; }
+extern "C" int dt_planes_ld(int Ho, int Wo, int pH, int pW) { return (Ho + 2 * pH) * ((Wo + 2 * pW + 7) / 8 * 8); }
 
-extern "C" int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, void* out,
-                            void* stream) {
+extern "C" int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, int wshift,
+                            void* out, void* stream) {
   DT_CHECK_ARG(F >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && ldx >= C && ldx % 8 == 0 && sh >= 1 && sw >= 1 && pH >= 0 && pW >= 0,
                "dt_to_planes: bad shape F=%d H=%d W=%d C=%d ldx=%d", F, H, W, C, ldx);
+  DT_CHECK_ARG(wshift >= -pW && wshift <= pW, "dt_to_planes: wshift %d outside [-%d, %d]", wshift, pW, pW);
   if (F == 0) return 0;
   DT_CHECK_ARG(x && out, "dt_to_planes: null pointer");
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   const int Pld = dt_planes_ld(Ho, Wo, pH, pW);
   dim3 grid((Pld + 63) / 64, (C + 63) / 64, F);
-  to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, F, H, W, C, ldx, sh, sw, pH, pW, Ho, Wo, Pld,
+  to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, F, H, W, C, ldx, sh, sw, pH, pW, wshift, Ho, Wo, Pld,
                                                            (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
@@ -422,8 +427,8 @@ extern "C" int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int 
                "dt_wgrad: bad shape N=%d T=%d %dx%d Cout=%d Cin=%d k=%dx%dx%d (odd 'same' kernels, Cin %% 8 == 0)", N, T, Ho, Wo, Cout, Cin, kT, kH, kW);
   DT_CHECK_ARG(gz_planes && x_planes && dW, "dt_wgrad: null pointer");
   const int pT = kT / 2, pH = kH / 2, pW = kW / 2;
-  const int Wp = Wo + 2 * pW, plane = (Ho + 2 * pH) * Wp;
   const int Pld = dt_planes_ld(Ho, Wo, pH, pW);
+  const int Wp = (Wo + 2 * pW + 7) / 8 * 8, plane = Pld;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.Cout = Cout; p.Cin = Cin; p.taps = kT * kH * kW; p.kT = kT; p.kH = kH; p.kW = kW; p.pT = pT; p.pH = pH; p.pW = pW;
@@ -443,11 +448,11 @@ extern "C" int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int 
     uint32_t b[4] = {64, 128, 1, 1}, e[4] = {1, 1, 1, 1};
     if (encode_map(&tmG, false, 4, gz_planes, d, s, b, e)) return 1;
   }
-  {
-    uint64_t d[4] = {(uint64_t)plane, (uint64_t)Cin, (uint64_t)T, (uint64_t)N};
-    uint64_t s[3] = {(uint64_t)Pld * 2, (uint64_t)Pld * 2 * Cin, (uint64_t)Pld * 2 * Cin * T};
-    uint32_t b[4] = {64, (uint32_t)BN, 1, 1}, e[4] = {1, 1, 1, 1};
-    if (encode_map(&tmX, false, 4, x_planes, d, s, b, e)) return 1;
+  {   // x planes: kW pre-shifted copies [kW][N*T, Cin, Pld]
+    uint64_t d[5] = {(uint64_t)plane, (uint64_t)Cin, (uint64_t)T, (uint64_t)N, (uint64_t)kW};
+    uint64_t s[4] = {(uint64_t)Pld * 2, (uint64_t)Pld * 2 * Cin, (uint64_t)Pld * 2 * Cin * T, (uint64_t)Pld * 2 * Cin * T * N};
+    uint32_t b[5] = {64, (uint32_t)BN, 1, 1, 1}, e[5] = {1, 1, 1, 1, 1};
+    if (encode_map(&tmX, false, 5, x_planes, d, s, b, e)) return 1;
   }
   switch (BN) {
     case 256: return launch_wgrad<256>(tmG, tmX, p, stream);

@@ -108,7 +108,7 @@ class TrainConv(object):
         N, T, Ho, Wo, _ = gz.shape
         sp = (self.pad[1], self.pad[2])
         if x_planes is None:
-            x_planes = to.to_planes(x, pad=sp, stride=self.stride[1:], channels=self.cin)
+            x_planes = to.to_planes(x, pad=sp, stride=self.stride[1:], channels=self.cin, copies=True)
         assert self.cout % 8 == 0 and gz.shape[-1] == self.cout
         to.wgrad(to.to_planes(gz, pad=sp), x_planes, (Ho, Wo), self.k, self.g)
         if self.bias is not None:

@@ -27,16 +27,12 @@ def bbox_overlaps(boxes, query, T=None):
     return out
 
 
-_ws_cache = {}
-
-
 def _workspace(nbytes, torch, slot='nms'):
-    key = (torch.cuda.current_device(), slot)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device='cuda')
-        _ws_cache[key] = ws
-    return ws
+    """Scratch buffer of a call.  Allocated per call (the caching allocator makes that free): a process-wide cached
+    buffer that is re-allocated when a later call needs more would be freed under a previously CAPTURED CUDA graph
+    that still points at it (two ClipPipelines of different batch sizes) — under capture the allocation comes from
+    that graph's own pool and lives as long as the graph."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device='cuda')
 
 
 def nms_batched(dets, counts=None, thresh=0.5, cmp_mode=None, out_order=None, max_keep=0):

@@ -10,26 +10,31 @@ def planes_ld(Ho, Wo, pH, pW):
     return int(L.lib().dt_planes_ld(int(Ho), int(Wo), int(pH), int(pW)))
 
 
-def to_planes(x, pad=(0, 0), stride=(1, 1), channels=None):
-    """x [N, T, H, W, ld] bf16 -> planes [N, T, C, Pld] (zero border pad, spatial subsampling stride)."""
+def to_planes(x, pad=(0, 0), stride=(1, 1), channels=None, copies=False):
+    """x [N, T, H, W, ld] bf16 -> planes [N, T, C, Pld] (zero border pad, spatial subsampling stride).
+    copies=True: the wgrad INPUT operand [2*pad_w + 1, N, T, C, Pld], copy kw pre-shifted by kw - pad_w columns."""
     torch = L.require_cuda()
     N, T, H, W, ld = x.shape
     Cc = channels or ld
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
     Ho, Wo = (H + stride[0] - 1) // stride[0], (W + stride[1] - 1) // stride[1]
-    out = torch.empty((N, T, Cc, planes_ld(Ho, Wo, pad[0], pad[1])), dtype=torch.bfloat16, device='cuda')
-    L.call('dt_to_planes', L.ptr(x), N * T, H, W, Cc, ld, stride[0], stride[1], pad[0], pad[1], L.ptr(out), L.stream_ptr())
-    return out
+    Pld = planes_ld(Ho, Wo, pad[0], pad[1])
+    shifts = list(range(-pad[1], pad[1] + 1)) if copies else [0]
+    out = torch.empty((len(shifts), N, T, Cc, Pld), dtype=torch.bfloat16, device='cuda')
+    for i, d in enumerate(shifts):
+        L.call('dt_to_planes', L.ptr(x), N * T, H, W, Cc, ld, stride[0], stride[1], pad[0], pad[1], d, L.ptr(out[i]), L.stream_ptr())
+    return out if copies else out[0]
 
 
 def wgrad(gz_planes, x_planes, out_hw, ksize, dW=None):
-    """gz_planes [N,T,Cout,Pld], x_planes [N,T,Cin,Pld] (same geometry, pad = k // 2) -> dW [taps, Cout, Cin] fp32
+    """gz_planes [N,T,Cout,Pld], x_planes [kW,N,T,Cin,Pld] (to_planes(copies=True), pad = k // 2) -> dW [taps, Cout, Cin] fp32
     (accumulated into `dW` if given, else a zeroed buffer)."""
     torch = L.require_cuda()
     N, T, Cout, Pld = gz_planes.shape
-    Cin = x_planes.shape[2]
     kT, kH, kW = ksize
-    assert x_planes.shape[0] == N and x_planes.shape[1] == T and x_planes.shape[3] == Pld
+    assert x_planes.dim() == 5 and x_planes.shape[0] == kW, 'x_planes: to_planes(..., copies=True) -> [kW, N, T, Cin, Pld]'
+    Cin = x_planes.shape[3]
+    assert x_planes.shape[1] == N and x_planes.shape[2] == T and x_planes.shape[4] == Pld and x_planes.is_contiguous()
     assert Pld == planes_ld(out_hw[0], out_hw[1], kH // 2, kW // 2)
     if dW is None:
         dW = L.zeros((kT * kH * kW, Cout, Cin), torch.float32)

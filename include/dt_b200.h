@@ -311,16 +311,20 @@ int dt_fold_tube_heads(const float* in, int ld, int R, int T, int C, float* cls,
  *   the elementwise joins (Relu / Sum / AffineChannelNd gradient, lib/ops/affine_channel_nd_op.cu:73-92) dt_bwd_pointwise,
  *   the FPN top-down join dt_upsample_add_bwd, the update dt_sgd_update.  All tensors bf16 unless noted. */
 
-/* row length (in positions, multiple of 8) of one channel-major plane of an Ho x Wo map with a zero border pH / pW */
+/* positions of one channel-major plane of an Ho x Wo map with a zero border pH / pW: (Ho + 2 pH) rows of Wp = (Wo + 2 pW)
+ * rounded up to 8 positions (so a filter-row offset keeps TMA's 16-byte coordinate alignment) */
 int dt_planes_ld(int Ho, int Wo, int pH, int pW);
 
 /* x [F = N*T frames, H, W, ldx] (first C channels) -> planes [F, C, dt_planes_ld(Ho, Wo, pH, pW)], Ho = ceil(H / sh),
- * Wo = ceil(W / sw): plane position (ho + pH) * (Wo + 2 pW) + wo + pW holds x[f, ho*sh, wo*sw, c]; border and tail zero. */
-int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, void* out, void* stream);
+ * Wo = ceil(W / sw): plane position (ho + pH) * Wp + wo + pW - wshift holds x[f, ho*sh, wo*sw, c]; border and tail zero.
+ * wshift in [-pW, pW]: the copy in which column c holds the pixel of column c + wshift (dt_wgrad's operand for kw = pW + wshift). */
+int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, int wshift, void* out,
+                 void* stream);
 
 /* Filter gradient of a stride-1 'same' conv (odd kT/kH/kW, pads k/2): dW [kT*kH*kW][Cout][Cin] fp32 +=
- * sum_{n,t,h,w} gz[n,t,h,w,co] * x[n, t+kt-pT, h+kh-pH, w+kw-pW, ci].  gz_planes [N*T, Cout, Pld], x_planes
- * [N*T, Cin, Pld] from dt_to_planes with pH = kH/2, pW = kW/2 (strided 1x1 convs: x subsampled by dt_to_planes).
+ * sum_{n,t,h,w} gz[n,t,h,w,co] * x[n, t+kt-pT, h+kh-pH, w+kw-pW, ci].  gz_planes [N*T, Cout, Pld] (wshift 0), x_planes
+ * [kW][N*T, Cin, Pld]: copy kw from dt_to_planes with pH = kH/2, pW = kW/2, wshift = kw - pW (strided 1x1 convs: x
+ * subsampled by dt_to_planes).
  * dW is ACCUMULATED into (split-K partial sums, red.global): the caller zeroes it (dt_memset). */
 int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int T, int Ho, int Wo, int Cout, int Cin, int kT, int kH, int kW,
              float* dW, void* stream);

@@ -45,7 +45,7 @@ def _cases():
         ('dt_fold_tube_heads', (None, 4, 10, 99, 2, None, None, None), b'dt_fold_tube_heads'),
         ('dt_memset', (None, 0, 16, None), b'dt_memset'),
         ('dt_scale_rois', (None, 2, 10, 4, None, 1, 1.0, None, None), b'dt_scale_rois'),
-        ('dt_to_planes', (None, 1, 8, 8, 12, 12, 1, 1, 0, 0, None, None), b'dt_to_planes'),
+        ('dt_to_planes', (None, 1, 8, 8, 12, 12, 1, 1, 0, 0, 0, None, None), b'dt_to_planes'),
         ('dt_wgrad', (None, None, 1, 1, 8, 8, 64, 60, 1, 3, 3, None, None), b'Cin % 8'),
         ('dt_bwd_pointwise', (None, None, None, None, 10, 12, None, None), b'C % 8'),
         ('dt_upsample_add_bwd', (None, None, 1, 4, 4, 12, None, None), b'dt_upsample_add_bwd'),

@@ -39,7 +39,7 @@ def test_wgrad_vs_autograd(case):
     cpad = (Cout + 7) // 8 * 8
     gzd = torch.zeros((N, T, H, W, cpad), dtype=torch.bfloat16)
     gzd[..., :Cout] = gz
-    xp = to.to_planes(x.cuda(), pad=pad[1:])
+    xp = to.to_planes(x.cuda(), pad=pad[1:], copies=True)
     gp = to.to_planes(gzd.cuda(), pad=pad[1:], channels=cpad)[:, :, :Cout].contiguous() if cpad != Cout else to.to_planes(gzd.cuda(), pad=pad[1:])
     dW = to.wgrad(gp, xp, (H, W), k)
     torch.cuda.synchronize()
@@ -58,7 +58,7 @@ def test_wgrad_strided_pointwise():
     gz = torch.randn((2, 3, 13, 21, 128), generator=g).bfloat16()
     w = torch.zeros((128, 256, 1, 1, 1), requires_grad=True)
     F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, None, (1, 2, 2)).backward(gz.float().permute(0, 4, 1, 2, 3))
-    dW = to.wgrad(to.to_planes(gz.cuda()), to.to_planes(x.cuda(), stride=(2, 2)), (13, 21), (1, 1, 1))
+    dW = to.wgrad(to.to_planes(gz.cuda()), to.to_planes(x.cuda(), stride=(2, 2), copies=True), (13, 21), (1, 1, 1))
     ref = w.grad.reshape(1, 128, 256)
     assert (dW.cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 

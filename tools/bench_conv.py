@@ -1,6 +1,7 @@
 """Micro-benchmark of the tcgen05 conv kernel on the layer shapes that dominate the
 R50-FPN-3D clip.  CUDA-event timing, L2 flushed between iterations.
-    python tools/bench_conv.py [--dtype bf16|tf32] [--iters 5]
+    python tools/bench_conv.py [--dtype bf16|tf32|bf16x3|tf32x3] [--iters 5]
+(split modes: [hi | lo] pair inputs / outputs, 3 MMAs per k-block; TFLOP/s are ALGORITHMIC: 2*MACs of the fp32 conv)
 """
 import argparse
 import json
@@ -38,18 +39,21 @@ def main():
     ap.add_argument('--only', default='')
     ap.add_argument('--n', type=int, default=1, help='clips per launch (body layers)')
     a = ap.parse_args()
-    dtype = cv.BF16 if a.dtype == 'bf16' else cv.TF32
-    tdt = torch.bfloat16 if dtype == cv.BF16 else torch.float32
+    dtype = cv.MODE_NAMES[a.dtype]
+    split = dtype in cv.SPLIT_MODES
+    tdt = torch.bfloat16 if dtype in (cv.BF16, cv.BF16X3) else torch.float32
+    of32 = None if split else (dtype == cv.TF32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     rows = []
     for (name, T, H, W, Cin, Cout, k, s, p) in LAYERS:
         if a.only and a.only not in name:
             continue
         nb = a.n if H > 14 and H * W > 1000 else 1
-        x = torch.randn((nb, T, H, W, Cin), device='cuda').to(tdt)
+        x = torch.randn((nb, T, H, W, Cin), device='cuda')
+        x = cv.split_for(dtype, x) if split else x.to(tdt)
         w = cv.pack_weight(torch.randn((Cout, Cin) + k) * 0.02, dtype)
         sc = torch.ones(Cout, device='cuda'); bi = torch.zeros(Cout, device='cuda')
-        y = cv.conv3d(x, w, k, s, p, sc, bi, relu=True, out_f32=(dtype == cv.TF32), dtype=dtype)
+        y = cv.conv3d(x, w, k, s, p, sc, bi, relu=True, out_f32=of32, dtype=dtype)
         res = torch.randn_like(y) if name.endswith('+res') else None
         rm = 1 if res is not None else 0
         torch.cuda.synchronize()
@@ -58,11 +62,11 @@ def main():
             flush.zero_()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            cv.conv3d(x, w, k, s, p, sc, bi, res, rm, relu=True, out_f32=(dtype == cv.TF32), dtype=dtype, out=y)
+            cv.conv3d(x, w, k, s, p, sc, bi, res, rm, relu=True, out_f32=of32, dtype=dtype, out=y, split_out=split)
             e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
-        flops = 2.0 * y.numel() * Cin * k[0] * k[1] * k[2]
+        flops = 2.0 * (y.numel() // (2 if split else 1)) * Cin * k[0] * k[1] * k[2]
         rows.append(dict(layer=name, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), gflop=round(flops / 1e9, 1)))
         print(json.dumps(rows[-1]), flush=True)
     os.makedirs('gpurun_out', exist_ok=True)
