@@ -16,6 +16,7 @@ _sz = C.c_size_t
 SIGNATURES = {
     'dt_abi_version': [],
     'dt_memset': [_p, _i, _sz, _p],
+    'dt_pairs_to_f16': [_p, C.c_longlong, _i, _p, _p],
     'dt_scale_rois': [_p, _i, _i, _i, _p, _i, C.c_double, _p, _p],
     'dt_bbox_overlaps': [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p],
     'dt_nms_workspace_bytes': [_i, _i, C.POINTER(_sz)],

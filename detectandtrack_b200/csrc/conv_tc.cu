@@ -86,6 +86,7 @@ struct ConvKernelParams {
   int nrbuf;                   // > 0: bf16 residual chunks arrive by TMA in a ring of this many staged chunks
   int res_up;                  // with nrbuf > 0: the residual is the (Ho/2, Wo/2) map of the FPN top-down add;
                                // its (TH/2 x TW/2) box is loaded and every row is read by its four children
+  int ab_format;               // tcgen05 kind::f16 operand format: 1 bf16, 0 fp16 (kind::tf32: 2)
   int round_tf32;              // fp32 output is rounded (RNE) to tf32 so the next tcgen05 kind::tf32 MMA,
                                // which TRUNCATES its 32-bit operands, sees exactly representable values
 };
@@ -333,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-    constexpr uint32_t idesc = make_idesc(128, BN, TF32 ? 2 : 1);
+    const uint32_t idesc = make_idesc(128, BN, TF32 ? 2 : p.ab_format);
     const uint32_t smem_u = smem_u32(smem);
     const uint32_t full_u = smem_u32(full);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -694,7 +695,7 @@ static int encode_out_map(CUtensorMap* m, void* y, int out_f32, int Cout, int Wo
                     time_major ? frame : frame * To};
   uint32_t b[5] = {(uint32_t)(128 / oesz), (uint32_t)ts.tw, (uint32_t)ts.th, (uint32_t)ts.tt, (uint32_t)ts.tb};
   uint32_t e[5] = {1, 1, 1, 1, 1};
-  return encode_map(m, out_f32 != 0, 5, y, d, st, b, e);
+  return encode_map(m, out_f32 != 0 ? 1 : 0, 5, y, d, st, b, e);
 }
 
 template <int BN, bool TF32, bool SPLIT>
@@ -746,8 +747,11 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
                          const void* residual, void* y, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DT_CHECK_ARG(d != nullptr, "dt_conv3d: null descriptor");
-  DT_CHECK_ARG(d->dtype == DT_DTYPE_BF16 || d->dtype == DT_DTYPE_TF32, "dt_conv3d: dtype %d not in {BF16, TF32}", d->dtype);
+  DT_CHECK_ARG(d->dtype == DT_DTYPE_BF16 || d->dtype == DT_DTYPE_TF32 || d->dtype == DT_DTYPE_F16, "dt_conv3d: dtype %d not in {BF16, TF32, F16}", d->dtype);
   const bool tf32 = d->dtype == DT_DTYPE_TF32;
+  const bool f16 = d->dtype == DT_DTYPE_F16;          // fp16 x and w (11-bit operands, one MMA per product); outputs stay bf16 / fp32
+  DT_CHECK_ARG(!f16 || (!(d->x3 & 1) && d->res_mode == 0), "dt_conv3d: DT_DTYPE_F16 inputs are plain rows and take no residual");
+  const int in_dt = tf32 ? 1 : (f16 ? 2 : 0);
   const int esz = tf32 ? 4 : 2;
   const int BK = tf32 ? 32 : 64;
   DT_CHECK_ARG(d->N >= 1 && d->Ti >= 1 && d->Hi >= 1 && d->Wi >= 1 && d->Cin >= 1 && d->Cout >= 1,
@@ -800,6 +804,7 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
   p.split_in = (d->x3 & 1) ? 1 : 0;
   p.split_out = (d->x3 & 2) ? 1 : 0;
   p.nsub = p.split_in ? 3 : 1;
+  p.ab_format = f16 ? 0 : 1;
   DT_CHECK_ARG(!p.split_in || d->Cin % BK == 0, "dt_conv3d: x3 inputs need Cin %% %d == 0 (Cin=%d)", BK, d->Cin);
   DT_CHECK_ARG(!p.split_out || ((tf32 ? out_f32 : !out_f32) && d->Cout % (out_f32 ? 32 : 64) == 0),
                "dt_conv3d: x3 outputs are fp32 pairs (TF32) / bf16 pairs (BF16) with Cout %% %d == 0 (Cout=%d)", out_f32 ? 32 : 64, d->Cout);
@@ -850,14 +855,14 @@ extern "C" int dt_conv3d(const dt_conv_desc* d, const void* x, const void* w, co
     estr[1] = d->sW; estr[2] = d->sH;
     DT_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "dt_conv3d: strided tile too large for a TMA box");
   }
-  if (encode_map(&tmA, tf32, 5, x, dims, strides, box, estr)) return 1;
+  if (encode_map(&tmA, in_dt, 5, x, dims, strides, box, estr)) return 1;
   {
     const int taps = d->kT * d->kH * d->kW;
     uint64_t wd[3] = {p.split_in ? (uint64_t)w_ld : (uint64_t)d->Cin, (uint64_t)d->Cout, (uint64_t)taps};
     uint64_t ws[2] = {(uint64_t)w_ld * esz, (uint64_t)w_ld * esz * d->Cout};
     uint32_t wb[3] = {(uint32_t)BK, (uint32_t)BN, 1};
     uint32_t we[3] = {1, 1, 1};
-    if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
+    if (encode_map(&tmB, in_dt, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC, tmR;
   if (encode_out_map(&tmC, y, out_f32, p.split_out ? out_ld : d->Cout, Wo, Ho, To, d->N, out_ld, ts, d->out_time_major != 0)) return 1;
@@ -971,6 +976,7 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
   p.kT = 1; p.kH = 7; p.kW = 1; p.sT = 1; p.sH = 1; p.sW = 1; p.pT = 0; p.pH = 0; p.pW = 0;
   p.row_planes = 1;
   p.kchunks = 1;
+  p.ab_format = 1;
   p.nsub = x3 ? 2 : 1;
   p.split_out = x3 ? 1 : 0;
   p.out_lo_off = out_ld / 2;
@@ -992,14 +998,14 @@ extern "C" int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int C
     uint64_t strides[4] = {2 * pix, row, plane, frame};
     uint32_t box[5] = {(uint32_t)BKe, (uint32_t)TW, (uint32_t)TH, 1, 1};
     uint32_t estr[5] = {1, 1, 1, 1, 1};
-    if (encode_map(&tmA, tf32, 5, (const char*)x_padded + pix, dims, strides, box, estr)) return 1;
+    if (encode_map(&tmA, tf32 ? 1 : 0, 5, (const char*)x_padded + pix, dims, strides, box, estr)) return 1;
   }
   {
     uint64_t wd[3] = {(uint64_t)BKe, (uint64_t)Cout, (uint64_t)(x3 ? 14 : 7)};
     uint64_t ws[2] = {128, (uint64_t)128 * Cout};
     uint32_t wb[3] = {(uint32_t)BKe, 64, 1};
     uint32_t we[3] = {1, 1, 1};
-    if (encode_map(&tmB, tf32, 3, w, wd, ws, wb, we)) return 1;
+    if (encode_map(&tmB, tf32 ? 1 : 0, 3, w, wd, ws, wb, we)) return 1;
   }
   CUtensorMap tmC;
   if (encode_out_map(&tmC, y, out_f32, x3 ? out_ld : Cout, Wo, Ho, 1, F, out_ld, ts)) return 1;

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "../../include/dt_b200.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 namespace dt {
@@ -627,6 +628,22 @@ conv1_f32_kernel(const float* __restrict__ blob, int F, int Hp, int Wp, int Cp, 
   }
 }
 
+// bf16 pair rows [rows, 2C] -> fp16 rows [rows, C]: v = hi + lo (exact in fp32), fp16 round-to-nearest, saturating
+__global__ void pairs_to_f16_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int C, __half* __restrict__ out) {
+  const int cv = C / 8;
+  const long long total = rows * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * 8;
+    const long long r = idx / cv;
+    float v[8];
+    load_vals<__nv_bfloat16>(in + (size_t)r * 2 * C + c, C, v);
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(fminf(fmaxf(v[e], -65504.f), 65504.f));
+    *reinterpret_cast<uint4*>(out + (size_t)r * C + c) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
 }  // namespace dt
 
 using namespace dt;
@@ -789,6 +806,15 @@ extern "C" int dt_conv1_7x7s2_f32(const float* blob, int F, int Hp, int Wp, int 
     conv1_f32_kernel<__nv_bfloat16><<<(unsigned)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(blob, F, Hp, Wp, Cp, w, scale, bias, (__nv_bfloat16*)y);
   else
     conv1_f32_kernel<float><<<(unsigned)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(blob, F, Hp, Wp, Cp, w, scale, bias, (float*)y);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_pairs_to_f16(const void* pairs, long long rows, int C, void* out, void* stream) {
+  DT_CHECK_ARG(rows >= 0 && C >= 8 && C % 8 == 0, "dt_pairs_to_f16: bad shape rows=%lld C=%d (C %% 8 == 0)", rows, C);
+  if (rows == 0) return 0;
+  DT_CHECK_ARG(pairs && out, "dt_pairs_to_f16: null pointer");
+  pairs_to_f16_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)pairs, rows, C, (__half*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }

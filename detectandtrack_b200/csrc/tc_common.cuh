@@ -280,14 +280,14 @@ static inline PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static inline int encode_map(CUtensorMap* m, bool f32, int rank, const void* base, const uint64_t* dims,
+static inline int encode_map(CUtensorMap* m, int dtype /*0 bf16, 1 f32, 2 f16*/, int rank, const void* base, const uint64_t* dims,
                       const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, const uint32_t* estr) {
   PFN_encodeTiled enc = get_encode();
   DT_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   cuuint64_t d[5], s[4]; cuuint32_t b[5], e[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = estr[i]; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+  CUresult r = enc(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), rank,
                    const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DT_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu ..., box %u %u %u)",

@@ -446,13 +446,13 @@ extern "C" int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int 
     uint64_t d[4] = {(uint64_t)plane, (uint64_t)Cout, (uint64_t)T, (uint64_t)N};
     uint64_t s[3] = {(uint64_t)Pld * 2, (uint64_t)Pld * 2 * Cout, (uint64_t)Pld * 2 * Cout * T};
     uint32_t b[4] = {64, 128, 1, 1}, e[4] = {1, 1, 1, 1};
-    if (encode_map(&tmG, false, 4, gz_planes, d, s, b, e)) return 1;
+    if (encode_map(&tmG, 0, 4, gz_planes, d, s, b, e)) return 1;
   }
   {   // x planes: kW pre-shifted copies [kW][N*T, Cin, Pld]
     uint64_t d[5] = {(uint64_t)plane, (uint64_t)Cin, (uint64_t)T, (uint64_t)N, (uint64_t)kW};
     uint64_t s[4] = {(uint64_t)Pld * 2, (uint64_t)Pld * 2 * Cin, (uint64_t)Pld * 2 * Cin * T, (uint64_t)Pld * 2 * Cin * T * N};
     uint32_t b[5] = {64, (uint32_t)BN, 1, 1, 1}, e[5] = {1, 1, 1, 1, 1};
-    if (encode_map(&tmX, false, 5, x_planes, d, s, b, e)) return 1;
+    if (encode_map(&tmX, 0, 5, x_planes, d, s, b, e)) return 1;
   }
   switch (BN) {
     case 256: return launch_wgrad<256>(tmG, tmX, p, stream);

@@ -69,10 +69,13 @@ class DetectionEngine(object):
         # 'bf16x3': the parity mode (default of the drop-in surface): activations / weights as [hi | lo] bf16 pairs,
         # 3 bf16 MMAs per k-block -> 16 mantissa bits, <= 1e-3 end to end (tests) at the full kind::f16 MMA rate;
         # 'tf32x3': the same scheme on tf32 pairs (fp32 storage, ~21 bits, half MMA rate, twice the bytes);
-        # 'tf32': fp32 storage, one tf32 MMA (1e-3 per layer, ~1.5e-3 end to end); 'bf16': fast, ~1e-2 end to end
+        # 'tf32': fp32 storage, one tf32 MMA (1e-3 per layer, ~1.5e-3 end to end); 'bf16': fast, ~1e-2 end to end;
+        # 'bf16x3h': bf16x3 everywhere except the four post-hoc FPN convs (the largest single kernels), which run as ONE
+        # fp16 MMA per product on fp16 copies of the inner maps — 11-bit operands on one layer of any path
         self.dtype_name = dtype
         self.dtype = cv.MODE_NAMES[dtype]
         self.x3 = self.dtype in cv.SPLIT_MODES
+        self.fp16_posthoc = dtype == 'bf16x3h'
         self.act_dtype = torch.bfloat16 if dtype in ('bf16', 'bf16x3') else torch.float32
         self.cin_pad = 8 if dtype in ('bf16', 'bf16x3') else 4
         self.skip_dead_frames = False       # compute only the consumed (centre) frame of the post-hoc FPN convs
@@ -144,6 +147,8 @@ class DetectionEngine(object):
             self.fpn_inner.append(self._c(blobs, 'fpn_inner_%s_lateral' % names[i], bias=True))
         tk = s.tk_body
         self.fpn_out = [self._c(blobs, 'fpn_' + n, bias=True, pad=(tk // 2, 1, 1)) for n in names]
+        if self.fp16_posthoc:
+            self.fpn_out = [_Conv(torch, blobs['fpn_%s_w' % n], cv.F16, None, blobs['fpn_%s_b' % n], pad=(tk // 2, 1, 1)) for n in names]
         # RPN (shared across levels): 3x3 + fused [cls | bbox] 1x1
         k = str(s.rpn_levels[0])
         A = s.num_anchors
@@ -248,6 +253,14 @@ class DetectionEngine(object):
             inner.append(self.fpn_inner[i](coarse_first[i], residual=inner[i - 1], res_mode=2))
         outs = []
         for i, x in enumerate(inner):
+            tm = s.link == 'slice-center' and x.shape[1] > 1
+            if self.fp16_posthoc:
+                x16 = dense_ops.pairs_to_f16(x)
+                c = int(self.cfg.VIDEO.NUM_FRAMES_MID / 2)
+                of = (c, 1) if (self.skip_dead_frames and tm) else None
+                outs.append(cv.conv3d(x16, self.fpn_out[i].w, self.fpn_out[i].k, (1, 1, 1), self.fpn_out[i].pad, None, self.fpn_out[i].bias,
+                                      dtype=cv.F16, split_out=True, time_major=(tm and of is None), out_frames=of))
+                continue
             if self.skip_dead_frames and s.link == 'slice-center' and x.shape[1] > 1:
                 # only the frame the link slices is consumed: compute just that output frame
                 c = int(self.cfg.VIDEO.NUM_FRAMES_MID / 2)

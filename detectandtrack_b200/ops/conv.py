@@ -9,17 +9,19 @@ BF16, TF32 = 0, 1
 TF32X3 = 2      # host-level mode: DT_DTYPE_TF32 kernels on [hi | lo] tf32 pairs (3 MMAs per k-block, ~fp32 accuracy)
 BF16X3 = 3      # host-level mode: DT_DTYPE_BF16 kernels on [hi | lo] bf16 pairs (3 MMAs per k-block at the full
                 # kind::f16 rate, 16 mantissa bits: the headline parity mode)
+F16 = 4         # per-layer operand type, not an engine mode: fp16 x and w (DT_DTYPE_F16), one MMA per product at 11-bit
+                # operands; used by the 'bf16x3h' engine mode for the post-hoc FPN convs
 SPLIT_MODES = (TF32X3, BF16X3)
-MODE_NAMES = {'bf16': BF16, 'tf32': TF32, 'tf32x3': TF32X3, 'bf16x3': BF16X3}
+MODE_NAMES = {'bf16': BF16, 'tf32': TF32, 'tf32x3': TF32X3, 'bf16x3': BF16X3, 'bf16x3h': BF16X3}
 
 
 def _dt(dtype, torch):
-    return torch.bfloat16 if dtype in (BF16, BF16X3) else torch.float32
+    return torch.float16 if dtype == F16 else (torch.bfloat16 if dtype in (BF16, BF16X3) else torch.float32)
 
 
 def kernel_dtype(dtype):
     """Host-level mode -> DT_DTYPE_* of the kernels."""
-    return BF16 if dtype in (BF16, BF16X3) else TF32
+    return 2 if dtype == F16 else (BF16 if dtype in (BF16, BF16X3) else TF32)
 
 
 def pack_weight(w, dtype=BF16):
@@ -32,9 +34,9 @@ def pack_weight(w, dtype=BF16):
     elif w.dim() == 4:
         w = w[:, :, None, :, :]
     Cout, Cin, kT, kH, kW = w.shape
-    mult = 8 if dtype in (BF16, BF16X3) else 4
+    mult = 8 if dtype in (BF16, BF16X3, F16) else 4
     Cp = (Cin + mult - 1) // mult * mult
-    out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=torch.bfloat16 if dtype == BF16 else torch.float32, device='cuda')
+    out = torch.zeros((kT * kH * kW, Cout, Cp), dtype=torch.bfloat16 if dtype == BF16 else (torch.float16 if dtype == F16 else torch.float32), device='cuda')
     out[:, :, :Cin] = w.to('cuda').permute(2, 3, 4, 0, 1).reshape(kT * kH * kW, Cout, Cin).to(out.dtype)
     if dtype == TF32:
         out = round_tf32(out)
@@ -111,7 +113,7 @@ def conv3d(x, w_packed, ksize, stride=(1, 1, 1), pad=(0, 0, 0), scale=None, bias
             out_f32 = (dtype == TF32X3) or not split_out
         assert out_f32 == (dtype == TF32X3) or not split_out, 'split outputs are fp32 pairs (tf32x3) / bf16 pairs (bf16x3)'
     else:
-        split_out = False
+        split_out = bool(split_out) and dtype == F16       # an fp16-operand conv may write bf16 pairs for a bf16x3 consumer
     cin = cin if cin is not None else min(Cx, w_ld)
     sT, sH, sW = stride
     pT, pH, pW = pad

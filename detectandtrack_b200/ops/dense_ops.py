@@ -87,6 +87,16 @@ def scale_rois(boxes, ncols, im_scale, batch_idx=None, per_image=1):
     return rois
 
 
+def pairs_to_f16(x):
+    """bf16 pair rows [..., 2C] -> fp16 [..., C] = fp16(hi + lo): the operand of a DT_DTYPE_F16 conv."""
+    torch = L.require_cuda()
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[-1] % 16 == 0
+    Cc = x.shape[-1] // 2
+    out = torch.empty(tuple(x.shape[:-1]) + (Cc,), dtype=torch.float16, device='cuda')
+    L.call('dt_pairs_to_f16', L.ptr(x), x.numel() // x.shape[-1], Cc, L.ptr(out), L.stream_ptr())
+    return out
+
+
 def spatial_mean(x, round_tf32=False, x3=False):
     """x [N, H, W, C] -> [N, C]: mean over W, then over H (ReduceBackMean twice)."""
     torch = L.require_cuda()

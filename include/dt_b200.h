@@ -114,6 +114,8 @@ int dt_prune_detections(const float* boxes, int nframes, int dmax, int ld, int T
 
 #define DT_DTYPE_BF16 0   /* bf16 activations/weights, fp32 accumulate (tcgen05 kind::f16)   */
 #define DT_DTYPE_TF32 1   /* fp32 storage, tf32 multiply, fp32 accumulate (tcgen05 kind::tf32) */
+#define DT_DTYPE_F16 2    /* fp16 x and w (11-bit operands at the full kind::f16 rate), fp32 accumulate; plain rows, no residual;
+                             y is bf16 / bf16 pairs (x3 bit 1) / fp32 as for DT_DTYPE_BF16 */
 
 /* Geometry + fused epilogue of one convolution (host struct, plain ints).
  * Replaces a Caffe2 Conv/ConvNd (engine=CUDNN) followed by AffineChannel[Nd]
@@ -182,6 +184,10 @@ int dt_conv_plan(const dt_conv_desc* desc /*host*/, int residual_aligned, dt_con
 int dt_conv1_7x7s2(const void* x_padded, int F, int Hp, int Wp, int Cp, const void* w, int Cout,
                    const float* scale, const float* bias, int relu, int dtype, int out_f32,
                    int out_round_tf32, int x3, void* y, int out_ld, void* stream);
+
+/* bf16 pair rows [rows, 2C] = [hi | lo] -> fp16 rows [rows, C] = fp16(hi + lo) (round to nearest, saturating): the operand of a
+ * DT_DTYPE_F16 conv fed by a bf16x3 producer. */
+int dt_pairs_to_f16(const void* pairs, long long rows, int C, void* out, void* stream);
 
 /* ---- proposals.cu -------------------------------------------------------- */
 

@@ -44,6 +44,7 @@ def _cases():
         ('dt_time_mean', (None, 1, 3, 49, 10, 10, 1, 0, 0, None, 10, None), b'multiples of 4'),
         ('dt_fold_tube_heads', (None, 4, 10, 99, 2, None, None, None), b'dt_fold_tube_heads'),
         ('dt_memset', (None, 0, 16, None), b'dt_memset'),
+        ('dt_pairs_to_f16', (None, 10, 12, None, None), b'C % 8'),
         ('dt_scale_rois', (None, 2, 10, 4, None, 1, 1.0, None, None), b'dt_scale_rois'),
         ('dt_to_planes', (None, 1, 8, 8, 12, 12, 1, 1, 0, 0, 0, None, None), b'dt_to_planes'),
         ('dt_wgrad', (None, None, 1, 1, 8, 8, 64, 60, 1, 3, 3, None, None), b'Cin % 8'),

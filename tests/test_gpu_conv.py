@@ -60,7 +60,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('mode', ['bf16', 'tf32', 'tf32x3', 'bf16x3', 'bf16x3-f32out'])
+@pytest.mark.parametrize('mode', ['bf16', 'tf32', 'tf32x3', 'bf16x3', 'bf16x3-f32out', 'f16'])
 @pytest.mark.parametrize('case', range(len(CASES)))
 def test_conv_parity(case, mode):
     import torch
@@ -84,8 +84,15 @@ def test_conv_parity(case, mode):
         res = torch.randn((N, To, Ho // 2, Wo // 2, Cout), generator=g)
     f32out = mode.endswith('-f32out')
     mode = mode.split('-')[0]
-    dtype = cv.MODE_NAMES[mode]
-    if mode == 'bf16x3':
+    dtype = cv.F16 if mode == 'f16' else cv.MODE_NAMES[mode]
+    if mode == 'f16':
+        # fp16 operands (DT_DTYPE_F16: the post-hoc FPN convs of the bf16x3h mode): reference on the SAME fp16-rounded x, w
+        if rm:
+            pytest.skip('fp16-operand convs take no residual')
+        x = x.half().float(); w = w.half().float()
+        xd = x.half().cuda()
+        tol = 2e-4
+    elif mode == 'bf16x3':
         if Cin % 64 or (Cout % 64 and not f32out):
             pytest.skip('bf16-pair storage needs channel counts that are multiples of 64 (true for every layer that uses it)')
         xd = cv.split_bf16(x.cuda())

@@ -32,11 +32,19 @@ def _match(a, b, tol):
     return j, d[np.arange(a.shape[0]), j] <= tol
 
 
-def _compare(cfg, blobs, frames, mode, kp_tol=1e-3):
+_ORACLE = {}
+
+
+def _compare(cfg, blobs, frames, mode, kp_tol=1e-3, key=None):
     import torch
     from detectandtrack_b200.modeling import params as P
     from detectandtrack_b200.modeling.engine import DetectionEngine
-    ref = opipe.detect_clip(cfg, blobs, frames, want_heatmaps=True)
+    ref = _ORACLE.get(key) if key else None           # the CPU oracle of a workload is computed once per test session
+    if ref is None:
+        ref = opipe.detect_clip(cfg, blobs, frames, want_heatmaps=True)
+        ref.pop('feats', None)
+        if key:
+            _ORACLE[key] = ref
     eng = DetectionEngine(cfg, blobs, P.GraphSpec(cfg), dtype=mode)
     fr = torch.from_numpy(frames[None]).cuda()
     size = float(max(frames.shape[1:3]))
@@ -77,20 +85,21 @@ def _compare(cfg, blobs, frames, mode, kp_tol=1e-3):
     return r
 
 
-@pytest.mark.parametrize('mode', ['bf16x3', 'tf32x3'])
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16x3h', 'tf32x3'])
 def test_small_clip_outputs_match_oracle_pipeline(mode):
     from test_gpu_engine import _cfg
     from detectandtrack_b200.modeling import params as P
     cfg = _cfg()
     blobs, _ = P.random_blobs(cfg, seed=3)
     frames = np.random.RandomState(0).randint(0, 256, (3, 96, 128, 3)).astype(np.uint8)
-    r = _compare(cfg, blobs, frames, mode)
+    r = _compare(cfg, blobs, frames, mode, key='small')
     assert r['n_det'] > 0 and r['n_roi'] > 20
 
 
-def test_full_size_clip_outputs_match_oracle_pipeline():
-    """BASELINE.json configs[3] at its real size: ONE 800x1333 clip (R = 1000, D = 100), headline mode, vs the oracle's
-    values (the CPU side takes a minute on the GPU box)."""
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16x3h'])
+def test_full_size_clip_outputs_match_oracle_pipeline(mode):
+    """BASELINE.json configs[3] at its real size: ONE 800x1333 clip (R = 1000, D = 100), the parity modes, vs the oracle's
+    values (the CPU side takes a minute on the GPU box; computed once for both modes)."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
@@ -102,7 +111,7 @@ def test_full_size_clip_outputs_match_oracle_pipeline():
         torch.set_num_threads(min(os.cpu_count() or 8, 32))
         blobs, _ = P.random_blobs(cfg)
         frames = bench.synth_frames(1, 3, 800, 1333, 7)[0]
-        r = _compare(cfg, blobs, frames, 'bf16x3')
+        r = _compare(cfg, blobs, frames, mode, key='full')
         assert r['n_roi'] == 1000 and r['n_det'] == 100
     finally:
         reset_cfg()
