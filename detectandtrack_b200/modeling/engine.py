@@ -76,8 +76,8 @@ class DetectionEngine(object):
         self.dtype = cv.MODE_NAMES[dtype]
         self.x3 = self.dtype in cv.SPLIT_MODES
         self.fp16_posthoc = dtype == 'bf16x3h'
-        self.act_dtype = torch.bfloat16 if dtype in ('bf16', 'bf16x3') else torch.float32
-        self.cin_pad = 8 if dtype in ('bf16', 'bf16x3') else 4
+        self.act_dtype = torch.bfloat16 if dtype.startswith('bf16') else torch.float32
+        self.cin_pad = 8 if dtype.startswith('bf16') else 4
         self.skip_dead_frames = False       # compute only the consumed (centre) frame of the post-hoc FPN convs
         self._geom = {}
         self._build(blobs)
