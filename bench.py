@@ -441,7 +441,7 @@ def run_ours(args):
     head = measure_mode(head_mode, cfg, blobs, args, ctx, full=True)
     extras = []
     if args.dtype == 'auto' and world == 1 and not args.no_extras:
-        for m in ('bf16', 'tf32'):
+        for m in ('bf16x3h', 'bf16', 'tf32'):
             try:
                 extras.append(measure_mode(m, cfg, blobs, args, ctx, full=False))
             except Exception as e:                               # an extra must never cost the headline
@@ -458,7 +458,7 @@ def run_ours(args):
         achieved = conv_flops / (conv_ms / 1000.0) / 1e12
         mma_factor = 3.0 if head_mode in ('bf16x3', 'tf32x3', 'bf16x3h') else 1.0
         parity = {'bf16x3': '<= 1e-3 end to end vs the fp32 oracle BY TEST (tests/test_gpu_parity_e2e.py, test_gpu_engine.py: <= 5e-4)',
-                  'bf16x3h': '<= 1e-3 end to end vs the fp32 oracle BY TEST (tests/test_gpu_parity_e2e.py); bf16x3 with the four post-hoc FPN convs as one fp16 MMA per product',
+                  'bf16x3h': 'bf16x3 with the four post-hoc FPN convs as one fp16 MMA per product: heat maps ~1e-3 (no margin), 1 of 100 detections differs at 800x1333 (tests/test_gpu_parity_e2e.py) - NOT a parity mode, labelled extra only',
                   'tf32x3': '<= 1e-3 end to end by test (<= 5e-4)', 'tf32': '~1.5e-3 end to end (outside 1e-3)',
                   'bf16': '~1e-2 end to end (outside 1e-3): labelled extra only'}
         tr = conv_traffic(B, head_mode)

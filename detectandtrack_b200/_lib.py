@@ -24,6 +24,8 @@ SIGNATURES = {
     'dt_lsa_batched': [_p, _i, _i, _i, _p, _p, _i, _p, _p, _p],
     'dt_match_frames': [_p, _i, _i, _i, _i, _p, _p, _f, _i, _p, _p, _p],
     'dt_assign_track_ids': [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _p],
+    'dt_pose_pck_cost': [_p, _i, _p, _i, _i, _i, _i, _i, _f, _p, _p],
+    'dt_frame_costs': [_p, _i, _i, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _f, C.c_double, _p, _p],
     'dt_prune_detections': [_p, _i, _i, _i, _i, _i, _p, _p, _f, _f, _p, _p, _p, _p],
     'dt_conv_plan': [C.c_void_p, _i, C.c_void_p],
     'dt_conv3d': [_p, _p, _p, _p, _p, _p, _p, _p],

@@ -130,13 +130,42 @@ def _prune_bad_detections(dets, json_data, conf):
 
 
 # ------------------------------------------------------------------ matching
-def _check_default_cost(cost_types, cost_weights):
+POSETRACK_KEYPOINTS = ['nose', 'head_bottom', 'head_top', 'left_ear', 'right_ear', 'left_shoulder', 'right_shoulder', 'left_elbow',
+                       'right_elbow', 'left_wrist', 'right_wrist', 'left_hip', 'right_hip', 'left_knee', 'right_knee', 'left_ankle',
+                       'right_ankle']          # person_cat_info['keypoints'] of the PoseTrack json datasets
+
+
+def _cost_weights(cost_types, cost_weights):
+    """(w_iou, w_pck) of TRACKING.DISTANCE_METRICS / _WTS (tracking_engine.py:158-181); 'cnn-cosdist' needs a CNN feature
+    extractor (utils/pytorch_cnn_features, weight 0 in every shipped yaml) and is not on the device path."""
     assert len(cost_weights) == len(cost_types)
-    active = [(t, w) for t, w in zip(cost_types, cost_weights) if w != 0]
-    if len(active) != 1 or active[0][0] != 'bbox-overlap':
-        raise NotImplementedError(
-            'device tracking implements the bbox-overlap cost only (got %s)' % (active,))
-    return float(active[0][1])
+    w = {'bbox-overlap': 0.0, 'pose-pck': 0.0}
+    for t, wt in zip(cost_types, cost_weights):
+        if wt == 0:
+            continue
+        if t not in w:
+            raise NotImplementedError('device tracking implements the bbox-overlap and pose-pck costs (got %r)' % (t,))
+        w[t] += float(wt)
+    if w['bbox-overlap'] == 0.0 and w['pose-pck'] == 0.0:
+        raise NotImplementedError('no active tracking cost')
+    return w['bbox-overlap'], w['pose-pck']
+
+
+def _check_default_cost(cost_types, cost_weights):
+    w_iou, w_pck = _cost_weights(cost_types, cost_weights)
+    if w_pck != 0.0:
+        raise NotImplementedError('this call path takes boxes only; pose-pck needs the poses (see _tracks_for_videos)')
+    return w_iou
+
+
+def _pack_poses(pose_list, dmax, K):
+    """list (frames) of lists of [4|3, K] arrays -> [F, dmax, 4, K] fp32 (x row, y row used by the cost)."""
+    out = np.zeros((len(pose_list), dmax, 4, K), dtype=np.float32)
+    for f, poses in enumerate(pose_list):
+        for i, p in enumerate(poses or []):
+            p = np.asarray(p, dtype=np.float32)
+            out[f, i, :p.shape[0]] = p
+    return out
 
 
 def _compute_matches(prev_frame_data, cur_frame_data, prev_boxes, cur_boxes,
@@ -167,9 +196,10 @@ def _compute_matches(prev_frame_data, cur_frame_data, prev_boxes, cur_boxes,
     return m[1, :nboxes].cpu().numpy().astype(np.int32)
 
 
-def _tracks_for_videos(videos_boxes):
-    """videos_boxes: list (videos) of lists (frames) of (n,4T+1) arrays.
-    Returns list of list of python-int id lists, one batched device pass."""
+def _tracks_for_videos(videos_boxes, videos_poses=None, kpt_names=None):
+    """videos_boxes: list (videos) of lists (frames) of (n,4T+1) arrays; videos_poses (needed when the 'pose-pck' cost is
+    active): same nesting of lists of [4, K] keypoint arrays.  Returns list of list of python-int id lists, one batched
+    device pass."""
     import torch
     flat, first = [], []
     for vb in videos_boxes:
@@ -181,13 +211,24 @@ def _tracks_for_videos(videos_boxes):
     T = (packed.shape[2] - 1) // 4
     is_start = np.zeros(len(flat), dtype=np.uint8)
     is_start[np.array(first, dtype=np.int64)] = 1
-    weight = _check_default_cost(cfg.TRACKING.DISTANCE_METRICS, cfg.TRACKING.DISTANCE_METRIC_WTS)
+    w_iou, w_pck = _cost_weights(cfg.TRACKING.DISTANCE_METRICS, cfg.TRACKING.DISTANCE_METRIC_WTS)
     algo = cfg.TRACKING.BIPARTITE_MATCHING_ALGO
     if algo not in box_ops.ALGOS:
         raise NotImplementedError('Unknown matching algo: {}'.format(algo))
     d_counts = torch.from_numpy(counts).cuda()
     d_start = torch.from_numpy(is_start).cuda()
-    matches, _ = box_ops.match_frames(torch.from_numpy(packed).cuda(), d_counts, d_start, T=T, weight=weight, algo=algo)
+    if w_pck == 0.0:
+        matches, _ = box_ops.match_frames(torch.from_numpy(packed).cuda(), d_counts, d_start, T=T, weight=w_iou, algo=algo)
+    else:
+        # combined cost (tracking_engine.py:158-181): cost matrices of every frame pair in one launch, then the batched solver
+        assert videos_poses is not None, "the 'pose-pck' cost needs the poses of every detection"
+        names = list(kpt_names or POSETRACK_KEYPOINTS)
+        K = cfg.KRCNN.NUM_KEYPOINTS
+        poses = _pack_poses([p for vp in videos_poses for p in vp], packed.shape[1], K)
+        cost = box_ops.frame_costs(torch.from_numpy(packed).cuda(), d_counts, d_start, torch.from_numpy(poses).cuda(), T=T, w_iou=w_iou,
+                                   w_pck=w_pck, head_top=names.index('head_top'), head_bottom=names.index('head_bottom'))
+        nrows = torch.cat([d_counts[:1] * 0, d_counts[:-1]]) * (1 - d_start.to(torch.int32))
+        matches, status = box_ops.lsa_batched(cost, nrows, d_counts, algo)
     tracks = box_ops.assign_track_ids(matches, d_counts, torch.tensor(first, dtype=torch.int32), d_start)
     tracks = tracks.cpu().numpy()
     out = []
@@ -203,7 +244,8 @@ def _compute_tracks_video(video_json_data, dets):
             cfg.TRACKING.DEBUG.UPPER_BOUND_5_GT_KPS_ONLY):
         raise NotImplementedError('TRACKING.DEBUG.* upper-bound modes are not on the device path')
     boxes = [_get_boxes(dets, det_id) for (_, det_id) in video_json_data]
-    return _tracks_for_videos([boxes])[0]
+    poses = [_get_poses(dets, det_id) for (_, det_id) in video_json_data]
+    return _tracks_for_videos([boxes], [poses])[0]
 
 
 def compute_matches_tracks(json_data, dets, lstm_model=None):
@@ -225,7 +267,8 @@ def compute_matches_tracks(json_data, dets, lstm_model=None):
     assert num_imgs == sum(len(v) for v in all_video_roidb)
     logger.info('Computing tracks for %d videos.', len(all_video_roidb))
     vids = [[_get_boxes(dets, det_id) for (_, det_id) in v] for v in all_video_roidb]
-    tracks = _tracks_for_videos(vids)
+    vposes = [[_get_poses(dets, det_id) for (_, det_id) in v] for v in all_video_roidb]
+    tracks = _tracks_for_videos(vids, vposes)
     for v, entries in enumerate(all_video_roidb):
         for i, (_, det_id) in enumerate(entries):
             all_tracks[det_id] = tracks[v][i]

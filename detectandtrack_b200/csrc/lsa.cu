@@ -238,6 +238,60 @@ __global__ void lsa_kernel(int mode, int algo, const float* __restrict__ src, in
   }
 }
 
+// 'pose-pck' tracking cost (lib/core/tracking_engine.py:113-129 -> lib/utils/keypoints.py:266-291) in the reference's own
+// arithmetic: float32 head size |head_top - head_bottom| + 1 of the PREVIOUS-frame pose, float32 joint distances / head size,
+// count of joints closer than dist_thresh, cost = 1.0 - count / K in fp64.  Poses are the reference's [4, K] arrays (x row, y row).
+__device__ __forceinline__ double pck_cost(const float* __restrict__ a, const float* __restrict__ b, int K, int ht, int hb, float thr) {
+  const float hx = __fsub_rn(a[ht], a[hb]), hy = __fsub_rn(a[K + ht], a[K + hb]);
+  const float head = __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(hx, hx), __fmul_rn(hy, hy))), 1.f);
+  int cnt = 0;
+  for (int k = 0; k < K; ++k) {
+    const float dx = __fsub_rn(a[k], b[k]), dy = __fsub_rn(a[K + k], b[K + k]);
+    const float nd = __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), head);
+    cnt += nd < thr ? 1 : 0;
+  }
+  return 1.0 - (double)cnt / (double)K;
+}
+
+// out [P, Q] fp64 = pck cost of every (a_i, b_j) pair (the reference's _compute_pairwise_kpt_distance)
+__global__ void pose_pck_kernel(const float* __restrict__ a, int P, const float* __restrict__ b, int Q, int ld, int K, int ht, int hb,
+                                float thr, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * Q) return;
+  const int i = e / Q, j = e - i * Q;
+  out[e] = pck_cost(a + (size_t)i * ld, b + (size_t)j * ld, K, ht, hb, thr);
+}
+
+// Cost matrices of all frame pairs of a batch of videos (tracking_engine.py:158-181): cost[f][p][q] (p = detection of frame
+// f-1, q = detection of frame f) = fp32( w_iou * (1 - IoU) [float32, as the reference computes it] + w_pck * pck [fp64] ),
+// summed in fp64 like np.sum(np.stack(all_Cs)); first frames of videos and entries beyond the counts are 0.
+__global__ void frame_costs_kernel(const float* __restrict__ boxes, int ldb, int T, const float* __restrict__ poses, int ldp, int K,
+                                   int ht, int hb, float thr, const int* __restrict__ counts, const unsigned char* __restrict__ is_start,
+                                   int dmax, float w_iou, double w_pck, float* __restrict__ cost) {
+  const int f = blockIdx.x;
+  float* C = cost + (size_t)f * dmax * dmax;
+  const bool start = (f == 0) || (is_start && is_start[f]);
+  const int P = start ? 0 : min(counts[f - 1], dmax), Q = min(counts[f], dmax);
+  for (int e = threadIdx.x; e < dmax * dmax; e += blockDim.x) {
+    const int p = e / dmax, q = e - p * dmax;
+    float c = 0.f;
+    if (p < P && q < Q) {
+      double acc = 0.0;
+      if (w_iou != 0.f) {
+        const float* pb = boxes + ((size_t)(f - 1) * dmax + p) * ldb;
+        const float* qb = boxes + ((size_t)f * dmax + q) * ldb;
+        float s = iou_pair_ref_l(pb, qb);
+        for (int t = 1; t < T; ++t) s = __fadd_rn(s, iou_pair_ref_l(pb + 4 * t, qb + 4 * t));
+        acc = (double)__fmul_rn(__fsub_rn(1.f, __fdiv_rn(s, (float)T)), w_iou);
+      }
+      if (w_pck != 0.0)
+        acc = __dadd_rn(acc, __dmul_rn(pck_cost(poses + ((size_t)(f - 1) * dmax + p) * ldp, poses + ((size_t)f * dmax + q) * ldp, K, ht, hb, thr), w_pck));
+      c = __double2float_rn(acc);
+    }
+    C[e] = c;
+  }
+}
+
 // One thread per video: tracking_engine.py:272-350 (non-debug path).  Frames of a video are
 // contiguous; a frame with is_start != 0 (or frame 0) opens a new video and resets the counter.
 __global__ void track_ids_kernel(const int* __restrict__ matches, const int* __restrict__ counts,
@@ -379,6 +433,31 @@ extern "C" int dt_prune_detections(const float* boxes, int nframes, int dmax, in
   DT_CHECK_ARG(boxes && counts_in && hw && out && counts_out, "dt_prune_detections: null pointer");
   prune_kernel<<<nframes, 128, 0, (cudaStream_t)stream>>>(boxes, nframes, dmax, ld, T, center_only, counts_in, hw,
                                                           conf, min_area, out, counts_out, sel);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_pose_pck_cost(const float* a, int P, const float* b, int Q, int ld, int K, int head_top, int head_bottom,
+                                float dist_thresh, double* out, void* stream) {
+  DT_CHECK_ARG(P >= 0 && Q >= 0 && K >= 1 && ld >= 2 * K && head_top >= 0 && head_top < K && head_bottom >= 0 && head_bottom < K,
+               "dt_pose_pck_cost: bad shape P=%d Q=%d K=%d ld=%d", P, Q, K, ld);
+  if (P == 0 || Q == 0) return 0;
+  DT_CHECK_ARG(a && b && out, "dt_pose_pck_cost: null pointer");
+  pose_pck_kernel<<<cdiv(P * Q, 128), 128, 0, (cudaStream_t)stream>>>(a, P, b, Q, ld, K, head_top, head_bottom, dist_thresh, out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_frame_costs(const float* boxes, int ldb, int T, const float* poses, int ldp, int K, int head_top, int head_bottom,
+                              float dist_thresh, const int* counts, const unsigned char* is_start, int nframes, int dmax,
+                              float w_iou, double w_pck, float* cost, void* stream) {
+  DT_CHECK_ARG(nframes >= 0 && dmax >= 1 && T >= 1 && T <= DT_MAX_T && ldb >= 4 * T, "dt_frame_costs: bad shape nframes=%d dmax=%d T=%d ldb=%d", nframes, dmax, T, ldb);
+  DT_CHECK_ARG(w_pck == 0.0 || (poses && K >= 1 && ldp >= 2 * K && head_top >= 0 && head_top < K && head_bottom >= 0 && head_bottom < K),
+               "dt_frame_costs: the pose-pck term needs poses [nframes, dmax, ldp >= 2K] and valid head joint indices");
+  if (nframes == 0) return 0;
+  DT_CHECK_ARG(boxes && counts && cost, "dt_frame_costs: null pointer");
+  frame_costs_kernel<<<nframes, 256, 0, (cudaStream_t)stream>>>(boxes, ldb, T, poses, ldp, K, head_top, head_bottom, dist_thresh, counts,
+                                                                is_start, dmax, w_iou, w_pck, cost);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -96,6 +96,36 @@ def match_frames(frames, counts, is_start=None, T=1, weight=1.0, algo='hungarian
     return matches, status
 
 
+def pose_pck_cost(a, b, head_top, head_bottom, dist_thresh=0.5):
+    """a [P, 4|3, K], b [Q, 4|3, K] fp32 poses -> [P, Q] fp64 'pose-pck' cost (tracking_engine.py:113-129)."""
+    torch = L.require_cuda()
+    a, b = _f32c(a, torch), _f32c(b, torch)
+    P, _, K = a.shape
+    Q = b.shape[0]
+    out = torch.empty((P, Q), dtype=torch.float64, device='cuda')
+    L.call('dt_pose_pck_cost', L.ptr(a), P, L.ptr(b), Q, a.shape[1] * K, K, int(head_top), int(head_bottom), float(dist_thresh),
+           L.ptr(out), L.stream_ptr())
+    return out
+
+
+def frame_costs(boxes, counts, is_start, poses=None, T=1, w_iou=1.0, w_pck=0.0, head_top=2, head_bottom=1, dist_thresh=0.5):
+    """boxes [F, Dmax, ld], poses [F, Dmax, 4|3, K] (or None) -> cost [F, Dmax, Dmax] fp32 (rows = previous frame)."""
+    torch = L.require_cuda()
+    boxes = _f32c(boxes, torch)
+    F, dmax, ld = boxes.shape
+    counts = counts.to(device='cuda', dtype=torch.int32).contiguous()
+    if is_start is not None:
+        is_start = is_start.to(device='cuda', dtype=torch.uint8).contiguous()
+    K = ldp = 0
+    if poses is not None:
+        poses = _f32c(poses, torch)
+        K, ldp = poses.shape[3], poses.shape[2] * poses.shape[3]
+    cost = torch.empty((F, dmax, dmax), dtype=torch.float32, device='cuda')
+    L.call('dt_frame_costs', L.ptr(boxes), ld, T, L.ptr(poses), ldp, K, int(head_top), int(head_bottom), float(dist_thresh),
+           L.ptr(counts), L.ptr(is_start), F, dmax, float(w_iou), float(w_pck), L.ptr(cost), L.stream_ptr())
+    return cost
+
+
 def assign_track_ids(matches, counts, video_first, is_start=None,
                      first_id=FIRST_TRACK_ID, max_ids=MAX_TRACK_IDS):
     torch = L.require_cuda()

@@ -92,6 +92,22 @@ int dt_match_frames(const float* frames, int nframes, int dmax, int ld, int T, c
                     const unsigned char* is_start, float weight, int algo, int* matches, int* status,
                     void* stream);
 
+/* 'pose-pck' tracking cost (lib/core/tracking_engine.py:113-129, lib/utils/keypoints.py:266-291): a [P, ld], b [Q, ld]
+ * poses as the reference's [4, K] arrays (x row at 0, y row at K); out [P, Q] fp64 = 1 - (#joints with
+ * |a_k - b_k| / (|a_head_top - a_head_bottom| + 1) < dist_thresh) / K, in the reference's float32 arithmetic. */
+int dt_pose_pck_cost(const float* a, int P, const float* b, int Q, int ld, int K, int head_top, int head_bottom,
+                     float dist_thresh, double* out, void* stream);
+
+/* lib/core/tracking_engine.py:158-181 for all frame pairs at once: cost [nframes, dmax, dmax] fp32 with
+ * cost[f][p][q] = fp32(w_iou * (1 - IoU(boxes[f-1][p], boxes[f][q])) + w_pck * pck(poses[f-1][p], poses[f][q])) (fp64 sum, like
+ * np.sum(np.stack(all_Cs))); frames with is_start != 0 (and frame 0) and entries beyond counts are 0.  boxes [nframes, dmax,
+ * ldb], poses [nframes, dmax, ldp] (may be NULL when w_pck == 0).  Feed to dt_lsa_batched (nrows = counts[f-1] or 0, ncols =
+ * counts[f]).  The reference solves the fp64 sum; here it is rounded to fp32 first (identical indices unless two
+ * assignments' total costs differ by less than 1e-7). */
+int dt_frame_costs(const float* boxes, int ldb, int T, const float* poses, int ldp, int K, int head_top, int head_bottom,
+                   float dist_thresh, const int* counts, const unsigned char* is_start, int nframes, int dmax, float w_iou,
+                   double w_pck, float* cost, void* stream);
+
 /* lib/core/tracking_engine.py:272-350 id propagation.  video_first [nvideos]
  * (device) = index of the first frame of each video, ascending.  tracks
  * [nframes, dmax] (-1 beyond counts[f]).  ids: next_id++, and

@@ -44,6 +44,8 @@ def _cases():
         ('dt_time_mean', (None, 1, 3, 49, 10, 10, 1, 0, 0, None, 10, None), b'multiples of 4'),
         ('dt_fold_tube_heads', (None, 4, 10, 99, 2, None, None, None), b'dt_fold_tube_heads'),
         ('dt_memset', (None, 0, 16, None), b'dt_memset'),
+        ('dt_pose_pck_cost', (None, 2, None, 2, 10, 17, 2, 1, 0.5, None, None), b'dt_pose_pck_cost'),
+        ('dt_frame_costs', (None, 3, 1, None, 0, 0, 0, 0, 0.5, None, None, 2, 4, 1.0, 0.0, None, None), b'dt_frame_costs'),
         ('dt_pairs_to_f16', (None, 10, 12, None, None), b'C % 8'),
         ('dt_scale_rois', (None, 2, 10, 4, None, 1, 1.0, None, None), b'dt_scale_rois'),
         ('dt_to_planes', (None, 1, 8, 8, 12, 12, 1, 1, 0, 0, 0, None, None), b'dt_to_planes'),

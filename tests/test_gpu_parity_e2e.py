@@ -85,7 +85,7 @@ def _compare(cfg, blobs, frames, mode, kp_tol=1e-3, key=None):
     return r
 
 
-@pytest.mark.parametrize('mode', ['bf16x3', 'bf16x3h', 'tf32x3'])
+@pytest.mark.parametrize('mode', ['bf16x3', 'tf32x3'])
 def test_small_clip_outputs_match_oracle_pipeline(mode):
     from test_gpu_engine import _cfg
     from detectandtrack_b200.modeling import params as P
@@ -96,10 +96,24 @@ def test_small_clip_outputs_match_oracle_pipeline(mode):
     assert r['n_det'] > 0 and r['n_roi'] > 20
 
 
-@pytest.mark.parametrize('mode', ['bf16x3', 'bf16x3h'])
+def test_fp16_posthoc_mode_is_not_a_parity_mode():
+    """'bf16x3h' (bf16x3 with the four post-hoc FPN convs as ONE fp16 MMA per product: +20 % clips/s) is measured here so that
+    its status is a test result, not a claim: on the 96x128 clip the heat maps agree to ~1e-3 (9.6e-4 measured: no margin)
+    and at 800x1333 one of the 100 detections differs (round-2 gpurun).  It therefore stays a labelled extra in bench.py;
+    this test only bounds it at 2e-3 so a regression of the fp16 path is still caught."""
+    from test_gpu_engine import _cfg
+    from detectandtrack_b200.modeling import params as P
+    cfg = _cfg()
+    blobs, _ = P.random_blobs(cfg, seed=3)
+    frames = np.random.RandomState(0).randint(0, 256, (3, 96, 128, 3)).astype(np.uint8)
+    r = _compare(cfg, blobs, frames, 'bf16x3h', kp_tol=2e-3, key='small')
+    assert r['n_det'] > 0
+
+
+@pytest.mark.parametrize('mode', ['bf16x3'])
 def test_full_size_clip_outputs_match_oracle_pipeline(mode):
-    """BASELINE.json configs[3] at its real size: ONE 800x1333 clip (R = 1000, D = 100), the parity modes, vs the oracle's
-    values (the CPU side takes a minute on the GPU box; computed once for both modes)."""
+    """BASELINE.json configs[3] at its real size: ONE 800x1333 clip (R = 1000, D = 100), the headline mode, vs the oracle's
+    values (the CPU side takes a minute on the GPU box)."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench

@@ -167,3 +167,70 @@ def test_greedy_matching_vs_oracle():
     vid = ot.synth_video(rng, n_frames=3, n_dets=50)
     got = te._compute_matches(None, None, vid[0], vid[1], None, None, ('bbox-overlap',), (1.0,), 'greedy')
     assert np.array_equal(got, ot.compute_matches(vid[0], vid[1], algo='greedy'))
+
+
+# ---- 'pose-pck' tracking cost on the device (lib/core/tracking_engine.py:113-129,158-181) ----
+POSE_NAMES = ['nose', 'head_bottom', 'head_top', 'left_ear', 'right_ear', 'left_shoulder', 'right_shoulder', 'left_elbow',
+              'right_elbow', 'left_wrist', 'right_wrist', 'left_hip', 'right_hip', 'left_knee', 'right_knee', 'left_ankle', 'right_ankle']
+
+
+@pytest.mark.parametrize('tag', ['small', 'frame', 'far'])
+def test_pose_pck_cost_golden(tag):
+    """dt_pose_pck_cost == the reference's own _compute_pairwise_kpt_distance (goldens generated by source-executing
+    tracking_engine.py:113-129 + keypoints.py:266-291): bit-equal fp64 cost matrix."""
+    import os
+    import torch
+    from detectandtrack_b200.ops import box_ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'pose_pck.npz'))
+    a, b, ref = g[tag + '_a'], g[tag + '_b'], g[tag + '_dist']
+    got = box_ops.pose_pck_cost(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), POSE_NAMES.index('head_top'),
+                                POSE_NAMES.index('head_bottom')).cpu().numpy()
+    assert got.dtype == np.float64 and got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_tracks_with_pose_pck_cost_vs_reference_loop():
+    """TRACKING.DISTANCE_METRICS ('bbox-overlap', 'pose-pck') with weights (1.0, 0.5): ids == the reference's loop restated
+    with the oracle costs (fp64 sum of the two weighted matrices, scipy solver)."""
+    import scipy.optimize
+    from detectandtrack_b200.core import tracking_engine as te
+    from detectandtrack_b200.core.config import cfg, reset_cfg
+    from oracle import keypoints as okp
+    reset_cfg()
+    try:
+        cfg.TRACKING.DISTANCE_METRICS = ('bbox-overlap', 'cnn-cosdist', 'pose-pck'); cfg.TRACKING.DISTANCE_METRIC_WTS = (1.0, 0.0, 0.5)
+        rng = np.random.default_rng(11)
+        videos, vposes = [], []
+        for nf, nd in ((8, 40), (5, 17)):
+            frames = ot.synth_video(rng, n_frames=nf, n_dets=nd)
+            poses = []
+            for b in frames:                                  # a pose per box: 17 joints inside the box + jitter
+                cx = b[:, 0:1] + rng.uniform(0, 1, (b.shape[0], 17)) * (b[:, 2:3] - b[:, 0:1])
+                cy = b[:, 1:2] + rng.uniform(0, 1, (b.shape[0], 17)) * (b[:, 3:4] - b[:, 1:2])
+                p = np.stack([cx, cy, rng.normal(2, 1, cx.shape), rng.uniform(0, 1, cx.shape)], 1).astype(np.float32)
+                poses.append([p[i] for i in range(p.shape[0])])
+            videos.append(frames); vposes.append(poses)
+        got = te._tracks_for_videos(videos, vposes, POSE_NAMES)
+        for v, (frames, poses) in enumerate(zip(videos, vposes)):
+            tracks, next_id = [], 0
+            for f, cur in enumerate(frames):
+                ids = []
+                if f == 0:
+                    m = -np.ones(cur.shape[0], np.int32)
+                else:
+                    # tracking_engine.py:166-181: float32 (1 - IoU) * w stacked with the float64 pck * w, summed in float64
+                    C = np.sum(np.stack([ot.distance_matrix(frames[f - 1], cur, 1.0),
+                                         okp.pairwise_kpt_distance(poses[f - 1], poses[f], POSE_NAMES) * 0.5], 0), 0)
+                    m = -np.ones(cur.shape[0], np.int32)
+                    pi, qi = scipy.optimize.linear_sum_assignment(C)
+                    m[qi] = pi
+                for mm in m:
+                    if mm == -1:
+                        ids.append(next_id); next_id += 1
+                        if next_id >= 999:
+                            next_id %= 999
+                    else:
+                        ids.append(tracks[f - 1][mm])
+                tracks.append(ids)
+            assert got[v] == [[int(x) for x in t] for t in tracks], v
+    finally:
+        reset_cfg()
