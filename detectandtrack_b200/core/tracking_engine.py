@@ -224,6 +224,8 @@ def _tracks_for_videos(videos_boxes, videos_poses=None, kpt_names=None):
         assert videos_poses is not None, "the 'pose-pck' cost needs the poses of every detection"
         names = list(kpt_names or POSETRACK_KEYPOINTS)
         K = cfg.KRCNN.NUM_KEYPOINTS
+        if K <= 0:                                   # unset (config default -1): take it from the data
+            K = next((np.asarray(p).shape[-1] for vp in videos_poses for fr in vp for p in (fr or [])), len(names))
         poses = _pack_poses([p for vp in videos_poses for p in vp], packed.shape[1], K)
         cost = box_ops.frame_costs(torch.from_numpy(packed).cuda(), d_counts, d_start, torch.from_numpy(poses).cuda(), T=T, w_iou=w_iou,
                                    w_pck=w_pck, head_top=names.index('head_top'), head_bottom=names.index('head_bottom'))
