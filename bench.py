@@ -506,61 +506,110 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def synth_gt(B, H, W, seed, G=4, K=17):
+    """Synthetic ground truth of a training clip batch: G persons per clip (boxes 80..320 px, 17 joints inside, ~2/3 visible)."""
+    rng = np.random.RandomState(seed)
+    entries = []
+    for _ in range(B):
+        w = rng.uniform(80, 240, G); h = rng.uniform(160, 320, G)
+        x1 = rng.uniform(0, W - 1 - w); y1 = rng.uniform(0, H - 1 - h)
+        boxes = np.stack([x1, y1, x1 + w, y1 + h], 1).astype(np.float32)
+        kps = np.zeros((G, 3, K), np.int32)
+        for i in range(G):
+            kps[i, 0] = rng.randint(int(boxes[i, 0]), int(boxes[i, 2]) + 1, K)
+            kps[i, 1] = rng.randint(int(boxes[i, 1]), int(boxes[i, 3]) + 1, K)
+            kps[i, 2] = rng.randint(0, 3, K)
+        entries.append(dict(boxes=boxes, gt_keypoints=kps))
+    return entries
+
+
 def run_train(args):
-    """`--train`: training step of the RPN model trunk (modeling/trainer.py: res3..res5 + FPN3D + RPN heads and losses, bf16,
-    TRAIN.IMS_PER_BATCH = 2 clips per GPU) with the bucketed NCCL gradient all-reduce overlapped with the backward pass and
-    the fused SGD update.  It is the trainable conv trunk of BASELINE.json configs[4], NOT the whole keypoint R-CNN step (the
-    RoI heads' backward and the lib/roi_data target generators are not implemented): reported under its own metric name."""
+    """`--train`: BASELINE.json configs[4], the keypoint R-CNN training step (modeling/trainer.KeypointRcnnTrainer): frozen
+    stem, bf16 forward of res3..res5 + FPN3D + RPN + both RoI heads, ALL targets generated on the device (RPN anchor targets,
+    training proposals, RoI sampling, keypoint labels), losses, backward (dgrad / tcgen05 wgrad / RoIAlign backward), the
+    bucketed NCCL gradient all-reduce overlapped with the backward pass, fused SGD.  TRAIN.IMS_PER_BATCH = 2 clips per GPU.
+    `--train-trunk` times the RPN-model trunk alone (MODEL.TYPE rpn) under its own metric name."""
     import torch
     import torch.distributed as dist
     from detectandtrack_b200.modeling import params as P
-    from detectandtrack_b200.modeling.trainer import RpnTrainer
+    from detectandtrack_b200.modeling.trainer import RpnTrainer, KeypointRcnnTrainer, pack_gt
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     cfg = bench_cfg(args.height, args.width, 'r50fpn3d')
+    cfg.TRAIN.BATCH_SIZE_PER_IM = 512; cfg.TRAIN.RPN_PRE_NMS_TOP_N = 2000      # the shipped keypoint yamls (configs/video/2d_best)
     blobs, spec = P.random_blobs(cfg)
     B, T, H, W = cfg.TRAIN.IMS_PER_BATCH, 3, args.height, args.width
-    tr = RpnTrainer(cfg, blobs, spec, world=world, buckets=args.buckets)
-    frames = torch.from_numpy(synth_frames(B, T, H, W, 100 + rank)).cuda()
-    targets = tr.synthetic_targets(B, H, W, seed=rank)
+    full = not args.train_trunk
+    frames_h = torch.from_numpy(synth_frames(B, T, H, W, 100 + rank)).pin_memory()
+    frames = frames_h.cuda()
+    if full:
+        tr = KeypointRcnnTrainer(cfg, blobs, spec, world=world, buckets=args.buckets)
+        gt = pack_gt(synth_gt(B, H, W, 7 + rank))
+        step = lambda fr: tr.step(fr, gt)
+    else:
+        tr = RpnTrainer(cfg, blobs, spec, world=world, buckets=args.buckets)
+        targets = tr.synthetic_targets(B, H, W, seed=rank)
+        step = lambda fr: (tr.step(fr, targets), None)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out, sampler.stop() if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
-        loss = tr.step(frames, targets)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        loss = tr.step(frames, targets)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+        step(frames)
+    ms, (loss, lh), clocks = timed(lambda: step(frames), args.steps)
+    # e2e: the step a training loop makes — pinned host frames -> device every step, losses read back every step
+    loss_h = torch.empty(6, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        fr = frames_h.cuda(non_blocking=True)
+        l, h = step(fr)
+        loss_h[:2].copy_(l, non_blocking=True)
+        if h is not None:
+            loss_h[2:6].copy_(h, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return l, h
+    e2e_step()
+    ms2, _, _ = timed(e2e_step, args.steps)
     if rank == 0:
         nparam = int(tr.flat_g.numel())
-        line = dict(metric='training clips/sec, RPN-model trunk (res3..res5 + FPN3D + RPN heads/losses), T=3, %dx%d' % (H, W),
+        what = ('keypoint R-CNN training step (RPN + Fast R-CNN + keypoint heads, device-side targets)' if full else
+                'RPN-model trunk (res3..res5 + FPN3D + RPN heads/losses)')
+        cfgd = dict(workload='BASELINE.json configs[4]: R50-FPN-3D (T=3) %s, %d clips/GPU, bf16 forward/backward, fp32 master weights%s'
+                             % ('keypoint R-CNN, BATCH_SIZE_PER_IM 512, RPN 2000/level -> 2000, 4 gt persons/clip' if full else 'trunk only', B,
+                                '' if full else '; RoI heads / target generators NOT included (partial training step)'),
+                    trainable_params=nparam, allreduce_bytes_per_step=4 * nparam if world > 1 else 0,
+                    allreduce='NCCL SUM, %d buckets issued as their wgrads are enqueued (overlaps the backward pass)' % len(tr.bucket_ends),
+                    loss_rpn=[float(x) for x in loss.cpu().tolist()], eager_launches=True)
+        if full:
+            l4 = [float(x) for x in lh.cpu().tolist()]
+            cfgd.update(loss_cls=l4[0], loss_bbox=l4[1], loss_kps=l4[2], sampled_rois=float(tr.totals[0]), keypoint_targets=float(tr.totals[1]))
+        line = dict(metric='training clips/sec, %s, T=3, %dx%d' % (what, H, W),
                     value=world * B * args.steps / (ms / 1000.0), unit='clips/s', n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='bf16', data='synthetic',
-                    config=dict(workload='BASELINE.json configs[4] trunk: R50-FPN-3D, %d clips/GPU, bf16 forward/backward, fp32 master weights; '
-                                         'RoI heads / target generators NOT included (partial training step)' % B,
-                                trainable_params=nparam, allreduce_bytes_per_step=4 * nparam if world > 1 else 0,
-                                allreduce='NCCL SUM, %d buckets issued as their wgrads are enqueued (overlaps the backward pass)' % len(tr.bucket_ends),
-                                loss=[float(x) for x in loss.cpu().tolist()], eager_launches=True),
-                    clocks=sampler.stop())
+                    e2e=dict(value=world * B * args.steps / (ms2 / 1000.0), unit='clips/s', h2d_bytes_per_step=int(frames_h.numel()),
+                             d2h_bytes_per_step=24), config=cfgd, clocks=clocks)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -688,7 +737,8 @@ if __name__ == '__main__':
     ap.add_argument('--no-extras', action='store_true', help='skip the extra modes, the cuDNN stand-in and the tracking leg')
     ap.add_argument('--layers', action='store_true', help='dump per-conv timings to gpurun_out/conv_layers.json')
     ap.add_argument('--graph', type=int, default=1, help='(kept for old command lines; the step is always a captured graph)')
-    ap.add_argument('--train', action='store_true', help='training step of the RPN-model trunk with NCCL gradient all-reduce (see run_train)')
+    ap.add_argument('--train', action='store_true', help='BASELINE.json configs[4]: keypoint R-CNN training step with NCCL gradient all-reduce (see run_train)')
+    ap.add_argument('--train-trunk', action='store_true', help='with --train: the RPN-model trunk alone')
     ap.add_argument('--buckets', type=int, default=4, help='--train: gradient all-reduce buckets')
     a = ap.parse_args()
     if a.train:

@@ -53,6 +53,15 @@ SIGNATURES = {
     'dt_sgd_update': [_p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p],
     'dt_bias_grad': [_p, C.c_longlong, _i, _i, _p, _p],
     'dt_rpn_loss_grad': [_p, _i, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _p, _i, _p, _p],
+    'dt_grad_join_f32': [_p, _p, C.c_longlong, _p, _p],
+    'dt_roi_align_bwd': [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _i, _p],
+    'dt_frcnn_loss_grad': [_p, _i, _p, _p, _p, _p, _i, _i, _p, _f, _f, _p, _i, _p, _p, _p],
+    'dt_kps_loss_grad': [_p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _i, _p, _p],
+    'dt_subpixel_grad_fix': [_p, _p, _i, _i, _i, _p],
+    'dt_rpn_targets_workspace_bytes': [_i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i, C.POINTER(_sz)],
+    'dt_rpn_targets': [_p, _i, _i, _i, _p, _p, _i, _p, _f, _f, _f, _i, _f, C.c_ulonglong, _p, _sz, _p],
+    'dt_sample_rois': [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _f, _f, C.POINTER(_f), _i,
+                       C.c_ulonglong, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p],
 }
 # host-only helpers (not error-code functions)
 HOST_FUNCS = {'dt_planes_ld': ([_i, _i, _i, _i], C.c_int)}
@@ -63,6 +72,12 @@ class RpnLevel(C.Structure):
     """dt_rpn_level (include/dt_b200.h)."""
     _fields_ = [('logits', C.c_void_p), ('deltas', C.c_void_p), ('anchors', C.c_void_p), ('ld_s', C.c_int), ('ld_d', C.c_int),
                 ('H', C.c_int), ('W', C.c_int), ('feat_stride', C.c_double), ('out', C.c_void_p), ('counts', C.c_void_p)]
+
+
+class RpnTargetLevel(C.Structure):
+    """dt_rpn_target_level (include/dt_b200.h)."""
+    _fields_ = [('H', C.c_int), ('W', C.c_int), ('feat_stride', C.c_double), ('anchors', C.c_void_p), ('labels', C.c_void_p),
+                ('bbox_targets', C.c_void_p), ('inside_weights', C.c_void_p), ('outside_weights', C.c_void_p)]
 
 
 class ConvDesc(C.Structure):

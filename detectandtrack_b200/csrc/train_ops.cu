@@ -391,6 +391,250 @@ __global__ void rpn_loss_grad_kernel(const float* __restrict__ out, int ld_o, co
   if ((threadIdx.x & 31) == 0 && loss) { if (lc != 0.f) atomicAdd(loss, lc); if (lb != 0.f) atomicAdd(loss + 1, lb); }
 }
 
+
+// ------------------------------------------------------------------------------------------------ RoI heads (backward)
+// out = bf16(g + acc)
+__global__ void grad_join_f32_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ acc, long long n8,
+                                     __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a0 = reinterpret_cast<const float4*>(acc)[2 * i], a1 = reinterpret_cast<const float4*>(acc)[2 * i + 1];
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (g) {
+      const uint4 gv = reinterpret_cast<const uint4*>(g)[i];
+      const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __bfloat162float(ge[j]);
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+struct RoiBwdLevels {
+  float* dfeat[8];
+  int H[8], W[8];
+  float scale[8];
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// the forward's bilinear sample (dense_ops.cu bilinear_acc) transposed: v[8] * weight into the four corners
+__device__ __forceinline__ void bilinear_scatter(float* __restrict__ d, int H, int W, int C, float y, float x, const float* v, float wgt) {
+  if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return;
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+  const float w4[4] = {hy * hx * wgt, hy * lx * wgt, ly * hx * wgt, ly * lx * wgt};
+  float* p4[4] = {d + ((size_t)yl * W + xl) * C, d + ((size_t)yl * W + xh) * C, d + ((size_t)yh * W + xl) * C, d + ((size_t)yh * W + xh) * C};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (w4[q] == 0.f) continue;
+    red_add_v4(p4[q], v[0] * w4[q], v[1] * w4[q], v[2] * w4[q], v[3] * w4[q]);
+    red_add_v4(p4[q] + 4, v[4] * w4[q], v[5] * w4[q], v[6] * w4[q], v[7] * w4[q]);
+  }
+}
+
+// grid (R*T, P); threads over (pw, 8-channel vectors) exactly like roi_align_kernel
+__global__ void roi_align_bwd_kernel(RoiBwdLevels lv, int kmin, const float* __restrict__ rois, int ldr, const int* __restrict__ n_dev,
+                                     int R, int T, const int* __restrict__ levels, int C, int P, int sampling,
+                                     const __nv_bfloat16* __restrict__ grad) {
+  const int rt = blockIdx.x, ph = blockIdx.y;
+  const int r = rt / T, t = rt - r * T;
+  const int n = n_dev ? min(*n_dev, R) : R;
+  if (r >= n) return;
+  const int cv = C / 8;
+  const float* roi = rois + (size_t)r * ldr;
+  const int l = levels ? (levels[r] - kmin) : 0;
+  const int H = lv.H[l], W = lv.W[l];
+  const float sc = lv.scale[l];
+  const int img = (int)roi[0] * T + t;
+  float* d = lv.dfeat[l] + (size_t)img * H * W * C;
+  const float x1 = roi[1 + 4 * t] * sc, y1 = roi[2 + 4 * t] * sc, x2 = roi[3 + 4 * t] * sc, y2 = roi[4 + 4 * t] * sc;
+  const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+  const float bh = rh / (float)P, bw = rw / (float)P;
+  const int gh = sampling > 0 ? sampling : (int)ceilf(rh / P), gw = sampling > 0 ? sampling : (int)ceilf(rw / P);
+  const float inv_cnt = 1.f / (float)(gh * gw);
+  const __nv_bfloat16* gbase = grad + ((size_t)rt * P + ph) * P * C;
+  for (int i = threadIdx.x; i < P * cv; i += blockDim.x) {
+    const int pw = i / cv, c = (i - pw * cv) * 8;
+    const uint4 gv = *reinterpret_cast<const uint4*>(gbase + (size_t)pw * C + c);
+    const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gv);
+    float v[8];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = __bfloat162float(ge[j]); any |= v[j] != 0.f; }
+    if (!any) continue;
+    for (int iy = 0; iy < gh; ++iy) {
+      const float y = y1 + ph * bh + (iy + 0.5f) * bh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float x = x1 + pw * bw + (ix + 0.5f) * bw / (float)gw;
+        bilinear_scatter(d + c, H, W, C, y, x, v, inv_cnt);
+      }
+    }
+  }
+}
+
+// one thread per RoI row (C is small)
+__global__ void frcnn_loss_grad_kernel(const float* __restrict__ out, int ld_o, const int* __restrict__ labels,
+                                       const float* __restrict__ targets, const float* __restrict__ iw, const float* __restrict__ ow,
+                                       int rows, int C, const float* __restrict__ totals, float s_cls, float s_box,
+                                       __nv_bfloat16* __restrict__ grad, int ld_g, float* __restrict__ loss, float* __restrict__ acc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float lc = 0.f, lb = 0.f, hit = 0.f;
+  if (r < rows) {
+    __nv_bfloat16* g = grad + (size_t)r * ld_g;
+    const int lbl = labels[r];
+    const float N = totals[0];
+    if (lbl < 0 || !(N > 0.f)) {
+      for (int j = 0; j < ld_g; ++j) g[j] = __float2bfloat16_rn(0.f);
+    } else {
+      const float* o = out + (size_t)r * ld_o;
+      float m = o[0]; int am = 0;
+      for (int j = 1; j < C; ++j) if (o[j] > m) { m = o[j]; am = j; }
+      float se = 0.f;
+      for (int j = 0; j < C; ++j) se += expf(o[j] - m);
+      const float lse = logf(se);
+      lc = -(o[lbl] - m - lse) * s_cls / N;
+      hit = am == lbl ? 1.f : 0.f;
+      for (int j = 0; j < C; ++j) {
+        const float pj = expf(o[j] - m - lse);
+        g[j] = __float2bfloat16_rn((pj - (j == lbl ? 1.f : 0.f)) * s_cls / N);
+      }
+      for (int j = 0; j < 4 * C; ++j) {
+        const float w_in = iw[(size_t)r * 4 * C + j], w_out = ow[(size_t)r * 4 * C + j];
+        const float d = w_in * (o[C + j] - targets[(size_t)r * 4 * C + j]);
+        const float ad = fabsf(d);
+        lb += w_out * (ad < 1.f ? 0.5f * d * d : ad - 0.5f) * s_box / N;
+        g[C + j] = __float2bfloat16_rn(w_out * w_in * (ad < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * s_box / N);
+      }
+      for (int j = 5 * C; j < ld_g; ++j) g[j] = __float2bfloat16_rn(0.f);
+    }
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    lc += __shfl_xor_sync(0xffffffffu, lc, o2); lb += __shfl_xor_sync(0xffffffffu, lb, o2); hit += __shfl_xor_sync(0xffffffffu, hit, o2);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (loss) { if (lc != 0.f) atomicAdd(loss, lc); if (lb != 0.f) atomicAdd(loss + 1, lb); }
+    if (acc && hit != 0.f) atomicAdd(acc, hit);
+  }
+}
+
+// one CTA per (RoI d, joint k): 2S x 2S map -> bilinear 2x -> spatial softmax loss -> gradient back to the packed layout
+__global__ void __launch_bounds__(256)
+kps_loss_grad_kernel(const float* __restrict__ low, int ld, int S, int K, const int* __restrict__ loc, const float* __restrict__ wts,
+                     const float* __restrict__ totals, float scale, __nv_bfloat16* __restrict__ grad, int ld_g, float* __restrict__ loss) {
+  extern __shared__ float sm[];
+  const int d = blockIdx.x, k = blockIdx.y;
+  const int S2 = 2 * S, M = 4 * S;
+  float* Lm = sm;                       // [S2][S2]
+  float* U = Lm + S2 * S2;              // [M][M] upsampled logits, then their gradient
+  __shared__ float red[32];
+  __shared__ float s_max, s_sum;
+  const float w = wts[(size_t)d * K + k];
+  const float tw = totals[1];
+  __nv_bfloat16* gd = grad + (size_t)d * S * S * ld_g;
+  if (!(w > 0.f) || !(tw > 0.f)) {      // no target: zero gradient for this joint's four sub-pixel channels
+    for (int i = threadIdx.x; i < S * S * 4; i += blockDim.x) gd[(size_t)(i >> 2) * ld_g + (i & 3) * K + k] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float* ld_ = low + (size_t)d * S * S * ld;
+  for (int i = threadIdx.x; i < S2 * S2; i += blockDim.x) {
+    const int Y = i / S2, X = i - Y * S2;
+    Lm[i] = ld_[((size_t)(Y >> 1) * S + (X >> 1)) * ld + ((Y & 1) * 2 + (X & 1)) * K + k];
+  }
+  __syncthreads();
+  const float f4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  // ConvTranspose k4 s2 p1: U[o] = sum_i L[i] * f[o - 2i + 1]  -> i in {(o-2)/2 .. (o+1)/2}
+  float mx = -3.4e38f;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+    const int Y = i / M, X = i - Y * M;
+    float acc = 0.f;
+    for (int iy = (Y - 2 + 1) >> 1; iy <= (Y + 1) >> 1; ++iy) {
+      if (iy < 0 || iy >= S2) continue;
+      const int ky = Y - 2 * iy + 1;
+      if (ky < 0 || ky > 3) continue;
+      for (int ix = (X - 2 + 1) >> 1; ix <= (X + 1) >> 1; ++ix) {
+        if (ix < 0 || ix >= S2) continue;
+        const int kx = X - 2 * ix + 1;
+        if (kx < 0 || kx > 3) continue;
+        acc += Lm[iy * S2 + ix] * f4[ky] * f4[kx];
+      }
+    }
+    U[i] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) { float m = red[0]; for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]); s_max = m; }
+  __syncthreads();
+  mx = s_max;
+  float se = 0.f;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) se += expf(U[i] - mx);
+  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i]; s_sum = s; }
+  __syncthreads();
+  const float lse = logf(s_sum);
+  const int target = loc[(size_t)d * K + k];
+  const float gs = w * scale / tw;
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, -(U[target] - mx - lse) * gs);
+  __syncthreads();
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) U[i] = (expf(U[i] - mx - lse) - (i == target ? 1.f : 0.f)) * gs;
+  __syncthreads();
+  // dL[i] = sum_o dU[o] * f[o - 2i + 1], o in 2i-1 .. 2i+2
+  for (int i = threadIdx.x; i < S2 * S2; i += blockDim.x) {
+    const int iy = i / S2, ix = i - iy * S2;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int Y = 2 * iy - 1 + ky;
+      if (Y < 0 || Y >= M) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int X = 2 * ix - 1 + kx;
+        if (X < 0 || X >= M) continue;
+        acc += U[Y * M + X] * f4[ky] * f4[kx];
+      }
+    }
+    gd[((size_t)(iy >> 1) * S + (ix >> 1)) * ld_g + ((iy & 1) * 2 + (ix & 1)) * K + k] = __float2bfloat16_rn(acc);
+  }
+}
+
+__global__ void subpixel_grad_fix_kernel(float* __restrict__ gW, float* __restrict__ gb, int K, int Cin, int ldc) {
+  const long long total = 9ll * ldc * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)((i / Cin) % ldc), tap = (int)(i / ((long long)Cin * ldc));
+    bool live = co < 4 * K;
+    if (live) {
+      const int sub = co / K, py = sub >> 1, px = sub & 1;
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      const int ky = py + 1 - 2 * dy, kx = px + 1 - 2 * dx;
+      live = ky >= 0 && ky <= 3 && kx >= 0 && kx <= 3;
+    }
+    if (!live) gW[i] = 0.f;
+  }
+  if (gb && blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < ldc; k += blockDim.x) {
+      if (k < K) {
+        const float s = gb[k] + gb[K + k] + gb[2 * K + k] + gb[3 * K + k];
+        gb[k] = s; gb[K + k] = s; gb[2 * K + k] = s; gb[3 * K + k] = s;
+      } else if (k >= 4 * K) {
+        gb[k] = 0.f;
+      }
+    }
+  }
+}
+
 }  // namespace dt
 
 using namespace dt;
@@ -523,6 +767,69 @@ extern "C" int dt_rpn_loss_grad(const float* out, int ld_o, const int* labels, c
   DT_CHECK_ARG(out && labels && targets && inside_w && outside_w && grad, "dt_rpn_loss_grad: null pointer");
   rpn_loss_grad_kernel<<<grid_for(rows * ld_g, 256), 256, 0, (cudaStream_t)stream>>>(out, ld_o, labels, targets, inside_w, outside_w, rows, A,
                                                                                   scale_cls, scale_box, beta, (__nv_bfloat16*)grad, ld_g, loss);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_grad_join_f32(const void* g, const float* acc, long long n, void* out, void* stream) {
+  DT_CHECK_ARG(n >= 0 && n % 8 == 0, "dt_grad_join_f32: n=%lld must be a multiple of 8", n);
+  if (n == 0) return 0;
+  DT_CHECK_ARG(acc && out, "dt_grad_join_f32: null pointer");
+  grad_join_f32_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, acc, n / 8, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_roi_align_bwd(const void* grad, float* const* dfeats, const int* Hs, const int* Ws, const float* scales, int nlevels,
+                                int k_min, int C, const float* rois, int ldr, const int* n_dev, int R, int T, const int* levels, int P,
+                                int sampling_ratio, void* stream) {
+  DT_CHECK_ARG(nlevels >= 1 && nlevels <= 8 && C >= 8 && C % 8 == 0 && R >= 0 && T >= 1 && P >= 1 && ldr >= 4 * T + 1,
+               "dt_roi_align_bwd: bad shape (C=%d must be a multiple of 8)", C);
+  DT_CHECK_ARG(nlevels == 1 || levels, "dt_roi_align_bwd: multi-level pooling needs the per-RoI level array");
+  if (R == 0) return 0;
+  DT_CHECK_ARG(grad && dfeats && Hs && Ws && scales && rois, "dt_roi_align_bwd: null pointer");
+  RoiBwdLevels lv;
+  for (int l = 0; l < nlevels; ++l) {
+    DT_CHECK_ARG(dfeats[l], "dt_roi_align_bwd: null accumulator for level %d", l);
+    lv.dfeat[l] = dfeats[l]; lv.H[l] = Hs[l]; lv.W[l] = Ws[l]; lv.scale[l] = scales[l];
+  }
+  dim3 grid(R * T, P);
+  roi_align_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lv, k_min, rois, ldr, n_dev, R, T, levels, C, P, sampling_ratio,
+                                                              (const __nv_bfloat16*)grad);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_frcnn_loss_grad(const float* out, int ld_o, const int* labels, const float* targets, const float* inside_w,
+                                  const float* outside_w, int rows, int C, const float* totals, float scale_cls, float scale_box,
+                                  void* grad, int ld_g, float* loss, float* accuracy, void* stream) {
+  DT_CHECK_ARG(rows >= 0 && C >= 2 && ld_o >= 5 * C && ld_g >= 5 * C, "dt_frcnn_loss_grad: bad shape rows=%d C=%d ld_o=%d ld_g=%d", rows, C, ld_o, ld_g);
+  if (rows == 0) return 0;
+  DT_CHECK_ARG(out && labels && targets && inside_w && outside_w && totals && grad, "dt_frcnn_loss_grad: null pointer");
+  frcnn_loss_grad_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(out, ld_o, labels, targets, inside_w, outside_w, rows, C, totals,
+                                                                             scale_cls, scale_box, (__nv_bfloat16*)grad, ld_g, loss, accuracy);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_kps_loss_grad(const float* low, int ld, int S, int K, int D, const int* locations, const float* weights,
+                                const float* totals, float scale, void* grad, int ld_g, float* loss, void* stream) {
+  DT_CHECK_ARG(S >= 1 && S <= 32 && K >= 1 && D >= 0 && ld >= 4 * K && ld_g >= 4 * K, "dt_kps_loss_grad: bad shape S=%d K=%d D=%d ld=%d ld_g=%d", S, K, D, ld, ld_g);
+  if (D == 0) return 0;
+  DT_CHECK_ARG(low && locations && weights && totals && grad, "dt_kps_loss_grad: null pointer");
+  const size_t smem = (size_t)(4 * S * S + 16 * S * S) * sizeof(float);
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(kps_loss_grad_kernel, (int)smem, &grant));
+  dim3 grid(D, K);
+  kps_loss_grad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(low, ld, S, K, locations, weights, totals, scale, (__nv_bfloat16*)grad, ld_g, loss);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_subpixel_grad_fix(float* gW, float* gb, int K, int Cin, int ldc, void* stream) {
+  DT_CHECK_ARG(K >= 1 && Cin >= 1 && ldc >= 4 * K, "dt_subpixel_grad_fix: bad shape K=%d Cin=%d ldc=%d", K, Cin, ldc);
+  DT_CHECK_ARG(gW, "dt_subpixel_grad_fix: null pointer");
+  subpixel_grad_fix_kernel<<<grid_for(9ll * ldc * Cin, 256), 256, 0, (cudaStream_t)stream>>>(gW, gb, K, Cin, ldc);
   DT_CHECK_LAUNCH();
   return 0;
 }

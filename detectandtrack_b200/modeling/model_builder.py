@@ -45,7 +45,20 @@ def create(model_name, train=False, init_params=None, blobs=None, dtype=None):
     initialisation even at test time); weights are then overwritten from cfg.TEST.WEIGHTS by
     test_engine.initialize_model_from_cfg, exactly like the reference's two-step init."""
     if train:
-        raise NotImplementedError('training graphs (config 5) are out of scope this round')
+        # the training graph of the reference (:52-61 with train=True, build_data_parallel_model :908-951) is the trainer
+        # object: forward / device-side targets / losses / backward / all-reduce / SGD in its .step()
+        from . import trainer as T
+        import os
+        if blobs is None:
+            blobs, spec = (P.load_weights_file(cfg, cfg.TRAIN.WEIGHTS) if cfg.TRAIN.WEIGHTS else P.random_blobs(cfg))
+        else:
+            spec = P.GraphSpec(cfg)
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        if model_name == 'rpn':
+            return T.RpnTrainer(cfg, blobs, spec, world=world)
+        if model_name == 'keypoint_rcnn' and cfg.MODEL.FASTER_RCNN and cfg.MODEL.KEYPOINTS_ON:
+            return T.KeypointRcnnTrainer(cfg, blobs, spec, world=world)
+        raise NotImplementedError('training graph for MODEL.TYPE {!r}'.format(model_name))
     if model_name not in _GENERIC_TYPES:
         raise NotImplementedError('MODEL.TYPE {!r}'.format(model_name))
     if cfg.MODEL.MASK_ON:

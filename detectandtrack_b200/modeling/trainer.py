@@ -13,12 +13,19 @@ then a bucketed gradient SUM all-reduce over NCCL issued per bucket as soon as i
 (overlapping the rest of the backward pass; losses carry 1/NUM_GPUS like the reference, model_builder.py:484) and the fused
 MomentumSGDUpdate on fp32 master weights that re-emits the bf16 forward and dgrad filters.
 
-The RoI heads of the keypoint R-CNN training graph (RoIAlign backward, Fast R-CNN / keypoint losses, the target
-generators of lib/roi_data) are NOT implemented: config 5 proper is this trunk plus those heads."""
+KeypointRcnnTrainer is config 5 proper (``MODEL.TYPE keypoint_rcnn``, FASTER_RCNN end to end): the trunk above plus, per step
+and all on the device,
+    targets    dt_rpn_targets (lib/roi_data/rpn.py), proposals with the TRAIN settings (GenerateProposals + collect),
+               dt_sample_rois (json_dataset.add_proposals + lib/roi_data/fast_rcnn.py + keypoint_rcnn.py)
+    box head   RoIAlign 7x7 -> fc6 -> fc7 -> (cls_score | bbox_pred), SoftmaxWithLoss + SmoothL1Loss (dt_frcnn_loss_grad)
+    kps head   RoIAlign 14x14 -> 8 x conv3x3 -> sub-pixel deconv, spatial SoftmaxWithLoss through the fixed bilinear 2x
+               upsampling (dt_kps_loss_grad)
+    backward   the FC / conv layers through the same dgrad / wgrad kernels (an FC is a 1x1 conv over the RoI axis),
+               dt_roi_align_bwd into fp32 per-level accumulators that join the RPN's feature gradients."""
 import numpy as np
 
 from .. import _lib as L
-from ..ops import conv as cv, dense_ops, train_ops as to
+from ..ops import conv as cv, dense_ops, train_ops as to, rpn_ops, box_ops, target_ops
 from . import params as P
 from .engine import DetectionEngine
 from .generate_anchors import generate_anchors
@@ -76,6 +83,8 @@ class TrainConv(object):
 
     def __init__(self, torch, w, scale=None, shift=None, bias=None, stride=(1, 1, 1), relu=False):
         w = torch.from_numpy(np.ascontiguousarray(w)).float()
+        if w.dim() == 2:                                  # FC layer: a 1x1x1 conv over the RoI axis
+            w = w[:, :, None, None, None]
         if w.dim() == 4:
             w = w[:, :, None]
         self.k = tuple(w.shape[2:])
@@ -170,6 +179,7 @@ class RpnTrainer(object):
         bp = np.zeros((ld,), np.float32); bp[:5 * A] = b
         self.rpn_out = TrainConv(torch, wp, bias=bp)
         self.convs.append(self.rpn_out)
+        self._build_heads(blobs)                          # RoI heads of the full model (KeypointRcnnTrainer); none here
         # ---- flat gradient buffer in BACKWARD order (so a bucket finished early in the backward pass is contiguous)
         order = self.convs[::-1]
         total = sum(c.nparams() for c in order)
@@ -184,6 +194,9 @@ class RpnTrainer(object):
         self._order_end = {id(c): e for c, e in zip(order, bounds)}
         self.reducer = BucketReducer(self.flat_g, self.bucket_ends, world)
         self.loss = torch.zeros(2, dtype=torch.float32, device='cuda')
+
+    def _build_heads(self, blobs):
+        pass
 
     def _mk(self, blobs, name, affine=False, stride=(1, 1, 1), relu=False):
         c = TrainConv(self.torch, blobs[name + '_w'], scale=blobs[name + '_bn_s'] if affine else None,
@@ -241,13 +254,17 @@ class RpnTrainer(object):
         """Launch the all-reduce of every bucket whose last filter gradient has just been enqueued."""
         self.reducer.ready(self._order_end[id(conv)])
 
-    def backward(self, rpn_outs, targets):
-        """targets: per level (finest first) dict(labels [B,H,W,A] i32, bbox_targets / inside / outside [B,H,W,4A] f32)."""
+    def backward(self, rpn_outs, targets, head_grads=None, fresh=True):
+        """targets: per level (finest first) dict(labels [B,H,W,A] i32, bbox_targets / inside / outside [B,H,W,4A] f32).
+        head_grads: fp32 accumulators of the RoI heads' gradient wrt the per-level features (aligned with saved['feats'],
+        coarsest first; None entries for levels the heads do not read).  fresh=False: the gradient buffer already holds the
+        heads' filter gradients (KeypointRcnnTrainer zeroes it and resets the reducer itself)."""
         torch, cfg, s, sv = self.torch, self.cfg, self.spec, self.saved
         A = self.A
-        L.call('dt_memset', L.ptr(self.flat_g), 0, self.flat_g.numel() * 4, L.stream_ptr())
+        if fresh:
+            L.call('dt_memset', L.ptr(self.flat_g), 0, self.flat_g.numel() * 4, L.stream_ptr())
+            self.reducer.reset()
         L.call('dt_memset', L.ptr(self.loss), 0, 8, L.stream_ptr())
-        self.reducer.reset()
         pending = None
         B = rpn_outs[0].shape[0]
         s_cls = 1.0 / self.world / cfg.TRAIN.RPN_BATCH_SIZE_PER_IM / cfg.TRAIN.IMS_PER_BATCH
@@ -267,6 +284,8 @@ class RpnTrainer(object):
             gh, _ = self.rpn_out.backward(go, hs[li])
             gz = to.bwd_pointwise(gh, None, hs[li], None)                      # Relu of conv_rpn (bias conv: no scale)
             gfeat[li], _ = self.rpn_conv.backward(gz, feats[li])
+            if head_grads is not None and head_grads[li] is not None:      # + the RoI heads' gradient (RoIAlign backward)
+                gfeat[li] = to.grad_join_f32(head_grads[li].view(gfeat[li].shape), gfeat[li])
         self._bucket_ready(self.rpn_conv, pending)
         # P6 = stride-2 subsample of P5's centre frame: its gradient lands on P5's even positions
         Ps, inner = sv['P'], sv['inner']                                         # coarsest first (P5 ... P2)
@@ -373,3 +392,214 @@ class RpnTrainer(object):
             out.append(dict(labels=torch.from_numpy(labels).cuda(), bbox_targets=torch.from_numpy(bt).cuda(),
                             inside=torch.from_numpy(iw).cuda(), outside=torch.from_numpy(ow).cuda()))
         return out
+
+
+def pack_gt(entries, Gmax=None, K=17):
+    """roidb-style entries (dicts with 'boxes' [G,4] in ORIGINAL image coordinates, optional 'gt_classes', 'is_crowd',
+    'gt_keypoints' [G,3,K] int32) -> the fixed-capacity device tensors of dt_rpn_targets / dt_sample_rois.  The RPN sees the
+    non-crowd boxes only (rpn.py:84-86), the RoI sampler all of them (json_dataset.py:437)."""
+    import torch
+    B = len(entries)
+    Gmax = Gmax or max(8, max(len(e['boxes']) for e in entries))
+    boxes = np.zeros((B, Gmax, 4), np.float32); rboxes = np.zeros((B, Gmax, 4), np.float32)
+    classes = np.zeros((B, Gmax), np.int32); crowd = np.zeros((B, Gmax), np.int32)
+    kps = np.zeros((B, Gmax, 3, K), np.int32)
+    counts = np.zeros((B,), np.int32); rcounts = np.zeros((B,), np.int32)
+    for b, e in enumerate(entries):
+        g = len(e['boxes'])
+        assert g <= Gmax, 'more gt boxes than Gmax'
+        boxes[b, :g] = e['boxes']
+        classes[b, :g] = e.get('gt_classes', np.ones(g, np.int32))
+        cr = np.asarray(e.get('is_crowd', np.zeros(g, bool))).astype(bool)
+        crowd[b, :g] = cr
+        if 'gt_keypoints' in e:
+            kps[b, :g] = e['gt_keypoints']
+        counts[b] = g
+        keep = np.where((classes[b, :g] > 0) & ~cr)[0]
+        rboxes[b, :len(keep)] = boxes[b, keep]
+        rcounts[b] = len(keep)
+    t = lambda a: torch.from_numpy(a).cuda()
+    return dict(boxes=t(boxes), classes=t(classes), crowd=t(crowd), keypoints=t(kps), counts=t(counts), rpn_boxes=t(rboxes),
+                rpn_counts=t(rcounts))
+
+
+class KeypointRcnnTrainer(RpnTrainer):
+    """The end-to-end keypoint R-CNN training step (model_builder.py keypoint_rcnn: RPN + Fast R-CNN + keypoint heads)."""
+
+    def _build_heads(self, blobs):
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        res, fd = cfg.FAST_RCNN.ROI_XFORM_RESOLUTION, s.fpn_dim
+        n6 = blobs['fc6_w'].shape[0]
+        w6 = blobs['fc6_w'].reshape(n6, fd, res, res).transpose(0, 2, 3, 1).reshape(n6, -1)      # columns in RoIAlign (h, w, c) order
+        add = self.convs.append
+        self.fc6 = TrainConv(torch, w6, bias=blobs['fc6_b'], relu=True); add(self.fc6)
+        self.fc7 = TrainConv(torch, blobs['fc7_w'], bias=blobs['fc7_b'], relu=True); add(self.fc7)
+        C_ = self.C_ = s.num_classes
+        w = np.concatenate([blobs['cls_score_w'], blobs['bbox_pred_w']], 0)
+        b = np.concatenate([blobs['cls_score_b'], blobs['bbox_pred_b']], 0)
+        ld = self.cb_ld = (5 * C_ + 7) // 8 * 8
+        wp = np.zeros((ld, w.shape[1]), np.float32); wp[:5 * C_] = w
+        bp = np.zeros((ld,), np.float32); bp[:5 * C_] = b
+        self.cls_bbox = TrainConv(torch, wp, bias=bp); add(self.cls_bbox)
+        self.kps = []
+        for i in range(cfg.KRCNN.NUM_STACKED_CONVS):
+            c = TrainConv(torch, blobs['conv_fcn%d_w' % (i + 1)], bias=blobs['conv_fcn%d_b' % (i + 1)], relu=True)
+            self.kps.append(c); add(c)
+        wt = blobs['kps_score_lowres_w']                      # ConvTranspose (Cin, K, 4, 4), stride 2, pad 1
+        cin, K = wt.shape[0], wt.shape[1]
+        self.K = K
+        ldk = self.kp_ld = (4 * K + 7) // 8 * 8
+        w3 = np.zeros((ldk, cin, 3, 3), np.float32)           # four 2x2 sub-pixel filters on one 3x3 footprint (engine.py)
+        for py in range(2):
+            for px in range(2):
+                for dy in (-1, 0, 1):
+                    ky = py + 1 - 2 * dy
+                    if not 0 <= ky <= 3:
+                        continue
+                    for dx in (-1, 0, 1):
+                        kx = px + 1 - 2 * dx
+                        if 0 <= kx <= 3:
+                            w3[(py * 2 + px) * K:(py * 2 + px + 1) * K, :, dy + 1, dx + 1] = wt[:, :, ky, kx].T
+        b3 = np.zeros((ldk,), np.float32); b3[:4 * K] = np.tile(blobs['kps_score_lowres_b'], 4)
+        self.kps_lowres = TrainConv(torch, w3, bias=b3); add(self.kps_lowres)
+        self.loss_heads = torch.zeros(4, dtype=torch.float32, device='cuda')      # cls, bbox, kps, #correct
+        self.totals = torch.zeros(2, dtype=torch.float32, device='cuda')          # live RoIs, keypoint weight sum (loss normalisers)
+        self.iter = 0
+
+    # ------------------------------------------------------------------ geometry / proposals
+    def _train_geom(self, B, H, W):
+        g = self.eng._geom_tensors(B, H, W)
+        if 'im_info_train' not in g:                          # rpn.py:90: im_info = (round(h * scale), round(w * scale), scale)
+            g['im_info_train'] = self.torch.tensor([[g['hr'], g['wr'], g['scale']]] * B, dtype=self.torch.float32, device='cuda')
+        return g
+
+    def proposals(self, rpn_outs, im_info):
+        """GenerateProposals + collect with the TRAIN settings, from the fp32 RPN outputs (finest level first)."""
+        torch, cfg, s = self.torch, self.cfg, self.spec
+        B, Lv, A = rpn_outs[0].shape[0], len(rpn_outs), self.A
+        Kp = int(cfg.TRAIN.RPN_PRE_NMS_TOP_N)
+        props = L.zeros((B, Lv, Kp, 5), torch.float32)
+        counts = L.zeros((B, Lv), torch.int32)
+        levels = []
+        for l, o in enumerate(rpn_outs):
+            o4 = o.view(o.shape[0], o.shape[2], o.shape[3], o.shape[4])
+            levels.append(dict(logits=o4[..., :A], deltas=o4[..., A:5 * A], anchors=self.eng.anchors[l],
+                               feat_stride=2. ** s.rpn_levels[l], out=props[:, l], counts=counts[:, l]))
+        rpn_ops.rpn_proposals_levels(levels, im_info, Kp, A, float(cfg.TRAIN.RPN_MIN_SIZE), 1)
+        post = int(cfg.TRAIN.RPN_POST_NMS_TOP_N)
+        keep, nkeep = box_ops.nms_batched(props.view(B * Lv, Kp, 5), counts.view(-1), cfg.TRAIN.RPN_NMS_THRESH, box_ops.NMS_2D_GE,
+                                          box_ops.ORDER_INDEX, max_keep=post)
+        return rpn_ops.collect(props, keep, nkeep, post)
+
+    def make_targets(self, rpn_outs, gt, B, H, W, seed):
+        """All targets of one step on the device: RPN anchor targets, sampled RoIs + box targets, keypoint RoIs + labels."""
+        cfg, s = self.cfg, self.spec
+        g = self._train_geom(B, H, W)
+        shapes = [(o.shape[2], o.shape[3]) for o in rpn_outs]
+        rt = target_ops.rpn_targets(shapes, self.eng.anchors, [2. ** l for l in s.rpn_levels], self.A, gt['rpn_boxes'], gt['rpn_counts'],
+                                    g['im_info_train'], cfg.TRAIN, seed)
+        rois, scores, counts = self.proposals(rpn_outs, g['im_info_train'])
+        L.call('dt_memset', L.ptr(self.totals), 0, 8, L.stream_ptr())
+        smp = target_ops.sample_rois(rois, scores, counts, gt, g['im_info_train'], cfg, seed, keypoints=True, totals=self.totals)
+        return rt, smp
+
+    # ------------------------------------------------------------------ heads
+    def _roi_levels(self, rois_flat):
+        s, cfg = self.spec, self.cfg
+        lv, _, _ = rpn_ops.distribute(rois_flat, None, col0=1, T=1, k_min=s.roi_levels[0], k_max=s.roi_levels[-1],
+                                      s0=float(cfg.FPN.ROI_CANONICAL_SCALE), lvl0=float(cfg.FPN.ROI_CANONICAL_LEVEL), want_restore=False)
+        return lv
+
+    def forward_heads(self, smp):
+        torch, cfg, s, sv = self.torch, self.cfg, self.spec, self.saved
+        nl = len(s.roi_levels)
+        feats = sv['feats'][::-1][:nl]                        # finest first: P2 .. P5, each [B, 1, h, w, C]
+        fl = [f.view((f.shape[0] * f.shape[1],) + tuple(f.shape[2:])) for f in feats]
+        scales = [1. / 2 ** l for l in s.roi_levels]
+        h = sv['heads'] = dict(fl=fl, scales=scales)
+        # box head
+        rois = smp['rois'].view(-1, 5)
+        R = rois.shape[0]
+        lv = self._roi_levels(rois)
+        res = cfg.FAST_RCNN.ROI_XFORM_RESOLUTION
+        x = dense_ops.roi_align(fl, scales, rois, lv, res, cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO, T=1, k_min=s.roi_levels[0])
+        x6 = x.view(1, 1, 1, R, -1)
+        h6 = self.fc6.forward(x6)
+        h7 = self.fc7.forward(h6)
+        o = torch.empty((1, 1, 1, R, self.cb_ld), dtype=torch.float32, device='cuda')
+        self.cls_bbox.forward(h7, out_f32=True, out=o)
+        h.update(rois=rois, lv=lv, x6=x6, h6=h6, h7=h7, o=o)
+        # keypoint head
+        krois = smp['kp_rois'].view(-1, 5)
+        D = krois.shape[0]
+        klv = self._roi_levels(krois)
+        kres = cfg.KRCNN.ROI_XFORM_RESOLUTION
+        xk = dense_ops.roi_align(fl, scales, krois, klv, kres, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO, T=1, k_min=s.roi_levels[0])
+        acts = [xk.view(D, 1, kres, kres, -1)]
+        for c in self.kps:
+            acts.append(c.forward(acts[-1]))
+        low = torch.empty((D, 1, kres, kres, self.kp_ld), dtype=torch.float32, device='cuda')
+        self.kps_lowres.forward(acts[-1], out_f32=True, out=low)
+        h.update(krois=krois, klv=klv, kacts=acts, low=low)
+        return o.view(R, self.cb_ld), low.view(D, kres, kres, self.kp_ld)
+
+    def backward_heads(self, smp):
+        """Losses + backward of both RoI heads; returns the fp32 feature-gradient accumulators (coarsest first, aligned with
+        saved['feats']: None for P6)."""
+        torch, cfg, s, sv = self.torch, self.cfg, self.spec, self.saved
+        h = sv['heads']
+        fl, scales = h['fl'], h['scales']
+        dfe = [L.zeros(tuple(f.shape), torch.float32) for f in fl]                 # finest first
+        w = 1.0 / self.world
+        L.call('dt_memset', L.ptr(self.loss_heads), 0, 16, L.stream_ptr())
+        # keypoint head (model_builder.py:873-888: scale = KRCNN.LOSS_WEIGHT / NUM_GPUS)
+        low = h['low']
+        D, _, S, _, ldk = low.shape
+        g = to.kps_loss_grad(low.view(D, S, S, ldk), self.K, smp['kp_locations'].view(D, self.K), smp['kp_weights'].view(D, self.K),
+                             self.totals, cfg.KRCNN.LOSS_WEIGHT * w, ldk, loss=self.loss_heads[2:3])
+        acts = h['kacts']
+        gh, _ = self.kps_lowres.backward(g.view(D, 1, S, S, ldk), acts[-1])
+        to.subpixel_grad_fix(self.kps_lowres.g, self.kps_lowres.bias_g, self.K)
+        self._bucket_ready(self.kps_lowres)
+        for i in range(len(self.kps) - 1, -1, -1):
+            gz = to.bwd_pointwise(gh, None, acts[i + 1], None)
+            gh, _ = self.kps[i].backward(gz, acts[i])
+            self._bucket_ready(self.kps[i])
+        to.roi_align_bwd(gh, dfe, scales, h['krois'], h['klv'], S, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO, T=1, k_min=s.roi_levels[0])
+        # box head (model_builder.py:481-493: both losses scaled by 1 / NUM_GPUS)
+        o = h['o']
+        R = o.shape[3]
+        C_ = self.C_
+        go = to.frcnn_loss_grad(o.view(R, self.cb_ld), smp['labels'].view(-1), smp['bbox_targets'].view(R, 4 * C_),
+                                smp['inside'].view(R, 4 * C_), smp['outside'].view(R, 4 * C_), C_, self.totals, w, w, self.cb_ld,
+                                loss=self.loss_heads[0:2], accuracy=self.loss_heads[3:4])
+        g7, _ = self.cls_bbox.backward(go.view(1, 1, 1, R, self.cb_ld), h['h7'])
+        self._bucket_ready(self.cls_bbox)
+        g6, _ = self.fc7.backward(to.bwd_pointwise(g7, None, h['h7'], None), h['h6'])
+        self._bucket_ready(self.fc7)
+        gx, _ = self.fc6.backward(to.bwd_pointwise(g6, None, h['h6'], None), h['x6'])
+        self._bucket_ready(self.fc6)
+        res = cfg.FAST_RCNN.ROI_XFORM_RESOLUTION
+        to.roi_align_bwd(gx.view(R, 1, res, res, -1), dfe, scales, h['rois'], h['lv'], res, cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO, T=1,
+                         k_min=s.roi_levels[0])
+        nf = len(sv['feats'])
+        out = [None] * nf
+        for i, d in enumerate(dfe):                                                # dfe[i] = level roi_levels[i]; feats coarsest first
+            out[nf - 1 - i] = d
+        return out
+
+    def step(self, frames_u8, gt, seed=None):
+        """One SGD iteration from uint8 frames and packed ground truth (pack_gt): returns (rpn loss [2], head losses [4])."""
+        B, T, H, W, _ = frames_u8.shape
+        seed = self.cfg.RNG_SEED + self.iter if seed is None else seed
+        outs = self.forward_all(frames_u8)
+        rt, smp = self.make_targets(outs, gt, B, H, W, seed)
+        self.forward_heads(smp)
+        L.call('dt_memset', L.ptr(self.flat_g), 0, self.flat_g.numel() * 4, L.stream_ptr())
+        self.reducer.reset()
+        hg = self.backward_heads(smp)
+        loss = self.backward(outs, rt, head_grads=hg, fresh=False)
+        self.update()
+        self.iter += 1
+        self.last = dict(rpn_targets=rt, sampled=smp)
+        return loss, self.loss_heads

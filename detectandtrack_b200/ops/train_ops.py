@@ -89,3 +89,58 @@ def pack_dgrad_weight(w):
         w = w[:, :, None]
     wt = w.to('cuda').float().flip(2, 3, 4).permute(1, 0, 2, 3, 4).contiguous()      # (Cin, Cout, kT, kH, kW), flipped
     return cv.pack_weight(wt, cv.BF16)
+
+
+# ---------------------------------------------------------------------- RoI heads (backward) and their losses
+def grad_join_f32(acc, g=None):
+    """bf16(g + acc): joins the fp32 RoIAlign-backward accumulator with an (optional) bf16 gradient of the same shape."""
+    torch = L.require_cuda()
+    assert acc.dtype == torch.float32 and acc.is_contiguous() and (g is None or (g.shape == acc.shape and g.dtype == torch.bfloat16))
+    out = torch.empty(acc.shape, dtype=torch.bfloat16, device='cuda')
+    L.call('dt_grad_join_f32', L.ptr(g), L.ptr(acc), acc.numel(), L.ptr(out), L.stream_ptr())
+    return out
+
+
+def roi_align_bwd(grad, dfeats, scales, rois, levels, P, sampling_ratio, T=1, k_min=2, n_dev=None):
+    """grad [R, T, P, P, C] bf16 -> accumulated into dfeats (list of fp32 [Nimg*T, H_l, W_l, C], finest first, zeroed by the
+    caller); the arguments mirror dense_ops.roi_align."""
+    torch = L.require_cuda()
+    nl = len(dfeats)
+    Cc = grad.shape[-1]
+    R = rois.shape[0]
+    assert grad.dtype == torch.bfloat16 and grad.is_contiguous() and grad.numel() == R * T * P * P * Cc
+    fp = (C.c_void_p * nl)(*[f.data_ptr() for f in dfeats])
+    Hs = (C.c_int * nl)(*[f.shape[1] for f in dfeats])
+    Ws = (C.c_int * nl)(*[f.shape[2] for f in dfeats])
+    sc = (C.c_float * nl)(*[float(s) for s in scales])
+    for f in dfeats:
+        assert f.dtype == torch.float32 and f.is_contiguous() and f.shape[-1] == Cc
+    rois = rois.contiguous()
+    L.call('dt_roi_align_bwd', L.ptr(grad), fp, Hs, Ws, sc, nl, k_min, Cc, L.ptr(rois), rois.shape[1], L.ptr(n_dev), R, T,
+           L.ptr(levels), P, sampling_ratio, L.stream_ptr())
+
+
+def frcnn_loss_grad(out, labels, targets, inside, outside, C_, totals, scale_cls, scale_box, ld_g, loss=None, accuracy=None):
+    """out [rows, ld_o] fp32 (C_ logits | 4C_ deltas) -> grad [rows, ld_g] bf16; loss [2] += (cls, bbox)."""
+    torch = L.require_cuda()
+    rows, ld_o = out.shape
+    grad = torch.empty((rows, ld_g), dtype=torch.bfloat16, device='cuda')
+    L.call('dt_frcnn_loss_grad', L.ptr(out), ld_o, L.ptr(labels), L.ptr(targets), L.ptr(inside), L.ptr(outside), rows, C_, L.ptr(totals),
+           float(scale_cls), float(scale_box), L.ptr(grad), ld_g, L.ptr(loss), L.ptr(accuracy), L.stream_ptr())
+    return grad
+
+
+def kps_loss_grad(low, K, locations, weights, totals, scale, ld_g, loss=None):
+    """low [D, S, S, ld] fp32 (sub-pixel packed kps_score_lowres) -> grad [D, S, S, ld_g] bf16 of the spatial-softmax loss."""
+    torch = L.require_cuda()
+    D, S, _, ld = low.shape
+    grad = L.zeros((D, S, S, ld_g), torch.bfloat16)
+    L.call('dt_kps_loss_grad', L.ptr(low), ld, S, K, D, L.ptr(locations), L.ptr(weights), L.ptr(totals), float(scale), L.ptr(grad), ld_g,
+           L.ptr(loss), L.stream_ptr())
+    return grad
+
+
+def subpixel_grad_fix(gW, gb, K):
+    taps, ldc, Cin = gW.shape
+    assert taps == 9
+    L.call('dt_subpixel_grad_fix', L.ptr(gW), L.ptr(gb), K, Cin, ldc, L.stream_ptr())

@@ -379,6 +379,71 @@ int dt_rpn_loss_grad(const float* out, int ld_o, const int* labels, const float*
                      const float* outside_w, long long rows, int A, float scale_cls, float scale_box, float beta, void* grad,
                      int ld_g, float* loss, void* stream);
 
+/* fp32 accumulator joins of the RoI-head backward: out (bf16) = g (bf16, may be NULL) + acc (fp32) */
+int dt_grad_join_f32(const void* g, const float* acc, long long n, void* out, void* stream);
+
+/* RoIAlign backward (the Caffe2 RoIAlignGradient the reference gets from AddGradientOperators for
+ * lib/modeling/detector.py:216-310): grad [R, T, P, P, C] bf16 is scattered with the forward's bilinear weights into
+ * fp32 accumulators dfeat[l] [Nimg*T, H_l, W_l, C] (caller zeroes them; red.global.add.v4.f32).  Arguments as dt_roi_align. */
+int dt_roi_align_bwd(const void* grad, float* const* dfeats /*host array [nlevels] of device ptrs*/, const int* Hs, const int* Ws,
+                     const float* scales, int nlevels, int k_min, int C, const float* rois, int ldr, const int* n_dev, int R,
+                     int T, const int* levels, int P, int sampling_ratio, void* stream);
+
+/* Fast R-CNN losses and their gradients (lib/modeling/model_builder.py:481-493: SoftmaxWithLoss(cls_score, labels_int32,
+ * scale) + SmoothL1Loss(bbox_pred, targets, inside, outside, beta 1, scale)): out [rows, ld_o] fp32 = [C class logits |
+ * 4C box deltas]; labels [rows] int32 (-1 = padding row, ignored); targets / inside_w / outside_w [rows, 4C] fp32.
+ * Both losses average over the LIVE row count totals[0] (device; dt_sample_rois).  grad [rows, ld_g] bf16, padding 0;
+ * loss (may be NULL) [2] += (cls, bbox); accuracy (may be NULL) [1] += correctly classified live rows. */
+int dt_frcnn_loss_grad(const float* out, int ld_o, const int* labels, const float* targets, const float* inside_w,
+                       const float* outside_w, int rows, int C, const float* totals, float scale_cls, float scale_box, void* grad,
+                       int ld_g, float* loss, float* accuracy, void* stream);
+
+/* Keypoint heat-map loss and gradient (lib/modeling/model_builder.py:873-888 on top of :755-870): per (RoI, joint) the 2S x 2S
+ * low-resolution map (sub-pixel packed conv output low [D, S, S, ld], channel (py*2+px)*K + k) is upsampled 2x by the fixed
+ * bilinear ConvTranspose (BilinearInterpolation, lib/modeling/detector.py:348-380), SoftmaxWithLoss over the (4S)^2 positions
+ * with the location label and weight, averaged over the weight sum totals[1] (device) and scaled; the gradient is taken back
+ * through the upsampling and written in the same packed layout: grad [D, S, S, ld_g] bf16 (caller zeroes padding channels). */
+int dt_kps_loss_grad(const float* low, int ld, int S, int K, int D, const int* locations, const float* weights, const float* totals,
+                     float scale, void* grad, int ld_g, float* loss, void* stream);
+
+/* Keeps the sub-pixel form of the k4-s2-p1 ConvTranspose consistent during training: zeroes the gradient of the structural
+ * zeros of the 3x3-footprint filter gW [9][ldc][Cin] (and of the padding filters >= 4K) and ties the 4 copies of each bias
+ * gradient gb [ldc] (their sum, written to all four). */
+int dt_subpixel_grad_fix(float* gW, float* gb, int K, int Cin, int ldc, void* stream);
+
+/* ---- targets.cu (training target generators on the device) ---------------------------------------
+ * Random draws are the counter-based choice / randint of oracle/targets.py (seed, stream, image, index). */
+typedef struct dt_rpn_target_level {
+  int H, W;
+  double feat_stride;
+  const double* anchors;           /* [A, 4] cell anchors (generate_anchors.py) */
+  int* labels;                     /* out [B, H, W, A]  (1 fg, 0 bg, -1 ignore) */
+  float* bbox_targets;             /* out [B, H, W, 4A] */
+  float* inside_weights;           /* out [B, H, W, 4A] */
+  float* outside_weights;          /* out [B, H, W, 4A] */
+} dt_rpn_target_level;
+int dt_rpn_targets_workspace_bytes(int B, int n_levels, const int* Hs, const int* Ws, int A, int Gmax, size_t* bytes /*host out*/);
+/* lib/roi_data/rpn.py:206-381 for every image of the batch and every FPN level (T = 1): gt_boxes [B, Gmax, 4] fp32 in
+ * ORIGINAL image coordinates (non-crowd, gt_classes > 0), gt_counts [B], im_info [B, 3] = (blob h, blob w, scale). */
+int dt_rpn_targets(const dt_rpn_target_level* levels /*host*/, int n_levels, int A, int B, const float* gt_boxes, const int* gt_counts,
+                   int Gmax, const float* im_info, float straddle_thresh, float positive_overlap, float negative_overlap,
+                   int batch_size_per_im, float fg_fraction, unsigned long long seed, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* add_proposals + _sample_rois + add_keypoint_rcnn_blobs (lib/datasets/json_dataset.py:423-534, lib/roi_data/fast_rcnn.py:118-238,
+ * lib/roi_data/keypoint_rcnn.py:24-99) for every image: rois [B, R, 5] / roi_scores [B, R] / roi_counts [B] = dt_collect_rpn's
+ * per-image output (descending score); only the batch-wide top post_nms_topn are used (the training branch of collect).
+ * gt_* [B, Gmax, ...]: boxes fp32 (original coordinates, ALL gt incl. crowd), classes, crowd flags, keypoints [B,Gmax,3,K] int32.
+ * Outputs (fixed capacity, padding rows have label -1 / zero weights): rois_out [B, batch, 5], labels [B, batch],
+ * bbox_targets / inside / outside [B, batch, 4*num_classes], out_counts [B]; kp_rois [B, kcap, 5] (may be NULL),
+ * kp_locations [B, kcap, K] int32, kp_weights [B, kcap, K], kp_counts [B]; totals [2] += (live RoIs, keypoint weight sum). */
+int dt_sample_rois(const float* rois, const float* roi_scores, const int* roi_counts, int B, int R, int post_nms_topn,
+                   const float* gt_boxes, const int* gt_classes, const int* gt_crowd, const int* gt_keypoints,
+                   const int* gt_counts, int Gmax, int K, const float* im_info, int num_classes, int batch_size_per_im,
+                   float fg_fraction, float fg_thresh, float bg_thresh_hi, float bg_thresh_lo, const float* bbox_reg_weights /*host [4]*/,
+                   int heatmap_size, unsigned long long seed, float* rois_out, int* labels, float* bbox_targets,
+                   float* inside_weights, float* outside_weights, int* out_counts, float* kp_rois, int* kp_locations,
+                   float* kp_weights, int* kp_counts, int kcap, float* totals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

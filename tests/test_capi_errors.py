@@ -19,6 +19,7 @@ def _cases():
     onef = (C.c_float * 1)(1.0)
     ptrs = (C.c_void_p * 1)(None)
     lv = (L.RpnLevel * 1)()
+    tl = (L.RpnTargetLevel * 1)()
     return [
         ('dt_bbox_overlaps', (None, 4, 4, None, 4, 4, 99, None, 4, None), b'T=99'),
         ('dt_nms_batched', (None, 1, 9000, 5, 1, None, 0.5, 0, 0, 0, None, None, None, 0, None), b'exceeds'),
@@ -56,6 +57,14 @@ def _cases():
         ('dt_sgd_update', (None, None, None, 1, 8, 8, 0.1, 0.9, 0.0, 1.0, None, None, None), b'dt_sgd_update'),
         ('dt_bias_grad', (None, 10, 8, 4, None, None), b'dt_bias_grad'),
         ('dt_rpn_loss_grad', (None, 8, None, None, None, None, 10, 3, 1.0, 1.0, 0.1, None, 16, None, None), b'dt_rpn_loss_grad'),
+        ('dt_grad_join_f32', (None, None, 12, None, None), b'multiple of 8'),
+        ('dt_roi_align_bwd', (None, ptrs, one, one, onef, 1, 2, 12, None, 5, None, 10, 1, None, 7, 2, None), b'multiple of 8'),
+        ('dt_frcnn_loss_grad', (None, 8, None, None, None, None, 10, 2, None, 1.0, 1.0, None, 16, None, None, None), b'dt_frcnn_loss_grad'),
+        ('dt_kps_loss_grad', (None, 72, 99, 17, 4, None, None, None, 1.0, None, 72, None, None), b'S=99'),
+        ('dt_subpixel_grad_fix', (None, None, 17, 8, 60, None), b'ldc=60'),
+        ('dt_rpn_targets', (tl, 1, 3, 1, None, None, 4096, None, 0.0, 0.7, 0.3, 256, 0.5, 3, None, 0, None), b'Gmax'),
+        ('dt_sample_rois', (None, None, None, 1, 0, 2000, None, None, None, None, None, 8, 17, None, 2, 512, 0.25, 0.5, 0.5, 0.0, f4, 56, 3,
+                            None, None, None, None, None, None, None, None, None, None, 128, None, None), b'dt_sample_rois'),
     ]
 
 
@@ -72,5 +81,5 @@ def test_entry_point_rejects_bad_arguments_without_a_gpu(name, args, msg):
 
 def test_every_compute_entry_point_has_an_error_case():
     covered = {c[0] for c in _cases()}
-    host_only = {'dt_abi_version', 'dt_nms_workspace_bytes', 'dt_rpn_workspace_bytes'}
+    host_only = {'dt_abi_version', 'dt_nms_workspace_bytes', 'dt_rpn_workspace_bytes', 'dt_rpn_targets_workspace_bytes'}
     assert set(L.SIGNATURES) - host_only <= covered, set(L.SIGNATURES) - host_only - covered

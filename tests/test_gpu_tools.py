@@ -95,3 +95,38 @@ def test_test_net_then_compute_tracks(tmp_path):
     for first in (0, 3):
         ids = trk2['all_tracks'][1][first]
         assert ids == list(range(len(ids)))
+
+
+TRAIN_YAML = YAML + '''
+TRAIN:
+  DATASET: synthetic_1x2_96x128
+  SCALES: (96,)
+  MAX_SIZE: 128
+  IMS_PER_BATCH: 2
+  BATCH_SIZE_PER_IM: 64
+  RPN_BATCH_SIZE_PER_IM: 64
+  RPN_PRE_NMS_TOP_N: 300
+  RPN_POST_NMS_TOP_N: 200
+SOLVER:
+  BASE_LR: 0.001
+  LR_POLICY: steps_with_decay
+  STEPS: [0, 30]
+  MAX_ITER: 61
+  WARM_UP_ITERS: 5
+  WEIGHT_DECAY: 0.0001
+'''
+
+
+def test_train_net_loss_goes_down(tmp_path):
+    """tools/train_net.py (reference CLI) on a 2-clip synthetic dataset: the same minibatch every iteration, so the total loss
+    of the keypoint R-CNN step must fall (lr 1e-3 with warm-up and one decay step; 2e-3 diverges on these random weights)."""
+    import re
+    cfg = tmp_path / 'cfg.yaml'
+    cfg.write_text(TRAIN_YAML)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'train_net.py'), '--cfg', str(cfg), 'OUTPUT_DIR', str(tmp_path / 'out')],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    losses = [float(m.group(1)) for m in re.finditer(r'iter \d+ lr [\d.]+ loss ([\d.]+)', r.stdout)]
+    assert len(losses) == 4 and all(np.isfinite(losses)), r.stdout[-2000:]
+    assert losses[-1] < 0.6 * losses[0], losses          # measured on B200: 13.76 -> 8.24 -> 6.18 -> 5.23 (new RoI draws every iteration)

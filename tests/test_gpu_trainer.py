@@ -111,3 +111,170 @@ def test_rpn_trunk_training_step_vs_autograd():
         assert not bad, bad
     finally:
         _cfg()
+
+
+def _oracle_full_step(cfg, blobs, frames, rt_np, smp, world=1):
+    """The whole keypoint R-CNN training loss in torch fp32 on the CPU, teacher-forced with the DEVICE's targets (rt_np: RPN
+    targets per level; smp: sampled RoIs / labels / box targets / keypoint RoIs + labels as numpy) -> losses and gradients."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import keypoints as okp
+    spec = OracleSpec(cfg)
+    tb = {k: torch.from_numpy(np.ascontiguousarray(v)).clone() for k, v in blobs.items()}
+    pref = ('res3', 'res4', 'res5', 'fpn_', 'conv_rpn', 'rpn_', 'fc6', 'fc7', 'cls_score', 'bbox_pred', 'conv_fcn', 'kps_score_lowres')
+    train = [k for k in tb if (k.startswith(pref) and not k.endswith(('_bn_s', '_bn_b')))]
+    for k in train:
+        tb[k].requires_grad_(True)
+    means = np.asarray(cfg.PIXEL_MEANS, np.float32).reshape(1, 1, 1, 1, 3)
+    data = torch.from_numpy(frames.astype(np.float32) - means).permute(0, 4, 1, 2, 3).contiguous()
+    pyr = onet.fpn(tb, spec, onet.conv_body(tb, spec, data))                      # [P6..P2]
+    feats = [onet.time_pool(p, 'slice-center', cfg.VIDEO.NUM_FRAMES_MID) for p in pyr]
+    heads = onet.rpn_heads_fpn(tb, spec, feats)
+    B = frames.shape[0]
+    s_cls = 1.0 / world / cfg.TRAIN.RPN_BATCH_SIZE_PER_IM / cfg.TRAIN.IMS_PER_BATCH
+    s_box = 1.0 / world / B
+    beta = 1.0 / 9.0
+    lc, lb = 0., 0.
+    for (lg, dl), t in zip(heads, rt_np):
+        lab = torch.from_numpy(t['labels']).permute(0, 3, 1, 2)
+        m = lab >= 0
+        lc = lc + s_cls * F.binary_cross_entropy_with_logits(lg[m], lab[m].float(), reduction='sum')
+        tg, iw, ow = (torch.from_numpy(t[k]).permute(0, 3, 1, 2) for k in ('bbox_targets', 'inside', 'outside'))
+        d = iw * (dl - tg)
+        ad = d.abs()
+        lb = lb + s_box * (ow * torch.where(ad < beta, 0.5 * d * d / beta, ad - 0.5 * beta)).sum()
+    # RoI heads on the live rows
+    fine = feats[::-1][:4]
+    scales = [1. / 2 ** l for l in range(2, 6)]
+    live = smp['labels'].reshape(-1) >= 0
+    rois = smp['rois'].reshape(-1, 5)[live]
+    labels = torch.from_numpy(smp['labels'].reshape(-1)[live].astype(np.int64))
+    N = float(live.sum())
+    x = onet.roi_features(fine, scales, rois, cfg.FAST_RCNN.ROI_XFORM_RESOLUTION, cfg.FAST_RCNN.ROI_XFORM_SAMPLING_RATIO)
+    cls, bb = onet.box_head_2mlp(tb, x)
+    l_cls = F.cross_entropy(cls, labels, reduction='sum') / N / world
+    C4 = smp['bbox_targets'].shape[-1]
+    tg, iw, ow = (torch.from_numpy(smp[k].reshape(-1, C4)[live]) for k in ('bbox_targets', 'inside', 'outside'))
+    d = iw * (bb - tg)
+    ad = d.abs()
+    l_box = (ow * torch.where(ad < 1, 0.5 * d * d, ad - 0.5)).sum() / N / world
+    K = cfg.KRCNN.NUM_KEYPOINTS
+    kl = np.zeros(smp['kp_rois'].shape[:2], bool)
+    for b in range(kl.shape[0]):
+        kl[b, :smp['kp_counts'][b]] = True
+    kl = kl.reshape(-1)
+    krois = smp['kp_rois'].reshape(-1, 5)[kl]
+    xk = onet.roi_features(fine, scales, krois, cfg.KRCNN.ROI_XFORM_RESOLUTION, cfg.KRCNN.ROI_XFORM_SAMPLING_RATIO)
+    up, _ = onet.keypoint_head_2d(tb, xk, cfg.KRCNN.NUM_STACKED_CONVS)          # (D, K, 56, 56)
+    lp = F.log_softmax(up.reshape(up.shape[0] * K, -1), dim=1)
+    loc = torch.from_numpy(smp['kp_locations'].reshape(-1, K)[kl].reshape(-1).astype(np.int64))
+    w = torch.from_numpy(smp['kp_weights'].reshape(-1, K)[kl].reshape(-1))
+    l_kps = (-(lp[torch.arange(lp.shape[0]), loc]) * w).sum() / w.sum() * cfg.KRCNN.LOSS_WEIGHT / world
+    (lc + lb + l_cls + l_box + l_kps).backward()
+    return [float(v) for v in (lc, lb, l_cls, l_box, l_kps)], {k: tb[k].grad for k in train}
+
+
+def test_keypoint_rcnn_training_step_vs_autograd():
+    """Config 5 proper at a size the CPU oracle finishes in seconds: device targets (bit-exact vs their own oracle in
+    tests/test_gpu_targets.py) are fed to the torch-fp32 graph, and every loss / checked gradient must agree."""
+    import torch
+    from test_gpu_engine import _cfg
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.trainer import KeypointRcnnTrainer, pack_gt
+    cfg = _cfg()
+    cfg.TEST.SCALES = (96,); cfg.TEST.MAX_SIZE = 128
+    cfg.TRAIN.BATCH_SIZE_PER_IM = 64; cfg.TRAIN.RPN_PRE_NMS_TOP_N = 300; cfg.TRAIN.RPN_POST_NMS_TOP_N = 200
+    cfg.TRAIN.RPN_BATCH_SIZE_PER_IM = 64
+    try:
+        blobs, spec = P.random_blobs(cfg, seed=3)
+        rng = np.random.RandomState(0)
+        frames = rng.randint(0, 256, (2, 3, 96, 128, 3)).astype(np.uint8)
+        entries = []
+        for b in range(2):
+            g = 2 + b
+            x1 = rng.uniform(0, 60, g); y1 = rng.uniform(0, 40, g)
+            boxes = np.stack([x1, y1, x1 + rng.uniform(25, 60, g), y1 + rng.uniform(25, 50, g)], 1).astype(np.float32)
+            kps = np.zeros((g, 3, 17), np.int32)
+            for i in range(g):
+                kps[i, 0] = rng.randint(int(boxes[i, 0]), int(boxes[i, 2]) + 1, 17)
+                kps[i, 1] = rng.randint(int(boxes[i, 1]), int(boxes[i, 3]) + 1, 17)
+                kps[i, 2] = rng.randint(0, 3, 17)
+            entries.append(dict(boxes=boxes, gt_keypoints=kps))
+        gt = pack_gt(entries)
+        tr = KeypointRcnnTrainer(cfg, blobs, spec, lr=0.01, weight_decay=1e-4)
+        fr = torch.from_numpy(frames).cuda()
+        outs = tr.forward_all(fr)
+        rt, smp = tr.make_targets(outs, gt, 2, 96, 128, seed=5)
+        tr.forward_heads(smp)
+        L_ = __import__('detectandtrack_b200._lib', fromlist=['x'])
+        L_.call('dt_memset', L_.ptr(tr.flat_g), 0, tr.flat_g.numel() * 4, L_.stream_ptr())
+        tr.reducer.reset()
+        hg = tr.backward_heads(smp)
+        loss = tr.backward(outs, rt, head_grads=hg, fresh=False).cpu().numpy()
+        lh = tr.loss_heads.cpu().numpy()
+        counts = smp['counts'].cpu().numpy()
+        assert counts.min() > 8 and int(smp['kp_counts'].sum()) > 0 and float(tr.totals[1]) > 0
+        rt_np = [{k: v.cpu().numpy() for k, v in t.items()} for t in rt]
+        smp_np = {k: v.cpu().numpy() for k, v in smp.items()}
+        ref_l, grads = _oracle_full_step(cfg, blobs, frames, rt_np, smp_np)
+        got_l = [loss[0], loss[1], lh[0], lh[1], lh[2]]
+        for name, a, b in zip(('rpn_cls', 'rpn_bbox', 'cls', 'bbox', 'kps'), got_l, ref_l):
+            assert abs(a - b) <= 3e-2 * abs(b) + 1e-6, (name, a, b)
+
+        def dev_grad(c):
+            kT, kH, kW = c.k
+            return c.g.view(kT, kH, kW, c.cout, c.cin).permute(3, 4, 0, 1, 2).cpu()
+
+        bad, errs = [], {}
+
+        def check(name, got, ref, tol=0.25):
+            ref = ref.reshape(got.shape)
+            if float(ref.abs().max()) == 0.0 and float(got.abs().max()) == 0.0:
+                errs[name] = 'both zero'      # e.g. P4 / P5 on a 96 x 128 image: no anchor of that size lies inside, no RoI maps there
+                return
+            err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-30)
+            cos = float((got.flatten() * ref.flatten()).sum() / (got.norm() * ref.norm() + 1e-30))
+            errs[name] = (round(err, 4), round(cos, 5))
+            if err > tol or cos < 0.985:
+                bad.append((name, round(err, 4), round(cos, 5)))
+
+        # box head: fc6 columns are stored in RoIAlign (h, w, c) order
+        g6 = dev_grad(tr.fc6)[:, :, 0, 0, 0].view(-1, 7, 7, 256).permute(0, 3, 1, 2).reshape(-1, 12544)
+        check('fc6_w', g6, grads['fc6_w']); check('fc6_b', tr.fc6.bias_g.cpu(), grads['fc6_b'])
+        check('fc7_w', dev_grad(tr.fc7)[:, :, 0, 0, 0], grads['fc7_w'])
+        C_ = tr.C_
+        gcb = dev_grad(tr.cls_bbox)[:5 * C_, :, 0, 0, 0]
+        check('cls_score_w', gcb[:C_], grads['cls_score_w']); check('bbox_pred_w', gcb[C_:], grads['bbox_pred_w'])
+        check('cls_bbox_b', tr.cls_bbox.bias_g[:5 * C_].cpu(), torch.cat([grads['cls_score_b'], grads['bbox_pred_b']]))
+        for i in (0, 3, 7):
+            check('conv_fcn%d_w' % (i + 1), dev_grad(tr.kps[i])[:, :, 0], grads['conv_fcn%d_w' % (i + 1)])
+        # deconv: gradient of wt[cin, k, ky, kx] sits at the sub-pixel filter (py, px), tap (dy, dx) with ky = py + 1 - 2 dy
+        K = tr.K
+        g3 = dev_grad(tr.kps_lowres)[:, :, 0]                                   # [ldk, cin, 3, 3]
+        gwt = torch.zeros_like(grads['kps_score_lowres_w'])
+        for py in range(2):
+            for px in range(2):
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        ky, kx = py + 1 - 2 * dy, px + 1 - 2 * dx
+                        if 0 <= ky <= 3 and 0 <= kx <= 3:
+                            gwt[:, :, ky, kx] = g3[(py * 2 + px) * K:(py * 2 + px + 1) * K, :, dy + 1, dx + 1].t()
+        check('kps_score_lowres_w', gwt, grads['kps_score_lowres_w'])
+        check('kps_score_lowres_b', tr.kps_lowres.bias_g[:K].cpu(), grads['kps_score_lowres_b'])
+        # trunk layers now also receive the RoI heads' gradient through RoIAlign backward
+        names = spec.stage_blobs[::-1]
+        for i, n in enumerate(names):
+            check('fpn_' + n, dev_grad(tr.post[i]), grads['fpn_%s_w' % n])
+        check('conv_rpn', dev_grad(tr.rpn_conv), grads['conv_rpn_fpn2_w'])
+        check('res5_2_branch2c', dev_grad(tr.stages[-1][-1]['c']), grads['res5_2_branch2c_w'])
+        check('res3_0_branch2a', dev_grad(tr.stages[0][0]['a']), grads['res3_0_branch2a_w'])
+        print('losses (device, oracle)', list(zip(got_l, ref_l)))
+        print('grad (max-norm rel err, cosine) per layer', errs)
+        assert not bad, bad
+        # one whole step() runs end to end and moves the head weights
+        w0 = tr.fc7.w.clone()
+        l1, l2 = tr.step(fr, gt)
+        torch.cuda.synchronize()
+        assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and not torch.equal(w0, tr.fc7.w)
+    finally:
+        _cfg()
