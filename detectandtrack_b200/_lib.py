@@ -45,8 +45,9 @@ SIGNATURES = {
     'dt_spatial_mean': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_time_mean': [_p, _i, _i, C.c_longlong, _i, _i, _i, _i, _i, _p, _i, _p],
     'dt_fold_tube_heads': [_p, _i, _i, _i, _i, _p, _p, _p],
-    'dt_to_planes': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_to_planes': [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_wgrad': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    'dt_wgrad_nhwc': [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_bwd_pointwise': [_p, _p, _p, _p, C.c_longlong, _i, _p, _p],
     'dt_upsample_add_bwd': [_p, _p, _i, _i, _i, _i, _p, _p],
     'dt_scatter_stride2': [_p, _i, _i, _i, _i, _i, _i, _p, _p],

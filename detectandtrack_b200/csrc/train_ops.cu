@@ -191,24 +191,200 @@ static int launch_wgrad(const CUtensorMap& tmG, const CUtensorMap& tmX, const Wg
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, NDHWC operands
+// The same GEMM read STRAIGHT from the NDHWC tensors (no channel-major copies): a TMA box (64 channels = 128 B, TW, TH, TT, TB)
+// of 64 positions lands in shared memory as 64 rows of 128 bytes — positions down the rows, 64 channels along each swizzled
+// row.  Read as an MN-MAJOR tcgen05 operand (instruction descriptor bits 15 / 16) that is exactly the canonical layout
+// ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) with K = the position axis: 8 positions x 128 B per swizzle atom (SBO = 1024 B between
+// 8-position groups) and LBO = 8 KB between 64-channel groups.  The filter tap is a coordinate shift of the input box (TMA
+// zero fill = the conv's padding), exactly as in the forward kernel, so kw needs no pre-shifted copies.
+struct WgradNParams {
+  int Cout, Cin, taps;
+  int kT, kH, kW, pT, pH, pW;
+  int TW, TH, TT, TB;
+  int nW, nH, nT, nN;       // position tiles per axis
+  int T;                    // frames (temporal bounds of the tap shift when TT == 1)
+  int tiles_m, tiles_n, ksplit;
+  float* dW;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // LBO: stride between 64-element groups along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                   // SBO: stride between 8-row groups along K
+  d |= (uint64_t)1 << 46;                             // version
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_nhwc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradNParams p) {
+  constexpr int GRP = 64 * 128;                                    // one (64 positions x 64 channels) box
+  constexpr int A_BYTES = 2 * GRP, B_BYTES = (BN / 64) * GRP, ST_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * ST_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* acc_full = empty + WG_STAGES;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    prefetch_tmap(&tmG); prefetch_tmap(&tmX);
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_base_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  int w = blockIdx.x;
+  const int ks = w % p.ksplit; w /= p.ksplit;
+  const int nt = w % p.tiles_n; w /= p.tiles_n;
+  const int mt = w % p.tiles_m;
+  const int tap = w / p.tiles_m;
+  const int kw = tap % p.kW, kh = (tap / p.kW) % p.kH, kt = tap / (p.kW * p.kH);
+  const int dw = kw - p.pW, dh = kh - p.pH, dt_ = kt - p.pT;
+  const long long total = (long long)p.nN * p.nT * p.nH * p.nW;
+  const long long k0 = total * ks / p.ksplit, k1 = total * (ks + 1) / p.ksplit;
+  // a k-block whose tap-shifted frames all lie outside the clip contributes zero: skipped by producer and issuer alike
+  auto live = [&](int it) -> bool { const int t0 = it * p.TT + dt_; return t0 + p.TT > 0 && t0 < p.T; };
+  auto decode = [&](long long kb, int& iw, int& ih, int& it, int& in) {
+    iw = (int)(kb % p.nW); kb /= p.nW;
+    ih = (int)(kb % p.nH); kb /= p.nH;
+    it = (int)(kb % p.nT); in = (int)(kb / p.nT);
+  };
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    int iw, ih, it, in;
+    decode(k0, iw, ih, it, in);
+    for (long long kb = k0; kb < k1; ++kb) {
+      if (live(it)) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          const uint32_t dst = smem_u32(smem) + stage * ST_BYTES;
+          const uint32_t bar = smem_u32(&full[stage]);
+          mbar_expect_tx_u(bar, (uint32_t)ST_BYTES);
+          const int w0 = iw * p.TW, h0 = ih * p.TH, t0 = it * p.TT, n0 = in * p.TB;
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                         ::"r"(dst + g * GRP), "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(bar), "r"(mt * 128 + g * 64), "r"(w0), "r"(h0), "r"(t0), "r"(n0) : "memory");
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g)
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                         ::"r"(dst + A_BYTES + g * GRP), "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar), "r"(nt * BN + g * 64), "r"(w0 + dw), "r"(h0 + dh),
+                           "r"(t0 + dt_), "r"(n0) : "memory");
+        }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++iw == p.nW) { iw = 0; if (++ih == p.nH) { ih = 0; if (++it == p.nT) { it = 0; ++in; } } }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(128, BN, 1) | (1u << 15) | (1u << 16);      // A and B MN-major
+    int stage = 0; uint32_t phase = 0;
+    int iw, ih, it, in;
+    decode(k0, iw, ih, it, in);
+    uint32_t first = 1;
+    for (long long kb = k0; kb < k1; ++kb) {
+      if (live(it)) {
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t a_addr = smem_u32(smem) + stage * ST_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                                // 16 positions (2 swizzle atoms of 8 rows) per MMA
+            const uint64_t adesc = make_sw128_mnmajor_desc(a_addr + k * 2048, GRP);
+            const uint64_t bdesc = make_sw128_mnmajor_desc(a_addr + A_BYTES + k * 2048, GRP);
+            umma<false>(tmem_base, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+          }
+          umma_commit(&empty[stage]);
+        }
+        first = 0;
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++iw == p.nW) { iw = 0; if (++ih == p.nH) { ih = 0; if (++it == p.nT) { it = 0; ++in; } } }
+    }
+    if (elect_one()) umma_commit(acc_full);
+  } else {
+    bool nothing = true;
+    {
+      int iw, ih, it, in;
+      decode(k0, iw, ih, it, in);
+      for (long long kb = k0; kb < k1 && nothing; ++kb) {
+        if (live(it)) nothing = false;
+        if (++iw == p.nW) { iw = 0; if (++ih == p.nH) { ih = 0; if (++it == p.nT) { it = 0; ++in; } } }
+      }
+    }
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    const int lg = warp & 3;
+    const int row = mt * 128 + lg * 32 + lane;
+    if (!nothing) {
+      float* out = p.dW + ((size_t)tap * p.Cout + row) * p.Cin + nt * BN;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row < p.Cout) {
+          const int col = nt * BN + c0;
+          if (col + 16 <= p.Cin && (p.Cin & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                           "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3])) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.Cin) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+template <int BN>
+static int launch_wgrad_nhwc(const CUtensorMap& tmG, const CUtensorMap& tmX, const WgradNParams& p, cudaStream_t stream) {
+  constexpr int smem = WG_STAGES * (2 + BN / 64) * 64 * 128 + 256;
+  static DynSmemGrant grant;
+  DT_CHECK_CUDA(grant_dyn_smem(wgrad_nhwc_kernel<BN>, smem, &grant));
+  const long long grid = (long long)p.taps * p.tiles_m * p.tiles_n * p.ksplit;
+  DT_CHECK_ARG(grid < (1ll << 31), "dt_wgrad_nhwc: grid too large");
+  wgrad_nhwc_kernel<BN><<<(unsigned)grid, WG_THREADS, smem, stream>>>(tmG, tmX, p);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ planes
-// x [N*T frames, H, W, ldx] (first C channels) -> planes [N*T, C, Pld]: plane position ((h / sh) + pH) * Wp + (w / sw) + pW
-// for h % sh == 0, w % sw == 0; border and row tail zero.  Tile: 64 plane positions x 64 channels through shared memory.
+// x [N*T frames, H, W, ldx] (first C channels) -> planes [copies][N*T, C, Pld]: plane position ((h / sh) + pH) * Wp + (w / sw) + pW
+// for h % sh == 0, w % sw == 0; border and row tail zero.  Copy j holds the plane shifted by wshift0 + j columns (column c of
+// the copy = pixel column c + shift; the wgrad input operand: one copy per filter column).  Tile: 64 plane positions (+ the
+// shift halo) x 64 channels staged ONCE in shared memory, every copy written from it.
+constexpr int TP_HALO = 3;
 __global__ void __launch_bounds__(256)
 to_planes_kernel(const __nv_bfloat16* __restrict__ x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW,
-                 int wshift, int Ho, int Wo, int Pld, __nv_bfloat16* __restrict__ out) {
-  __shared__ __nv_bfloat16 tile[64][66];
+                 int wshift0, int ncopies, int Ho, int Wo, int Pld, long long copy_stride, __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[64 + 2 * TP_HALO][66];
   const int Wp = (Wo + 2 * pW + 7) / 8 * 8;
   const int plane = (Ho + 2 * pH) * Wp;
   const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, f = blockIdx.z;
-  // load: thread -> (position, 16-byte channel group)
-  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+  // load the UNSHIFTED plane positions p0 - HALO .. p0 + 64 + HALO: thread -> (position, 16-byte channel group)
+  for (int i = threadIdx.x; i < (64 + 2 * TP_HALO) * 8; i += blockDim.x) {
     const int pp = i >> 3, cg = (i & 7) * 8;
-    const int pos = p0 + pp;
+    const int pos = p0 - TP_HALO + pp;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (pos < plane && c0 + cg < C) {
+    if (pos >= 0 && pos < plane && c0 + cg < C) {
       const int hp = pos / Wp, wp = pos - hp * Wp;
-      const int ho = hp - pH, wo = wp - pW + wshift;         // copy `wshift`: column c holds the pixel of column c + wshift
+      const int ho = hp - pH, wo = wp - pW;
       if (ho >= 0 && ho < Ho && wo >= 0 && wo < Wo)
         v = *reinterpret_cast<const uint4*>(x + (((size_t)f * H + (size_t)ho * sh) * W + (size_t)wo * sw) * ldx + c0 + cg);
     }
@@ -217,14 +393,22 @@ to_planes_kernel(const __nv_bfloat16* __restrict__ x, int F, int H, int W, int C
     for (int j = 0; j < 8; ++j) tile[pp][cg + j] = e[j];
   }
   __syncthreads();
-  // store: thread -> (channel, 8 consecutive positions)
-  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-    const int cc = i >> 3, pg = (i & 7) * 8;
+  // store: thread -> (copy, channel, 8 consecutive positions).  Copy with shift d at column wp shows the pixel of column
+  // wp + d, i.e. the staged position + d, unless that column falls outside the padded row (then zero: rows do not wrap).
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int i = threadIdx.x; i < ncopies * 64 * 8; i += blockDim.x) {
+    const int cp = i / 512, rem = i - cp * 512;
+    const int cc = rem >> 3, pg = (rem & 7) * 8;
     if (c0 + cc >= C || p0 + pg >= Pld) continue;
+    const int d = wshift0 + cp;
     __align__(16) __nv_bfloat16 v[8];
+    const int hp0 = (p0 + pg) / Wp, wp0 = (p0 + pg) - hp0 * Wp;       // Wp % 8 == 0: the 8 positions share a row
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = tile[pg + j][cc];
-    *reinterpret_cast<uint4*>(out + ((size_t)f * C + c0 + cc) * Pld + p0 + pg) = *reinterpret_cast<const uint4*>(v);
+    for (int j = 0; j < 8; ++j) {
+      const int wsrc = wp0 + j + d;
+      v[j] = (wsrc >= 0 && wsrc < Wp) ? tile[pg + j + d + TP_HALO][cc] : zero;
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)cp * copy_stride + ((size_t)f * C + c0 + cc) * Pld + p0 + pg) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -322,36 +506,69 @@ __global__ void scatter_stride2_kernel(const __nv_bfloat16* __restrict__ src, in
 // Caffe2 MomentumSGDUpdate (non-Nesterov): g' = lr * (grad_scale * g + wd * w) + momentum * m;  m = g';  w -= g'
 // w / g / m [taps][Cout][Cin] fp32.  Re-emits wf [taps][Cout][Cin] bf16 (forward operand) and wd_ [taps][Cin][Cout] bf16
 // with the taps FLIPPED (dgrad of a stride-1 "same" conv is the conv of the gradient with the flipped, transposed filter).
-__global__ void sgd_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, long long n,
-                                  int taps, int Cout, int Cin, float lr, float momentum, float wd, float grad_scale,
-                                  __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wdg) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float wi = w[i];
-    const float adj = lr * (grad_scale * g[i] + wd * wi) + momentum * m[i];
-    m[i] = adj;
-    const float nw = wi - adj;
-    w[i] = nw;
-    if (wf) wf[i] = __float2bfloat16_rn(nw);
-    if (wdg) {
-      const int ci = (int)(i % Cin);
-      const long long r = i / Cin;
-      const int co = (int)(r % Cout);
-      const int tap = (int)(r / Cout);
-      wdg[((size_t)(taps - 1 - tap) * Cin + ci) * Cout + co] = __float2bfloat16_rn(nw);
+// grid (ci tiles of 32, co tiles of 32, taps), block (32, 8): coalesced fp32 reads / writes along Cin, the transposed dgrad
+// filter written through a shared-memory tile so that its stores are coalesced along Cout as well
+__global__ void __launch_bounds__(256)
+sgd_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, int taps, int Cout, int Cin, float lr,
+                  float momentum, float wd, float grad_scale, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wdg) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    float nw = 0.f;
+    if (co < Cout && ci < Cin) {
+      const size_t i = ((size_t)tap * Cout + co) * Cin + ci;
+      const float wi = w[i];
+      const float adj = lr * (grad_scale * g[i] + wd * wi) + momentum * m[i];
+      m[i] = adj;
+      nw = wi - adj;
+      w[i] = nw;
+      if (wf) wf[i] = __float2bfloat16_rn(nw);
     }
+    tile[r][tx] = nw;
+  }
+  if (!wdg) return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (ci < Cin && co < Cout) wdg[((size_t)(taps - 1 - tap) * Cin + ci) * Cout + co] = __float2bfloat16_rn(tile[tx][r]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradient, RPN losses
-// db[c] += sum over rows of g[row, c]   (Conv bias gradient; biases of the FPN / RPN convs are trainable)
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C, int ld, float* __restrict__ db) {
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// db[c] += sum over rows of g[row, c]   (Conv bias gradient; biases of the FPN / RPN / head convs are trainable)
+// block (32 channel groups of 8, 8 row lanes): 16-byte loads, fp32 partial sums, shared-memory reduction, one atomic per channel
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C, int ld, float* __restrict__ db) {
+  __shared__ float part[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = (blockIdx.y * 32 + tx) * 8;
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = per * blockIdx.x, r1 = min(rows, r0 + per);
-  float acc = 0.f;
-  for (long long r = r0; r < r1; ++r) acc += __bfloat162float(g[(size_t)r * ld + c]);
-  if (r1 > r0) atomicAdd(db + c, acc);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < C) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(g + (size_t)r * ld + c0);
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(e[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[ty][tx][j] = acc[j];
+  __syncthreads();
+  // 256 threads -> 256 channels of this block
+  const int cc = threadIdx.x;                      // channel inside the 256-channel tile
+  const int c = blockIdx.y * 256 + cc;
+  if (c < C && r1 > r0) {
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += part[y][cc >> 3][cc & 7];
+    atomicAdd(db + c, s);
+  }
 }
 
 // FPN RPN losses and their gradients at one level (lib/modeling/FPN.py:282-321 with the Detectron ops
@@ -648,17 +865,18 @@ static int grid_for(long long total, int block) {
 extern "C" int dt_planes_ld(int Ho, int Wo, int pH, int pW) { return (Ho + 2 * pH) * ((Wo + 2 * pW + 7) / 8 * 8); }
 
 extern "C" int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, int wshift,
-                            void* out, void* stream) {
+                            int ncopies, void* out, void* stream) {
   DT_CHECK_ARG(F >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && ldx >= C && ldx % 8 == 0 && sh >= 1 && sw >= 1 && pH >= 0 && pW >= 0,
                "dt_to_planes: bad shape F=%d H=%d W=%d C=%d ldx=%d", F, H, W, C, ldx);
-  DT_CHECK_ARG(wshift >= -pW && wshift <= pW, "dt_to_planes: wshift %d outside [-%d, %d]", wshift, pW, pW);
+  DT_CHECK_ARG(ncopies >= 1 && wshift >= -pW && wshift + ncopies - 1 <= pW && pW <= TP_HALO,
+               "dt_to_planes: shifts %d..%d outside [-%d, %d] (pW <= %d)", wshift, wshift + ncopies - 1, pW, pW, TP_HALO);
   if (F == 0) return 0;
   DT_CHECK_ARG(x && out, "dt_to_planes: null pointer");
   const int Ho = (H + sh - 1) / sh, Wo = (W + sw - 1) / sw;
   const int Pld = dt_planes_ld(Ho, Wo, pH, pW);
   dim3 grid((Pld + 63) / 64, (C + 63) / 64, F);
-  to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, F, H, W, C, ldx, sh, sw, pH, pW, wshift, Ho, Wo, Pld,
-                                                           (__nv_bfloat16*)out);
+  to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, F, H, W, C, ldx, sh, sw, pH, pW, wshift, ncopies, Ho, Wo, Pld,
+                                                           (long long)F * C * Pld, (__nv_bfloat16*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }
@@ -705,6 +923,63 @@ extern "C" int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int 
   }
 }
 
+extern "C" int dt_wgrad_nhwc(const void* gz, int ld_g, const void* x, int ld_x, int N, int T, int Ho, int Wo, int Hi, int Wi, int Cout,
+                             int Cin, int kT, int kH, int kW, int sH, int sW, float* dW, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DT_CHECK_ARG(N >= 1 && T >= 1 && Ho >= 1 && Wo >= 1 && Cout >= 1 && Cin >= 8 && Cin % 4 == 0 && kT >= 1 && kH >= 1 && kW >= 1 && (kT & 1) &&
+                   (kH & 1) && (kW & 1) && ld_g >= Cout && ld_g % 8 == 0 && ld_x >= Cin && ld_x % 8 == 0 && sH >= 1 && sW >= 1,
+               "dt_wgrad_nhwc: bad shape N=%d T=%d %dx%d Cout=%d (ld %d) Cin=%d (ld %d) k=%dx%dx%d", N, T, Ho, Wo, Cout, ld_g, Cin, ld_x, kT, kH, kW);
+  const bool strided = sH != 1 || sW != 1;
+  DT_CHECK_ARG(!strided || (kT == 1 && kH == 1 && kW == 1), "dt_wgrad_nhwc: only pointwise convs may be strided");
+  DT_CHECK_ARG(strided ? (Ho == (Hi + sH - 1) / sH && Wo == (Wi + sW - 1) / sW) : (Ho == Hi && Wo == Wi), "dt_wgrad_nhwc: output %dx%d does not match input %dx%d / stride", Ho, Wo, Hi, Wi);
+  DT_CHECK_ARG(gz && x && dW, "dt_wgrad_nhwc: null pointer");
+  WgradNParams p;
+  memset(&p, 0, sizeof(p));
+  p.Cout = Cout; p.Cin = Cin; p.taps = kT * kH * kW; p.kT = kT; p.kH = kH; p.kW = kW; p.pT = kT / 2; p.pH = kH / 2; p.pW = kW / 2;
+  p.T = T; p.dW = dW;
+  // 64-position tile (TW, TH, TT, TB), powers of two: the largest useful fraction, then the widest rows
+  {
+    double best = -1.0;
+    for (int tw = 64; tw >= 1; tw >>= 1)
+      for (int th = 64 / tw; th >= 1; th >>= 1)
+        for (int tt = 64 / (tw * th); tt >= 1; tt >>= 1) {
+          const int tb = 64 / (tw * th * tt);
+          if (tt > 1 && kT > 1) continue;                                   // temporal taps shift whole frames: one frame per box
+          const double cover = (double)cdiv(Wo, tw) * tw * cdiv(Ho, th) * th * cdiv(T, tt) * tt * (double)cdiv(N, tb) * tb;
+          const double eff = (double)Wo * Ho * T * N / cover;
+          if (eff > best + 1e-9) { best = eff; p.TW = tw; p.TH = th; p.TT = tt; p.TB = tb; }
+        }
+  }
+  p.nW = cdiv(Wo, p.TW); p.nH = cdiv(Ho, p.TH); p.nT = cdiv(T, p.TT); p.nN = cdiv(N, p.TB);
+  const int BN = Cin >= 256 ? 256 : (Cin > 64 ? 128 : 64);
+  p.tiles_m = cdiv(Cout, 128); p.tiles_n = cdiv(Cin, BN);
+  const long long units = (long long)p.taps * p.tiles_m * p.tiles_n;
+  const long long kblocks = (long long)p.nW * p.nH * p.nT * p.nN;
+  long long ksplit = (148 * 3 + units - 1) / units;
+  if (ksplit > kblocks / 4) ksplit = kblocks / 4;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = (int)ksplit;
+  CUtensorMap tmG, tmX;
+  const uint32_t box[5] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TT, (uint32_t)p.TB}, e[5] = {1, 1, 1, 1, 1};
+  {
+    uint64_t d[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)T, (uint64_t)N};
+    const uint64_t sC = (uint64_t)ld_g * 2;
+    uint64_t st[4] = {sC, sC * Wo, sC * Wo * Ho, sC * Wo * Ho * T};
+    if (encode_map(&tmG, 0, 5, gz, d, st, box, e)) return 1;
+  }
+  {   // strided pointwise convs: the stride is folded into the global strides (positions of the OUTPUT grid)
+    uint64_t d[5] = {(uint64_t)Cin, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)T, (uint64_t)N};
+    const uint64_t sC = (uint64_t)ld_x * 2;
+    uint64_t st[4] = {sC * sW, sC * Wi * sH, sC * Wi * Hi, sC * Wi * Hi * T};
+    if (encode_map(&tmX, 0, 5, x, d, st, box, e)) return 1;
+  }
+  switch (BN) {
+    case 256: return launch_wgrad_nhwc<256>(tmG, tmX, p, stream);
+    case 128: return launch_wgrad_nhwc<128>(tmG, tmX, p, stream);
+    default: return launch_wgrad_nhwc<64>(tmG, tmX, p, stream);
+  }
+}
+
 extern "C" int dt_bwd_pointwise(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
                                 void* stream) {
   DT_CHECK_ARG(rows >= 0 && C >= 8 && C % 8 == 0, "dt_bwd_pointwise: bad shape rows=%lld C=%d (C %% 8 == 0)", rows, C);
@@ -739,22 +1014,22 @@ extern "C" int dt_scatter_stride2(const void* src, int F, int Hs, int Ws, int H,
 
 extern "C" int dt_sgd_update(float* w, const float* g, float* m, int taps, int Cout, int Cin, float lr, float momentum, float wd,
                              float grad_scale, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream) {
-  DT_CHECK_ARG(taps >= 1 && Cout >= 1 && Cin >= 1, "dt_sgd_update: bad shape");
+  DT_CHECK_ARG(taps >= 1 && taps <= 65535 && Cout >= 1 && Cin >= 1 && (Cout + 31) / 32 <= 65535, "dt_sgd_update: bad shape");
   DT_CHECK_ARG(w && g && m, "dt_sgd_update: null pointer");
-  const long long n = (long long)taps * Cout * Cin;
-  sgd_update_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, n, taps, Cout, Cin, lr, momentum, wd, grad_scale,
-                                                                        (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps);
+  sgd_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, g, m, taps, Cout, Cin, lr, momentum, wd, grad_scale,
+                                                            (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
   DT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int dt_bias_grad(const void* g, long long rows, int C, int ld, float* db, void* stream) {
-  DT_CHECK_ARG(rows >= 0 && C >= 1 && ld >= C, "dt_bias_grad: bad shape rows=%lld C=%d ld=%d", rows, C, ld);
+  DT_CHECK_ARG(rows >= 0 && C >= 8 && C % 8 == 0 && ld >= C && ld % 8 == 0, "dt_bias_grad: bad shape rows=%lld C=%d ld=%d (multiples of 8)", rows, C, ld);
   if (rows == 0) return 0;
   DT_CHECK_ARG(g && db, "dt_bias_grad: null pointer");
-  long long gx = rows / 256; if (gx < 1) gx = 1; if (gx > 592) gx = 592;
-  dim3 grid((unsigned)gx, (C + 127) / 128);
-  bias_grad_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, rows, C, ld, db);
+  long long gx = rows / 128; if (gx < 1) gx = 1; if (gx > 148 * 8) gx = 148 * 8;
+  dim3 grid((unsigned)gx, (C + 255) / 256);
+  bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, rows, C, ld, db);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -22,6 +22,8 @@ and all on the device,
                upsampling (dt_kps_loss_grad)
     backward   the FC / conv layers through the same dgrad / wgrad kernels (an FC is a 1x1 conv over the RoI axis),
                dt_roi_align_bwd into fp32 per-level accumulators that join the RPN's feature gradients."""
+import os
+
 import numpy as np
 
 from .. import _lib as L
@@ -29,6 +31,9 @@ from ..ops import conv as cv, dense_ops, train_ops as to, rpn_ops, box_ops, targ
 from . import params as P
 from .engine import DetectionEngine
 from .generate_anchors import generate_anchors
+
+
+WGRAD_PLANES = os.environ.get('DT_WGRAD_PLANES', '0') == '1'
 
 
 def plan_buckets(counts, nbuckets):
@@ -115,11 +120,14 @@ class TrainConv(object):
         """gz: gradient wrt the conv's raw output (after the pointwise joins), x: the saved input.  Accumulates dW (and db),
         returns (dx or None, x_planes)."""
         N, T, Ho, Wo, _ = gz.shape
-        sp = (self.pad[1], self.pad[2])
-        if x_planes is None:
-            x_planes = to.to_planes(x, pad=sp, stride=self.stride[1:], channels=self.cin, copies=True)
         assert self.cout % 8 == 0 and gz.shape[-1] == self.cout
-        to.wgrad(to.to_planes(gz, pad=sp), x_planes, (Ho, Wo), self.k, self.g)
+        if WGRAD_PLANES:      # the first implementation: channel-major plane copies of both operands (kept for A/B runs)
+            sp = (self.pad[1], self.pad[2])
+            if x_planes is None:
+                x_planes = to.to_planes(x, pad=sp, stride=self.stride[1:], channels=self.cin, copies=True)
+            to.wgrad(to.to_planes(gz, pad=sp), x_planes, (Ho, Wo), self.k, self.g)
+        else:                 # operands read straight from NDHWC (MN-major tcgen05 operands, tap = TMA coordinate shift)
+            to.wgrad_nhwc(gz, x, self.k, self.stride[1:], self.g, cout=self.cout, cin=self.cin)
         if self.bias is not None:
             L.call('dt_bias_grad', L.ptr(gz), gz.numel() // gz.shape[-1], self.cout, gz.shape[-1], L.ptr(self.bias_g), L.stream_ptr())
         dx = None

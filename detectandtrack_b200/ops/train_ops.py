@@ -21,8 +21,8 @@ def to_planes(x, pad=(0, 0), stride=(1, 1), channels=None, copies=False):
     Pld = planes_ld(Ho, Wo, pad[0], pad[1])
     shifts = list(range(-pad[1], pad[1] + 1)) if copies else [0]
     out = torch.empty((len(shifts), N, T, Cc, Pld), dtype=torch.bfloat16, device='cuda')
-    for i, d in enumerate(shifts):
-        L.call('dt_to_planes', L.ptr(x), N * T, H, W, Cc, ld, stride[0], stride[1], pad[0], pad[1], d, L.ptr(out[i]), L.stream_ptr())
+    L.call('dt_to_planes', L.ptr(x), N * T, H, W, Cc, ld, stride[0], stride[1], pad[0], pad[1], shifts[0], len(shifts), L.ptr(out),
+           L.stream_ptr())
     return out if copies else out[0]
 
 
@@ -40,6 +40,23 @@ def wgrad(gz_planes, x_planes, out_hw, ksize, dW=None):
         dW = L.zeros((kT * kH * kW, Cout, Cin), torch.float32)
     assert dW.dtype == torch.float32 and tuple(dW.shape) == (kT * kH * kW, Cout, Cin) and dW.is_contiguous()
     L.call('dt_wgrad', L.ptr(gz_planes), L.ptr(x_planes), N, T, out_hw[0], out_hw[1], Cout, Cin, kT, kH, kW, L.ptr(dW), L.stream_ptr())
+    return dW
+
+
+def wgrad_nhwc(gz, x, ksize, stride=(1, 1), dW=None, cout=None, cin=None):
+    """Filter gradient straight from the NDHWC tensors: gz [N,T,Ho,Wo,ld_g], x [N,T,Hi,Wi,ld_x] bf16 -> dW [taps, Cout, Cin] fp32
+    (accumulated into `dW` if given).  stride (sH, sW) > 1 only for pointwise convs."""
+    torch = L.require_cuda()
+    N, T, Ho, Wo, ld_g = gz.shape
+    _, _, Hi, Wi, ld_x = x.shape
+    Cout, Cin = cout or ld_g, cin or ld_x
+    kT, kH, kW = ksize
+    assert gz.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and gz.is_contiguous() and x.is_contiguous() and x.shape[0] == N and x.shape[1] == T
+    if dW is None:
+        dW = L.zeros((kT * kH * kW, Cout, Cin), torch.float32)
+    assert dW.dtype == torch.float32 and tuple(dW.shape) == (kT * kH * kW, Cout, Cin) and dW.is_contiguous()
+    L.call('dt_wgrad_nhwc', L.ptr(gz), ld_g, L.ptr(x), ld_x, N, T, Ho, Wo, Hi, Wi, Cout, Cin, kT, kH, kW, int(stride[0]), int(stride[1]),
+           L.ptr(dW), L.stream_ptr())
     return dW
 
 

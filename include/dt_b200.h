@@ -339,9 +339,10 @@ int dt_planes_ld(int Ho, int Wo, int pH, int pW);
 
 /* x [F = N*T frames, H, W, ldx] (first C channels) -> planes [F, C, dt_planes_ld(Ho, Wo, pH, pW)], Ho = ceil(H / sh),
  * Wo = ceil(W / sw): plane position (ho + pH) * Wp + wo + pW - wshift holds x[f, ho*sh, wo*sw, c]; border and tail zero.
- * wshift in [-pW, pW]: the copy in which column c holds the pixel of column c + wshift (dt_wgrad's operand for kw = pW + wshift). */
-int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, int wshift, void* out,
-                 void* stream);
+ * wshift in [-pW, pW]: the copy in which column c holds the pixel of column c + wshift (dt_wgrad's operand for kw = pW + wshift).
+ * ncopies >= 1 consecutive shifts wshift .. wshift + ncopies - 1 are written to out [ncopies][F, C, Pld] from one staged read. */
+int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int sw, int pH, int pW, int wshift, int ncopies,
+                 void* out, void* stream);
 
 /* Filter gradient of a stride-1 'same' conv (odd kT/kH/kW, pads k/2): dW [kT*kH*kW][Cout][Cin] fp32 +=
  * sum_{n,t,h,w} gz[n,t,h,w,co] * x[n, t+kt-pT, h+kh-pH, w+kw-pW, ci].  gz_planes [N*T, Cout, Pld] (wshift 0), x_planes
@@ -350,6 +351,13 @@ int dt_to_planes(const void* x, int F, int H, int W, int C, int ldx, int sh, int
  * dW is ACCUMULATED into (split-K partial sums, red.global): the caller zeroes it (dt_memset). */
 int dt_wgrad(const void* gz_planes, const void* x_planes, int N, int T, int Ho, int Wo, int Cout, int Cin, int kT, int kH, int kW,
              float* dW, void* stream);
+
+/* The same filter gradient read straight from the NDHWC tensors (no planes): gz [N, T, Ho, Wo, ld_g] (first Cout channels),
+ * x [N, T, Hi, Wi, ld_x] (first Cin channels), both bf16.  Positions are the K axis of MN-major tcgen05 operands staged by
+ * 5-D TMA boxes; the tap is a coordinate shift (zero fill = padding).  sH / sW > 1 only for pointwise convs
+ * (Ho = ceil(Hi / sH)).  dW [taps][Cout][Cin] fp32 is accumulated into (caller zeroes). */
+int dt_wgrad_nhwc(const void* gz, int ld_g, const void* x, int ld_x, int N, int T, int Ho, int Wo, int Hi, int Wi, int Cout, int Cin,
+                  int kT, int kH, int kW, int sH, int sW, float* dW, void* stream);
 
 /* out = (g1 + g2?) * [y > 0]? * scale[c]? over [rows, C] (any of g2 / y / scale may be NULL) */
 int dt_bwd_pointwise(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,

@@ -49,13 +49,14 @@ def _cases():
         ('dt_frame_costs', (None, 3, 1, None, 0, 0, 0, 0, 0.5, None, None, 2, 4, 1.0, 0.0, None, None), b'dt_frame_costs'),
         ('dt_pairs_to_f16', (None, 10, 12, None, None), b'C % 8'),
         ('dt_scale_rois', (None, 2, 10, 4, None, 1, 1.0, None, None), b'dt_scale_rois'),
-        ('dt_to_planes', (None, 1, 8, 8, 12, 12, 1, 1, 0, 0, 0, None, None), b'dt_to_planes'),
+        ('dt_to_planes', (None, 1, 8, 8, 12, 12, 1, 1, 0, 0, 0, 1, None, None), b'dt_to_planes'),
         ('dt_wgrad', (None, None, 1, 1, 8, 8, 64, 60, 1, 3, 3, None, None), b'Cin % 8'),
+        ('dt_wgrad_nhwc', (None, 64, None, 60, 1, 1, 8, 8, 8, 8, 64, 60, 1, 3, 3, 1, 1, None, None), b'dt_wgrad_nhwc'),
         ('dt_bwd_pointwise', (None, None, None, None, 10, 12, None, None), b'C % 8'),
         ('dt_upsample_add_bwd', (None, None, 1, 4, 4, 12, None, None), b'dt_upsample_add_bwd'),
         ('dt_scatter_stride2', (None, 1, 4, 4, 9, 8, 64, None, None), b'dt_scatter_stride2'),
         ('dt_sgd_update', (None, None, None, 1, 8, 8, 0.1, 0.9, 0.0, 1.0, None, None, None), b'dt_sgd_update'),
-        ('dt_bias_grad', (None, 10, 8, 4, None, None), b'dt_bias_grad'),
+        ('dt_bias_grad', (None, 10, 12, 16, None, None), b'dt_bias_grad'),
         ('dt_rpn_loss_grad', (None, 8, None, None, None, None, 10, 3, 1.0, 1.0, 0.1, None, 16, None, None), b'dt_rpn_loss_grad'),
         ('dt_grad_join_f32', (None, None, 12, None, None), b'multiple of 8'),
         ('dt_roi_align_bwd', (None, ptrs, one, one, onef, 1, 2, 12, None, 5, None, 10, 1, None, 7, 2, None), b'multiple of 8'),

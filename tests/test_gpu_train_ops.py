@@ -8,6 +8,8 @@ up to ~10^5 positions (fp32 split-K partials); bf16-stored outputs add 2^-9."""
 import numpy as np
 import pytest
 
+from detectandtrack_b200.ops import train_ops as to
+
 pytestmark = pytest.mark.gpu
 
 WG_CASES = [
@@ -124,3 +126,82 @@ def test_sgd_update_matches_caffe2_momentum_sgd():
     # the dgrad filter equals packing the flipped / transposed 5-D filter
     w5 = wd_.cpu().view(3, 3, 3, Cout, Cin).permute(3, 4, 0, 1, 2)
     assert torch.equal(wdg.cpu(), to.pack_dgrad_weight(w5).cpu())
+
+
+@pytest.mark.parametrize('shape', [(2, 2, 13, 21, 64, 1, 1), (1, 3, 9, 30, 24, 1, 1), (3, 1, 14, 14, 136, 0, 0), (1, 1, 16, 17, 8, 2, 2)])
+def test_to_planes_all_copies_vs_numpy(shape):
+    """Every pre-shifted copy of the channel-major planes (written from ONE staged read) against a direct numpy build."""
+    import torch
+    N, T, H, W, C, pad, strided = shape
+    rng = np.random.RandomState(7)
+    x = torch.from_numpy(rng.randn(N, T, H, W, C).astype(np.float32)).to(torch.bfloat16)
+    st = (2, 2) if strided else (1, 1)
+    pH = pW = pad if not strided else 0
+    got = to.to_planes(x.cuda(), pad=(pH, pW), stride=st, copies=True).float().cpu().numpy()
+    xs = x.float().numpy()[:, :, ::st[0], ::st[1]]
+    Ho, Wo = xs.shape[2], xs.shape[3]
+    Wp = (Wo + 2 * pW + 7) // 8 * 8
+    assert got.shape == (2 * pW + 1, N, T, C, (Ho + 2 * pH) * Wp)
+    for j, d in enumerate(range(-pW, pW + 1)):
+        ref = np.zeros((N, T, C, Ho + 2 * pH, Wp), np.float32)
+        for wp in range(Wp):
+            wo = wp - pW + d
+            if 0 <= wo < Wo:
+                ref[:, :, :, pH:pH + Ho, wp] = xs[:, :, :, wo, :].transpose(0, 1, 3, 2)
+        assert np.array_equal(got[j], ref.reshape(N, T, C, -1)), (j, d)
+
+
+def test_bias_grad_vs_sum():
+    import torch
+    from detectandtrack_b200 import _lib as L
+    rng = np.random.RandomState(8)
+    for rows, C, ld in ((1000, 256, 256), (37, 16, 16), (5000, 72, 72), (300, 520, 528)):
+        g = torch.from_numpy(rng.randn(rows, ld).astype(np.float32)).to(torch.bfloat16).cuda()
+        db = torch.zeros(C, dtype=torch.float32, device='cuda')
+        L.call('dt_bias_grad', L.ptr(g), rows, C, ld, L.ptr(db), L.stream_ptr())
+        ref = g.float()[:, :C].sum(0)
+        assert torch.allclose(db, ref, rtol=1e-4, atol=1e-3), (rows, C)
+
+
+NHWC_CASES = WG_CASES + [
+    (1, 1, 1, 300, 264, 16, (1, 1, 1)),          # an FC layer: RoIs along W
+    (37, 1, 14, 14, 64, 72, (1, 3, 3)),          # keypoint-head maps: many small images per position tile
+    (2, 3, 25, 42, 128, 128, (3, 3, 3)),         # ragged tiles in H and W, temporal taps
+]
+
+
+@pytest.mark.parametrize('case', range(len(NHWC_CASES)))
+def test_wgrad_nhwc_vs_autograd(case):
+    """dt_wgrad_nhwc (operands straight from NDHWC as MN-major tcgen05 operands) against torch autograd in fp32."""
+    import torch
+    import torch.nn.functional as F
+    N, T, H, W, Cin, Cout, k = NHWC_CASES[case]
+    g = torch.Generator().manual_seed(900 + case)
+    x = torch.randn((N, T, H, W, Cin), generator=g).bfloat16()
+    gz = torch.randn((N, T, H, W, Cout), generator=g).bfloat16()
+    pad = (k[0] // 2, k[1] // 2, k[2] // 2)
+    w = torch.zeros((Cout, Cin) + k, requires_grad=True)
+    F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, None, 1, pad).backward(gz.float().permute(0, 4, 1, 2, 3))
+    ref = w.grad.permute(2, 3, 4, 0, 1).reshape(k[0] * k[1] * k[2], Cout, Cin)
+    cpad = (Cout + 7) // 8 * 8
+    gzd = torch.zeros((N, T, H, W, cpad), dtype=torch.bfloat16)
+    gzd[..., :Cout] = gz
+    dW = to.wgrad_nhwc(gzd.cuda(), x.cuda(), k, cout=cpad)
+    torch.cuda.synchronize()
+    got = dW.cpu()[:, :Cout]
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+    assert float(dW[:, Cout:].abs().sum()) == 0.0
+
+
+def test_wgrad_nhwc_strided_pointwise():
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((2, 3, 25, 41, 256), generator=g).bfloat16()
+    gz = torch.randn((2, 3, 13, 21, 128), generator=g).bfloat16()
+    w = torch.zeros((128, 256, 1, 1, 1), requires_grad=True)
+    F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, None, (1, 2, 2)).backward(gz.float().permute(0, 4, 1, 2, 3))
+    dW = to.wgrad_nhwc(gz.cuda(), x.cuda(), (1, 1, 1), stride=(2, 2))
+    ref = w.grad.reshape(1, 128, 256)
+    assert (dW.cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
