@@ -604,12 +604,21 @@ def run_train(args):
         if full:
             l4 = [float(x) for x in lh.cpu().tolist()]
             cfgd.update(loss_cls=l4[0], loss_bbox=l4[1], loss_kps=l4[2], sampled_rois=float(tr.totals[0]), keypoint_targets=float(tr.totals[1]))
+        pk = peaks()
+        fl = tr.step_flops()
+        tf = fl / (ms / args.steps / 1000.0) / 1e12
+        peak = pk['tflops']
+        roof = dict(bound='tensor', kernel='conv_tc_kernel (forward + dgrad) + wgrad_nhwc_kernel, whole step', achieved=tf, peak=peak, unit='TFLOP/s',
+                    frac=tf / peak, traffic=None,
+                    note='achieved = algorithmic FLOPs of the trainable convs / FCs (forward + filter gradient + input gradient, %.1f GFLOP per '
+                         'step of %d clips; frozen stem excluded) / WHOLE step time incl. targets, losses, joins, all-reduce and SGD' % (fl / 1e9, B),
+                    peak_source=pk['src'])
         line = dict(metric='training clips/sec, %s, T=3, %dx%d' % (what, H, W),
                     value=world * B * args.steps / (ms / 1000.0), unit='clips/s', n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='bf16', data='synthetic',
                     e2e=dict(value=world * B * args.steps / (ms2 / 1000.0), unit='clips/s', h2d_bytes_per_step=int(frames_h.numel()),
-                             d2h_bytes_per_step=24), config=cfgd, clocks=clocks)
+                             d2h_bytes_per_step=24), roofline=roof, config=cfgd, clocks=clocks)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

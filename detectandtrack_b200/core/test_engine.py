@@ -69,7 +69,18 @@ class JsonListDataset(object):
             self.entries = json.load(f)
 
     def get_roidb(self, gt=False):
-        return self.entries
+        """Per-frame entries ('image' a path) of a video model are assembled into T-frame clips exactly like the reference's
+        json_dataset -> utils/video.get_clip (neighbours at VIDEO.TIME_INTERVAL, clamped at the video ends); entries that
+        already carry a frame list pass through."""
+        roidb = self.entries
+        if cfg.MODEL.VIDEO_ON and roidb and not isinstance(roidb[0]['image'], (list, tuple)):
+            from ..utils import video
+            for e in roidb:
+                for k in ('boxes', 'gt_keypoints', 'tracks', 'gt_classes', 'is_crowd'):
+                    if k in e and not isinstance(e[k], np.ndarray):
+                        e[k] = np.asarray(e[k], dtype={'boxes': np.float32, 'is_crowd': bool}.get(k, np.int32))
+            roidb = video.get_clip(roidb)
+        return roidb
 
 
 def get_dataset(name):

@@ -96,6 +96,8 @@ class TrainConv(object):
         self.pad = tuple(x // 2 for x in self.k)
         self.stride, self.relu = stride, relu
         self.cout, self.cin = w.shape[0], w.shape[1]
+        self.cout_live = self.cout                        # output channels that are not zero padding (set by the builder)
+        self._accumulate = 0                              # 1: the conv runs several times per step (RPN heads: once per level)
         self.taps = self.k[0] * self.k[1] * self.k[2]
         self.w = w.permute(2, 3, 4, 0, 1).reshape(self.taps, self.cout, self.cin).contiguous().cuda()
         self.m = torch.zeros_like(self.w)
@@ -113,6 +115,9 @@ class TrainConv(object):
         return self.w.numel() + (self.bias.numel() if self.bias is not None else 0)
 
     def forward(self, x, residual=None, res_mode=0, out_f32=False, out=None):
+        N, T, H, W, _ = x.shape                                  # algorithmic MACs of this launch (the roofline's numerator)
+        self.macs = (N * T * ((H + self.stride[1] - 1) // self.stride[1]) * ((W + self.stride[2] - 1) // self.stride[2]) *
+                     self.cout_live * self.cin * self.taps) + getattr(self, 'macs', 0) * self._accumulate
         return cv.conv3d(x, self.w_fwd, self.k, self.stride, self.pad, self.scale, self.shift if self.bias is None else self.bias,
                          residual, res_mode, self.relu, out_f32=out_f32, dtype=cv.BF16, out=out)
 
@@ -186,6 +191,8 @@ class RpnTrainer(object):
         wp = np.zeros((ld,) + w.shape[1:], np.float32); wp[:5 * A] = w
         bp = np.zeros((ld,), np.float32); bp[:5 * A] = b
         self.rpn_out = TrainConv(torch, wp, bias=bp)
+        self.rpn_out.cout_live = 5 * A
+        self.rpn_out._accumulate = self.rpn_conv._accumulate = 1
         self.convs.append(self.rpn_out)
         self._build_heads(blobs)                          # RoI heads of the full model (KeypointRcnnTrainer); none here
         # ---- flat gradient buffer in BACKWARD order (so a bucket finished early in the backward pass is contiguous)
@@ -218,6 +225,7 @@ class RpnTrainer(object):
         """stem -> res2 (frozen) -> res3..5 -> FPN -> RPN heads; returns per level the fp32 RPN outputs [B,1,H,W,ld]."""
         torch, eng, s, cfg = self.torch, self.eng, self.spec, self.cfg
         B, T, H, W, _ = frames_u8.shape
+        self.rpn_conv.macs = self.rpn_out.macs = 0
         g = eng._geom_tensors(B, H, W)
         x = eng._blob(frames_u8, g['scale'], g['hr'], g['wr'], g['hp'], g['wp'])
         xs = x.view((B * T,) + tuple(x.shape[2:]))
@@ -359,6 +367,17 @@ class RpnTrainer(object):
         self.reducer.wait()
         return self.loss
 
+    def step_flops(self):
+        """Algorithmic FLOPs of the last step's tensor-core work: 2 * MACs of every trainable conv / FC, once forward, once for
+        the filter gradient and once for the input gradient where one is needed (everything except the first trainable convs
+        after the frozen stem).  The frozen stem's forward (conv1, res2) is not counted."""
+        first = {id(self.stages[0][0]['a']), id(self.stages[0][0]['sc'])}
+        tot = 0
+        for c in self.convs:
+            m = getattr(c, 'macs', 0)
+            tot += 2 * m * (2 if id(c) in first else 3)
+        return tot
+
     def update(self):
         gs = 1.0            # losses already carry 1/NUM_GPUS; the all-reduce is a SUM (model_builder.py:484,938-942)
         for c in self.convs:
@@ -449,6 +468,7 @@ class KeypointRcnnTrainer(RpnTrainer):
         wp = np.zeros((ld, w.shape[1]), np.float32); wp[:5 * C_] = w
         bp = np.zeros((ld,), np.float32); bp[:5 * C_] = b
         self.cls_bbox = TrainConv(torch, wp, bias=bp); add(self.cls_bbox)
+        self.cls_bbox.cout_live = 5 * C_
         self.kps = []
         for i in range(cfg.KRCNN.NUM_STACKED_CONVS):
             c = TrainConv(torch, blobs['conv_fcn%d_w' % (i + 1)], bias=blobs['conv_fcn%d_b' % (i + 1)], relu=True)
@@ -470,6 +490,7 @@ class KeypointRcnnTrainer(RpnTrainer):
                             w3[(py * 2 + px) * K:(py * 2 + px + 1) * K, :, dy + 1, dx + 1] = wt[:, :, ky, kx].T
         b3 = np.zeros((ldk,), np.float32); b3[:4 * K] = np.tile(blobs['kps_score_lowres_b'], 4)
         self.kps_lowres = TrainConv(torch, w3, bias=b3); add(self.kps_lowres)
+        self.kps_lowres.cout_live = 4 * K
         self.loss_heads = torch.zeros(4, dtype=torch.float32, device='cuda')      # cls, bbox, kps, #correct
         self.totals = torch.zeros(2, dtype=torch.float32, device='cuda')          # live RoIs, keypoint weight sum (loss normalisers)
         self.iter = 0
