@@ -54,6 +54,7 @@ SIGNATURES = {
     'dt_sgd_update': [_p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p],
     'dt_bias_grad': [_p, C.c_longlong, _i, _i, _p, _p],
     'dt_rpn_loss_grad': [_p, _i, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _p, _i, _p, _p],
+    'dt_embed_frame': [_p, _i, _i, C.c_longlong, _i, _p, _p],
     'dt_grad_join_f32': [_p, _p, C.c_longlong, _p, _p],
     'dt_roi_align_bwd': [_p, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _i, _p],
     'dt_frcnn_loss_grad': [_p, _i, _p, _p, _p, _p, _i, _i, _p, _f, _f, _p, _i, _p, _p, _p],

@@ -169,6 +169,7 @@ rpn_sample_kernel(int NA, int batch, int num_fg, float neg_thresh, unsigned long
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining, s_total;
   __shared__ unsigned s_draw[1024];
+  extern __shared__ int gcnt[];                       // candidate counts / prefix per 32-anchor group
   const int b = blockIdx.x;
   const float* am = amax + (size_t)b * NA;
   signed char* lb = lab + (size_t)b * NA;
@@ -210,25 +211,37 @@ rpn_sample_kernel(int NA, int batch, int num_fg, float neg_thresh, unsigned long
   }
   const int num_bg = batch - kept_fg;
   if (nbc > num_bg && num_bg > 0) {
-    // num_bg draws WITH replacement from the candidates in index order: draw j picks candidate number (hash(j) * nbc) >> 32
+    // num_bg draws WITH replacement from the candidates in index order: draw j picks candidate number (hash(j) * nbc) >> 32.
+    // Candidate counts per 32-anchor group (coalesced ballots) -> exclusive prefix in shared memory -> each draw finds its
+    // group by binary search and its anchor inside the group.
     const int nd = min(num_bg, 1024);
     for (int j = threadIdx.x; j < nd; j += blockDim.x) s_draw[j] = (unsigned)(((unsigned long long)hash_u32(base1, (unsigned long long)j) * (unsigned long long)nbc) >> 32);
-    const int per = (NA + blockDim.x - 1) / blockDim.x;
-    const int i0 = min(NA, (int)threadIdx.x * per), i1 = min(NA, i0 + per);
+    const int ng = (NA + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int gidx = warp; gidx < ng; gidx += 32) {
+      const int i = gidx * 32 + lane;
+      const float m = i < NA ? am[i] : -2.f;
+      const unsigned bal = __ballot_sync(0xffffffffu, m > -1.5f && m < neg_thresh);
+      if (lane == 0) gcnt[gidx] = __popc(bal);
+    }
+    __syncthreads();
+    const int per = (ng + blockDim.x - 1) / blockDim.x;
+    const int g0 = min(ng, (int)threadIdx.x * per), g1 = min(ng, g0 + per);
     int c = 0;
-    for (int i = i0; i < i1; ++i) { const float m = am[i]; c += (m > -1.5f && m < neg_thresh) ? 1 : 0; }
-    const int off = block_scan_excl(c, warp_sums, &s_total);
-    if (c > 0) {
-      for (int j = 0; j < nd; ++j) {
-        const int r = (int)s_draw[j] - off;
-        if (r < 0 || r >= c) continue;
-        int seen = 0;
-        for (int i = i0; i < i1; ++i) {
-          const float m = am[i];
-          if (m > -1.5f && m < neg_thresh) {
-            if (seen == r) { lb[i] = (lb[i] == 1 || lb[i] == 2) ? 2 : 0; break; }   // 2: label 0, but still a "fg_ind" for the box targets
-            ++seen;
-          }
+    for (int q = g0; q < g1; ++q) c += gcnt[q];
+    int run = block_scan_excl(c, warp_sums, &s_total);
+    for (int q = g0; q < g1; ++q) { const int t = gcnt[q]; gcnt[q] = run; run += t; }      // exclusive prefix per group
+    __syncthreads();
+    for (int j = threadIdx.x; j < nd; j += blockDim.x) {
+      const int r = (int)s_draw[j];
+      int lo = 0, hi = ng - 1;                         // last group whose prefix <= r
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (gcnt[mid] <= r) lo = mid; else hi = mid - 1; }
+      int want = r - gcnt[lo];
+      for (int i = lo * 32; i < min(NA, lo * 32 + 32); ++i) {
+        const float m = am[i];
+        if (m > -1.5f && m < neg_thresh) {
+          if (want == 0) { const signed char v = lb[i]; lb[i] = (v == 1 || v == 2) ? 2 : 0; break; }   // 2: label 0, still a "fg_ind" for the box targets
+          --want;
         }
       }
     }
@@ -560,7 +573,11 @@ extern "C" int dt_rpn_targets(const dt_rpn_target_level* levels, int n_levels, i
   rpn_label_kernel<<<grid, 256, 0, stream>>>(lv, (int)NA, gt_boxes, gt_counts, Gmax, im_info, positive_overlap, negative_overlap, amax, gmax, lab, cnt);
   DT_CHECK_LAUNCH();
   const int num_fg = (int)(fg_fraction * batch_size_per_im);
-  rpn_sample_kernel<<<B, 1024, 0, stream>>>((int)NA, batch_size_per_im, num_fg, negative_overlap, seed, amax, lab, cnt);
+  const int sample_smem = (int)((NA + 31) / 32) * 4;
+  DT_CHECK_ARG(sample_smem <= 200 * 1024, "dt_rpn_targets: %lld anchors per image exceed the draw kernel's shared memory", NA);
+  static DynSmemGrant sample_grant;
+  DT_CHECK_CUDA(grant_dyn_smem(rpn_sample_kernel, sample_smem, &sample_grant));
+  rpn_sample_kernel<<<B, 1024, sample_smem, stream>>>((int)NA, batch_size_per_im, num_fg, negative_overlap, seed, amax, lab, cnt);
   DT_CHECK_LAUNCH();
   rpn_write_kernel<<<grid, 256, 0, stream>>>(lv, (int)NA, gt_boxes, gt_counts, Gmax, im_info, aarg, lab, cnt);
   DT_CHECK_LAUNCH();

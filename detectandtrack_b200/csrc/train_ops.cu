@@ -502,6 +502,17 @@ __global__ void scatter_stride2_kernel(const __nv_bfloat16* __restrict__ src, in
   }
 }
 
+// out [B, T, P, C]: frame c = src [B, P, C], every other frame zero (backward of the slice-center body/head link)
+__global__ void embed_frame_kernel(const uint4* __restrict__ src, long long per_frame_v, int B, int T, int c, uint4* __restrict__ out) {
+  const long long total = (long long)B * T * per_frame_v;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i % per_frame_v;
+    const long long bt = i / per_frame_v;
+    const int t = (int)(bt % T);
+    out[i] = (t == c) ? src[(bt / T) * per_frame_v + e] : make_uint4(0, 0, 0, 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ SGD
 // Caffe2 MomentumSGDUpdate (non-Nesterov): g' = lr * (grad_scale * g + wd * w) + momentum * m;  m = g';  w -= g'
 // w / g / m [taps][Cout][Cin] fp32.  Re-emits wf [taps][Cout][Cin] bf16 (forward operand) and wd_ [taps][Cin][Cout] bf16
@@ -1008,6 +1019,15 @@ extern "C" int dt_scatter_stride2(const void* src, int F, int Hs, int Ws, int H,
   DT_CHECK_ARG(src && out, "dt_scatter_stride2: null pointer");
   scatter_stride2_kernel<<<grid_for((long long)F * H * W * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)src, F, Hs, Ws, H, W, C, (__nv_bfloat16*)out);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_embed_frame(const void* src, int B, int T, long long frame_elems, int c, void* out, void* stream) {
+  DT_CHECK_ARG(B >= 0 && T >= 1 && c >= 0 && c < T && frame_elems >= 8 && frame_elems % 8 == 0, "dt_embed_frame: bad shape B=%d T=%d c=%d elems=%lld", B, T, c, frame_elems);
+  if (B == 0) return 0;
+  DT_CHECK_ARG(src && out, "dt_embed_frame: null pointer");
+  embed_frame_kernel<<<grid_for((long long)B * T * (frame_elems / 8), 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, frame_elems / 8, B, T, c, (uint4*)out);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -114,12 +114,12 @@ class TrainConv(object):
     def nparams(self):
         return self.w.numel() + (self.bias.numel() if self.bias is not None else 0)
 
-    def forward(self, x, residual=None, res_mode=0, out_f32=False, out=None):
+    def forward(self, x, residual=None, res_mode=0, out_f32=False, out=None, time_major=False):
         N, T, H, W, _ = x.shape                                  # algorithmic MACs of this launch (the roofline's numerator)
         self.macs = (N * T * ((H + self.stride[1] - 1) // self.stride[1]) * ((W + self.stride[2] - 1) // self.stride[2]) *
                      self.cout_live * self.cin * self.taps) + getattr(self, 'macs', 0) * self._accumulate
         return cv.conv3d(x, self.w_fwd, self.k, self.stride, self.pad, self.scale, self.shift if self.bias is None else self.bias,
-                         residual, res_mode, self.relu, out_f32=out_f32, dtype=cv.BF16, out=out)
+                         residual, res_mode, self.relu, out_f32=out_f32, dtype=cv.BF16, out=out, time_major=time_major)
 
     def backward(self, gz, x, x_planes=None, need_dx=True):
         """gz: gradient wrt the conv's raw output (after the pointwise joins), x: the saved input.  Accumulates dW (and db),
@@ -185,6 +185,7 @@ class RpnTrainer(object):
         k = str(s.rpn_levels[0])
         A = self.A = s.num_anchors
         self.rpn_conv = mk(blobs, 'conv_rpn_fpn' + k, relu=True)
+        self.blobs0 = blobs                                   # the initial weights dict (export_blobs fills the trained ones in)
         w = np.concatenate([blobs['rpn_cls_logits_fpn%s_w' % k], blobs['rpn_bbox_pred_fpn%s_w' % k]], 0)
         b = np.concatenate([blobs['rpn_cls_logits_fpn%s_b' % k], blobs['rpn_bbox_pred_fpn%s_b' % k]], 0)
         ld = self.rpn_ld = (5 * A + 7) // 8 * 8           # padded with zero filters so the planes are 16-byte rows
@@ -217,6 +218,7 @@ class RpnTrainer(object):
         c = TrainConv(self.torch, blobs[name + '_w'], scale=blobs[name + '_bn_s'] if affine else None,
                       shift=blobs[name + '_bn_b'] if affine else None, bias=None if affine else blobs[name + '_b'],
                       stride=stride, relu=relu)
+        c.name = name
         self.convs.append(c)
         return c
 
@@ -248,11 +250,13 @@ class RpnTrainer(object):
         inner = [self.lat[0].forward(Cs[0])]
         for i in range(1, len(Cs)):
             inner.append(self.lat[i].forward(Cs[i], residual=inner[i - 1], res_mode=2))
-        Ps = [self.post[i].forward(inner[i]) for i in range(len(inner))]          # [B, T, h, w, 256], coarsest first
+        tm = s.link == 'slice-center' and T > 1        # frames-outermost storage: the centre-frame link below is a view
+        Ps = [self.post[i].forward(inner[i], time_major=tm) for i in range(len(inner))]   # [B, T, h, w, 256], coarsest first
         sv['inner'], sv['P'] = inner, Ps
         c = int(cfg.VIDEO.NUM_FRAMES_MID / 2) if (s.link == 'slice-center' and T > 1) else 0
         sv['center'] = c
-        feats = [p[:, c:c + 1].contiguous() if T > 1 else p for p in Ps]          # slice-center link
+        feats = [p[:, c:c + 1] if T > 1 else p for p in Ps]                       # slice-center link (contiguous [B, 1, h, w, C] views)
+        assert all(f.is_contiguous() for f in feats)
         p6 = dense_ops.maxpool2d(feats[0].view((B,) + tuple(feats[0].shape[2:])), 1, 2, 0)
         feats = [p6.view((B, 1) + tuple(p6.shape[1:]))] + feats                   # P6 first (coarsest)
         sv['feats'] = feats
@@ -313,8 +317,8 @@ class RpnTrainer(object):
             if i == 0:
                 g = to.bwd_pointwise(g, to.scatter_stride2(gfeat[0], (g.shape[2], g.shape[3])))
             if T > 1:                                                            # slice-center: the other frames get zero
-                full = L.zeros(tuple(Ps[i].shape), torch.bfloat16)
-                full[:, c:c + 1].copy_(g)
+                full = torch.empty(tuple(Ps[i].shape), dtype=torch.bfloat16, device='cuda')
+                L.call('dt_embed_frame', L.ptr(g), g.shape[0], T, g.numel() // g.shape[0], c, L.ptr(full), L.stream_ptr())
                 g = full
             gP.append(g)
         # FPN: finest level first (its inner gradient flows into the next coarser one through the top-down add)
@@ -377,6 +381,34 @@ class RpnTrainer(object):
             m = getattr(c, 'macs', 0)
             tot += 2 * m * (2 if id(c) in first else 3)
         return tot
+
+    # ------------------------------------------------------------------ weights back to the reference's blob names
+    @staticmethod
+    def _blob_w(c, shape):
+        """packed master filter [taps, Cout, Cin] -> the blob layout (Cout, Cin[, kT], kH, kW) of `shape`."""
+        kT, kH, kW = c.k
+        w = c.w.view(kT, kH, kW, c.cout, c.cin).permute(3, 4, 0, 1, 2).contiguous().cpu().numpy()
+        return w.reshape((c.cout, c.cin) + tuple(shape[2:])) if len(shape) >= 2 else w
+
+    def export_blobs(self, blobs):
+        """The trained parameters written back into a copy of the weights dict under the reference's blob names
+        (lib/utils/net.py:252-294 save_model_to_weights_file): what tools/test_net.py loads through TEST.WEIGHTS."""
+        out = dict(blobs)
+        for c in self.convs:
+            n = getattr(c, 'name', None)
+            if n is None:
+                continue
+            out[n + '_w'] = self._blob_w(c, blobs[n + '_w'].shape).astype(np.float32)
+            if c.bias is not None:
+                out[n + '_b'] = c.bias.cpu().numpy()
+        k = str(self.spec.rpn_levels[0])
+        A = self.A
+        w = self.rpn_out.w[0].cpu().numpy()                                   # [ld, Cin]
+        b = self.rpn_out.bias.cpu().numpy()
+        out['rpn_cls_logits_fpn%s_w' % k] = w[:A].reshape(blobs['rpn_cls_logits_fpn%s_w' % k].shape)
+        out['rpn_bbox_pred_fpn%s_w' % k] = w[A:5 * A].reshape(blobs['rpn_bbox_pred_fpn%s_w' % k].shape)
+        out['rpn_cls_logits_fpn%s_b' % k], out['rpn_bbox_pred_fpn%s_b' % k] = b[:A].copy(), b[A:5 * A].copy()
+        return out
 
     def update(self):
         gs = 1.0            # losses already carry 1/NUM_GPUS; the all-reduce is a SUM (model_builder.py:484,938-942)
@@ -494,6 +526,35 @@ class KeypointRcnnTrainer(RpnTrainer):
         self.loss_heads = torch.zeros(4, dtype=torch.float32, device='cuda')      # cls, bbox, kps, #correct
         self.totals = torch.zeros(2, dtype=torch.float32, device='cuda')          # live RoIs, keypoint weight sum (loss normalisers)
         self.iter = 0
+
+    def export_blobs(self, blobs):
+        out = RpnTrainer.export_blobs(self, blobs)
+        cfg, s = self.cfg, self.spec
+        res, fd = cfg.FAST_RCNN.ROI_XFORM_RESOLUTION, s.fpn_dim
+        w6 = self.fc6.w[0].cpu().numpy()                                      # columns in (h, w, c) order -> (c, h, w)
+        out['fc6_w'] = w6.reshape(-1, res, res, fd).transpose(0, 3, 1, 2).reshape(w6.shape[0], -1).copy()
+        out['fc6_b'] = self.fc6.bias.cpu().numpy()
+        out['fc7_w'], out['fc7_b'] = self.fc7.w[0].cpu().numpy().copy(), self.fc7.bias.cpu().numpy()
+        C_ = self.C_
+        w, b = self.cls_bbox.w[0].cpu().numpy(), self.cls_bbox.bias.cpu().numpy()
+        out['cls_score_w'], out['bbox_pred_w'] = w[:C_].copy(), w[C_:5 * C_].copy()
+        out['cls_score_b'], out['bbox_pred_b'] = b[:C_].copy(), b[C_:5 * C_].copy()
+        for i, c in enumerate(self.kps):
+            out['conv_fcn%d_w' % (i + 1)] = self._blob_w(c, blobs['conv_fcn%d_w' % (i + 1)].shape).astype(np.float32)
+            out['conv_fcn%d_b' % (i + 1)] = c.bias.cpu().numpy()
+        K = self.K
+        w3 = self._blob_w(self.kps_lowres, (self.kp_ld, self.kps_lowres.cin, 3, 3))        # [ldk, cin, 3, 3]
+        wt = np.zeros_like(blobs['kps_score_lowres_w'])                                  # (cin, K, 4, 4)
+        for py in range(2):
+            for px in range(2):
+                for dy in (-1, 0, 1):
+                    for dx in (-1, 0, 1):
+                        ky, kx = py + 1 - 2 * dy, px + 1 - 2 * dx
+                        if 0 <= ky <= 3 and 0 <= kx <= 3:
+                            wt[:, :, ky, kx] = w3[(py * 2 + px) * K:(py * 2 + px + 1) * K, :, dy + 1, dx + 1].T
+        out['kps_score_lowres_w'] = wt
+        out['kps_score_lowres_b'] = self.kps_lowres.bias.cpu().numpy()[:K].copy()
+        return out
 
     # ------------------------------------------------------------------ geometry / proposals
     def _train_geom(self, B, H, W):

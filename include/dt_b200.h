@@ -387,6 +387,10 @@ int dt_rpn_loss_grad(const float* out, int ld_o, const int* labels, const float*
                      const float* outside_w, long long rows, int A, float scale_cls, float scale_box, float beta, void* grad,
                      int ld_g, float* loss, void* stream);
 
+/* Backward of the slice-center body/head link (lib/modeling/model_builder.py:1024-1042 SliceKeyFrame): out [B, T, frame_elems]
+ * bf16 = src [B, frame_elems] in frame c, zero in every other frame. */
+int dt_embed_frame(const void* src, int B, int T, long long frame_elems, int c, void* out, void* stream);
+
 /* fp32 accumulator joins of the RoI-head backward: out (bf16) = g (bf16, may be NULL) + acc (fp32) */
 int dt_grad_join_f32(const void* g, const float* acc, long long n, void* out, void* stream);
 

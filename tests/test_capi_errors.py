@@ -58,6 +58,7 @@ def _cases():
         ('dt_sgd_update', (None, None, None, 1, 8, 8, 0.1, 0.9, 0.0, 1.0, None, None, None), b'dt_sgd_update'),
         ('dt_bias_grad', (None, 10, 12, 16, None, None), b'dt_bias_grad'),
         ('dt_rpn_loss_grad', (None, 8, None, None, None, None, 10, 3, 1.0, 1.0, 0.1, None, 16, None, None), b'dt_rpn_loss_grad'),
+        ('dt_embed_frame', (None, 2, 3, 64, 5, None, None), b'dt_embed_frame'),
         ('dt_grad_join_f32', (None, None, 12, None, None), b'multiple of 8'),
         ('dt_roi_align_bwd', (None, ptrs, one, one, onef, 1, 2, 12, None, 5, None, 10, 1, None, 7, 2, None), b'multiple of 8'),
         ('dt_frcnn_loss_grad', (None, 8, None, None, None, None, 10, 2, None, 1.0, 1.0, None, 16, None, None, None), b'dt_frcnn_loss_grad'),

@@ -189,3 +189,38 @@ def test_sample_rois_batch_wide_topn_vs_oracle():
         ref = ot.sample_rois(gts[b], cls[b], crowd[b], kps[b], kept[b][:, 1:], scale, b, 21, batch=batch)
         _check_sampled(o, b, ref, batch)
     assert int(o['kp_counts'][1]) == len(gts[1])                      # the no-visible-keypoint fallback (keypoint_rcnn.py:45-46)
+
+
+def test_targets_edge_cases_empty_inputs():
+    """Empty inputs: an image without ground truth (the reference's loader filters those out; here every anchor is ignored
+    and every proposal is background) and an image without proposals (its gt boxes are the only RoIs), in one batch."""
+    import torch
+    from detectandtrack_b200.ops import target_ops
+    rng = np.random.default_rng(3)
+    shapes = [(24, 32), (12, 16), (6, 8), (3, 4), (2, 2)]
+    gb = np.zeros((2, 8, 4), np.float32)
+    gb[1, :2] = [[10, 12, 60, 90], [40, 20, 100, 80]]
+    counts = np.array([0, 2], np.int32)
+    im = np.array([[96, 128, 1.0]] * 2, np.float32)
+    out = target_ops.rpn_targets(shapes, _anchors(torch), [2. ** l for l in range(2, 7)], 3, torch.from_numpy(gb).cuda(),
+                                 torch.from_numpy(counts).cuda(), torch.from_numpy(im).cuda(), _TrainCfg(64), 1)
+    for o in out:
+        assert int((o['labels'][0] != -1).sum()) == 0 and float(o['outside'][0].abs().sum()) == 0 and float(o['inside'][0].abs().sum()) == 0
+    assert sum(int((o['labels'][1] == 1).sum()) for o in out) > 0
+    # RoI sampling: image 0 has proposals but no gt, image 1 has gt but no proposals
+    R = 50
+    x1 = rng.uniform(0, 60, R); y1 = rng.uniform(0, 40, R)
+    rois = np.zeros((2, R, 5), np.float32); rois[1, :, 0] = 1
+    rois[0, :, 1:] = np.stack([x1, y1, x1 + 30, y1 + 40], 1)
+    scores = np.zeros((2, R), np.float32); scores[0] = np.linspace(1, 0.1, R)
+    kps = np.zeros((2, 8, 3, 17), np.int32)
+    kps[1, :2, 0] = 50; kps[1, :2, 1] = 50; kps[1, :2, 2] = 2
+    gt = dict(boxes=torch.from_numpy(gb).cuda(), classes=torch.ones((2, 8), dtype=torch.int32).cuda(), crowd=torch.zeros((2, 8), dtype=torch.int32).cuda(),
+              keypoints=torch.from_numpy(kps).cuda(), counts=torch.from_numpy(counts).cuda())
+    o = target_ops.sample_rois(torch.from_numpy(rois).cuda(), torch.from_numpy(scores).cuda(), torch.tensor([R, 0], dtype=torch.int32).cuda(), gt,
+                               torch.from_numpy(im).cuda(), _Cfg(32), 2)
+    assert o['counts'].tolist() == [32, 2]                               # 32 background RoIs; the two gt boxes as foreground
+    assert int((o['labels'][0, :32] != 0).sum()) == 0 and o['labels'][1, :2].tolist() == [1, 1] and int((o['labels'][1, 2:] != -1).sum()) == 0
+    assert o['kp_counts'].tolist() == [0, 2]
+    ref = ot.sample_rois(gb[1, :2], np.ones(2, np.int32), np.zeros(2, np.int32), kps[1, :2], np.zeros((0, 4), np.float32), 1.0, 1, 2, batch=32)
+    _check_sampled(o, 1, ref, 32)

@@ -129,4 +129,12 @@ def test_train_net_loss_goes_down(tmp_path):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     losses = [float(m.group(1)) for m in re.finditer(r'iter \d+ lr [\d.]+ loss ([\d.]+)', r.stdout)]
     assert len(losses) == 4 and all(np.isfinite(losses)), r.stdout[-2000:]
+    # the snapshot is a weights file of the reference's format that tools/test_net.py runs on
+    snap = os.path.join(str(tmp_path / 'out'), 'train', 'synthetic_1x2_96x128', 'keypoint_rcnn', 'model_final.pkl')
+    w = pickle.load(open(snap, 'rb'))
+    assert 'blobs' in w and w['blobs']['fc6_w'].shape == (1024, 12544) and w['blobs']['kps_score_lowres_w'].shape == (512, 17, 4, 4)
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'test_net.py'), '--cfg', str(cfg), 'OUTPUT_DIR', str(tmp_path / 'out2'),
+                         'TEST.WEIGHTS', snap], env=env, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    assert os.path.exists(os.path.join(str(tmp_path / 'out2'), 'test', 'synthetic_2x3_96x128', 'keypoint_rcnn', 'detections.pkl'))
     assert losses[-1] < 0.6 * losses[0], losses          # measured on B200: 13.76 -> 8.24 -> 6.18 -> 5.23 (new RoI draws every iteration)

@@ -202,6 +202,10 @@ def test_keypoint_rcnn_training_step_vs_autograd():
             entries.append(dict(boxes=boxes, gt_keypoints=kps))
         gt = pack_gt(entries)
         tr = KeypointRcnnTrainer(cfg, blobs, spec, lr=0.01, weight_decay=1e-4)
+        exp = tr.export_blobs(blobs)                     # packed master weights -> reference blob names: an exact round trip
+        assert set(exp) == set(blobs)
+        for k in blobs:
+            assert exp[k].shape == blobs[k].shape and np.array_equal(exp[k], blobs[k]), k
         fr = torch.from_numpy(frames).cuda()
         outs = tr.forward_all(fr)
         rt, smp = tr.make_targets(outs, gt, 2, 96, 128, seed=5)

@@ -77,6 +77,13 @@ def train_model():
             if rank == 0:
                 log.info('iter %d lr %.6f loss %.4f (rpn_cls %.4f rpn_bbox %.4f cls %.4f bbox %.4f kps %.4f) accuracy_cls %.3f', it, model.lr,
                          sum(l[:5]), l[0], l[1], l[2], l[3], l[4], l[5] / max(1.0, float(model.totals[0])))
+    if rank == 0:             # tools/train_net.py:214-218: the final weights under the reference's blob names (TEST.WEIGHTS of test_net.py)
+        from detectandtrack_b200.core.config import get_output_dir
+        from detectandtrack_b200.modeling import params as P
+        import yaml
+        path = os.path.join(get_output_dir(training=True), 'model_final.pkl')
+        P.save_weights_file(model.export_blobs(model.blobs0), yaml.dump({'MODEL': {'TYPE': cfg.MODEL.TYPE, 'CONV_BODY': cfg.MODEL.CONV_BODY}}), path)
+        log.info('Wrote %s', path)
     if world > 1:
         dist.destroy_process_group()
     return smooth
