@@ -138,3 +138,28 @@ def test_train_net_loss_goes_down(tmp_path):
     assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
     assert os.path.exists(os.path.join(str(tmp_path / 'out2'), 'test', 'synthetic_2x3_96x128', 'keypoint_rcnn', 'detections.pkl'))
     assert losses[-1] < 0.6 * losses[0], losses          # measured on B200: 13.76 -> 8.24 -> 6.18 -> 5.23 (new RoI draws every iteration)
+
+
+def test_multi_gpu_testing_equals_single_gpu(tmp_path):
+    """tools/test_net.py --multi-gpu-testing (lib/utils/subprocess.py:27-74: one child per GPU over contiguous index ranges,
+    results concatenated in rank order, no collective) gives the detections of the single-process run, bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    cfg = tmp_path / 'cfg.yaml'
+    cfg.write_text(YAML)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    outs = []
+    for tag, extra in (('one', []), ('two', ['--multi-gpu-testing'])):
+        out = str(tmp_path / tag)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'test_net.py'), '--cfg', str(cfg)] + extra +
+                           ['OUTPUT_DIR', out, 'NUM_GPUS', '2' if extra else '1'], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(pickle.load(open(os.path.join(out, 'test', 'synthetic_2x3_96x128', 'keypoint_rcnn', 'detections.pkl'), 'rb')))
+    a, b = outs
+    assert len(a['all_boxes'][1]) == len(b['all_boxes'][1]) == 6
+    for i in range(6):
+        assert np.array_equal(a['all_boxes'][1][i], b['all_boxes'][1][i])
+        assert len(a['all_keyps'][1][i]) == len(b['all_keyps'][1][i])
+        for ka, kb in zip(a['all_keyps'][1][i], b['all_keyps'][1][i]):
+            assert np.array_equal(ka, kb)
