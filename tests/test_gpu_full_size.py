@@ -118,3 +118,68 @@ def test_detect_step_full_size_properties():
     assert torch.equal(a['xy'][:n], a['xy'][cap:cap + n])
     assert torch.isfinite(a['xy'][:n]).all()
     reset_cfg()                                                               # the global cfg is shared between test modules
+
+
+def test_training_step_full_size_properties():
+    """BASELINE.json configs[4] at its full size (2 clips of 3 x 800 x 1333, 512 RoIs per image, 2000 proposals per level):
+    the oracle graph would take many minutes on the CPU, so size-independent properties are checked — the target generators
+    are deterministic in (seed, image) and independent of the other images of the batch, every sampled RoI / anchor count
+    obeys the reference's quotas, losses are finite and the wgrad of a linear layer is linear in its upstream gradient."""
+    import torch
+    import bench
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.trainer import KeypointRcnnTrainer, pack_gt
+    from detectandtrack_b200.ops import train_ops as to
+    cfg = bench.bench_cfg(800, 1333, 'r50fpn3d')
+    cfg.TRAIN.BATCH_SIZE_PER_IM = 512; cfg.TRAIN.RPN_PRE_NMS_TOP_N = 2000
+    try:
+        blobs, spec = P.random_blobs(cfg)
+        tr = KeypointRcnnTrainer(cfg, blobs, spec)
+        frames = torch.from_numpy(bench.synth_frames(2, 3, 800, 1333, 5)).cuda()
+        entries = bench.synth_gt(2, 800, 1333, 11)
+        gt = pack_gt(entries)
+        outs = tr.forward_all(frames)
+        rt, smp = tr.make_targets(outs, gt, 2, 800, 1333, seed=9)
+        rt2, smp2 = tr.make_targets(outs, gt, 2, 800, 1333, seed=9)
+        for a, b in zip(rt, rt2):
+            for k in a:
+                assert torch.equal(a[k], b[k]), k                         # same (seed, image) -> same draws
+        for k in ('rois', 'labels', 'bbox_targets', 'kp_rois', 'kp_locations', 'kp_weights'):
+            assert torch.equal(smp[k], smp2[k]), k
+        # RPN quotas (rpn.py:266-283): <= 128 foreground, <= 256 labelled anchors per image, outside weight = 1 / #labelled
+        for b in range(2):
+            nfg = sum(int((t['labels'][b] == 1).sum()) for t in rt)
+            nlab = sum(int((t['labels'][b] >= 0).sum()) for t in rt)
+            assert 0 < nfg <= 128 and nfg < nlab <= 256
+            ow = torch.cat([t['outside'][b].reshape(-1) for t in rt])
+            assert torch.equal(torch.unique(ow[ow > 0]), torch.tensor([np.float32(1.0 / nlab)], device='cuda'))
+        # image 1's RPN targets do not depend on image 0 (swap the batch order, same per-image seeds are used by position)
+        gt_one = pack_gt([entries[1], entries[1]])
+        rt3, _ = tr.make_targets(outs, gt_one, 2, 800, 1333, seed=9)
+        for a, c in zip(rt, rt3):
+            assert torch.equal(a['labels'][1], c['labels'][1]) and torch.equal(a['bbox_targets'][1], c['bbox_targets'][1])
+        # RoI quotas (fast_rcnn.py:118-147): 512 RoIs per image, <= 128 foreground first, labels in {0, 1}
+        assert smp['counts'].tolist() == [512, 512] and float(smp['totals'][0]) == 1024.0
+        lab = smp['labels']
+        for b in range(2):
+            nf = int((lab[b] == 1).sum())
+            assert 0 < nf <= 128 and int((lab[b, :nf] == 1).sum()) == nf and int((lab[b, nf:] == 0).sum()) == 512 - nf
+            assert float(smp['inside'][b, nf:].abs().sum()) == 0.0
+        assert 0 < int(smp['kp_counts'].min()) and int(smp['kp_counts'].max()) <= 128
+        loc = smp['kp_locations']
+        assert int(loc.min()) >= 0 and int(loc.max()) < 56 * 56
+        l1, l2 = tr.step(frames, gt, seed=9)
+        torch.cuda.synchronize()
+        assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and float(l2[2]) > 0
+        # linearity of the filter gradient in the upstream gradient at a full-size layer (P3 post-hoc conv shape)
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn((2, 3, 100, 168, 256), generator=g).bfloat16().cuda()
+        g1 = (torch.randint(-4, 5, (2, 3, 100, 168, 256), generator=g).float() / 8).bfloat16().cuda()
+        g2 = (torch.randint(-4, 5, (2, 3, 100, 168, 256), generator=g).float() / 8).bfloat16().cuda()
+        d1, d2 = to.wgrad_nhwc(g1, x, (3, 3, 3)), to.wgrad_nhwc(g2, x, (3, 3, 3))
+        d12 = to.wgrad_nhwc((g1.float() + g2.float()).bfloat16(), x, (3, 3, 3))      # sums of eighths stay exact in bf16
+        ref = d1 + d2
+        assert float((d12 - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    finally:
+        from test_gpu_engine import _cfg
+        _cfg()
