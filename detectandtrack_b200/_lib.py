@@ -49,6 +49,7 @@ SIGNATURES = {
     'dt_wgrad': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_wgrad_nhwc': [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_bwd_pointwise': [_p, _p, _p, _p, C.c_longlong, _i, _p, _p],
+    'dt_bwd_pointwise2': [_p, _p, _p, _p, C.c_longlong, _i, _p, _p, _p, _p],
     'dt_upsample_add_bwd': [_p, _p, _i, _i, _i, _i, _p, _p],
     'dt_scatter_stride2': [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_sgd_update': [_p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p],

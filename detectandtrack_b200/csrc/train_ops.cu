@@ -415,7 +415,8 @@ to_planes_kernel(const __nv_bfloat16* __restrict__ x, int F, int H, int W, int C
 // ------------------------------------------------------------------------------------------------ pointwise backward
 __global__ void bwd_pointwise_kernel(const __nv_bfloat16* __restrict__ g1, const __nv_bfloat16* __restrict__ g2,
                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, long long rows,
-                                     int C, __nv_bfloat16* __restrict__ out) {
+                                     int C, __nv_bfloat16* __restrict__ out, const float* __restrict__ scale2,
+                                     __nv_bfloat16* __restrict__ out2) {
   const int cv = C / 8;
   const long long total = rows * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -438,11 +439,16 @@ __global__ void bwd_pointwise_kernel(const __nv_bfloat16* __restrict__ g1, const
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(me[j]) > 0.f ? v[j] : 0.f;
     }
+    __align__(16) __nv_bfloat16 o[8];
+    if (out2) {                                           // second consumer of the same masked sum (its own channel scale, or none)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(scale2 ? v[j] * scale2[c + j] : v[j]);
+      *reinterpret_cast<uint4*>(out2 + off) = *reinterpret_cast<const uint4*>(o);
+    }
     if (scale) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= scale[c + j];
     }
-    __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(v[j]);
     *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(o);
@@ -993,11 +999,17 @@ extern "C" int dt_wgrad_nhwc(const void* gz, int ld_g, const void* x, int ld_x, 
 
 extern "C" int dt_bwd_pointwise(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
                                 void* stream) {
+  return dt_bwd_pointwise2(g1, g2, y, scale, rows, C, out, nullptr, nullptr, stream);
+}
+
+extern "C" int dt_bwd_pointwise2(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
+                                 const float* scale2, void* out2, void* stream) {
   DT_CHECK_ARG(rows >= 0 && C >= 8 && C % 8 == 0, "dt_bwd_pointwise: bad shape rows=%lld C=%d (C %% 8 == 0)", rows, C);
   if (rows == 0) return 0;
   DT_CHECK_ARG(g1 && out, "dt_bwd_pointwise: null pointer");
   bwd_pointwise_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale, rows, C, (__nv_bfloat16*)out);
+      (const __nv_bfloat16*)g1, (const __nv_bfloat16*)g2, (const __nv_bfloat16*)y, scale, rows, C, (__nv_bfloat16*)out, scale2,
+      (__nv_bfloat16*)out2);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -348,7 +348,9 @@ class RpnTrainer(object):
             blk = sb['blk']
             g1, g2 = g_parts
             last_of_trunk = bidx == 0
-            gz3 = to.bwd_pointwise(g1, g2, sb['y'], blk['c'].scale)
+            # gradient wrt the block output, masked by its ReLU, for BOTH consumers (branch2c and the shortcut) from one read
+            gz3, gsc = to.bwd_pointwise(g1, g2, sb['y'], blk['c'].scale, second=True,
+                                        scale2=blk['sc'].scale if blk['sc'] is not None else None)
             gb, _ = blk['c'].backward(gz3, sb['b'])
             gz2 = to.bwd_pointwise(gb, None, sb['b'], blk['b'].scale)
             ga, _ = blk['b'].backward(gz2, sb['a'])
@@ -356,10 +358,9 @@ class RpnTrainer(object):
             need_dx = not last_of_trunk                                          # res2 is frozen: stop at the input of res3_0
             gx1, xpl = blk['a'].backward(gz1, sb['x'], need_dx=need_dx)
             if blk['sc'] is not None:
-                gz4 = to.bwd_pointwise(g1, g2, sb['y'], blk['sc'].scale)
-                gx2, _ = blk['sc'].backward(gz4, sb['x'], x_planes=xpl, need_dx=need_dx)
+                gx2, _ = blk['sc'].backward(gsc, sb['x'], x_planes=xpl, need_dx=need_dx)
             else:
-                gx2 = to.bwd_pointwise(g1, g2, sb['y'], None)
+                gx2 = gsc
             for cnv in (blk['c'], blk['b'], blk['a'], blk['sc']):
                 if cnv is not None:
                     self._bucket_ready(cnv, pending)

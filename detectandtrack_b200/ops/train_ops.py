@@ -60,15 +60,21 @@ def wgrad_nhwc(gz, x, ksize, stride=(1, 1), dW=None, cout=None, cin=None):
     return dW
 
 
-def bwd_pointwise(g1, g2=None, y=None, scale=None):
-    """(g1 + g2) * [y > 0] * scale[c] over NDHWC bf16 tensors of one shape."""
+def bwd_pointwise(g1, g2=None, y=None, scale=None, second=False, scale2=None):
+    """(g1 + g2) * [y > 0] * scale[c] over NDHWC bf16 tensors of one shape.  second=True: also returns the same masked sum
+    times scale2[c] (or unscaled) from the same read of the inputs -> (out, out2)."""
     torch = L.require_cuda()
     Cc = g1.shape[-1]
     out = torch.empty_like(g1)
     for t in (g1, g2, y):
         assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape == g1.shape)
-    L.call('dt_bwd_pointwise', L.ptr(g1), L.ptr(g2), L.ptr(y), L.ptr(scale), g1.numel() // Cc, Cc, L.ptr(out), L.stream_ptr())
-    return out
+    if not second:
+        L.call('dt_bwd_pointwise', L.ptr(g1), L.ptr(g2), L.ptr(y), L.ptr(scale), g1.numel() // Cc, Cc, L.ptr(out), L.stream_ptr())
+        return out
+    out2 = torch.empty_like(g1)
+    L.call('dt_bwd_pointwise2', L.ptr(g1), L.ptr(g2), L.ptr(y), L.ptr(scale), g1.numel() // Cc, Cc, L.ptr(out), L.ptr(scale2), L.ptr(out2),
+           L.stream_ptr())
+    return out, out2
 
 
 def upsample_add_bwd(fine, coarse_in=None):

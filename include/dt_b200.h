@@ -362,6 +362,10 @@ int dt_wgrad_nhwc(const void* gz, int ld_g, const void* x, int ld_x, int N, int 
 /* out = (g1 + g2?) * [y > 0]? * scale[c]? over [rows, C] (any of g2 / y / scale may be NULL) */
 int dt_bwd_pointwise(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
                      void* stream);
+/* The same with a second output of the same masked sum, out2 = (g1 + g2) * [y > 0] * scale2[c] (scale2 NULL: no scale): the two
+ * consumers of a block output's gradient (branch2c and the shortcut) from one read of the three inputs. */
+int dt_bwd_pointwise2(const void* g1, const void* g2, const void* y, const float* scale, long long rows, int C, void* out,
+                      const float* scale2, void* out2, void* stream);
 
 /* out[f,h,w,c] = coarse_in?[f,h,w,c] + sum of the 2x2 children fine[f, 2h+dy, 2w+dx, c]; fine is [F, 2Hc, 2Wc, C] */
 int dt_upsample_add_bwd(const void* fine, const void* coarse_in, int F, int Hc, int Wc, int C, void* out, void* stream);

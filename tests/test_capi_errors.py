@@ -53,6 +53,7 @@ def _cases():
         ('dt_wgrad', (None, None, 1, 1, 8, 8, 64, 60, 1, 3, 3, None, None), b'Cin % 8'),
         ('dt_wgrad_nhwc', (None, 64, None, 60, 1, 1, 8, 8, 8, 8, 64, 60, 1, 3, 3, 1, 1, None, None), b'dt_wgrad_nhwc'),
         ('dt_bwd_pointwise', (None, None, None, None, 10, 12, None, None), b'C % 8'),
+        ('dt_bwd_pointwise2', (None, None, None, None, 10, 12, None, None, None, None), b'C % 8'),
         ('dt_upsample_add_bwd', (None, None, 1, 4, 4, 12, None, None), b'dt_upsample_add_bwd'),
         ('dt_scatter_stride2', (None, 1, 4, 4, 9, 8, 64, None, None), b'dt_scatter_stride2'),
         ('dt_sgd_update', (None, None, None, 1, 8, 8, 0.1, 0.9, 0.0, 1.0, None, None, None), b'dt_sgd_update'),

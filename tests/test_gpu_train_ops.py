@@ -95,6 +95,21 @@ def test_pointwise_joins():
     ref = ((g1.float() + g2.float()) * (y.float() > 0) * sc).bfloat16().float()
     assert torch.equal(out, ref)
     assert torch.equal(to.bwd_pointwise(g1.cuda()).cpu(), g1)
+    # two consumers of the same masked sum from one read: (scaled, other scale) and (scaled, unscaled)
+    sc3 = torch.rand(64, generator=g) + 0.5
+    o1, o2 = to.bwd_pointwise(g1.cuda(), g2.cuda(), y.cuda(), sc.cuda(), second=True, scale2=sc3.cuda())
+    assert torch.equal(o1.cpu().float(), ref)
+    assert torch.equal(o2.cpu().float(), ((g1.float() + g2.float()) * (y.float() > 0) * sc3).bfloat16().float())
+    o1, o2 = to.bwd_pointwise(g1.cuda(), None, y.cuda(), sc.cuda(), second=True)
+    assert torch.equal(o1.cpu().float(), (g1.float() * (y.float() > 0) * sc).bfloat16().float())
+    assert torch.equal(o2.cpu().float(), (g1.float() * (y.float() > 0)).bfloat16().float())
+    # slice-center gradient embedding
+    from detectandtrack_b200 import _lib as L
+    gc = torch.randn((2, 1, 5, 7, 64), generator=g).bfloat16().cuda()
+    full = torch.empty((2, 3, 5, 7, 64), dtype=torch.bfloat16, device='cuda')
+    L.call('dt_embed_frame', L.ptr(gc), 2, 3, 5 * 7 * 64, 1, L.ptr(full), L.stream_ptr())
+    exp = torch.zeros((2, 3, 5, 7, 64), dtype=torch.bfloat16, device='cuda'); exp[:, 1:2] = gc
+    assert torch.equal(full, exp)
     fine = torch.randn((2, 3, 10, 14, 64), generator=g).bfloat16()
     coarse = torch.randn((2, 3, 5, 7, 64), generator=g).bfloat16()
     up = to.upsample_add_bwd(fine.cuda(), coarse.cuda()).cpu().float()
