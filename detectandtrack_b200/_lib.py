@@ -53,6 +53,7 @@ SIGNATURES = {
     'dt_upsample_add_bwd': [_p, _p, _i, _i, _i, _i, _p, _p],
     'dt_scatter_stride2': [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     'dt_sgd_update': [_p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p],
+    'dt_sgd_update_multi': [_p, _p, _i, _i, _f, _f, _f, _f, _p],
     'dt_bias_grad': [_p, C.c_longlong, _i, _i, _p, _p],
     'dt_rpn_loss_grad': [_p, _i, _p, _p, _p, _p, C.c_longlong, _i, _f, _f, _f, _p, _i, _p, _p],
     'dt_embed_frame': [_p, _i, _i, C.c_longlong, _i, _p, _p],
@@ -81,6 +82,13 @@ class RpnTargetLevel(C.Structure):
     """dt_rpn_target_level (include/dt_b200.h)."""
     _fields_ = [('H', C.c_int), ('W', C.c_int), ('feat_stride', C.c_double), ('anchors', C.c_void_p), ('labels', C.c_void_p),
                 ('bbox_targets', C.c_void_p), ('inside_weights', C.c_void_p), ('outside_weights', C.c_void_p)]
+
+
+class SgdItem(C.Structure):
+    """dt_sgd_item (include/dt_b200.h)."""
+    _fields_ = [('w', C.c_void_p), ('g', C.c_void_p), ('m', C.c_void_p), ('w_fwd', C.c_void_p), ('w_dgrad', C.c_void_p),
+                ('taps', C.c_int), ('Cout', C.c_int), ('Cin', C.c_int), ('tiles_ci', C.c_int), ('tiles_co', C.c_int),
+                ('lr_mult', C.c_float), ('wd_mult', C.c_float)]
 
 
 class ConvDesc(C.Structure):

@@ -233,7 +233,7 @@ struct RoiLevels {
 template <typename ET>
 __device__ __forceinline__ void bilinear_acc(const ET* __restrict__ f, int H, int W, int ld, int lo_in, float y, float x, float* acc) {
   constexpr int V = Vec<ET>::N;
-  if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return;      // contributes 0
+  if (!(y >= -1.f && y <= (float)H && x >= -1.f && x <= (float)W)) return;      // contributes 0 (also for a non-finite RoI)
   if (y <= 0.f) y = 0.f;
   if (x <= 0.f) x = 0.f;
   int yl = (int)y, xl = (int)x, yh, xh;

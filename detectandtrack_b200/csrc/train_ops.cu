@@ -553,6 +553,50 @@ sgd_update_kernel(float* __restrict__ w, const float* __restrict__ g, float* __r
   }
 }
 
+// Every parameter tensor of the model in ONE launch: a table of items (device memory, built once by the trainer) and the
+// exclusive prefix of their 32x32 tile counts; a block finds its item by binary search and runs the same tile update.
+struct SgdItem {
+  float* w; const float* g; float* m; __nv_bfloat16* wf; __nv_bfloat16* wdg;
+  int taps, Cout, Cin, tiles_ci, tiles_co;
+  float lr_mult, wd_mult;
+};
+
+__global__ void __launch_bounds__(256)
+sgd_update_multi_kernel(const SgdItem* __restrict__ items, const int* __restrict__ first_block, int n_items, float lr, float momentum,
+                        float wd, float grad_scale) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (first_block[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+  const SgdItem it = items[lo];
+  int t = (int)blockIdx.x - first_block[lo];
+  const int tci = t % it.tiles_ci; t /= it.tiles_ci;
+  const int tco = t % it.tiles_co;
+  const int tap = t / it.tiles_co;
+  const int co0 = tco * 32, ci0 = tci * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float lr_i = lr * it.lr_mult, wd_i = wd * it.wd_mult;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    float nw = 0.f;
+    if (co < it.Cout && ci < it.Cin) {
+      const size_t i = ((size_t)tap * it.Cout + co) * it.Cin + ci;
+      const float wi = it.w[i];
+      const float adj = lr_i * (grad_scale * it.g[i] + wd_i * wi) + momentum * it.m[i];
+      it.m[i] = adj;
+      nw = wi - adj;
+      it.w[i] = nw;
+      if (it.wf) it.wf[i] = __float2bfloat16_rn(nw);
+    }
+    tile[r][tx] = nw;
+  }
+  if (!it.wdg) return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (ci < it.Cin && co < it.Cout) it.wdg[((size_t)(it.taps - 1 - tap) * it.Cin + ci) * it.Cout + co] = __float2bfloat16_rn(tile[tx][r]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ bias gradient, RPN losses
 // db[c] += sum over rows of g[row, c]   (Conv bias gradient; biases of the FPN / RPN / head convs are trainable)
 // block (32 channel groups of 8, 8 row lanes): 16-byte loads, fp32 partial sums, shared-memory reduction, one atomic per channel
@@ -658,7 +702,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // the forward's bilinear sample (dense_ops.cu bilinear_acc) transposed: v[8] * weight into the four corners
 __device__ __forceinline__ void bilinear_scatter(float* __restrict__ d, int H, int W, int C, float y, float x, const float* v, float wgt) {
-  if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return;
+  if (!(y >= -1.f && y <= (float)H && x >= -1.f && x <= (float)W)) return;      // also for a non-finite RoI (diverged weights)
   if (y <= 0.f) y = 0.f;
   if (x <= 0.f) x = 0.f;
   int yl = (int)y, xl = (int)x, yh, xh;
@@ -1051,6 +1095,16 @@ extern "C" int dt_sgd_update(float* w, const float* g, float* m, int taps, int C
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps);
   sgd_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, g, m, taps, Cout, Cin, lr, momentum, wd, grad_scale,
                                                             (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
+  DT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int dt_sgd_update_multi(const void* items, const int* first_block, int n_items, int total_blocks, float lr, float momentum,
+                                   float wd, float grad_scale, void* stream) {
+  DT_CHECK_ARG(n_items >= 1 && total_blocks >= 1, "dt_sgd_update_multi: empty table (n_items=%d, blocks=%d)", n_items, total_blocks);
+  DT_CHECK_ARG(items && first_block, "dt_sgd_update_multi: null pointer");
+  static_assert(sizeof(SgdItem) == 72, "dt_sgd_item layout");
+  sgd_update_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const SgdItem*)items, first_block, n_items, lr, momentum, wd, grad_scale);
   DT_CHECK_LAUNCH();
   return 0;
 }

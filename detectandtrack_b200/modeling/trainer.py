@@ -411,10 +411,34 @@ class RpnTrainer(object):
         out['rpn_cls_logits_fpn%s_b' % k], out['rpn_bbox_pred_fpn%s_b' % k] = b[:A].copy(), b[A:5 * A].copy()
         return out
 
+    def _sgd_table(self):
+        """One dt_sgd_item per parameter tensor (filters, then the biases: 2x learning rate, no weight decay,
+        model_builder.py:971-976) + the block prefix of the single-launch update; the pointers are stable for the trainer's life."""
+        import ctypes as C
+        torch = self.torch
+        items, first, nb = [], [], 0
+
+        def add(w, g, m, wf, wdg, taps, co, ci, lr_mult, wd_mult):
+            nonlocal nb
+            tci, tco = (ci + 31) // 32, (co + 31) // 32
+            items.append(L.SgdItem(w.data_ptr(), g.data_ptr(), m.data_ptr(), wf.data_ptr() if wf is not None else None,
+                                   wdg.data_ptr() if wdg is not None else None, taps, co, ci, tci, tco, lr_mult, wd_mult))
+            first.append(nb)
+            nb += taps * tci * tco
+        for c in self.convs:
+            add(c.w, c.g, c.m, c.w_fwd, c.w_dg, c.taps, c.cout, c.cin, 1.0, 1.0)
+            if c.bias is not None:
+                add(c.bias, c.bias_g, c.bias_m, None, None, 1, 1, c.bias.numel(), 2.0, 0.0)
+        arr = (L.SgdItem * len(items))(*items)
+        buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+        return buf, torch.tensor(first, dtype=torch.int32).cuda(), len(items), nb
+
     def update(self):
         gs = 1.0            # losses already carry 1/NUM_GPUS; the all-reduce is a SUM (model_builder.py:484,938-942)
-        for c in self.convs:
-            c.update(self.lr, self.momentum, self.wd, gs)
+        if not hasattr(self, '_sgd'):
+            self._sgd = self._sgd_table()
+        buf, first, n, nb = self._sgd
+        L.call('dt_sgd_update_multi', L.ptr(buf), L.ptr(first), n, nb, float(self.lr), float(self.momentum), float(self.wd), gs, L.stream_ptr())
 
     def step(self, frames_u8, targets):
         outs = self.forward_all(frames_u8)

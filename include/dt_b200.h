@@ -379,6 +379,17 @@ int dt_scatter_stride2(const void* src, int F, int Hs, int Ws, int H, int W, int
 int dt_sgd_update(float* w, const float* g, float* m, int taps, int Cout, int Cin, float lr, float momentum, float wd,
                   float grad_scale, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);
 
+/* The same update for EVERY parameter tensor in one launch.  items: device array of dt_sgd_item; first_block [n_items]: device,
+ * exclusive prefix of taps * ceil(Cout/32) * ceil(Cin/32) per item; total_blocks = their sum.  Per item the learning rate is
+ * lr * lr_mult and the weight decay wd * wd_mult (biases: 2x / 0, model_builder.py:971-976). */
+typedef struct dt_sgd_item {
+  float* w; const float* g; float* m; void* w_fwd_bf16; void* w_dgrad_bf16;
+  int taps, Cout, Cin, tiles_ci, tiles_co;
+  float lr_mult, wd_mult;
+} dt_sgd_item;
+int dt_sgd_update_multi(const void* items, const int* first_block, int n_items, int total_blocks, float lr, float momentum, float wd,
+                        float grad_scale, void* stream);
+
 /* db [C] fp32 += column sums of g [rows, ld] bf16 (first C columns): the conv-bias gradient (caller zeroes db) */
 int dt_bias_grad(const void* g, long long rows, int C, int ld, float* db, void* stream);
 

@@ -57,6 +57,7 @@ def _cases():
         ('dt_upsample_add_bwd', (None, None, 1, 4, 4, 12, None, None), b'dt_upsample_add_bwd'),
         ('dt_scatter_stride2', (None, 1, 4, 4, 9, 8, 64, None, None), b'dt_scatter_stride2'),
         ('dt_sgd_update', (None, None, None, 1, 8, 8, 0.1, 0.9, 0.0, 1.0, None, None, None), b'dt_sgd_update'),
+        ('dt_sgd_update_multi', (None, None, 0, 0, 0.1, 0.9, 0.0, 1.0, None), b'empty table'),
         ('dt_bias_grad', (None, 10, 12, 16, None, None), b'dt_bias_grad'),
         ('dt_rpn_loss_grad', (None, 8, None, None, None, None, 10, 3, 1.0, 1.0, 0.1, None, 16, None, None), b'dt_rpn_loss_grad'),
         ('dt_embed_frame', (None, 2, 3, 64, 5, None, None), b'dt_embed_frame'),

@@ -133,3 +133,25 @@ def test_subpixel_grad_fix():
     for k in range(K):
         assert np.all(b[[k, K + k, 2 * K + k, 3 * K + k]] == 4 * k + 6 * K)
     assert np.all(b[4 * K:] == 0)
+
+
+def test_roi_align_forward_backward_ignore_non_finite_rois():
+    """A diverging training run can emit NaN / inf proposal coordinates: such a RoI must pool zeros and scatter nothing
+    (no wild address), leaving the other RoIs untouched."""
+    import torch
+    from detectandtrack_b200.ops import dense_ops, train_ops as to
+    feat = torch.randn((1, 20, 28, 16), device='cuda').to(torch.bfloat16)
+    rois = torch.tensor([[0, 4, 4, 40, 60], [0, float('nan'), 3, 50, 50], [0, 2, float('inf'), 30, 40], [0, 10, 8, 70, 44]],
+                        dtype=torch.float32, device='cuda')
+    out = dense_ops.roi_align([feat], [0.25], rois, None, 7, 2)
+    torch.cuda.synchronize()
+    assert float(out[1].float().abs().sum()) == 0.0 and torch.isfinite(out.float()).all()
+    ref = dense_ops.roi_align([feat], [0.25], rois[[0, 3]].contiguous(), None, 7, 2)
+    assert torch.equal(out[[0, 3]], ref)
+    d = [torch.zeros((1, 20, 28, 16), dtype=torch.float32, device='cuda')]
+    g = torch.ones((4, 1, 7, 7, 16), dtype=torch.bfloat16, device='cuda')
+    to.roi_align_bwd(g, d, [0.25], rois, None, 7, 2)
+    d2 = [torch.zeros((1, 20, 28, 16), dtype=torch.float32, device='cuda')]
+    to.roi_align_bwd(g[[0, 3]].contiguous(), d2, [0.25], rois[[0, 3]].contiguous(), None, 7, 2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(d[0]).all() and torch.allclose(d[0], d2[0], rtol=1e-5, atol=1e-5)

@@ -282,3 +282,39 @@ def test_keypoint_rcnn_training_step_vs_autograd():
         assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and not torch.equal(w0, tr.fc7.w)
     finally:
         _cfg()
+
+
+def test_multi_tensor_sgd_equals_the_formula_on_every_parameter():
+    """dt_sgd_update_multi (one launch over the table of every filter and bias) against Caffe2's MomentumSGDUpdate formula
+    (model_builder.py:954-985) evaluated with torch on every parameter tensor: master weights, momentum, the bf16 forward
+    filter and the flipped / transposed bf16 dgrad filter; biases at 2x learning rate without weight decay."""
+    import torch
+    from test_gpu_engine import _cfg
+    from detectandtrack_b200.modeling import params as P
+    from detectandtrack_b200.modeling.trainer import KeypointRcnnTrainer
+    cfg = _cfg()
+    try:
+        blobs, spec = P.random_blobs(cfg, seed=3)
+        tr = KeypointRcnnTrainer(cfg, blobs, spec, lr=0.02, momentum=0.9, weight_decay=1e-3)
+        g = torch.Generator(device='cuda').manual_seed(1)
+        tr.flat_g.copy_(torch.randn(tr.flat_g.shape, generator=g, device='cuda') * 0.1)
+        for c in tr.convs:
+            c.m.copy_(torch.randn(c.m.shape, generator=g, device='cuda') * 0.01)
+            if c.bias is not None:
+                c.bias_m.copy_(torch.randn(c.bias_m.shape, generator=g, device='cuda') * 0.01)
+        before = [(c.w.clone(), c.g.clone(), c.m.clone(), None if c.bias is None else (c.bias.clone(), c.bias_g.clone(), c.bias_m.clone())) for c in tr.convs]
+        tr.update()
+        torch.cuda.synchronize()
+        for c, (w0, g0, m0, b0) in zip(tr.convs, before):
+            adj = 0.02 * (g0 + 1e-3 * w0) + 0.9 * m0
+            assert torch.allclose(c.m, adj, rtol=1e-6, atol=1e-9) and torch.allclose(c.w, w0 - adj, rtol=1e-6, atol=1e-8)
+            assert torch.equal(c.w_fwd, c.w.to(torch.bfloat16))
+            kT, kH, kW = c.k
+            exp_dg = c.w.flip(0).permute(0, 2, 1).contiguous().to(torch.bfloat16)          # taps flipped, [Cin, Cout] per tap
+            assert torch.equal(c.w_dg, exp_dg)
+            if b0 is not None:
+                bw, bg, bm = b0
+                adjb = 0.04 * bg + 0.9 * bm
+                assert torch.allclose(c.bias_m, adjb, rtol=1e-6, atol=1e-9) and torch.allclose(c.bias, bw - adjb, rtol=1e-6, atol=1e-8)
+    finally:
+        _cfg()
