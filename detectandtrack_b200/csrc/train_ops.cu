@@ -26,6 +26,7 @@
 #include "tc_common.cuh"
 #include "../../include/dt_b200.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace dt {
 
@@ -1016,7 +1017,13 @@ extern "C" int dt_wgrad_nhwc(const void* gz, int ld_g, const void* x, int ld_x, 
   p.tiles_m = cdiv(Cout, 128); p.tiles_n = cdiv(Cin, BN);
   const long long units = (long long)p.taps * p.tiles_m * p.tiles_n;
   const long long kblocks = (long long)p.nW * p.nH * p.nT * p.nN;
-  long long ksplit = (148 * 3 + units - 1) / units;
+  // K split: every CTA adds its 128 x BN partial tile into dW with red.global, so the split count is also the atomic
+  // traffic multiplier.  DT_WGRAD_WAVES overrides the wave count (tuning knob of tools/bench_wgrad.py).
+  // Measured on B200 (tools/bench_wgrad.py, profiles/wgrad_waves_r02.md): pointwise layers are fastest with ONE wave of CTAs
+  // (a 1x1 filter has few (tap, tile) units, so 3 waves meant ~100 partial tiles added per output tile), multi-tap layers with 2.
+  static const int waves_env = [] { const char* e = getenv("DT_WGRAD_WAVES"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 16 ? v : 0; }();
+  const int waves = waves_env ? waves_env : (p.taps == 1 ? 1 : 2);
+  long long ksplit = (148 * waves + units - 1) / units;
   if (ksplit > kblocks / 4) ksplit = kblocks / 4;
   if (ksplit < 1) ksplit = 1;
   p.ksplit = (int)ksplit;

@@ -21,6 +21,9 @@ LAYERS = [
     ('fpn posthoc P2 256>256 3x3x3', 2, 3, 200, 336, 256, 256, (3, 3, 3)),
     ('fpn posthoc P3 256>256 3x3x3', 2, 3, 100, 168, 256, 256, (3, 3, 3)),
     ('rpn conv P2 256>256 1x3x3', 2, 1, 200, 336, 256, 256, (1, 3, 3)),
+    ('res3 branch2a 512>128 1x1x1', 2, 3, 100, 168, 512, 128, (1, 1, 1)),
+    ('res5 branch2c 512>2048 1x1x1', 2, 3, 25, 42, 512, 2048, (1, 1, 1)),
+    ('fpn lateral P2 256>256 1x1x1', 2, 3, 200, 336, 256, 256, (1, 1, 1)),
     ('kps conv_fcn 512>512 1x3x3 (256 RoIs)', 256, 1, 14, 14, 512, 512, (1, 3, 3)),
     ('fc6 12544>1024 (1024 RoIs)', 1, 1, 1, 1024, 12544, 1024, (1, 1, 1)),
 ]
