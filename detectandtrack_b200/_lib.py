@@ -62,13 +62,14 @@ SIGNATURES = {
     'dt_frcnn_loss_grad': [_p, _i, _p, _p, _p, _p, _i, _i, _p, _f, _f, _p, _i, _p, _p, _p],
     'dt_kps_loss_grad': [_p, _i, _i, _i, _i, _p, _p, _p, _f, _p, _i, _p, _p],
     'dt_subpixel_grad_fix': [_p, _p, _i, _i, _i, _p],
+    'dt_jpeg_decode': [C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, _p, _p],
     'dt_rpn_targets_workspace_bytes': [_i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i, C.POINTER(_sz)],
     'dt_rpn_targets': [_p, _i, _i, _i, _p, _p, _i, _p, _f, _f, _f, _i, _f, C.c_ulonglong, _p, _sz, _p],
     'dt_sample_rois': [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _f, _f, C.POINTER(_f), _i,
                        C.c_ulonglong, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p],
 }
 # host-only helpers (not error-code functions)
-HOST_FUNCS = {'dt_planes_ld': ([_i, _i, _i, _i], C.c_int)}
+HOST_FUNCS = {'dt_planes_ld': ([_i, _i, _i, _i], C.c_int), 'dt_jpeg_available': ([], C.c_int)}
 
 
 

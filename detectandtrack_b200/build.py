@@ -56,7 +56,7 @@ def build_lib(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ['-shared', '-Xcompiler', '-fPIC', '-o', LIB] + objs + ['-lcudart_static', '-ldl', '-lpthread', '-lrt']
+        cmd = [NVCC] + ARCH + ['-shared', '-Xcompiler', '-fPIC', '-o', LIB] + objs + ['-lcudart_static', '-ldl', '-lpthread', '-lrt']     # nvJPEG is dlopen'ed by jpeg.cu, not linked
         run(cmd)
     return LIB
 

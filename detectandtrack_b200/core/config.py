@@ -63,6 +63,8 @@ def assert_and_infer_cfg():
 def get_output_dir(training=True):
     """<OUTPUT_DIR>/<train|test>/<dataset>/<model-type>/  (config.py:777-785)."""
     dataset = cfg.TRAIN.DATASET if training else cfg.TEST.DATASET
+    if os.sep in str(dataset):                   # a JSON roidb given by path (test_engine.JsonListDataset): its file stem names the directory
+        dataset = osp.splitext(osp.basename(str(dataset)))[0]
     outdir = osp.join(cfg.OUTPUT_DIR, 'train' if training else 'test', dataset, cfg.MODEL.TYPE)
     os.makedirs(outdir, exist_ok=True)
     return outdir

@@ -28,7 +28,10 @@ class ClipPipeline(object):
     run(n, fill, on_result): ``fill(i, dst)`` writes clip i into the pinned [T, H, W, 3] view ``dst`` (called on a
     loader thread, ahead of time); ``on_result(i, cls_boxes, cls_segms, cls_keyps)`` receives the reference's
     per-clip containers (lib/core/test.py:897-958) in index order.  A short last batch is padded with its last
-    clip and the padding results are dropped."""
+    clip and the padding results are dropped.
+    run(..., fill_device=f): ``f(i, dev_dst, stream)`` instead produces clip i DIRECTLY in the device view ``dev_dst``
+    [T, H, W, 3] with GPU work on ``stream`` (device-side JPEG decode, ops/image_ops.jpeg_decode): no pinned staging, only
+    the compressed bytes cross PCIe."""
 
     def __init__(self, model, B, T, H, W, depth=2, loader_threads=2):
         eng = model.engine
@@ -47,6 +50,9 @@ class ClipPipeline(object):
         self.host_out = [dict(dets=pin(out['dets']), cnt=pin(out['det_counts']), xy=pin(out['xy']) if self.has_kps else None)
                          for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream()
+        self.device = torch.cuda.current_device()
+        self.loader_streams = [torch.cuda.Stream() for _ in range(depth)]      # device-side producers (fill_device) of a slot
+        self.dev_ready = [torch.cuda.Event() for _ in range(depth)]
         self.h2d_done = [torch.cuda.Event() for _ in range(depth)]
         self.consumed = [torch.cuda.Event() for _ in range(depth)]
         self.out_done = [torch.cuda.Event() for _ in range(depth)]
@@ -56,14 +62,17 @@ class ClipPipeline(object):
         self.d2h_bytes = sum(int(v.numel() * v.element_size()) for v in self.host_out[0].values() if v is not None)
 
     # ---- one device step ---------------------------------------------------------------------------
-    def _enqueue(self, slot):
+    def _enqueue(self, slot, from_device=False):
         torch = self.torch
         cur = torch.cuda.current_stream()
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.consumed[slot])            # the step that last read dev_in[slot] is past it
-            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
-            self.h2d_done[slot].record(self.copy_stream)
-        cur.wait_event(self.h2d_done[slot])
+        if from_device:                                                   # dev_in[slot] was produced on the loader stream
+            cur.wait_event(self.dev_ready[slot])
+        else:
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.consumed[slot])            # the step that last read dev_in[slot] is past it
+                self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+                self.h2d_done[slot].record(self.copy_stream)
+            cur.wait_event(self.h2d_done[slot])
         if self.pre_step is not None:
             self.pre_step()
         self.static_in.copy_(self.dev_in[slot], non_blocking=True)
@@ -110,29 +119,40 @@ class ClipPipeline(object):
         self._enqueue(0)
         return self._results(0, 1)[0]
 
-    def run(self, n, fill, on_result):
+    def run(self, n, fill, on_result, fill_device=None):
         B, depth = self.B, self.depth
         if n <= 0:
             return
         nsteps = (n + B - 1) // B
+        torch = self.torch
 
         def load(step):
-            dst = self.np_in[step % depth]
+            slot = step % depth
+            if fill_device is None:
+                dst = self.np_in[slot]
+                for j in range(B):
+                    fill(min(step * B + j, n - 1), dst[j])
+                return
+            torch.cuda.set_device(self.device)                         # loader threads start on device 0
+            st = self.loader_streams[slot]
+            st.wait_event(self.consumed[slot])                         # the step that last read dev_in[slot] is past it
             for j in range(B):
-                fill(min(step * B + j, n - 1), dst[j])
+                fill_device(min(step * B + j, n - 1), self.dev_in[slot][j], st)
+            self.dev_ready[slot].record(st)
 
         fut = {s: self.pool.submit(load, s) for s in range(min(depth, nsteps))}
         pending = deque()
         for step in range(nsteps):
             slot = step % depth
             fut.pop(step).result()
-            self._enqueue(slot)
+            self._enqueue(slot, from_device=fill_device is not None)
             pending.append((step, slot))
             if len(pending) > 1:                               # results of the previous step while this one computes
                 self._emit(pending.popleft(), n, on_result)
             if step + depth < nsteps:
-                self.h2d_done[slot].synchronize()              # pinned buffer read out: the loader may refill it
-                fut[step + depth] = self.pool.submit(load, step + depth)
+                if fill_device is None:
+                    self.h2d_done[slot].synchronize()          # pinned buffer read out: the loader may refill it
+                fut[step + depth] = self.pool.submit(load, step + depth)   # (device path: ordered by the consumed[slot] event)
         while pending:
             self._emit(pending.popleft(), n, on_result)
 

@@ -159,6 +159,16 @@ def test_net(ind_range=None):
     return all_boxes, all_segms, all_keyps
 
 
+def _all_jpeg(entries):
+    for e in entries:
+        if e.get('synthetic'):
+            return False
+        paths = e['image'] if isinstance(e['image'], (list, tuple)) else [e['image']]
+        if not all(str(p).lower().endswith(('.jpg', '.jpeg')) for p in paths):
+            return False
+    return True
+
+
 def detect_roidb(model, roidb, all_boxes, all_keyps, timers=None, log=None):
     """The loop of test_net (:142-165) on the batched device step: runs of same-sized entries go through one
     ClipPipeline (cfg.TEST.CLIPS_PER_STEP clips per captured graph replay; frames are read by loader threads straight
@@ -190,8 +200,18 @@ def detect_roidb(model, roidb, all_boxes, all_keyps, timers=None, log=None):
             timers['im_detect_bbox'].tic()
             if log is not None and (base + i) % 10 == 0:
                 log(base + i, timers['im_detect_bbox'].average_time)
+        fill_device = None
+        if cfg.TEST.DEVICE_JPEG_DECODE and _all_jpeg(roidb[i0:i1]):
+            from ..ops import image_ops
+            if not image_ops.jpeg_available():
+                raise RuntimeError('TEST.DEVICE_JPEG_DECODE needs nvJPEG (libnvjpeg.so.12), which is not available here')
+
+            def fill_device(i, dev_dst, stream):      # loader thread: file bytes -> frames decoded straight into the device buffer
+                e = roidb[base + i]
+                paths = e['image'] if isinstance(e['image'], (list, tuple)) else [e['image']]
+                image_ops.jpeg_decode([open(p, 'rb').read() for p in paths], hw[0], hw[1], out=dev_dst, stream=stream)
         timers['im_detect_bbox'].tic()
-        pipe.run(i1 - i0, fill, on_result)
+        pipe.run(i1 - i0, fill, on_result, fill_device=fill_device)
         i0 = i1
 
 

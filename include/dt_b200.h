@@ -438,6 +438,14 @@ int dt_kps_loss_grad(const float* low, int ld, int S, int K, int D, const int* l
  * gradient gb [ldc] (their sum, written to all four). */
 int dt_subpixel_grad_fix(float* gW, float* gb, int K, int Cin, int ldc, void* stream);
 
+/* ---- jpeg.cu (frame decode on the device) ----------------------------------------------------------
+ * jpegs / sizes: HOST arrays of n JPEG byte streams (the file contents cv2.imread would parse, lib/utils/image.py:51-63), all
+ * H x W; out_bgr: DEVICE [n, H, W, 3] uint8 in cv2's BGR interleaved order.  Decoded through nvJPEG (library code, dlopen'ed
+ * on first use: dt_jpeg_available() == 0 and a clean error without it).  Host-side entropy decoding on the calling thread,
+ * GPU work on `stream`; one decoder per host thread, so loader threads may call it concurrently. */
+int dt_jpeg_available(void);
+int dt_jpeg_decode(const unsigned char* const* jpegs, const size_t* sizes, int n, int H, int W, void* out_bgr, void* stream);
+
 /* ---- targets.cu (training target generators on the device) ---------------------------------------
  * Random draws are the counter-based choice / randint of oracle/targets.py (seed, stream, image, index). */
 typedef struct dt_rpn_target_level {
