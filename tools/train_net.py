@@ -30,6 +30,21 @@ def parse_args():
     return p.parse_args()
 
 
+def find_resume_point(output_dir):
+    """tools/train_net.py:79-105 (CLUSTER.AUTO_RESUME): ('final', path) if model_final.pkl exists, else (start_iter, path) of
+    the newest model_iter<N>.pkl (training resumes at N + 1), else (0, None)."""
+    import re
+    final = os.path.join(output_dir, 'model_final.pkl')
+    if os.path.exists(final):
+        return 'final', final
+    start, path = 0, None
+    for f in os.listdir(output_dir) if os.path.isdir(output_dir) else []:
+        m = re.findall(r'(?<=model_iter)\d+(?=\.pkl)', f)
+        if m and int(m[0]) + 1 > start:
+            start, path = int(m[0]) + 1, os.path.join(output_dir, f)
+    return start, path
+
+
 def _synthetic_gt(entry, K):
     rng = np.random.RandomState(entry['seed'] % (2 ** 31))
     H, W, G = entry['height'], entry['width'], 3
@@ -57,13 +72,30 @@ def train_model():
     if world > 1:
         dist.init_process_group('nccl')
     cfg.TEST.SCALES, cfg.TEST.MAX_SIZE = (cfg.TRAIN.SCALES[-1],), cfg.TRAIN.MAX_SIZE       # one training scale per run (the blob geometry)
+    from detectandtrack_b200.core.config import get_output_dir
+    from detectandtrack_b200.modeling import params as P
+    import yaml
+    output_dir = get_output_dir(training=True)
+    start_iter, resume = find_resume_point(output_dir) if (cfg.CLUSTER.ON_CLUSTER and cfg.CLUSTER.AUTO_RESUME) else (0, None)
+    if start_iter == 'final':
+        log.info('model_final.pkl exists; no need to train!')
+        return []
+    if resume:
+        cfg.TRAIN.WEIGHTS = resume
+        log.info('========> Resuming from checkpoint %s with start iter %d', resume, start_iter)
     model = model_builder.create(cfg.MODEL.TYPE, train=True)
+    snap_every = max(1, int(cfg.TRAIN.SNAPSHOT_ITERS / max(1, cfg.NUM_GPUS)))
+
+    def snapshot(name):
+        path = os.path.join(output_dir, name)
+        P.save_weights_file(model.export_blobs(model.blobs0), yaml.dump({'MODEL': {'TYPE': cfg.MODEL.TYPE, 'CONV_BODY': cfg.MODEL.CONV_BODY}}), path)
+        log.info('Wrote %s', path)
     roidb = te.get_dataset(cfg.TRAIN.DATASET).get_roidb(gt=True)
     K = cfg.KRCNN.NUM_KEYPOINTS
     B = cfg.TRAIN.IMS_PER_BATCH
     order = np.random.RandomState(cfg.RNG_SEED).permutation(len(roidb))
     smooth = []
-    for it in range(cfg.SOLVER.MAX_ITER):
+    for it in range(start_iter, cfg.SOLVER.MAX_ITER):
         idx = [order[(it * world * B + rank * B + j) % len(order)] for j in range(B)]
         entries = [roidb[i] for i in idx]
         frames = torch.from_numpy(np.stack([np.stack(te.read_image_video(e)) for e in entries])).cuda()
@@ -71,6 +103,8 @@ def train_model():
                                                                     gt_keypoints=np.asarray(e['gt_keypoints'], np.int32))) for e in entries]
         model.lr = float(get_lr_at_iter(it))
         l_rpn, l_heads = model.step(frames, pack_gt(gts, K=K))
+        if rank == 0 and (it + 1) % snap_every == 0 and it > start_iter:      # :208-212
+            snapshot('model_iter{}.pkl'.format(it))
         if it % 20 == 0 or it == cfg.SOLVER.MAX_ITER - 1:
             l = l_rpn.tolist() + l_heads.tolist()
             smooth.append(sum(l[:5]))
@@ -78,12 +112,7 @@ def train_model():
                 log.info('iter %d lr %.6f loss %.4f (rpn_cls %.4f rpn_bbox %.4f cls %.4f bbox %.4f kps %.4f) accuracy_cls %.3f', it, model.lr,
                          sum(l[:5]), l[0], l[1], l[2], l[3], l[4], l[5] / max(1.0, float(model.totals[0])))
     if rank == 0:             # tools/train_net.py:214-218: the final weights under the reference's blob names (TEST.WEIGHTS of test_net.py)
-        from detectandtrack_b200.core.config import get_output_dir
-        from detectandtrack_b200.modeling import params as P
-        import yaml
-        path = os.path.join(get_output_dir(training=True), 'model_final.pkl')
-        P.save_weights_file(model.export_blobs(model.blobs0), yaml.dump({'MODEL': {'TYPE': cfg.MODEL.TYPE, 'CONV_BODY': cfg.MODEL.CONV_BODY}}), path)
-        log.info('Wrote %s', path)
+        snapshot('model_final.pkl')
     if world > 1:
         dist.destroy_process_group()
     return smooth
