@@ -53,39 +53,54 @@ def randint(n, size, seed, stream, image):
     return ((h * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
 
 
-def bbox_transform_inv(ex, gt, weights):
-    """utils/boxes.py:205-230 on fp32 rows (fp32 arithmetic, numpy weak python-float scalars)."""
-    ex = np.asarray(ex, np.float32); gt = np.asarray(gt, np.float32)
-    ew = ex[:, 2] - ex[:, 0] + np.float32(1.0)
-    eh = ex[:, 3] - ex[:, 1] + np.float32(1.0)
-    ecx = ex[:, 0] + np.float32(0.5) * ew
-    ecy = ex[:, 1] + np.float32(0.5) * eh
-    gw = gt[:, 2] - gt[:, 0] + np.float32(1.0)
-    gh = gt[:, 3] - gt[:, 1] + np.float32(1.0)
-    gcx = gt[:, 0] + np.float32(0.5) * gw
-    gcy = gt[:, 1] + np.float32(0.5) * gh
-    wx, wy, ww, wh = [np.float32(w) for w in weights]
+def _transform_inv_frame(ex, gt, weights, dt):
+    one, half = dt(1.0), dt(0.5)
+    ew = ex[:, 2] - ex[:, 0] + one
+    eh = ex[:, 3] - ex[:, 1] + one
+    ecx = ex[:, 0] + half * ew
+    ecy = ex[:, 1] + half * eh
+    gw = gt[:, 2] - gt[:, 0] + one
+    gh = gt[:, 3] - gt[:, 1] + one
+    gcx = gt[:, 0] + half * gw
+    gcy = gt[:, 1] + half * gh
+    wx, wy, ww, wh = [dt(w) for w in weights]
     return np.vstack((wx * (gcx - ecx) / ew, wy * (gcy - ecy) / eh, ww * np.log(gw / ew), wh * np.log(gh / eh))).transpose()
 
 
+def bbox_transform_inv(ex, gt, weights):
+    """utils/boxes.py:205-240 -> fp32 targets.  Boxes [n, 4]: fp32 arithmetic (numpy weak python-float scalars).  Tubes
+    [n, 4T] go through split_tube_into_boxes (:28-58), whose np.hstack with an empty fp64 score column promotes every frame
+    to fp64, so the tube targets are fp64 arithmetic on the fp32 coordinates, rounded to fp32 once (rpn.py:384-387)."""
+    ex = np.asarray(ex, np.float32); gt = np.asarray(gt, np.float32)
+    if ex.shape[1] > 4:
+        e64, g64 = ex.astype(np.float64), gt.astype(np.float64)
+        return np.concatenate([_transform_inv_frame(e64[:, 4 * t:4 * t + 4], g64[:, 4 * t:4 * t + 4], weights, np.float64)
+                               for t in range(ex.shape[1] // 4)], axis=1).astype(np.float32)
+    return _transform_inv_frame(ex, gt, weights, np.float32)
+
+
 def field_of_anchors(cell_anchors, stride, H, W):
-    """rpn.py:160-203 on an H x W grid: [(H*W*A), 4] fp32, enumeration (h, w, a)."""
+    """rpn.py:160-203 on an H x W grid: [(H*W*A), 4T] fp32, enumeration (h, w, a); cell anchors [A, 4T] (tube anchors are the
+    2-D anchor replicated over the T frames, generate_anchors.py:64-67, and so are the shifts)."""
     sx, sy = np.meshgrid(np.arange(W) * stride, np.arange(H) * stride)
     shifts = np.vstack((sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel())).transpose()
-    A = cell_anchors.shape[0]
-    f = cell_anchors.reshape((1, A, 4)) + shifts.reshape((1, -1, 4)).transpose((1, 0, 2))
-    return f.reshape((-1, 4)).astype(np.float32)
+    A, D = cell_anchors.shape
+    shifts = np.tile(shifts, [1, D // 4])
+    f = cell_anchors.reshape((1, A, D)) + shifts.reshape((1, -1, D)).transpose((1, 0, 2))
+    return f.reshape((-1, D)).astype(np.float32)
 
 
-def rpn_targets(levels, gt_boxes, im_h, im_w, seed, image, straddle=0.0, pos=0.7, neg=0.3, batch=256, fg_frac=0.5):
-    """rpn.py:206-381 for one image and T = 1.  levels: list of (cell_anchors [A,4], stride, H, W); gt_boxes [G,4] fp32 already
-    scaled.  Returns per level dict(labels [H,W,A] i32, bbox_targets / inside / outside [H,W,4A] f32) and the pre-sampling
-    diagnostics dict(max, argmax, fg, bgcand)."""
+def rpn_targets(levels, gt_boxes, im_h, im_w, seed, image, straddle=0.0, pos=0.7, neg=0.3, batch=256, fg_frac=0.5, visible=None):
+    """rpn.py:206-381 for one image.  levels: list of (cell_anchors [A,4T], stride, H, W); gt_boxes [G,4T] fp32 already scaled;
+    visible [G,T] bool (track_visible; all True when None).  Returns per level dict(labels [H,W,A] i32, bbox_targets / inside /
+    outside [H,W,4T*A] f32, vis_labels [H,W,T*A] i32) and the pre-sampling diagnostics dict(max, argmax, fg, bgcand)."""
     all_anchors = np.concatenate([field_of_anchors(c, s, H, W) for (c, s, H, W) in levels])
     total = all_anchors.shape[0]
     gt_boxes = np.asarray(gt_boxes, np.float32)
-    inside = np.where((all_anchors[:, 0] >= -straddle) & (all_anchors[:, 1] >= -straddle) &
-                      (all_anchors[:, 2] < im_w + straddle) & (all_anchors[:, 3] < im_h + straddle))[0]
+    T = all_anchors.shape[1] // 4
+    visible = np.full((len(gt_boxes), T), True) if visible is None else np.asarray(visible, bool)
+    inside = np.where(np.all(all_anchors[:, 0::4] >= -straddle, axis=1) & np.all(all_anchors[:, 1::4] >= -straddle, axis=1) &
+                      np.all(all_anchors[:, 2::4] < im_w + straddle, axis=1) & np.all(all_anchors[:, 3::4] < im_h + straddle, axis=1))[0]
     anchors = all_anchors[inside]
     n = len(inside)
     labels = np.full((n,), -1, np.int32)
@@ -106,26 +121,29 @@ def rpn_targets(levels, gt_boxes, im_h, im_w, seed, image, straddle=0.0, pos=0.7
     diag['bgcand'] = bg_inds.copy()
     if len(bg_inds) > num_bg:
         labels[bg_inds[randint(len(bg_inds), num_bg, seed, 1, image)]] = 0
-    bt = np.zeros((n, 4), np.float32)
+    bt = np.zeros((n, 4 * T), np.float32)
     bt[fg_inds] = bbox_transform_inv(anchors[fg_inds], gt_boxes[argmax[fg_inds]], (1.0, 1.0, 1.0, 1.0))
-    iw = np.zeros((n, 4), np.float32)
-    iw[fg_inds] = 1.0
-    ow = np.zeros((n, 4), np.float32)
+    iw = np.zeros((n, 4 * T), np.float32)
+    iw[fg_inds] = np.repeat(visible[argmax[fg_inds]], 4, axis=1).astype(np.float32)     # invisible frames of a tube: no box loss
+    ow = np.zeros((n, 4 * T), np.float32)
     nex = np.sum(labels >= 0)
     ow[labels == 1] = 1.0 / nex
     ow[labels == 0] = 1.0 / nex
+    vis = np.tile(labels[:, None], [1, T])
+    vis[fg_inds] *= visible[argmax[fg_inds]].astype(np.int32)
 
     def unmap(d, fill):
         r = np.full((total,) + d.shape[1:], fill, d.dtype)
         r[inside] = d
         return r
-    labels, bt, iw, ow = unmap(labels, -1), unmap(bt, 0), unmap(iw, 0), unmap(ow, 0)
+    labels, bt, iw, ow, vis = unmap(labels, -1), unmap(bt, 0), unmap(iw, 0), unmap(ow, 0), unmap(vis, -1)
     out, s = [], 0
     for (c, st, H, W) in levels:
         A = c.shape[0]
         e = s + H * W * A
-        out.append(dict(labels=labels[s:e].reshape(H, W, A), bbox_targets=bt[s:e].reshape(H, W, 4 * A),
-                        inside=iw[s:e].reshape(H, W, 4 * A), outside=ow[s:e].reshape(H, W, 4 * A)))
+        out.append(dict(labels=labels[s:e].reshape(H, W, A), bbox_targets=bt[s:e].reshape(H, W, 4 * T * A),
+                        inside=iw[s:e].reshape(H, W, 4 * T * A), outside=ow[s:e].reshape(H, W, 4 * T * A),
+                        vis_labels=vis[s:e].reshape(H, W, T * A)))
         s = e
     return out, diag
 

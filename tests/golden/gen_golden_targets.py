@@ -138,6 +138,34 @@ def main():
             out['%s_labels%d' % (tag, l)] = b['rpn_labels_int32_wide'][0].transpose(1, 2, 0)              # [H, W, A]
             for k, n in (('rpn_bbox_targets_wide', 'bt'), ('rpn_bbox_inside_weights_wide', 'iw'), ('rpn_bbox_outside_weights_wide', 'ow')):
                 out['%s_%s%d' % (tag, n, l)] = b[k][0].transpose(1, 2, 0)                                   # [H, W, 4A]
+    # tube anchors / tube ground truth (T = 3, the reference's 3-D RPN: rpn.py with time_dim > 1, per-frame visibility)
+    for tag, (H, W, G, batch) in {'rpnT3': (200, 300, 4, 128)}.items():
+        T = 3
+        cfg.TRAIN.RPN_BATCH_SIZE_PER_IM = batch
+        rrpn._threadlocal_foa.__dict__.pop('cache', None)
+        e = synth_entry(H, W, G)
+        tubes = np.concatenate([np.clip(e['boxes'] + rng.normal(0, 4, e['boxes'].shape), 0, [W - 1, H - 1, W - 1, H - 1]) for _ in range(T)], 1).astype(np.float32)
+        vis = rng.uniform(0, 1, (G, T)) > 0.25
+        vis[0] = True
+        tubes[np.repeat(~vis, 4, axis=1)] = 0                        # utils/video._combine_clips leaves the boxes of missing frames at 0
+        foas = [rrpn._get_field_of_anchors(2. ** lvl, (cfg.FPN.RPN_ANCHOR_START_SIZE * 2. ** (lvl - 2),), cfg.FPN.RPN_ASPECT_RATIOS, T)
+                for lvl in range(2, 7)]
+        all_anchors = np.concatenate([f.field_of_anchors for f in foas])
+        CTX['image'] = 2
+        blobs = rrpn._get_rpn_blobs(float(H), float(W), foas, all_anchors, tubes, vis)
+        out[tag + '_gt'], out[tag + '_vis'] = tubes, vis
+        out[tag + '_im'] = np.array([H, W, 1.0], np.float32)
+        out[tag + '_field'] = np.array([f.field_size for f in foas], np.int32)
+        out[tag + '_batch'] = np.int32(batch)
+        for l, b in enumerate(blobs):
+            out['%s_labels%d' % (tag, l)] = b['rpn_labels_int32_wide'][0].transpose(1, 2, 0)
+            out['%s_vis%d' % (tag, l)] = b['rpn_vis_labels_int32_wide'][0].transpose(1, 2, 0)
+            for k, n in (('rpn_bbox_targets_wide', 'bt'), ('rpn_bbox_inside_weights_wide', 'iw'), ('rpn_bbox_outside_weights_wide', 'ow')):
+                out['%s_%s%d' % (tag, n, l)] = b[k][0].transpose(1, 2, 0)
+        for lvl in range(2, 7):
+            out['cell_anchors_T3_%d' % lvl] = generate_anchors(stride=2. ** lvl, sizes=(cfg.FPN.RPN_ANCHOR_START_SIZE * 2. ** (lvl - 2),),
+                                                               aspect_ratios=cfg.FPN.RPN_ASPECT_RATIOS, time_dim=T)
+    rrpn._threadlocal_foa.__dict__.pop('cache', None)
     for lvl in range(2, 7):
         out['cell_anchors%d' % lvl] = generate_anchors(stride=2. ** lvl, sizes=(cfg.FPN.RPN_ANCHOR_START_SIZE * 2. ** (lvl - 2),),
                                                        aspect_ratios=cfg.FPN.RPN_ASPECT_RATIOS, time_dim=1)

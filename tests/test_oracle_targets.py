@@ -74,3 +74,20 @@ def test_collect_train_is_batch_wide():
     thr = np.sort(np.concatenate(sc))[::-1][39]
     for b in range(2):
         assert np.array_equal(kept[b][:, 0] - 100 * b, np.where(sc[b] >= thr)[0])
+
+
+def test_rpn_tube_targets_equal_reference():
+    """T = 3: tube anchors, tube IoU (mean over frames), per-frame targets, inside weights and vis labels from track_visible."""
+    tag = 'rpnT3'
+    im_h, im_w, _ = G[tag + '_im']
+    lv = [(G['cell_anchors_T3_%d' % lvl], 2. ** lvl, int(G[tag + '_field'][l]), int(G[tag + '_field'][l])) for l, lvl in enumerate(range(2, 7))]
+    out, _ = ot.rpn_targets(lv, G[tag + '_gt'], float(im_h), float(im_w), SEED, 2, batch=int(G[tag + '_batch']), visible=G[tag + '_vis'])
+    some_invisible = 0
+    for l, o in enumerate(out):
+        assert np.array_equal(o['labels'], G['%s_labels%d' % (tag, l)])
+        assert np.array_equal(o['vis_labels'], G['%s_vis%d' % (tag, l)])
+        assert np.array_equal(o['bbox_targets'], G['%s_bt%d' % (tag, l)]) and o['bbox_targets'].shape[-1] == 3 * 4 * 3
+        assert np.array_equal(o['inside'], G['%s_iw%d' % (tag, l)]) and np.array_equal(o['outside'], G['%s_ow%d' % (tag, l)])
+        fg = o['labels'] == 1
+        some_invisible += int((o['vis_labels'].reshape(o['labels'].shape + (3,))[fg] == 0).sum())
+    assert sum(int((o['labels'] == 1).sum()) for o in out) > 0 and some_invisible > 0
