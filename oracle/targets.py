@@ -218,8 +218,9 @@ def keypoints_to_heatmap_labels(kps, rois, M):
 
 def sample_rois(gt_boxes, gt_classes, is_crowd, gt_keypoints, proposals_scaled, im_scale, image, seed, num_classes=2,
                 batch=512, fg_frac=0.25, fg_thresh=0.5, bg_hi=0.5, bg_lo=0.0, weights=(10., 10., 5., 5.), M=56):
-    """add_proposals + _sample_rois + add_keypoint_rcnn_blobs for one image (T = 1).  proposals_scaled [P,4] fp32 in blob
-    coordinates (the RPN's rois); im_scale fp32.  Returns the blobs of fast_rcnn.py:118-186 / keypoint_rcnn.py:24-83."""
+    """add_proposals + _sample_rois + add_keypoint_rcnn_blobs for one image.  proposals_scaled [P,4T] fp32 in blob coordinates
+    (the RPN's rois / tubes); gt_boxes [G,4T]; gt_keypoints [G,3,K*T]; im_scale fp32.  Returns the blobs of
+    fast_rcnn.py:118-186 / keypoint_rcnn.py:24-83 (tubes: box targets 4T per class, heat-map labels frame by frame)."""
     s = np.float32(im_scale)
     inv = np.float32(1.0) / s
     props = (np.asarray(proposals_scaled, np.float32) * inv).astype(np.float32)
@@ -240,12 +241,14 @@ def sample_rois(gt_boxes, gt_classes, is_crowd, gt_keypoints, proposals_scaled, 
     sb = boxes[keep]
     gt_assign = bmap[keep]                               # gt_inds[...]: the gt rows are rows 0..G-1 (negative index -> last gt)
     tg = bbox_transform_inv(sb, np.asarray(gt_boxes, np.float32)[gt_assign], weights).astype(np.float32)
-    bt = np.zeros((len(keep), 4 * num_classes), np.float32)
+    D = boxes.shape[1]                                   # tube_dim = 4T (fast_rcnn.py:213)
+    T = D // 4
+    bt = np.zeros((len(keep), D * num_classes), np.float32)
     iw = np.zeros_like(bt)
     for i in np.where(labels > 0)[0]:
         c = int(labels[i])
-        bt[i, 4 * c:4 * c + 4] = tg[i]
-        iw[i, 4 * c:4 * c + 4] = 1.0
+        bt[i, D * c:D * c + D] = tg[i]
+        iw[i, D * c:D * c + D] = 1.0
     ow = (iw > 0).astype(np.float32)
     rois = np.hstack((np.full((len(keep), 1), image, np.float32), sb * s)).astype(np.float32)
     # keypoints (keypoint_rcnn.py:24-83)
@@ -267,7 +270,10 @@ def sample_rois(gt_boxes, gt_classes, is_crowd, gt_keypoints, proposals_scaled, 
     for ii in range(len(kb)):
         if km[ii] >= 0:
             sk[ii] = kp[km[ii]]
-    heat, wts = keypoints_to_heatmap_labels(sk, kb, M)
+    Kf = kp.shape[2] // T                                # per-frame joints (keypoint_rcnn.py:62-70)
+    hw = [keypoints_to_heatmap_labels(sk[..., t * Kf:(t + 1) * Kf], kb[:, 4 * t:4 * t + 4], M) for t in range(T)]
+    heat = np.concatenate([h for h, _ in hw], axis=-1)
+    wts = np.concatenate([w for _, w in hw], axis=-1)
     krois = np.hstack((np.full((len(kb), 1), image, np.float32), kb * s)).astype(np.float32)
     return dict(rois=rois, labels=labels.astype(np.int32), bbox_targets=bt, inside=iw, outside=ow, keypoint_rois=krois,
                 keypoint_locations=heat.astype(np.int32), keypoint_weights=wts,

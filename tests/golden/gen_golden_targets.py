@@ -202,6 +202,38 @@ def main():
         for k in ('rois', 'labels_int32', 'bbox_targets', 'bbox_inside_weights', 'bbox_outside_weights', 'keypoint_rois',
                   'keypoint_locations_int32', 'keypoint_weights'):
             out['%s_%s' % (tag, k)] = blobs[k]
+    # tubes (T = 3): tube proposals, tube IoU, 4T box targets per class, per-frame heat-map labels
+    for tag, (H, W, G, P, scale, batch) in {'roiT3': (240, 320, 3, 200, 1.5, 128)}.items():
+        T = 3
+        cfg.TRAIN.BATCH_SIZE_PER_IM = batch
+        out[tag + '_batch'] = np.int32(batch)
+        e0 = synth_entry(H, W, G)
+        jit = lambda b, s_: np.clip(b + rng.normal(0, s_, b.shape), 0, [W - 1, H - 1, W - 1, H - 1]).astype(np.float32)
+        e0['boxes'] = np.concatenate([jit(e0['boxes'], 3) for _ in range(T)], 1)
+        kp1 = e0['gt_keypoints']
+        e0['gt_keypoints'] = np.concatenate([kp1 + rng.integers(-2, 3, kp1.shape).astype(np.int32) * np.array([1, 1, 0], np.int32)[None, :, None]
+                                             for _ in range(T)], 2)
+        nf = P // 3
+        src = e0['boxes'][rng.integers(0, G, nf)]
+        props = np.concatenate([src + rng.normal(0, 5, src.shape),
+                                np.tile(np.stack([rng.uniform(0, W - 40, P - nf), rng.uniform(0, H - 40, P - nf),
+                                                  rng.uniform(0, W - 40, P - nf) + 40, rng.uniform(0, H - 40, P - nf) + 40], 1), [1, T])], 0).astype(np.float32)
+        for t in range(T):
+            props[:, 4 * t + 2:4 * t + 4] = np.maximum(props[:, 4 * t + 2:4 * t + 4], props[:, 4 * t:4 * t + 2] + 1)
+        props = props[rng.permutation(P)]
+        rois = np.hstack([np.zeros((P, 1), np.float32), props * np.float32(scale)]).astype(np.float32)
+        im_scales = np.array([scale], np.float32)
+        roidb = [dict((k, (v.copy() if hasattr(v, 'copy') else v)) for k, v in e0.items())]
+        jd.add_proposals(roidb, rois, im_scales)
+        CTX['image'] = 0
+        blobs = rfr._sample_rois(roidb[0], im_scales[0], 0)
+        for k in ('boxes', 'gt_classes', 'is_crowd', 'gt_keypoints'):
+            out['%s_gt_%s' % (tag, k)] = e0[k]
+        out[tag + '_rois_in'] = rois
+        out[tag + '_scale'] = np.float32(scale)
+        for k in ('rois', 'labels_int32', 'bbox_targets', 'bbox_inside_weights', 'bbox_outside_weights', 'keypoint_rois',
+                  'keypoint_locations_int32', 'keypoint_weights'):
+            out['%s_%s' % (tag, k)] = blobs[k]
     # heat-map labels alone (utils/keypoints.py:152-207), incl. boundary and out-of-box joints
     n = 64
     rois = np.stack([rng.uniform(0, 200, n), rng.uniform(0, 200, n), rng.uniform(210, 400, n), rng.uniform(210, 400, n)], 1).astype(np.float32)

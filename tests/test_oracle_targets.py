@@ -91,3 +91,17 @@ def test_rpn_tube_targets_equal_reference():
         fg = o['labels'] == 1
         some_invisible += int((o['vis_labels'].reshape(o['labels'].shape + (3,))[fg] == 0).sum())
     assert sum(int((o['labels'] == 1).sum()) for o in out) > 0 and some_invisible > 0
+
+
+def test_sample_tube_rois_equal_reference():
+    tag = 'roiT3'
+    rois_in = G[tag + '_rois_in']
+    r = ot.sample_rois(G[tag + '_gt_boxes'], G[tag + '_gt_gt_classes'], G[tag + '_gt_is_crowd'], G[tag + '_gt_gt_keypoints'],
+                       rois_in[:, 1:], G[tag + '_scale'], 0, SEED, batch=int(G[tag + '_batch']))
+    for k, gk in (('rois', 'rois'), ('labels', 'labels_int32'), ('bbox_targets', 'bbox_targets'), ('inside', 'bbox_inside_weights'),
+                  ('outside', 'bbox_outside_weights'), ('keypoint_rois', 'keypoint_rois')):
+        assert np.array_equal(r[k], G['%s_%s' % (tag, gk)]), k
+    assert r['rois'].shape[1] == 13 and r['bbox_targets'].shape[1] == 24
+    assert np.array_equal(r['keypoint_locations'].reshape(-1, 1), G[tag + '_keypoint_locations_int32'])
+    assert np.array_equal(r['keypoint_weights'].reshape(-1, 1), G[tag + '_keypoint_weights'])
+    assert r['keypoint_weights'].shape[1] == 51 and (r['labels'] == 1).sum() > 0
