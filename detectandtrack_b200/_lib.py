@@ -64,7 +64,7 @@ SIGNATURES = {
     'dt_subpixel_grad_fix': [_p, _p, _i, _i, _i, _p],
     'dt_jpeg_decode': [C.POINTER(C.c_char_p), C.POINTER(_sz), _i, _i, _i, _p, _p],
     'dt_rpn_targets_workspace_bytes': [_i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i, C.POINTER(_sz)],
-    'dt_rpn_targets': [_p, _i, _i, _i, _p, _p, _i, _p, _f, _f, _f, _i, _f, C.c_ulonglong, _p, _sz, _p],
+    'dt_rpn_targets': [_p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _f, _f, _f, _i, _f, C.c_ulonglong, _p, _sz, _p],
     'dt_sample_rois': [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _f, _f, C.POINTER(_f), _i,
                        C.c_ulonglong, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p],
 }
@@ -82,7 +82,8 @@ class RpnLevel(C.Structure):
 class RpnTargetLevel(C.Structure):
     """dt_rpn_target_level (include/dt_b200.h)."""
     _fields_ = [('H', C.c_int), ('W', C.c_int), ('feat_stride', C.c_double), ('anchors', C.c_void_p), ('labels', C.c_void_p),
-                ('bbox_targets', C.c_void_p), ('inside_weights', C.c_void_p), ('outside_weights', C.c_void_p)]
+                ('bbox_targets', C.c_void_p), ('inside_weights', C.c_void_p), ('outside_weights', C.c_void_p),
+                ('vis_labels', C.c_void_p)]
 
 
 class SgdItem(C.Structure):

@@ -45,14 +45,30 @@ __device__ __forceinline__ void transform_inv(const float* ex, const float* gt, 
   out[3] = __fmul_rn(wh, logf(__fdiv_rn(gh, eh)));
 }
 
+// Tubes (T > 1): the reference's split_tube_into_boxes promotes every frame to fp64 (np.hstack with an empty fp64 score column,
+// utils/boxes.py:28-58), so its tube targets are fp64 arithmetic on the fp32 coordinates, rounded to fp32 once.
+__device__ __forceinline__ void transform_inv64(const float* ex, const float* gt, double wx, double wy, double ww, double wh, float* out) {
+  const double ew = __dadd_rn(__dsub_rn((double)ex[2], (double)ex[0]), 1.0), eh = __dadd_rn(__dsub_rn((double)ex[3], (double)ex[1]), 1.0);
+  const double ecx = __dadd_rn((double)ex[0], __dmul_rn(0.5, ew)), ecy = __dadd_rn((double)ex[1], __dmul_rn(0.5, eh));
+  const double gw = __dadd_rn(__dsub_rn((double)gt[2], (double)gt[0]), 1.0), gh = __dadd_rn(__dsub_rn((double)gt[3], (double)gt[1]), 1.0);
+  const double gcx = __dadd_rn((double)gt[0], __dmul_rn(0.5, gw)), gcy = __dadd_rn((double)gt[1], __dmul_rn(0.5, gh));
+  out[0] = (float)__ddiv_rn(__dmul_rn(wx, __dsub_rn(gcx, ecx)), ew);
+  out[1] = (float)__ddiv_rn(__dmul_rn(wy, __dsub_rn(gcy, ecy)), eh);
+  out[2] = (float)__dmul_rn(ww, log(__ddiv_rn(gw, ew)));
+  out[3] = (float)__dmul_rn(wh, log(__ddiv_rn(gh, eh)));
+}
+
 // ------------------------------------------------------------------------------------------------ RPN targets
+constexpr int TG_TMAX = 4;            // frames per tube supported by the target generators
+
 struct RpnTL {
-  int n_levels, A;
+  int n_levels, A, T;
   int H[8], W[8], start[9];
   double stride[8];
-  const double* cell[8];              // [A, 4] fp64 (generate_anchors.py)
+  const double* cell[8];              // [A, 4T] fp64 (generate_anchors.py; tube anchors replicate the 2-D anchor over the frames)
   int* labels[8];                     // [B, H, W, A]
-  float* bt[8]; float* iw[8]; float* ow[8];   // [B, H, W, 4A]
+  float* bt[8]; float* iw[8]; float* ow[8];   // [B, H, W, 4T*A]
+  int* vis[8];                        // [B, H, W, T*A] or NULL
 };
 
 struct AnchorRef { int l, loc; };     // level, index inside the level (h, w, a)
@@ -64,7 +80,7 @@ __device__ __forceinline__ AnchorRef anchor_box(const RpnTL& lv, int i, float* b
   const int a = loc % lv.A, pos = loc / lv.A;
   const int w = pos % lv.W[l], h = pos / lv.W[l];
   const double sx = (double)w * lv.stride[l], sy = (double)h * lv.stride[l];
-  const double* c = lv.cell[l] + 4 * a;
+  const double* c = lv.cell[l] + 4 * lv.T * a;          // first frame of the (replicated) tube anchor
   box[0] = (float)(c[0] + sx); box[1] = (float)(c[1] + sy); box[2] = (float)(c[2] + sx); box[3] = (float)(c[3] + sy);
   AnchorRef r; r.l = l; r.loc = loc;
   return r;
@@ -72,17 +88,25 @@ __device__ __forceinline__ AnchorRef anchor_box(const RpnTL& lv, int i, float* b
 
 constexpr int TG_GMAX = 128;
 
+// IoU of a (replicated) tube anchor with a gt tube: utils/boxes.py:60-69, sequential fp32 sum over the frames, / T
+__device__ __forceinline__ float anchor_tube_iou(const float* box, const float* gt_tube, int T) {
+  float acc = iou_pair_ref(box, gt_tube);
+  for (int t = 1; t < T; ++t) acc = __fadd_rn(acc, iou_pair_ref(box, gt_tube + 4 * t));
+  return T == 1 ? acc : __fdiv_rn(acc, (float)T);
+}
+
 // pass 1: per anchor max / first-argmax IoU over the gt boxes; per gt the max over the inside anchors
 __global__ void __launch_bounds__(256)
 rpn_anchor_iou_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const int* __restrict__ gt_counts, int Gmax,
                       const float* __restrict__ im_info, float straddle, float* __restrict__ amax, int* __restrict__ aarg,
                       unsigned* __restrict__ gmax) {
-  __shared__ float sgt[TG_GMAX * 4];
+  __shared__ float sgt[TG_GMAX * 4 * TG_TMAX];
   __shared__ unsigned sgm[TG_GMAX];
   const int b = blockIdx.y;
   const int G = min(gt_counts[b], Gmax);
   const float scale = im_info[b * 3 + 2];
-  for (int j = threadIdx.x; j < G * 4; j += blockDim.x) sgt[j] = __fmul_rn(gt[(size_t)b * Gmax * 4 + j], scale);
+  const int D = 4 * lv.T;
+  for (int j = threadIdx.x; j < G * D; j += blockDim.x) sgt[j] = __fmul_rn(gt[(size_t)b * Gmax * D + j], scale);
   for (int j = threadIdx.x; j < G; j += blockDim.x) sgm[j] = 0u;
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +118,7 @@ rpn_anchor_iou_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const int*
     float best = -2.f; int arg = -1;                  // -2: not inside the image
     if (inside && G > 0) {
       for (int g = 0; g < G; ++g) {
-        const float v = iou_pair_ref(box, sgt + 4 * g);
+        const float v = anchor_tube_iou(box, sgt + D * g, lv.T);
         if (g == 0 || v > best) { best = v; arg = g; }
         if (v > 0.f) atomicMax(&sgm[g], __float_as_uint(v));
       }
@@ -111,13 +135,14 @@ __global__ void __launch_bounds__(256)
 rpn_label_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const int* __restrict__ gt_counts, int Gmax,
                  const float* __restrict__ im_info, float pos_thresh, float neg_thresh, const float* __restrict__ amax,
                  const unsigned* __restrict__ gmax, signed char* __restrict__ lab, int* __restrict__ cnt /*[B,4]*/) {
-  __shared__ float sgt[TG_GMAX * 4];
+  __shared__ float sgt[TG_GMAX * 4 * TG_TMAX];
   __shared__ float sgm[TG_GMAX];
   __shared__ int s_cnt[2];
   const int b = blockIdx.y;
   const int G = min(gt_counts[b], Gmax);
   const float scale = im_info[b * 3 + 2];
-  for (int j = threadIdx.x; j < G * 4; j += blockDim.x) sgt[j] = __fmul_rn(gt[(size_t)b * Gmax * 4 + j], scale);
+  const int D = 4 * lv.T;
+  for (int j = threadIdx.x; j < G * D; j += blockDim.x) sgt[j] = __fmul_rn(gt[(size_t)b * Gmax * D + j], scale);
   for (int j = threadIdx.x; j < G; j += blockDim.x) sgm[j] = __uint_as_float(gmax[b * Gmax + j]);
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -129,7 +154,7 @@ rpn_label_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const int* __re
       float box[4];
       anchor_box(lv, i, box);
       bool fg = m >= pos_thresh;
-      for (int g = 0; g < G && !fg; ++g) fg = iou_pair_ref(box, sgt + 4 * g) == sgm[g];   // rpn.py:254-259, incl. the 0 == 0 ties
+      for (int g = 0; g < G && !fg; ++g) fg = anchor_tube_iou(box, sgt + D * g, lv.T) == sgm[g];   // rpn.py:254-259, incl. the 0 == 0 ties
       if (fg) { l = 1; atomicAdd(&s_cnt[0], 1); }
       if (m < neg_thresh) atomicAdd(&s_cnt[1], 1);
     }
@@ -255,33 +280,42 @@ rpn_sample_kernel(int NA, int batch, int num_fg, float neg_thresh, unsigned long
 
 // pass 4: the per-level target blobs
 __global__ void __launch_bounds__(256)
-rpn_write_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const int* __restrict__ gt_counts, int Gmax,
-                 const float* __restrict__ im_info, const int* __restrict__ aarg, const signed char* __restrict__ lab,
+rpn_write_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const unsigned char* __restrict__ gt_vis, const int* __restrict__ gt_counts,
+                 int Gmax, const float* __restrict__ im_info, const int* __restrict__ aarg, const signed char* __restrict__ lab,
                  const int* __restrict__ cnt) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NA) return;
   float box[4];
   const AnchorRef r = anchor_box(lv, i, box);
+  const int T = lv.T;
   const size_t per = (size_t)lv.H[r.l] * lv.W[r.l] * lv.A;
   const size_t o = (size_t)b * per + r.loc;
   const int l = lab[(size_t)b * NA + i];
-  lv.labels[r.l][o] = l < 0 ? -1 : (l == 1 ? 1 : 0);
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  const int final_label = l < 0 ? -1 : (l == 1 ? 1 : 0);
+  lv.labels[r.l][o] = final_label;
   const bool fg = l == 1 || l == 2;
-  if (fg) {
-    const float scale = im_info[b * 3 + 2];
-    const float* g = gt + ((size_t)b * Gmax + aarg[(size_t)b * NA + i]) * 4;
-    float gs[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) gs[k] = __fmul_rn(g[k], scale);
-    transform_inv(box, gs, 1.f, 1.f, 1.f, 1.f, t);
-  }
-  const float w_in = fg ? 1.f : 0.f;
   const float w_out = l >= 0 ? (float)(1.0 / (double)cnt[b * 4 + 2]) : 0.f;
-  reinterpret_cast<float4*>(lv.bt[r.l])[o] = make_float4(t[0], t[1], t[2], t[3]);
-  reinterpret_cast<float4*>(lv.iw[r.l])[o] = make_float4(w_in, w_in, w_in, w_in);
-  reinterpret_cast<float4*>(lv.ow[r.l])[o] = make_float4(w_out, w_out, w_out, w_out);
+  const int ga = fg ? aarg[(size_t)b * NA + i] : 0;
+  const float scale = im_info[b * 3 + 2];
+  for (int t = 0; t < T; ++t) {
+    float tg[4] = {0.f, 0.f, 0.f, 0.f};
+    bool visible = true;
+    if (fg) {
+      const float* g = gt + ((size_t)b * Gmax + ga) * 4 * T + 4 * t;
+      float gs[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gs[k] = __fmul_rn(g[k], scale);
+      if (T == 1) transform_inv(box, gs, 1.f, 1.f, 1.f, 1.f, tg);
+      else transform_inv64(box, gs, 1.0, 1.0, 1.0, 1.0, tg);
+      visible = gt_vis ? gt_vis[((size_t)b * Gmax + ga) * T + t] != 0 : true;      // track_visible (rpn.py:300-303)
+    }
+    const float w_in = (fg && visible) ? 1.f : 0.f;
+    reinterpret_cast<float4*>(lv.bt[r.l])[o * T + t] = make_float4(tg[0], tg[1], tg[2], tg[3]);
+    reinterpret_cast<float4*>(lv.iw[r.l])[o * T + t] = make_float4(w_in, w_in, w_in, w_in);
+    reinterpret_cast<float4*>(lv.ow[r.l])[o * T + t] = make_float4(w_out, w_out, w_out, w_out);
+    if (lv.vis[r.l]) lv.vis[r.l][o * T + t] = (l == 1 && !visible) ? 0 : final_label;   // rpn.py:318-321: vis_labels[fg_inds] *= visible
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ RoI sampling
@@ -532,18 +566,18 @@ extern "C" int dt_rpn_targets_workspace_bytes(int B, int n_levels, const int* Hs
   return 0;
 }
 
-extern "C" int dt_rpn_targets(const dt_rpn_target_level* levels, int n_levels, int A, int B, const float* gt_boxes, const int* gt_counts,
-                              int Gmax, const float* im_info, float straddle_thresh, float positive_overlap, float negative_overlap,
-                              int batch_size_per_im, float fg_fraction, unsigned long long seed, void* workspace, size_t workspace_bytes,
-                              void* stream_) {
+extern "C" int dt_rpn_targets(const dt_rpn_target_level* levels, int n_levels, int A, int T, int B, const float* gt_boxes,
+                              const unsigned char* gt_visible, const int* gt_counts, int Gmax, const float* im_info, float straddle_thresh,
+                              float positive_overlap, float negative_overlap, int batch_size_per_im, float fg_fraction,
+                              unsigned long long seed, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DT_CHECK_ARG(levels && n_levels >= 1 && n_levels <= 8 && A >= 1 && B >= 1 && Gmax >= 1 && Gmax <= TG_GMAX && batch_size_per_im >= 1 &&
-                   batch_size_per_im <= 1024 && fg_fraction >= 0.f && fg_fraction <= 1.f,
-               "dt_rpn_targets: bad arguments (levels <= 8, Gmax <= %d, batch <= 1024)", TG_GMAX);
+  DT_CHECK_ARG(levels && n_levels >= 1 && n_levels <= 8 && A >= 1 && T >= 1 && T <= TG_TMAX && B >= 1 && Gmax >= 1 && Gmax <= TG_GMAX &&
+                   batch_size_per_im >= 1 && batch_size_per_im <= 1024 && fg_fraction >= 0.f && fg_fraction <= 1.f,
+               "dt_rpn_targets: bad arguments (levels <= 8, T <= %d, Gmax <= %d, batch <= 1024)", TG_TMAX, TG_GMAX);
   DT_CHECK_ARG(gt_boxes && gt_counts && im_info && workspace, "dt_rpn_targets: null pointer");
   RpnTL lv;
   memset(&lv, 0, sizeof(lv));
-  lv.n_levels = n_levels; lv.A = A;
+  lv.n_levels = n_levels; lv.A = A; lv.T = T;
   long long NA = 0;
   int Hs[8], Ws[8];
   for (int l = 0; l < n_levels; ++l) {
@@ -551,7 +585,7 @@ extern "C" int dt_rpn_targets(const dt_rpn_target_level* levels, int n_levels, i
     DT_CHECK_ARG(s.H >= 1 && s.W >= 1 && s.anchors && s.labels && s.bbox_targets && s.inside_weights && s.outside_weights && s.feat_stride > 0,
                  "dt_rpn_targets: level %d incomplete", l);
     lv.H[l] = s.H; lv.W[l] = s.W; lv.stride[l] = s.feat_stride; lv.cell[l] = s.anchors; lv.start[l] = (int)NA;
-    lv.labels[l] = s.labels; lv.bt[l] = s.bbox_targets; lv.iw[l] = s.inside_weights; lv.ow[l] = s.outside_weights;
+    lv.labels[l] = s.labels; lv.bt[l] = s.bbox_targets; lv.iw[l] = s.inside_weights; lv.ow[l] = s.outside_weights; lv.vis[l] = s.vis_labels;
     Hs[l] = s.H; Ws[l] = s.W;
     NA += (long long)s.H * s.W * A;
   }
@@ -579,7 +613,7 @@ extern "C" int dt_rpn_targets(const dt_rpn_target_level* levels, int n_levels, i
   DT_CHECK_CUDA(grant_dyn_smem(rpn_sample_kernel, sample_smem, &sample_grant));
   rpn_sample_kernel<<<B, 1024, sample_smem, stream>>>((int)NA, batch_size_per_im, num_fg, negative_overlap, seed, amax, lab, cnt);
   DT_CHECK_LAUNCH();
-  rpn_write_kernel<<<grid, 256, 0, stream>>>(lv, (int)NA, gt_boxes, gt_counts, Gmax, im_info, aarg, lab, cnt);
+  rpn_write_kernel<<<grid, 256, 0, stream>>>(lv, (int)NA, gt_boxes, gt_visible, gt_counts, Gmax, im_info, aarg, lab, cnt);
   DT_CHECK_LAUNCH();
   return 0;
 }

@@ -6,32 +6,36 @@ from .. import _lib as L
 from . import box_ops
 
 
-def rpn_targets(level_shapes, anchors, strides, A, gt_boxes, gt_counts, im_info, cfg_train, seed):
-    """level_shapes: [(H, W)] finest first; anchors: per level [A, 4] fp64 device cell anchors; gt_boxes [B, Gmax, 4] fp32
-    (original image coordinates, non-crowd), gt_counts [B] int32, im_info [B, 3].  Returns per level
-    dict(labels [B,H,W,A] i32, bbox_targets / inside / outside [B,H,W,4A] f32) (rpn.py:206-381, T = 1)."""
+def rpn_targets(level_shapes, anchors, strides, A, gt_boxes, gt_counts, im_info, cfg_train, seed, gt_visible=None):
+    """level_shapes: [(H, W)] finest first; anchors: per level [A, 4T] fp64 device cell anchors; gt_boxes [B, Gmax, 4T] fp32
+    (original image coordinates, non-crowd; T = 1 boxes or T <= 4 frame tubes), gt_visible [B, Gmax, T] uint8 or None,
+    gt_counts [B] int32, im_info [B, 3].  Returns per level dict(labels [B,H,W,A] i32, bbox_targets / inside / outside
+    [B,H,W,4T*A] f32, vis_labels [B,H,W,T*A] i32) (rpn.py:206-381)."""
     torch = L.require_cuda()
-    B, Gmax, _ = gt_boxes.shape
+    B, Gmax, D = gt_boxes.shape
+    T = D // 4
     nl = len(level_shapes)
     arr = (L.RpnTargetLevel * nl)()
     Hs, Ws = (C.c_int * nl)(), (C.c_int * nl)()
     out = []
     for i, (H, W) in enumerate(level_shapes):
         o = dict(labels=torch.empty((B, H, W, A), dtype=torch.int32, device='cuda'),
-                 bbox_targets=torch.empty((B, H, W, 4 * A), dtype=torch.float32, device='cuda'),
-                 inside=torch.empty((B, H, W, 4 * A), dtype=torch.float32, device='cuda'),
-                 outside=torch.empty((B, H, W, 4 * A), dtype=torch.float32, device='cuda'))
+                 bbox_targets=torch.empty((B, H, W, 4 * T * A), dtype=torch.float32, device='cuda'),
+                 inside=torch.empty((B, H, W, 4 * T * A), dtype=torch.float32, device='cuda'),
+                 outside=torch.empty((B, H, W, 4 * T * A), dtype=torch.float32, device='cuda'),
+                 vis_labels=torch.empty((B, H, W, T * A), dtype=torch.int32, device='cuda'))
         out.append(o)
         a = anchors[i]
-        assert a.dtype == torch.float64 and tuple(a.shape) == (A, 4) and a.is_contiguous()
+        assert a.dtype == torch.float64 and tuple(a.shape) == (A, 4 * T) and a.is_contiguous()
         arr[i] = L.RpnTargetLevel(H, W, float(strides[i]), a.data_ptr(), o['labels'].data_ptr(), o['bbox_targets'].data_ptr(),
-                                  o['inside'].data_ptr(), o['outside'].data_ptr())
+                                  o['inside'].data_ptr(), o['outside'].data_ptr(), o['vis_labels'].data_ptr())
         Hs[i], Ws[i] = H, W
     need = C.c_size_t(0)
     L.call('dt_rpn_targets_workspace_bytes', B, nl, Hs, Ws, A, Gmax, C.byref(need))
     ws = box_ops._workspace(need.value, torch, slot='rpn_targets')
     assert gt_boxes.dtype == torch.float32 and gt_counts.dtype == torch.int32 and im_info.dtype == torch.float32
-    L.call('dt_rpn_targets', arr, nl, A, B, L.ptr(gt_boxes), L.ptr(gt_counts), Gmax, L.ptr(im_info),
+    assert gt_visible is None or (gt_visible.dtype == torch.uint8 and tuple(gt_visible.shape) == (B, Gmax, T))
+    L.call('dt_rpn_targets', arr, nl, A, T, B, L.ptr(gt_boxes), L.ptr(gt_visible), L.ptr(gt_counts), Gmax, L.ptr(im_info),
            float(cfg_train.RPN_STRADDLE_THRESH), float(cfg_train.RPN_POSITIVE_OVERLAP), float(cfg_train.RPN_NEGATIVE_OVERLAP),
            int(cfg_train.RPN_BATCH_SIZE_PER_IM), float(cfg_train.RPN_FG_FRACTION), int(seed), L.ptr(ws), ws.numel(), L.stream_ptr())
     return out

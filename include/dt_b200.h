@@ -451,19 +451,23 @@ int dt_jpeg_decode(const unsigned char* const* jpegs, const size_t* sizes, int n
 typedef struct dt_rpn_target_level {
   int H, W;
   double feat_stride;
-  const double* anchors;           /* [A, 4] cell anchors (generate_anchors.py) */
+  const double* anchors;           /* [A, 4T] cell anchors (generate_anchors.py) */
   int* labels;                     /* out [B, H, W, A]  (1 fg, 0 bg, -1 ignore) */
   float* bbox_targets;             /* out [B, H, W, 4A] */
   float* inside_weights;           /* out [B, H, W, 4A] */
   float* outside_weights;          /* out [B, H, W, 4A] */
+  int* vis_labels;                 /* out [B, H, W, T*A] (rpn_vis_labels_int32_wide: label x frame visibility), may be NULL */
 } dt_rpn_target_level;
 int dt_rpn_targets_workspace_bytes(int B, int n_levels, const int* Hs, const int* Ws, int A, int Gmax, size_t* bytes /*host out*/);
-/* lib/roi_data/rpn.py:206-381 for every image of the batch and every FPN level (T = 1): gt_boxes [B, Gmax, 4] fp32 in
- * ORIGINAL image coordinates (non-crowd, gt_classes > 0), gt_counts [B], im_info [B, 3] = (blob h, blob w, scale). */
-int dt_rpn_targets(const dt_rpn_target_level* levels /*host*/, int n_levels, int A, int B, const float* gt_boxes, const int* gt_counts,
-                   int Gmax, const float* im_info, float straddle_thresh, float positive_overlap, float negative_overlap,
-                   int batch_size_per_im, float fg_fraction, unsigned long long seed, void* workspace, size_t workspace_bytes,
-                   void* stream);
+/* lib/roi_data/rpn.py:206-381 for every image of the batch and every FPN level, boxes (T = 1) or tubes (T <= 4 frames): gt_boxes
+ * [B, Gmax, 4T] fp32 in ORIGINAL image coordinates (non-crowd, gt_classes > 0), gt_visible [B, Gmax, T] bytes (track_visible;
+ * NULL: all visible), gt_counts [B], im_info [B, 3] = (blob h, blob w, scale).  Per level the anchors are [A, 4T] (the 2-D anchor
+ * replicated over the frames), the box blobs [B, H, W, 4T*A] (channel a*4T + t*4 + k).  Tubes: IoU = mean over the frames; the
+ * box targets follow the reference's fp64-promoted tube arithmetic (utils/boxes.py:28-58,233-240), rounded to fp32 once. */
+int dt_rpn_targets(const dt_rpn_target_level* levels /*host*/, int n_levels, int A, int T, int B, const float* gt_boxes,
+                   const unsigned char* gt_visible, const int* gt_counts, int Gmax, const float* im_info, float straddle_thresh,
+                   float positive_overlap, float negative_overlap, int batch_size_per_im, float fg_fraction, unsigned long long seed,
+                   void* workspace, size_t workspace_bytes, void* stream);
 /* add_proposals + _sample_rois + add_keypoint_rcnn_blobs (lib/datasets/json_dataset.py:423-534, lib/roi_data/fast_rcnn.py:118-238,
  * lib/roi_data/keypoint_rcnn.py:24-99) for every image: rois [B, R, 5] / roi_scores [B, R] / roi_counts [B] = dt_collect_rpn's
  * per-image output (descending score); only the batch-wide top post_nms_topn are used (the training branch of collect).

@@ -224,3 +224,28 @@ def test_targets_edge_cases_empty_inputs():
     assert o['kp_counts'].tolist() == [0, 2]
     ref = ot.sample_rois(gb[1, :2], np.ones(2, np.int32), np.zeros(2, np.int32), kps[1, :2], np.zeros((0, 4), np.float32), 1.0, 1, 2, batch=32)
     _check_sampled(o, 1, ref, 32)
+
+
+def test_rpn_tube_targets_equal_reference_goldens():
+    """T = 3 tubes: tube IoU, per-frame box targets in the reference's fp64-promoted arithmetic (bit-exact: the fp64 log rounds
+    to the same fp32), inside weights and vis labels from the track visibility."""
+    import torch
+    from detectandtrack_b200.ops import target_ops
+    tag, T = 'rpnT3', 3
+    gt, vis = G[tag + '_gt'], G[tag + '_vis']
+    im_h, im_w, _ = G[tag + '_im']
+    field = [int(f) for f in G[tag + '_field']]
+    Gn = gt.shape[0]
+    boxes = np.zeros((3, 8, 4 * T), np.float32); boxes[:, :Gn] = gt
+    v = np.zeros((3, 8, T), np.uint8); v[:, :Gn] = vis
+    anchors = [torch.from_numpy(np.ascontiguousarray(G['cell_anchors_T3_%d' % lvl], dtype=np.float64)).cuda() for lvl in range(2, 7)]
+    out = target_ops.rpn_targets([(f, f) for f in field], anchors, [2. ** l for l in range(2, 7)], 3, torch.from_numpy(boxes).cuda(),
+                                 torch.tensor([Gn] * 3, dtype=torch.int32).cuda(), torch.tensor([[im_h, im_w, 1.0]] * 3, dtype=torch.float32).cuda(),
+                                 _TrainCfg(int(G[tag + '_batch'])), SEED, gt_visible=torch.from_numpy(v).cuda())
+    for l, o in enumerate(out):
+        assert np.array_equal(o['labels'][2].cpu().numpy(), G['%s_labels%d' % (tag, l)]), l      # the goldens were drawn for image 2
+        assert np.array_equal(o['vis_labels'][2].cpu().numpy(), G['%s_vis%d' % (tag, l)]), l
+        got, ref = o['bbox_targets'][2].cpu().numpy(), G['%s_bt%d' % (tag, l)]
+        assert got.shape == ref.shape and _ulp_close(got, ref, 1), l
+        assert np.array_equal(o['inside'][2].cpu().numpy(), G['%s_iw%d' % (tag, l)])
+        assert np.array_equal(o['outside'][2].cpu().numpy(), G['%s_ow%d' % (tag, l)])
