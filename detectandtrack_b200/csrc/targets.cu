@@ -320,7 +320,7 @@ rpn_write_kernel(RpnTL lv, int NA, const float* __restrict__ gt, const unsigned 
 
 // ------------------------------------------------------------------------------------------------ RoI sampling
 struct SampleParams {
-  int B, R, topn, Gmax, K, num_classes, batch, fg_per, kcap, M;
+  int B, R, topn, Gmax, K, T, num_classes, batch, fg_per, kcap, M;      // K joints per frame, T frames per tube
   float fg_thresh, bg_hi, bg_lo, wx, wy, ww, wh;
   unsigned long long seed;
 };
@@ -347,8 +347,9 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
   const int b = blockIdx.x;
   const int G = min(gt_counts[b], p.Gmax);
   const int nmax = p.Gmax + p.R;
-  float* box = reinterpret_cast<float*>(smem_raw);                 // [nmax][4]
-  float* mov = box + (size_t)nmax * 4;                             // [nmax] max_overlaps
+  const int T = p.T, D = 4 * p.T;
+  float* box = reinterpret_cast<float*>(smem_raw);                 // [nmax][4T]
+  float* mov = box + (size_t)nmax * D;                             // [nmax] max_overlaps
   int* bmap = reinterpret_cast<int*>(mov + nmax);                  // [nmax] box_to_gt_ind_map
   int* cls = bmap + nmax;                                          // [nmax] max_classes
   int* list = cls + nmax;                                          // [nmax] candidate list
@@ -359,7 +360,7 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
   __shared__ float s_wsum;
   const float scale = im_info[b * 3 + 2];
   const float inv = __fdiv_rn(1.0f, scale);
-  const float* gb = gt_boxes + (size_t)b * p.Gmax * 4;
+  const float* gb = gt_boxes + (size_t)b * p.Gmax * D;
   // ---- proposals of this image inside the batch-wide top-N (collect, training branch): a prefix of its score-sorted list
   const int Pn = min(roi_counts[b], p.R);
   if (threadIdx.x == 0) { s_n = 0; s_wsum = 0.f; }
@@ -391,27 +392,26 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
   const int n = G + P;
   // ---- add_proposals: boxes = [gt ; proposals / scale], overlaps with the gt boxes (json_dataset.py:423-512)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float bx[4];
+    float bx[4 * TG_TMAX];
     float mx; int am, c;
     if (i < G) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) bx[k] = gb[i * 4 + k];
+      for (int k = 0; k < D; ++k) bx[k] = gb[i * D + k];
       const bool crowd = gt_crowd[b * p.Gmax + i] != 0;
       mx = crowd ? -1.f : 1.f; am = i; c = crowd ? 0 : gt_classes[b * p.Gmax + i];
     } else {
-      const float* r = rois + ((size_t)b * p.R + (i - G)) * 5;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) bx[k] = __fmul_rn(r[1 + k], inv);
+      const float* r = rois + ((size_t)b * p.R + (i - G)) * (D + 1);
+      for (int k = 0; k < D; ++k) bx[k] = __fmul_rn(r[1 + k], inv);
       mx = 0.f; am = -1; c = 0;
       float best = 0.f; int arg = 0;
       for (int g = 0; g < G; ++g) {
-        const float v = iou_pair_ref(bx, gb + 4 * g);
+        float v = iou_pair_ref(bx, gb + D * g);                      // tubes: mean over the frames (utils/boxes.py:60-69)
+        for (int t = 1; t < T; ++t) v = __fadd_rn(v, iou_pair_ref(bx + 4 * t, gb + D * g + 4 * t));
+        if (T > 1) v = __fdiv_rn(v, (float)T);
         if (g == 0 || v > best) { best = v; arg = g; }
       }
       if (G > 0 && best > 0.f) { mx = best; am = arg; c = gt_classes[b * p.Gmax + arg]; }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) box[i * 4 + k] = bx[k];
+    for (int k = 0; k < D; ++k) box[i * D + k] = bx[k];
     mov[i] = mx; bmap[i] = am; cls[i] = c;
   }
   __syncthreads();
@@ -443,30 +443,32 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
     __syncthreads();
   }
   const int nrows = k_fg + k_bg;
-  const int C4 = 4 * p.num_classes;
+  const int C4 = D * p.num_classes;
   for (int r = threadIdx.x; r < p.batch; r += blockDim.x) {
-    float* ro = rois_out + ((size_t)b * p.batch + r) * 5;
+    float* ro = rois_out + ((size_t)b * p.batch + r) * (D + 1);
     float* bto = bt + ((size_t)b * p.batch + r) * C4;
     float* iwo = iw + ((size_t)b * p.batch + r) * C4;
     float* owo = ow + ((size_t)b * p.batch + r) * C4;
     for (int k = 0; k < C4; ++k) { bto[k] = 0.f; iwo[k] = 0.f; owo[k] = 0.f; }
     ro[0] = (float)b;
     if (r >= nrows) {
-      ro[1] = ro[2] = ro[3] = ro[4] = 0.f;
+      for (int k = 0; k < D; ++k) ro[1 + k] = 0.f;
       labels[b * p.batch + r] = -1;                       // padding row: ignored by the losses
       continue;
     }
     const int i = rowof[r];
     const int lbl = r < k_fg ? cls[i] : 0;
     labels[b * p.batch + r] = lbl;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ro[1 + k] = __fmul_rn(box[i * 4 + k], scale);
+    for (int k = 0; k < D; ++k) ro[1 + k] = __fmul_rn(box[i * D + k], scale);
     if (lbl > 0) {
       int ga = bmap[i]; if (ga < 0) ga += G;              // gt_inds[-1]: python negative indexing
-      float t[4];
-      transform_inv(box + i * 4, gb + 4 * ga, p.wx, p.wy, p.ww, p.wh, t);
+      for (int f = 0; f < T; ++f) {                       // tubes: frame by frame, fp64-promoted like the reference
+        float t[4];
+        if (T == 1) transform_inv(box + i * D, gb + D * ga, p.wx, p.wy, p.ww, p.wh, t);
+        else transform_inv64(box + i * D + 4 * f, gb + D * ga + 4 * f, (double)p.wx, (double)p.wy, (double)p.ww, (double)p.wh, t);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { bto[4 * lbl + k] = t[k]; iwo[4 * lbl + k] = 1.f; owo[4 * lbl + k] = 1.f; }
+        for (int k = 0; k < 4; ++k) { bto[D * lbl + 4 * f + k] = t[k]; iwo[D * lbl + 4 * f + k] = 1.f; owo[D * lbl + 4 * f + k] = 1.f; }
+      }
     }
   }
   // ---- add_keypoint_rcnn_blobs (keypoint_rcnn.py:24-83)
@@ -474,18 +476,20 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
   bool by_index = true;
   if (kp_rois) {
     const unsigned long long base = hash_base(p.seed, 4ull, (unsigned long long)b);
-    const int* kps = gt_kps + (size_t)b * p.Gmax * 3 * p.K;
+    const int Kt = p.K * T;                               // gt_keypoints [G, 3, K*T] (utils/video.py:143-146)
+    const int* kps = gt_kps + (size_t)b * p.Gmax * 3 * Kt;
     int c = 0;
     const int per = (n + blockDim.x - 1) / blockDim.x;
     const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
     auto is_cand = [&](int i) -> bool {
       if (!(mov[i] >= p.fg_thresh) || G == 0) return false;
       int g = bmap[i]; if (g < 0) g += G;
-      const int* kp = kps + (size_t)g * 3 * p.K;
-      const double x1 = box[i * 4], y1 = box[i * 4 + 1], x2 = box[i * 4 + 2], y2 = box[i * 4 + 3];
-      for (int k = 0; k < p.K; ++k) {
-        const double x = kp[k], y = kp[p.K + k];
-        if (kp[2 * p.K + k] > 0 && x >= x1 && x <= x2 && y >= y1 && y <= y2) return true;
+      const int* kp = kps + (size_t)g * 3 * Kt;
+      // keypoint_rcnn.py:32-34: _within_box tests every joint of every frame against the FIRST frame's box
+      const double x1 = box[i * D], y1 = box[i * D + 1], x2 = box[i * D + 2], y2 = box[i * D + 3];
+      for (int k = 0; k < Kt; ++k) {
+        const double x = kp[k], y = kp[Kt + k];
+        if (kp[2 * Kt + k] > 0 && x >= x1 && x <= x2 && y >= y1 && y <= y2) return true;
       }
       return false;
     };
@@ -508,16 +512,17 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
     }
     __syncthreads();
     float wsum = 0.f;
-    for (int e = threadIdx.x; e < p.kcap * p.K; e += blockDim.x) {
-      const int r = e / p.K, k = e - r * p.K;
+    for (int e = threadIdx.x; e < p.kcap * Kt; e += blockDim.x) {
+      const int r = e / Kt, k = e - r * Kt;               // k = frame * K + joint
       int loc = 0; float wt = 0.f;
       if (r < nk) {
         const int i = rowof[p.batch + r];
         const int g = bmap[i];
         int kx = -1, ky = -1, kv = -1;                    // sampled_keypoints = -1 without a gt
-        if (g >= 0) { const int* kp = kps + (size_t)g * 3 * p.K; kx = kp[k]; ky = kp[p.K + k]; kv = kp[2 * p.K + k]; }
-        // utils/keypoints.py:152-207 in fp32
-        const float x1 = box[i * 4], y1 = box[i * 4 + 1], x2 = box[i * 4 + 2], y2 = box[i * 4 + 3];
+        if (g >= 0) { const int* kp = kps + (size_t)g * 3 * Kt; kx = kp[k]; ky = kp[Kt + k]; kv = kp[2 * Kt + k]; }
+        // utils/keypoints.py:152-207 in fp32, frame f = k / K against that frame's box (keypoint_rcnn.py:62-70)
+        const float* fb = box + i * D + 4 * (k / p.K);
+        const float x1 = fb[0], y1 = fb[1], x2 = fb[2], y2 = fb[3];
         const float sx = __fdiv_rn((float)p.M, __fadd_rn(__fsub_rn(x2, x1), 1.f));
         const float sy = __fdiv_rn((float)p.M, __fadd_rn(__fsub_rn(y2, y1), 1.f));
         const float xf = (float)kx, yf = (float)ky;
@@ -528,19 +533,18 @@ sample_rois_kernel(SampleParams p, const float* __restrict__ rois, const float* 
         const bool valid = x >= 0.f && y >= 0.f && x < (float)p.M && y < (float)p.M && kv > 0;
         if (valid) { loc = (int)__fadd_rn(__fmul_rn(y, (float)p.M), x); wt = 1.f; }
       }
-      kp_loc[((size_t)b * p.kcap + r) * p.K + k] = loc;
-      kp_w[((size_t)b * p.kcap + r) * p.K + k] = wt;
+      kp_loc[((size_t)b * p.kcap + r) * Kt + k] = loc;
+      kp_w[((size_t)b * p.kcap + r) * Kt + k] = wt;
       wsum += wt;
     }
     for (int r = threadIdx.x; r < p.kcap; r += blockDim.x) {
-      float* ro = kp_rois + ((size_t)b * p.kcap + r) * 5;
+      float* ro = kp_rois + ((size_t)b * p.kcap + r) * (D + 1);
       ro[0] = (float)b;
       if (r < nk) {
         const int i = rowof[p.batch + r];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ro[1 + k] = __fmul_rn(box[i * 4 + k], scale);
+        for (int k = 0; k < D; ++k) ro[1 + k] = __fmul_rn(box[i * D + k], scale);
       } else {
-        ro[1] = ro[2] = ro[3] = ro[4] = 0.f;
+        for (int k = 0; k < D; ++k) ro[1 + k] = 0.f;
       }
     }
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
@@ -620,21 +624,21 @@ extern "C" int dt_rpn_targets(const dt_rpn_target_level* levels, int n_levels, i
 
 extern "C" int dt_sample_rois(const float* rois, const float* roi_scores, const int* roi_counts, int B, int R, int post_nms_topn,
                               const float* gt_boxes, const int* gt_classes, const int* gt_crowd, const int* gt_keypoints,
-                              const int* gt_counts, int Gmax, int K, const float* im_info, int num_classes, int batch_size_per_im,
+                              const int* gt_counts, int Gmax, int K, int T, const float* im_info, int num_classes, int batch_size_per_im,
                               float fg_fraction, float fg_thresh, float bg_thresh_hi, float bg_thresh_lo, const float* bbox_reg_weights,
                               int heatmap_size, unsigned long long seed, float* rois_out, int* labels, float* bbox_targets,
                               float* inside_weights, float* outside_weights, int* out_counts, float* kp_rois, int* kp_locations,
                               float* kp_weights, int* kp_counts, int kcap, float* totals, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DT_CHECK_ARG(B >= 1 && R >= 1 && Gmax >= 1 && Gmax <= TG_GMAX && num_classes >= 2 && batch_size_per_im >= 1 && bbox_reg_weights,
-               "dt_sample_rois: bad arguments B=%d R=%d Gmax=%d", B, R, Gmax);
+  DT_CHECK_ARG(B >= 1 && R >= 1 && Gmax >= 1 && Gmax <= TG_GMAX && T >= 1 && T <= TG_TMAX && num_classes >= 2 && batch_size_per_im >= 1 &&
+                   bbox_reg_weights, "dt_sample_rois: bad arguments B=%d R=%d Gmax=%d T=%d (T <= %d)", B, R, Gmax, T, TG_TMAX);
   DT_CHECK_ARG(rois && roi_scores && roi_counts && gt_boxes && gt_classes && gt_crowd && gt_counts && im_info && rois_out && labels &&
                    bbox_targets && inside_weights && outside_weights && out_counts, "dt_sample_rois: null pointer");
   DT_CHECK_ARG(!kp_rois || (gt_keypoints && kp_locations && kp_weights && kp_counts && K >= 1 && kcap >= 1 && heatmap_size >= 1),
                "dt_sample_rois: keypoint outputs need gt_keypoints, K, kcap, heatmap_size");
   SampleParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.R = R; p.topn = post_nms_topn; p.Gmax = Gmax; p.K = K; p.num_classes = num_classes; p.batch = batch_size_per_im;
+  p.B = B; p.R = R; p.topn = post_nms_topn; p.Gmax = Gmax; p.K = K; p.T = T; p.num_classes = num_classes; p.batch = batch_size_per_im;
   p.fg_per = (int)nearbyint((double)fg_fraction * batch_size_per_im);
   p.kcap = kp_rois ? kcap : 0; p.M = heatmap_size;
   p.fg_thresh = fg_thresh; p.bg_hi = bg_thresh_hi; p.bg_lo = bg_thresh_lo;
@@ -642,7 +646,7 @@ extern "C" int dt_sample_rois(const float* rois, const float* roi_scores, const 
   p.seed = seed;
   DT_CHECK_ARG(!kp_rois || kcap >= (p.fg_per > Gmax ? p.fg_per : Gmax), "dt_sample_rois: kcap %d < max(fg rois per image %d, Gmax %d)", kcap, p.fg_per, Gmax);
   const int nmax = Gmax + R;
-  const size_t smem = (size_t)nmax * (16 + 4 * 5) + (size_t)(batch_size_per_im + p.kcap) * 4 + 16;
+  const size_t smem = (size_t)nmax * (16 * T + 4 * 5) + (size_t)(batch_size_per_im + p.kcap) * 4 + 16;
   DT_CHECK_ARG(smem <= 220 * 1024, "dt_sample_rois: %d proposals per image do not fit shared memory", R);
   static DynSmemGrant grant;
   DT_CHECK_CUDA(grant_dyn_smem(sample_rois_kernel, (int)smem, &grant));

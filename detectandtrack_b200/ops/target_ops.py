@@ -46,7 +46,9 @@ def sample_rois(rois, roi_scores, roi_counts, gt, im_info, cfg, seed, keypoints=
     classes / crowd [B,Gmax] i32, keypoints [B,Gmax,3,K] i32, counts [B] i32).  Returns the Fast R-CNN / keypoint blobs as
     fixed-capacity device tensors (see dt_sample_rois)."""
     torch = L.require_cuda()
-    B, R, _ = rois.shape
+    B, R, ldr = rois.shape
+    T = (ldr - 1) // 4
+    assert gt['boxes'].shape[2] == 4 * T, 'gt boxes must be [B, Gmax, 4T] like the rois'
     Gmax = gt['boxes'].shape[1]
     tr = cfg.TRAIN
     batch = int(tr.BATCH_SIZE_PER_IM)
@@ -55,18 +57,19 @@ def sample_rois(rois, roi_scores, roi_counts, gt, im_info, cfg, seed, keypoints=
     fg_per = int(round(tr.FG_FRACTION * batch))
     kcap = (max(fg_per, Gmax) + 7) // 8 * 8
     f32, i32 = torch.float32, torch.int32
-    o = dict(rois=torch.empty((B, batch, 5), dtype=f32, device='cuda'), labels=torch.empty((B, batch), dtype=i32, device='cuda'),
-             bbox_targets=torch.empty((B, batch, 4 * nc), dtype=f32, device='cuda'),
-             inside=torch.empty((B, batch, 4 * nc), dtype=f32, device='cuda'),
-             outside=torch.empty((B, batch, 4 * nc), dtype=f32, device='cuda'), counts=torch.empty((B,), dtype=i32, device='cuda'),
+    o = dict(rois=torch.empty((B, batch, 4 * T + 1), dtype=f32, device='cuda'), labels=torch.empty((B, batch), dtype=i32, device='cuda'),
+             bbox_targets=torch.empty((B, batch, 4 * T * nc), dtype=f32, device='cuda'),
+             inside=torch.empty((B, batch, 4 * T * nc), dtype=f32, device='cuda'),
+             outside=torch.empty((B, batch, 4 * T * nc), dtype=f32, device='cuda'), counts=torch.empty((B,), dtype=i32, device='cuda'),
              totals=totals if totals is not None else L.zeros((2,), f32))
     if keypoints:
-        o.update(kp_rois=torch.empty((B, kcap, 5), dtype=f32, device='cuda'), kp_locations=torch.empty((B, kcap, K), dtype=i32, device='cuda'),
-                 kp_weights=torch.empty((B, kcap, K), dtype=f32, device='cuda'), kp_counts=torch.empty((B,), dtype=i32, device='cuda'))
+        assert gt['keypoints'].shape[3] == K * T, 'gt keypoints must be [B, Gmax, 3, K*T]'
+        o.update(kp_rois=torch.empty((B, kcap, 4 * T + 1), dtype=f32, device='cuda'), kp_locations=torch.empty((B, kcap, K * T), dtype=i32, device='cuda'),
+                 kp_weights=torch.empty((B, kcap, K * T), dtype=f32, device='cuda'), kp_counts=torch.empty((B,), dtype=i32, device='cuda'))
     w4 = (C.c_float * 4)(*[float(x) for x in cfg.MODEL.BBOX_REG_WEIGHTS])
     L.call('dt_sample_rois', L.ptr(rois), L.ptr(roi_scores), L.ptr(roi_counts), B, R, int(tr.RPN_POST_NMS_TOP_N),
            L.ptr(gt['boxes']), L.ptr(gt['classes']), L.ptr(gt['crowd']), L.ptr(gt.get('keypoints') if keypoints else None),
-           L.ptr(gt['counts']), Gmax, K, L.ptr(im_info), nc, batch, float(tr.FG_FRACTION), float(tr.FG_THRESH),
+           L.ptr(gt['counts']), Gmax, K, T, L.ptr(im_info), nc, batch, float(tr.FG_FRACTION), float(tr.FG_THRESH),
            float(tr.BG_THRESH_HI), float(tr.BG_THRESH_LO), w4, int(cfg.KRCNN.HEATMAP_SIZE) if keypoints else 0, int(seed),
            L.ptr(o['rois']), L.ptr(o['labels']), L.ptr(o['bbox_targets']), L.ptr(o['inside']), L.ptr(o['outside']), L.ptr(o['counts']),
            L.ptr(o.get('kp_rois')), L.ptr(o.get('kp_locations')), L.ptr(o.get('kp_weights')), L.ptr(o.get('kp_counts')), kcap,

@@ -471,13 +471,16 @@ int dt_rpn_targets(const dt_rpn_target_level* levels /*host*/, int n_levels, int
 /* add_proposals + _sample_rois + add_keypoint_rcnn_blobs (lib/datasets/json_dataset.py:423-534, lib/roi_data/fast_rcnn.py:118-238,
  * lib/roi_data/keypoint_rcnn.py:24-99) for every image: rois [B, R, 5] / roi_scores [B, R] / roi_counts [B] = dt_collect_rpn's
  * per-image output (descending score); only the batch-wide top post_nms_topn are used (the training branch of collect).
- * gt_* [B, Gmax, ...]: boxes fp32 (original coordinates, ALL gt incl. crowd), classes, crowd flags, keypoints [B,Gmax,3,K] int32.
- * Outputs (fixed capacity, padding rows have label -1 / zero weights): rois_out [B, batch, 5], labels [B, batch],
- * bbox_targets / inside / outside [B, batch, 4*num_classes], out_counts [B]; kp_rois [B, kcap, 5] (may be NULL),
- * kp_locations [B, kcap, K] int32, kp_weights [B, kcap, K], kp_counts [B]; totals [2] += (live RoIs, keypoint weight sum). */
+ * gt_* [B, Gmax, ...]: boxes fp32 (original coordinates, ALL gt incl. crowd), classes, crowd flags, keypoints [B,Gmax,3,K] int32
+ * (K joints per frame).
+ * Outputs (fixed capacity, padding rows have label -1 / zero weights): rois_out [B, batch, 4T+1], labels [B, batch],
+ * bbox_targets / inside / outside [B, batch, 4T*num_classes], out_counts [B]; kp_rois [B, kcap, 4T+1] (may be NULL),
+ * kp_locations [B, kcap, K*T] int32, kp_weights [B, kcap, K*T], kp_counts [B]; totals [2] += (live RoIs, keypoint weight sum).
+ * T > 1 (tubes, T <= 4): rois [B, R, 4T+1], gt boxes [B, Gmax, 4T], gt keypoints [B, Gmax, 3, K*T]; tube IoU is the mean over the
+ * frames, box targets are computed frame by frame in the reference's fp64-promoted arithmetic, heat-map labels per frame. */
 int dt_sample_rois(const float* rois, const float* roi_scores, const int* roi_counts, int B, int R, int post_nms_topn,
                    const float* gt_boxes, const int* gt_classes, const int* gt_crowd, const int* gt_keypoints,
-                   const int* gt_counts, int Gmax, int K, const float* im_info, int num_classes, int batch_size_per_im,
+                   const int* gt_counts, int Gmax, int K, int T, const float* im_info, int num_classes, int batch_size_per_im,
                    float fg_fraction, float fg_thresh, float bg_thresh_hi, float bg_thresh_lo, const float* bbox_reg_weights /*host [4]*/,
                    int heatmap_size, unsigned long long seed, float* rois_out, int* labels, float* bbox_targets,
                    float* inside_weights, float* outside_weights, int* out_counts, float* kp_rois, int* kp_locations,

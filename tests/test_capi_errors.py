@@ -68,7 +68,7 @@ def _cases():
         ('dt_subpixel_grad_fix', (None, None, 17, 8, 60, None), b'ldc=60'),
         ('dt_jpeg_decode', (None, None, 2, 0, 10, None, None), b'dt_jpeg_decode'),
         ('dt_rpn_targets', (tl, 1, 3, 1, 1, None, None, None, 4096, None, 0.0, 0.7, 0.3, 256, 0.5, 3, None, 0, None), b'Gmax'),
-        ('dt_sample_rois', (None, None, None, 1, 0, 2000, None, None, None, None, None, 8, 17, None, 2, 512, 0.25, 0.5, 0.5, 0.0, f4, 56, 3,
+        ('dt_sample_rois', (None, None, None, 1, 0, 2000, None, None, None, None, None, 8, 17, 1, None, 2, 512, 0.25, 0.5, 0.5, 0.0, f4, 56, 3,
                             None, None, None, None, None, None, None, None, None, None, 128, None, None), b'dt_sample_rois'),
     ]
 

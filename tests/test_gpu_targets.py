@@ -249,3 +249,35 @@ def test_rpn_tube_targets_equal_reference_goldens():
         assert got.shape == ref.shape and _ulp_close(got, ref, 1), l
         assert np.array_equal(o['inside'][2].cpu().numpy(), G['%s_iw%d' % (tag, l)])
         assert np.array_equal(o['outside'][2].cpu().numpy(), G['%s_ow%d' % (tag, l)])
+
+
+def test_sample_tube_rois_equal_reference_goldens():
+    """T = 3: tube proposals merged with gt tubes (tube IoU), 4T box targets per class, per-frame heat-map labels."""
+    import torch
+    from detectandtrack_b200.ops import target_ops
+    tag, T = 'roiT3', 3
+    rois_in = G[tag + '_rois_in']
+    P = rois_in.shape[0]
+    batch = int(G[tag + '_batch'])
+    gb, gk = G[tag + '_gt_boxes'], G[tag + '_gt_gt_keypoints']
+    g = gb.shape[0]
+    boxes = np.zeros((1, 8, 4 * T), np.float32); boxes[0, :g] = gb
+    kps = np.zeros((1, 8, 3, 17 * T), np.int32); kps[0, :g] = gk
+    t = lambda a: torch.from_numpy(a).cuda()
+    gt = dict(boxes=t(boxes), classes=torch.ones((1, 8), dtype=torch.int32).cuda(), crowd=torch.zeros((1, 8), dtype=torch.int32).cuda(),
+              keypoints=t(kps), counts=torch.tensor([g], dtype=torch.int32).cuda())
+    scores = np.linspace(1.0, 0.1, P).astype(np.float32)[None]
+    o = target_ops.sample_rois(t(rois_in[None].copy()), t(scores), torch.tensor([P], dtype=torch.int32).cuda(), gt,
+                               torch.tensor([[0, 0, float(G[tag + '_scale'])]], dtype=torch.float32).cuda(), _Cfg(batch), SEED)
+    n = len(G[tag + '_rois'])
+    assert int(o['counts'][0]) == n and o['rois'].shape[2] == 13
+    assert np.array_equal(o['rois'][0, :n].cpu().numpy(), G[tag + '_rois'])
+    assert np.array_equal(o['labels'][0, :n].cpu().numpy(), G[tag + '_labels_int32'])
+    assert _ulp_close(o['bbox_targets'][0, :n].cpu().numpy(), G[tag + '_bbox_targets'], 1)
+    assert np.array_equal(o['inside'][0, :n].cpu().numpy(), G[tag + '_bbox_inside_weights'])
+    assert np.array_equal(o['outside'][0, :n].cpu().numpy(), G[tag + '_bbox_outside_weights'])
+    nk = len(G[tag + '_keypoint_rois'])
+    assert int(o['kp_counts'][0]) == nk
+    assert np.array_equal(o['kp_rois'][0, :nk].cpu().numpy(), G[tag + '_keypoint_rois'])
+    assert np.array_equal(o['kp_locations'][0, :nk].cpu().numpy().reshape(-1, 1), G[tag + '_keypoint_locations_int32'])
+    assert np.array_equal(o['kp_weights'][0, :nk].cpu().numpy().reshape(-1, 1), G[tag + '_keypoint_weights'])
