@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('DT_TEST_JPEG', '0') != '1', reason='pending first verification on a B200 box (set DT_TEST_JPEG=1)')]
+pytestmark = pytest.mark.gpu
 
 
 def _image(h, w, seed):
@@ -26,8 +26,8 @@ def test_jpeg_decode_vs_cv2():
         pytest.skip('nvJPEG is not installed on this machine')
     H, W = 240, 328
     ims = [_image(H, W, s) for s in range(3)]
-    for tag, flags, mean_tol, max_tol in (('444', [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], 0.6, 6),
-                                           ('420', [cv2.IMWRITE_JPEG_QUALITY, 92], 1.5, 48)):
+    for tag, flags, mean_tol, max_tol in (('444', [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], 0.8, 8),        # measured on B200: mean 0.51, max 4
+                                           ('420', [cv2.IMWRITE_JPEG_QUALITY, 92], 1.5, 24)):                                                        # measured: mean 1.02, max 8
         streams = [cv2.imencode('.jpg', im, flags)[1].tobytes() for im in ims]
         ref = np.stack([cv2.imdecode(np.frombuffer(s, np.uint8), cv2.IMREAD_COLOR) for s in streams])
         got = image_ops.jpeg_decode(streams, H, W)
