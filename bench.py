@@ -450,6 +450,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, conv_ms_max = t.tolist()
+    # BASELINE.json configs[4] next to the inference headline, on the same box and process group: the keypoint R-CNN training
+    # step with its NCCL gradient all-reduce (every rank takes part; a labelled extra of this line, `bench.py --train` alone
+    # prints it as its own line)
+    training = None
+    if args.dtype == 'auto' and args.config == 'r50fpn3d' and not args.no_extras and not args.dce:
+        try:
+            import gc
+            gc.collect(); torch.cuda.empty_cache()
+            tl = _train_measure(args, rank, world, local, steps=min(args.steps, 10))
+            if tl is not None:
+                training = dict(metric=tl['metric'], value=tl['value'], unit=tl['unit'], ms_per_step=tl['ms_per_step'], n_gpus=world,
+                                dtype='bf16', e2e=tl['e2e'], roofline=dict(achieved=tl['roofline']['achieved'], frac=tl['roofline']['frac'],
+                                                                          unit='TFLOP/s', note=tl['roofline']['note']),
+                                allreduce_bytes_per_step=tl['config']['allreduce_bytes_per_step'], allreduce=tl['config']['allreduce'],
+                                losses=dict(rpn=tl['config']['loss_rpn'], cls=tl['config'].get('loss_cls'), bbox=tl['config'].get('loss_bbox'),
+                                            kps=tl['config'].get('loss_kps')), workload=tl['config']['workload'])
+        except Exception as e:                                   # an extra must never cost the headline
+            training = dict(error=str(e)[:300])
     if rank == 0:
         pk = peaks()
         value = world * B * args.steps / (ms / 1000.0)
@@ -490,6 +508,8 @@ def run_ours(args):
                 dict(dtype=x['mode'], parity=parity.get(x['mode']), error=x.get('error')) if 'error' in x else
                 dict(dtype=x['mode'], parity=parity.get(x['mode']), value=B * args.steps / (x['ms'] / 1000.0),
                      e2e=B * args.steps / (x['ms_e2e'] / 1000.0), unit='clips/s') for x in extras]
+        if training is not None:
+            line['training'] = training
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(cfg, blobs, args)
         if world == 1 and not args.no_extras:
@@ -523,8 +543,9 @@ def synth_gt(B, H, W, seed, G=4, K=17):
     return entries
 
 
-def run_train(args):
-    """`--train`: BASELINE.json configs[4], the keypoint R-CNN training step (modeling/trainer.KeypointRcnnTrainer): frozen
+def _train_measure(args, rank, world, local, steps=None):
+    """One measured training leg on an initialised process group (all ranks call it); returns the JSON line as a dict on rank 0,
+    None elsewhere.  `--train`: BASELINE.json configs[4], the keypoint R-CNN training step (modeling/trainer.KeypointRcnnTrainer): frozen
     stem, bf16 forward of res3..res5 + FPN3D + RPN + both RoI heads, ALL targets generated on the device (RPN anchor targets,
     training proposals, RoI sampling, keypoint labels), losses, backward (dgrad / tcgen05 wgrad / RoIAlign backward), the
     bucketed NCCL gradient all-reduce overlapped with the backward pass, fused SGD.  TRAIN.IMS_PER_BATCH = 2 clips per GPU.
@@ -533,16 +554,12 @@ def run_train(args):
     import torch.distributed as dist
     from detectandtrack_b200.modeling import params as P
     from detectandtrack_b200.modeling.trainer import RpnTrainer, KeypointRcnnTrainer, pack_gt
-    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    nsteps = steps or args.steps
     cfg = bench_cfg(args.height, args.width, 'r50fpn3d')
     cfg.TRAIN.BATCH_SIZE_PER_IM = 512; cfg.TRAIN.RPN_PRE_NMS_TOP_N = 2000      # the shipped keypoint yamls (configs/video/2d_best)
     blobs, spec = P.random_blobs(cfg)
     B, T, H, W = cfg.TRAIN.IMS_PER_BATCH, 3, args.height, args.width
-    full = not args.train_trunk
+    full = not getattr(args, 'train_trunk', False)
     frames_h = torch.from_numpy(synth_frames(B, T, H, W, 100 + rank)).pin_memory()
     frames = frames_h.cuda()
     if full:
@@ -577,7 +594,7 @@ def run_train(args):
         return t.item(), out, sampler.stop() if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step(frames)
-    ms, (loss, lh), clocks = timed(lambda: step(frames), args.steps)
+    ms, (loss, lh), clocks = timed(lambda: step(frames), nsteps)
     # e2e: the step a training loop makes — pinned host frames -> device every step, losses read back every step
     loss_h = torch.empty(6, dtype=torch.float32).pin_memory()
 
@@ -590,7 +607,7 @@ def run_train(args):
         torch.cuda.current_stream().synchronize()
         return l, h
     e2e_step()
-    ms2, _, _ = timed(e2e_step, args.steps)
+    ms2, _, _ = timed(e2e_step, nsteps)
     if rank == 0:
         nparam = int(tr.flat_g.numel())
         what = ('keypoint R-CNN training step (RPN + Fast R-CNN + keypoint heads, device-side targets)' if full else
@@ -606,7 +623,7 @@ def run_train(args):
             cfgd.update(loss_cls=l4[0], loss_bbox=l4[1], loss_kps=l4[2], sampled_rois=float(tr.totals[0]), keypoint_targets=float(tr.totals[1]))
         pk = peaks()
         fl = tr.step_flops()
-        tf = fl / (ms / args.steps / 1000.0) / 1e12
+        tf = fl / (ms / nsteps / 1000.0) / 1e12
         peak = pk['tflops']
         roof = dict(bound='tensor', kernel='conv_tc_kernel (forward + dgrad) + wgrad_nhwc_kernel, whole step', achieved=tf, peak=peak, unit='TFLOP/s',
                     frac=tf / peak, traffic=None,
@@ -614,11 +631,25 @@ def run_train(args):
                          'step of %d clips; frozen stem excluded) / WHOLE step time incl. targets, losses, joins, all-reduce and SGD' % (fl / 1e9, B),
                     peak_source=pk['src'])
         line = dict(metric='training clips/sec, %s, T=3, %dx%d' % (what, H, W),
-                    value=world * B * args.steps / (ms / 1000.0), unit='clips/s', n_gpus=world, steps=args.steps,
-                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    value=world * B * nsteps / (ms / 1000.0), unit='clips/s', n_gpus=world, steps=nsteps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms / nsteps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='bf16', data='synthetic',
-                    e2e=dict(value=world * B * args.steps / (ms2 / 1000.0), unit='clips/s', h2d_bytes_per_step=int(frames_h.numel()),
+                    e2e=dict(value=world * B * nsteps / (ms2 / 1000.0), unit='clips/s', h2d_bytes_per_step=int(frames_h.numel()),
                              d2h_bytes_per_step=24), roofline=roof, config=cfgd, clocks=clocks)
+        return line
+    return None
+
+
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    line = _train_measure(args, rank, world, local)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
