@@ -86,3 +86,28 @@ def test_get_output_dir(tmp_path):
     C.cfg.MODEL.TYPE = 'keypoint_rcnn'
     d = C.get_output_dir(training=False)
     assert d.endswith(os.path.join('test', 'posetrack_v1.0_val', 'keypoint_rcnn')) and os.path.isdir(d)
+
+
+def test_output_dir_of_a_json_roidb_given_by_path(tmp_path):
+    """TEST.DATASET may be the path of a JSON roidb (test_engine.JsonListDataset): its file stem names the directory level the
+    reference fills with the dataset name (config.py:777-785), so the output stays under OUTPUT_DIR."""
+    import os
+    from detectandtrack_b200.core.config import cfg, reset_cfg, get_output_dir
+    reset_cfg()
+    try:
+        cfg.OUTPUT_DIR = str(tmp_path / 'out')
+        cfg.MODEL.TYPE = 'keypoint_rcnn'
+        cfg.TEST.DATASET = str(tmp_path / 'lists' / 'posetrack_val.json')
+        d = get_output_dir(training=False)
+        assert d == os.path.join(str(tmp_path / 'out'), 'test', 'posetrack_val', 'keypoint_rcnn') and os.path.isdir(d)
+        cfg.TEST.DATASET = 'synthetic_2x3'
+        assert get_output_dir(training=False).endswith(os.path.join('test', 'synthetic_2x3', 'keypoint_rcnn'))
+    finally:
+        reset_cfg()
+
+
+def test_device_jpeg_decode_only_for_jpeg_files():
+    from detectandtrack_b200.core.test_engine import _all_jpeg
+    assert _all_jpeg([dict(image=['a/1.jpg', 'a/2.JPEG']), dict(image='b/3.jpg')])
+    assert not _all_jpeg([dict(image=['a/1.jpg', 'a/2.png'])])
+    assert not _all_jpeg([dict(image='x.jpg', synthetic=True)])
